@@ -1,0 +1,111 @@
+"""
+Seeded synthetic geometry / rays / textures for tests and benchmarks (numpy, host side).
+
+The shapes follow SURVEY.md section 8(d): icosphere (config 1), displaced UV sphere (configs 2/4),
+ground grid + displaced spheres (config 3).  Nothing here touches the GPU.
+"""
+import math
+import numpy as np
+
+
+def icosphere(subdiv: int = 3, radius: float = 0.8):
+    """Icosahedron subdivided ``subdiv`` times: 10*4^s + 2 verts, 20*4^s faces (642 / 1280 at s=3)."""
+    p = (1.0 + math.sqrt(5.0)) / 2.0
+    v = [(-1, p, 0), (1, p, 0), (-1, -p, 0), (1, -p, 0), (0, -1, p), (0, 1, p), (0, -1, -p), (0, 1, -p),
+         (p, 0, -1), (p, 0, 1), (-p, 0, -1), (-p, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+         (8, 6, 7), (9, 8, 1)]
+    verts = [np.array(x, dtype=np.float64) / math.sqrt(1 + p * p) for x in v]
+    faces = list(f)
+    for _ in range(subdiv):
+        cache = {}
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+        nf = []
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nf
+    return (np.array(verts) * radius).astype(np.float32), np.array(faces, dtype=np.int32)
+
+
+def uv_sphere(n_theta: int, n_phi: int, radius: float = 0.8, bump: float = 0.05, noise: float = 0.01, seed: int = 0,
+              center=(0.0, 0.0, 0.0), with_attrs: bool = False):
+    """
+    Displaced UV sphere with n_theta x n_phi quads = 2*n_theta*n_phi triangles (pole rows are zero-area
+    triangles on purpose).  r = radius + bump*sin(7 theta)cos(5 phi) + noise*U(0,1).
+    With ``with_attrs`` also returns smooth normals (radial), uv and analytic tangents (d/dtheta, w=1).
+    """
+    rng = np.random.default_rng(seed)
+    th = np.linspace(0.0, 2.0 * np.pi, n_theta + 1)
+    ph = np.linspace(-0.5 * np.pi, 0.5 * np.pi, n_phi + 1)
+    T, P = np.meshgrid(th, ph, indexing='xy')  # (n_phi+1, n_theta+1)
+    r = radius + bump * np.sin(7 * T) * np.cos(5 * P) + noise * rng.random(T.shape)
+    r[:, -1] = r[:, 0]
+    x, y, z = r * np.sin(T) * np.cos(P), r * np.sin(P), r * np.cos(T) * np.cos(P)
+    verts = (np.stack([x, y, z], -1).reshape(-1, 3) + np.asarray(center)).astype(np.float32)
+    j, i = np.meshgrid(np.arange(n_phi), np.arange(n_theta), indexing='ij')
+    a = (j * (n_theta + 1) + i).reshape(-1)
+    b, c, d = a + 1, a + (n_theta + 1), a + (n_theta + 2)
+    tris = np.concatenate([np.stack([a, b, d], -1), np.stack([a, d, c], -1)], 0).astype(np.int32)
+    if not with_attrs:
+        return verts, tris
+    nrm = np.stack([np.sin(T) * np.cos(P), np.sin(P), np.cos(T) * np.cos(P)], -1).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([T / (2 * np.pi), (P + 0.5 * np.pi) / np.pi], -1).reshape(-1, 2).astype(np.float32)
+    tan = np.stack([np.cos(T), np.zeros_like(T), -np.sin(T), np.ones_like(T)], -1).reshape(-1, 4).astype(np.float32)
+    return verts, tris, nrm, uv, tan
+
+
+def ground_grid(n: int, half: float = 2.0, y: float = -1.0):
+    """n x n quad grid in the plane y = const: 2 n^2 triangles, normals +y, uv tiling 4x."""
+    g = np.linspace(-half, half, n + 1)
+    X, Z = np.meshgrid(g, g, indexing='xy')
+    verts = np.stack([X, np.full_like(X, y), Z], -1).reshape(-1, 3).astype(np.float32)
+    j, i = np.meshgrid(np.arange(n), np.arange(n), indexing='ij')
+    a = (j * (n + 1) + i).reshape(-1)
+    b, c, d = a + 1, a + (n + 1), a + (n + 2)
+    tris = np.concatenate([np.stack([a, d, b], -1), np.stack([a, c, d], -1)], 0).astype(np.int32)
+    nrm = np.tile(np.array([[0, 1, 0]], np.float32), (len(verts), 1))
+    uv = (np.stack([X, Z], -1).reshape(-1, 2) / (2 * half) * 4.0 + 0.5).astype(np.float32)
+    tan = np.tile(np.array([[1, 0, 0, 1]], np.float32), (len(verts), 1))
+    return verts, tris, nrm, uv, tan
+
+
+def random_rays(n: int, origin_radius: float = 3.0, target_sigma: float = 0.5, seed: int = 1):
+    """Origins uniform on a sphere, directions towards N(0, sigma^2) targets (config 2)."""
+    rng = np.random.default_rng(seed)
+    o = rng.standard_normal((n, 3))
+    o = o / np.linalg.norm(o, axis=-1, keepdims=True) * origin_radius
+    tgt = np.random.default_rng(seed + 1).standard_normal((n, 3)) * target_sigma
+    d = tgt - o
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    return o.astype(np.float32), d.astype(np.float32)
+
+
+def smooth_texture(h: int, w: int, c: int, seed: int, lo: float = 0.0, hi: float = 1.0, octaves: int = 4):
+    """Seeded band-limited fp32 texture in [lo, hi]."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, h, endpoint=False), np.linspace(0, 1, w, endpoint=False), indexing='ij')
+    img = np.zeros((h, w, c))
+    for k in range(c):
+        acc = np.zeros((h, w))
+        for o in range(octaves):
+            f = 2 ** o
+            ph = rng.random(4) * 2 * np.pi
+            acc += (np.sin(2 * np.pi * f * xx + ph[0]) * np.cos(2 * np.pi * f * yy + ph[1])
+                    + np.sin(2 * np.pi * f * (xx + yy) + ph[2]) * 0.5) / f
+        acc = (acc - acc.min()) / (acc.max() - acc.min() + 1e-12)
+        img[..., k] = lo + (hi - lo) * acc
+    return img.astype(np.float32)
+
+
+def gradient_env(h: int = 64, w: int = 128, top: float = 2.0):
+    """Deterministic lat-long environment: linspace(0, top) ramp (config 1)."""
+    return np.linspace(0.0, top, h * w * 3, dtype=np.float32).reshape(h, w, 3)

@@ -1,0 +1,191 @@
+/*
+ * diffrp_b200.h -- C ABI of libdiffrp_b200.so, the B200 (sm_100a) drop-in for diffrp's
+ * path-tracing hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * Every entry point returns 0 on success and a non-zero status on failure;
+ * drp_last_error() returns a human-readable description of the last failure on the calling
+ * thread.  All device pointers are raw CUDA device addresses (tensor.data_ptr()).  All work is
+ * enqueued on the caller-supplied cudaStream_t (passed as void*; NULL = legacy default stream)
+ * and is asynchronous with respect to the host unless stated otherwise.
+ *
+ * Which reference interface each entry point replaces (citations into eliphatfs/diffrp v0.2.7):
+ *
+ *   drp_set_log_level   torchoptix.set_log_level      called at diffrp/utils/raycaster.py:269-270
+ *   drp_build           torchoptix.build              called at diffrp/utils/raycaster.py:273-276
+ *                       NaivePBBVH.build              diffrp/utils/raycaster.py:122-187
+ *   drp_trace           torchoptix.trace_rays         called at diffrp/utils/raycaster.py:284-290
+ *                       NaivePBBVH.query              diffrp/utils/raycaster.py:226-260
+ *                       BruteForceRaycaster.query     diffrp/utils/raycaster.py:86-97
+ *   drp_release         torchoptix.release            called at diffrp/utils/raycaster.py:293-296
+ *   drp_render          PathTracingSession.trace_rays diffrp/rendering/path_tracing.py:310-347
+ *                       (section x bounce loop with the built-in sampler_brdf, :250-279)
+ *   drp_finalize        trace_rays epilogue           diffrp/rendering/path_tracing.py:348-352
+ *   drp_trace_bruteforce (validation aid)             BruteForceRaycaster semantics on the GPU
+ */
+#ifndef DIFFRP_B200_H
+#define DIFFRP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRP_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define DRP_OK 0
+#define DRP_ERR_INVALID 1   /* bad argument                        */
+#define DRP_ERR_CUDA 2      /* a CUDA runtime call failed          */
+#define DRP_ERR_HANDLE 3    /* unknown / released handle           */
+#define DRP_ERR_NOMEM 4     /* device allocation failed            */
+
+/* ---- textures / materials / flattened scene (device pointers) ------------------------------ */
+
+/* wrap modes follow GLTFSampler.wrap_mode (diffrp/materials/gltf_material.py:9-22) */
+#define DRP_WRAP_REPEAT 0 /* uv.remainder(1) then grid_sample padding 'reflection' */
+#define DRP_WRAP_CLAMP 1  /* grid_sample padding 'border'                          */
+#define DRP_WRAP_MIRROR 2 /* grid_sample padding 'reflection'                      */
+#define DRP_INTERP_POINT 0
+#define DRP_INTERP_LINEAR 1
+
+typedef struct drp_texture {
+    const float* data; /* (h, w, c) fp32, row 0 = top (v = 1)      */
+    int32_t h, w, c;   /* c in {1, 3, 4}; data == NULL => absent   */
+    int32_t wrap;      /* DRP_WRAP_*                               */
+    int32_t interp;    /* DRP_INTERP_*                             */
+    int32_t _pad;
+} drp_texture_t;
+
+#define DRP_MAT_DEFAULT 0 /* DefaultMaterial (diffrp/materials/default_material.py:21-24) */
+#define DRP_MAT_GLTF 1    /* GLTFMaterial    (diffrp/materials/gltf_material.py:48-67)    */
+#define DRP_ALPHA_OPAQUE 0
+#define DRP_ALPHA_MASK 1
+#define DRP_ALPHA_BLEND 2
+
+typedef struct drp_material {
+    int32_t kind;       /* DRP_MAT_*                                          */
+    int32_t alpha_mode; /* DRP_ALPHA_* (GLTF only)                            */
+    int32_t has_emissive;
+    int32_t has_normal_tex;
+    float tint[4];              /* Default: albedo = color.rgb * tint (1,1,1 when None) */
+    float base_color_factor[4]; /* GLTF                                                 */
+    float emissive_factor[4];   /* GLTF, xyz used                                       */
+    float metallic_factor;
+    float roughness_factor;
+    float alpha_cutoff;
+    float _pad;
+    drp_texture_t base_color_tex;
+    drp_texture_t mr_tex;
+    drp_texture_t normal_tex;
+    drp_texture_t emissive_tex;
+} drp_material_t;
+
+/* The scene flattened the way RenderSessionMixin.vertex_array_object does
+ * (diffrp/rendering/mixin.py:74-113), with per-vertex world-space normals / tangents already baked
+ * ('vectornor' / 'vector3norex1' of SurfaceInput.interpolate_ex, base_material.py:137-143). */
+typedef struct drp_scene {
+    const float* world_pos;      /* (V,3)                                              */
+    const float* world_nrm;      /* (V,3) normalize(M3x3 n)                            */
+    const float* color;          /* (V,4)                                              */
+    const float* uv;             /* (V,2)                                              */
+    const float* world_tan;      /* (V,4) (normalize(M3x3 t.xyz), w)                   */
+    const int32_t* tris;         /* (F,3)                                              */
+    const int32_t* tri_material; /* (F,)  index into materials (= stencil - 1)         */
+    const drp_material_t* materials; /* HOST pointer, n_materials entries (copied)      */
+    int64_t n_verts;
+    int64_t n_tris;
+    int32_t n_materials;
+    int32_t _pad;
+    drp_texture_t env; /* ImageEnvironmentLight.image_rh() (lights.py:49-50); NULL data => black */
+} drp_scene_t;
+
+#define DRP_RNG_NATIVE 0 /* Philox4x32-10 keyed by (seed; pixel, global sample, bounce) */
+#define DRP_RNG_REPLAY 1 /* consume caller-supplied uniforms in the reference's draw order */
+
+typedef struct drp_render_params {
+    int32_t height, width;
+    int32_t ray_depth;          /* PathTracingSessionOptions.ray_depth                      */
+    int32_t n_samples;          /* number of samples rendered by this call                  */
+    int32_t last_bounce_skybox; /* pbr_ray_last_bounce == 'skybox'                          */
+    int32_t rng_mode;           /* DRP_RNG_*                                                */
+    int32_t compaction;         /* 1: drop rays that provably contribute nothing (default)  */
+    int32_t _pad;
+    float step_epsilon;         /* pbr_ray_step_epsilon                                     */
+    float t_far;                /* camera_far()  (mixin.py:41-44)                           */
+    float t_near;               /* P[2,3]/(P[2,2]-1) (mixin.py:38)                          */
+    float _padf;
+    float cam_pos[4];           /* inv(V)[:3,3]                                             */
+    float inv_vp[16];           /* inv(P V), row-major                                      */
+    uint64_t seed;              /* native RNG key                                           */
+    const float* ndc_x;         /* (W,) pixel-centre NDC x  (coordinates.py:6-10)   device  */
+    const float* ndc_y;         /* (H,) pixel-centre NDC y, row 0 = bottom          device  */
+    const float* jitter_x;      /* (n_samples,) (q_x-0.5)*(2/W) (path_tracing.py:329) device */
+    const float* jitter_y;      /* (n_samples,)                                     device  */
+    const int32_t* sample_ids;  /* (n_samples,) global sample index (RNG counter)   device  */
+    const float* replay_u;      /* replay: (ray_depth, 6, n_samples*H*W)            device  */
+} drp_render_params_t;
+
+/* Accumulator layout: (H*W, 16) fp32, un-normalised sums, row 0 = bottom pixel row:
+ *   [0:3] radiance  [3] alpha  [4:7] albedo  [7:10] emission  [10:13] world_normal  [13:16] world_position */
+#define DRP_ACCUM_CHANNELS 16
+
+/* ---- entry points -------------------------------------------------------------------------- */
+
+int drp_abi_version(void);
+const char* drp_last_error(void);
+int drp_set_log_level(int level);
+
+/* Build the on-GPU LBVH over (verts, tris).  Copies what it needs: no lifetime coupling with the
+ * caller's buffers after the call returns (stream-ordered).  *out_handle identifies the structure. */
+int drp_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, int device, void* stream,
+              uint64_t* out_handle);
+
+/* Closest hit for n rays.  out_t[k] == t_far exactly on a miss; out_i[k] is the 0-based index into
+ * tris (int32), 0 on a miss.  Tie rule: minimum t, then minimum primitive index. */
+int drp_trace(uint64_t handle, const float* rays_o, const float* rays_d, float* out_t, int32_t* out_i, float t_far,
+              int64_t n_rays, void* stream);
+
+/* O(R*F) exhaustive closest hit with the same triangle test and tie rule (validation aid). */
+int drp_trace_bruteforce(const float* verts, const int32_t* tris, int64_t n_tris, const float* rays_o,
+                         const float* rays_d, float* out_t, int32_t* out_i, float t_far, int64_t n_rays,
+                         void* stream);
+
+int drp_release(uint64_t handle);
+
+/* Statistics about a built structure (host-synchronous; for tests / bench reporting). */
+typedef struct drp_bvh_stats {
+    int64_t n_tris;
+    int64_t n_nodes;
+    int64_t n_leaves;
+    int64_t node_bytes;
+    int64_t tri_bytes;
+    float sah_cost;
+    float bounds[6];
+    int32_t max_depth;
+} drp_bvh_stats_t;
+int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out);
+
+/* Fused wavefront: raygen -> [extend -> shade/sample/accumulate/compact] x ray_depth over
+ * n_samples samples of every pixel, added into accum (H*W, 16).  `handle` must have been built over
+ * scene->world_pos / scene->tris.  workspace may be NULL (internally allocated and cached on the handle). */
+int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_render_params_t* params, float* accum,
+               void* stream);
+
+/* accum (H*W,16) sums -> radiance (H,W,3), alpha (H,W,1) saturated, albedo/emission/world_normal/
+ * world_position (H,W,3) each; all divided by spp_total and flipped vertically (row 0 = top). */
+int drp_finalize(const float* accum, int32_t height, int32_t width, int32_t spp_total, float* radiance, float* alpha,
+                 float* albedo, float* emission, float* world_normal, float* world_position, void* stream);
+
+/* Counters of the last drp_render call on this handle (host-synchronous). */
+typedef struct drp_render_stats {
+    int64_t rays_traced;     /* live rays actually traced (sum over bounces)         */
+    int64_t rays_nominal;    /* H*W*n_samples*ray_depth                              */
+    int64_t kernel_launches; /* kernels launched by the call                         */
+} drp_render_stats_t;
+int drp_render_stats(uint64_t handle, drp_render_stats_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFRP_B200_H */
