@@ -1,0 +1,279 @@
+// api.cu -- C ABI of libdiffrp_b200.so: handle table, LBVH build, closest-hit trace.
+// See include/diffrp_b200.h for the contract and the reference call sites each entry point replaces.
+#include <cub/device/device_radix_sort.cuh>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <cstdio>
+#include "internal.h"
+#include "common.cuh"
+#include "lbvh.cuh"
+#include "traverse.cuh"
+#include "trace_kernels.cuh"
+
+// ---- error / handle plumbing ------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+int g_drp_log_level = 0;
+static std::mutex g_mutex;
+static std::unordered_map<uint64_t, BvhHandle*> g_handles;
+static uint64_t g_next_handle = 1;
+
+void drp_set_error(const std::string& msg) {
+    g_last_error = msg;
+    if (g_drp_log_level >= 1) fprintf(stderr, "[diffrp_b200] error: %s\n", msg.c_str());
+}
+BvhHandle* drp_lookup(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = g_handles.find(handle);
+    return it == g_handles.end() ? nullptr : it->second;
+}
+
+extern "C" int drp_abi_version(void) { return DRP_ABI_VERSION; }
+extern "C" const char* drp_last_error(void) { return g_last_error.c_str(); }
+extern "C" int drp_set_log_level(int level) {
+    g_drp_log_level = level;
+    return DRP_OK;
+}
+
+// ---- build kernels ----------------------------------------------------------------------------------------------
+__global__ void k_init_bounds(uint32_t* b) {
+    int i = threadIdx.x;
+    if (i < 12) b[i] = ((i / 3) % 2 == 0) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_prim_bounds(LbvhBuild b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float inf = i2f(0x7f800000);
+    float v[12] = {inf, inf, inf, -inf, -inf, -inf, inf, inf, inf, -inf, -inf, -inf};
+    if (i < b.n) {
+        Vec3 lo, hi;
+        lbvh_prim_bounds(b, i, lo, hi);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = hi.x; v[4] = hi.y; v[5] = hi.z;
+        v[6] = v[9] = 0.5f * (lo.x + hi.x); v[7] = v[10] = 0.5f * (lo.y + hi.y); v[8] = v[11] = 0.5f * (lo.z + hi.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        bool is_min = (k / 3) % 2 == 0;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            float o = __shfl_xor_sync(0xffffffffu, v[k], s);
+            v[k] = is_min ? fminf(v[k], o) : fmaxf(v[k], o);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            bool is_min = (k / 3) % 2 == 0;
+            if (is_min) atomicMin(&b.bounds[k], f2ord(v[k]));
+            else atomicMax(&b.bounds[k], f2ord(v[k]));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_morton(LbvhBuild b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n) lbvh_morton(b, i);
+}
+__global__ void __launch_bounds__(256) k_karras(LbvhBuild b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n - 1) lbvh_karras(b, i);
+}
+__global__ void __launch_bounds__(256) k_refit(LbvhBuild b) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < b.n) lbvh_refit(b, j, [](int* p) { return atomicAdd(p, 1); }, []() { __threadfence(); });
+}
+__global__ void __launch_bounds__(256) k_emit(LbvhBuild b, float* sah) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b.n < 2) {
+        if (i == 0) { lbvh_emit_tiny(b); *sah = 1.0f; }
+        return;
+    }
+    if (i < b.n - 1) lbvh_emit(b, i);
+    if (i == 0) *sah = b.box_lo[0].w / fmaxf(b.box_hi[0].w, 1e-30f);
+}
+__global__ void __launch_bounds__(256) k_pack(LbvhBuild b) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < b.n) lbvh_pack_tri(b, j);
+}
+
+template <typename T>
+static cudaError_t alloc_async(T** p, size_t count, cudaStream_t s) {
+    return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s);
+}
+
+extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, int device, void* stream,
+                         uint64_t* out_handle) {
+    if (!out_handle || n_tris < 0 || n_verts < 0 || (n_tris > 0 && (!verts || !tris))) {
+        drp_set_error("drp_build: invalid argument");
+        return DRP_ERR_INVALID;
+    }
+    if (n_tris >= (int64_t(1) << 27)) {
+        drp_set_error("drp_build: more than 2^27 triangles are not supported by the leaf encoding");
+        return DRP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { drp_set_error("drp_build: cannot select device"); return DRP_ERR_CUDA; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = (int)n_tris;
+    BvhHandle* h = new BvhHandle();
+    h->device = device;
+    h->n_tris = n_tris;
+    h->n_nodes = n > 1 ? n - 1 : 1;
+
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.verts = verts; b.tris = tris; b.n = n;
+    uint64_t* keys_in = nullptr; uint32_t* vals_in = nullptr; void* sort_tmp = nullptr;
+    size_t sort_bytes = 0;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->nodes, sizeof(float4) * 4 * (size_t)h->n_nodes));
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->packed, sizeof(float4) * 3 * nn));
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->sah, sizeof(float)));
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->dev_flags, sizeof(int) * 4));
+    DRP_CUDA_CHECK(cudaMemsetAsync(h->dev_flags, 0, sizeof(int) * 4, s));
+    b.bounds = h->bounds; b.nodes = h->nodes; b.packed = h->packed;
+    DRP_CUDA_CHECK(alloc_async(&b.prim_lo, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.prim_hi, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&keys_in, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&vals_in, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.keys, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.vals, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.left, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.right, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.parent, 2 * nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.range_first, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.range_last, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.box_lo, 2 * nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.box_hi, 2 * nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.arrive, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.collapsed, nn, s));
+    DRP_CUDA_CHECK(cudaMemsetAsync(b.arrive, 0, sizeof(int) * nn, s));
+    DRP_CUDA_CHECK(cudaMemsetAsync(b.collapsed, 0, nn, s));
+
+    const int T = 256;
+    const int G = (int)((nn + T - 1) / T);
+    k_init_bounds<<<1, 32, 0, s>>>(h->bounds);
+    if (n > 0) {
+        k_prim_bounds<<<G, T, 0, s>>>(b);
+        // phase 2 writes unsorted keys/vals into the *_in buffers; phase 3 sorts into b.keys / b.vals
+        LbvhBuild b2 = b;
+        b2.keys = keys_in; b2.vals = vals_in;
+        k_morton<<<G, T, 0, s>>>(b2);
+        DRP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, b.keys, vals_in, b.vals, n, 0, 63, s));
+        DRP_CUDA_CHECK(cudaMallocAsync(&sort_tmp, sort_bytes ? sort_bytes : 1, s));
+        DRP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, b.keys, vals_in, b.vals, n, 0, 63, s));
+        if (n > 1) {
+            k_karras<<<G, T, 0, s>>>(b);
+            k_refit<<<G, T, 0, s>>>(b);
+        }
+        k_pack<<<G, T, 0, s>>>(b);
+    }
+    k_emit<<<G, T, 0, s>>>(b, h->sah);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    void* temps[] = {b.prim_lo, b.prim_hi, keys_in, vals_in, b.keys, b.vals, b.left, b.right, b.parent, b.range_first,
+                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp};
+    for (void* p : temps)
+        if (p) DRP_CUDA_CHECK(cudaFreeAsync(p, s));
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        *out_handle = g_next_handle++;
+        g_handles[*out_handle] = h;
+    }
+    if (g_drp_log_level >= 3) fprintf(stderr, "[diffrp_b200] built LBVH over %lld triangles (handle %llu)\n", (long long)n_tris, (unsigned long long)*out_handle);
+    return DRP_OK;
+}
+
+extern "C" int drp_release(uint64_t handle) {
+    BvhHandle* h = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_handles.find(handle);
+        if (it == g_handles.end()) { drp_set_error("drp_release: unknown handle"); return DRP_ERR_HANDLE; }
+        h = it->second;
+        g_handles.erase(it);
+    }
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    drp_free_workspace(h);
+    cudaFree(h->nodes); cudaFree(h->packed); cudaFree(h->bounds); cudaFree(h->sah); cudaFree(h->dev_flags);
+    delete h;
+    return DRP_OK;
+}
+
+extern "C" int drp_set_epsilon(uint64_t handle, float epsilon) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_set_epsilon: unknown handle"); return DRP_ERR_HANDLE; }
+    h->eps = epsilon;
+    return DRP_OK;
+}
+
+extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h || !out) { drp_set_error("drp_bvh_stats: unknown handle"); return DRP_ERR_HANDLE; }
+    DeviceGuard guard(h->device);
+    DRP_CUDA_CHECK(cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    out->n_tris = h->n_tris;
+    out->n_nodes = h->n_nodes;
+    out->node_bytes = h->n_nodes * 64;
+    out->tri_bytes = h->n_tris * 48;
+    uint32_t ob[12];
+    DRP_CUDA_CHECK(cudaMemcpy(ob, h->bounds, sizeof(ob), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) out->bounds[k] = ord2f(ob[k]);
+    DRP_CUDA_CHECK(cudaMemcpy(&out->sah_cost, h->sah, sizeof(float), cudaMemcpyDeviceToHost));
+    // walk the emitted nodes on the host for leaf count / depth (debug-only path)
+    std::vector<float4> nodes((size_t)h->n_nodes * 4);
+    DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<int, int>> stack;
+    stack.push_back({0, 1});
+    int64_t leaves = 0, live_nodes = 0;
+    int max_depth = 0;
+    while (!stack.empty()) {
+        auto [node, depth] = stack.back();
+        stack.pop_back();
+        if (depth > max_depth) max_depth = depth;
+        if (node < 0) { ++leaves; continue; }
+        ++live_nodes;
+        float4 n3 = nodes[(size_t)node * 4 + 3];
+        stack.push_back({f2i(n3.x), depth + 1});
+        stack.push_back({f2i(n3.y), depth + 1});
+    }
+    out->n_leaves = leaves;
+    out->n_nodes = live_nodes;
+    out->max_depth = max_depth;
+    return DRP_OK;
+}
+
+// ---- trace ------------------------------------------------------------------------------------------------------
+extern "C" int drp_trace(uint64_t handle, const float* rays_o, const float* rays_d, float* out_t, int32_t* out_i, float t_far,
+                         int64_t n_rays, void* stream) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_trace: unknown handle"); return DRP_ERR_HANDLE; }
+    if (n_rays < 0 || (n_rays > 0 && (!rays_o || !rays_d || !out_t || !out_i))) {
+        drp_set_error("drp_trace: invalid argument");
+        return DRP_ERR_INVALID;
+    }
+    if (n_rays == 0) return DRP_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) { drp_set_error("drp_trace: cannot select device"); return DRP_ERR_CUDA; }
+    DRP_CUDA_CHECK(launch_trace_aos(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream));
+    return DRP_OK;
+}
+
+__global__ void __launch_bounds__(128) k_bruteforce(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t n_tris,
+                                                    const float* __restrict__ ro, const float* __restrict__ rd, float* __restrict__ out_t,
+                                                    int32_t* __restrict__ out_i, float t_far, float eps, int64_t n) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    RayHit h = bruteforce_one(verts, tris, n_tris, v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]), v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]), t_far, eps);
+    out_t[r] = h.t;
+    out_i[r] = h.id;
+}
+
+extern "C" int drp_trace_bruteforce(const float* verts, const int32_t* tris, int64_t n_tris, const float* rays_o, const float* rays_d,
+                                    float* out_t, int32_t* out_i, float t_far, float epsilon, int64_t n_rays, void* stream) {
+    if (n_rays <= 0) return DRP_OK;
+    k_bruteforce<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(verts, tris, n_tris, rays_o, rays_d, out_t, out_i, t_far, epsilon, n_rays);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}

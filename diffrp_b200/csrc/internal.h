@@ -1,0 +1,49 @@
+// internal.h -- host-side state shared by the translation units of libdiffrp_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/diffrp_b200.h"
+
+struct RenderWorkspace;
+
+struct BvhHandle {
+    int device = 0;
+    int64_t n_tris = 0;
+    int64_t n_nodes = 0;
+    float eps = 1e-8f;          // |det| threshold of the triangle test (raycaster_epsilon)
+    float4* nodes = nullptr;    // (n_nodes, 4)
+    float4* packed = nullptr;   // (n_tris, 3)
+    uint32_t* bounds = nullptr; // (12) ordered-uint scene bounds (device)
+    float* sah = nullptr;       // device: root cost / root area
+    int* dev_flags = nullptr;   // device: [0] traversal stack overflow count
+    RenderWorkspace* ws = nullptr;
+    drp_render_stats_t last_render = {0, 0, 0};
+};
+
+void drp_set_error(const std::string& msg);
+BvhHandle* drp_lookup(uint64_t handle);
+void drp_free_workspace(BvhHandle* h);
+extern int g_drp_log_level;
+
+#define DRP_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            drp_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+            return DRP_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};

@@ -1,0 +1,105 @@
+"""
+The ``Raycaster`` seam of diffrp (reference: diffrp/utils/raycaster.py:13-24) and its B200 implementation.
+
+``B200Raycaster`` is what ``PathTracingSessionOptions(raycaster_impl='b200')`` selects; it has the call shape of the
+reference's ``TorchOptiX`` wrapper (raycaster.py:263-296): raw device pointers go to a C-ABI library, the outputs are
+allocated by the caller, ``t == far`` on a miss and ``i`` is int32.
+"""
+import abc
+import ctypes as C
+from typing import Tuple
+
+import torch
+
+from . import _abi
+from ._lib import lib, check
+
+
+class Raycaster(metaclass=abc.ABCMeta):
+    """Same two-method interface as the reference's ``Raycaster`` (raycaster.py:13-24)."""
+
+    def __init__(self, verts: torch.Tensor, tris: torch.IntTensor, config: dict = None) -> None:
+        self.config = {} if config is None else config
+        self.build(verts, tris, self.config)
+
+    @abc.abstractmethod
+    def build(self, verts: torch.Tensor, tris: torch.IntTensor, config: dict) -> None:
+        raise NotImplementedError
+
+    @abc.abstractmethod
+    def query(self, rays_o: torch.Tensor, rays_d: torch.Tensor, far: float) -> Tuple[torch.Tensor, torch.Tensor]:
+        raise NotImplementedError
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class B200Raycaster(Raycaster):
+    """
+    On-GPU LBVH + closest-hit traversal in hand-written sm_100a CUDA.
+
+    Config keys (all optional, same names as the reference passes, path_tracing.py:144-153):
+    ``epsilon`` (|det| threshold of the Moller-Trumbore test), ``builder`` (accepted, ignored: there is one builder),
+    ``optix_log_level`` (verbosity).
+    """
+
+    @torch.no_grad()
+    def build(self, verts: torch.Tensor, tris: torch.IntTensor, config: dict) -> None:
+        self.handle = None
+        self._lib = lib()
+        if not verts.is_cuda:
+            raise ValueError("B200Raycaster needs CUDA tensors (there is no CPU path)")
+        self._lib.drp_set_log_level(int(config.get('optix_log_level', 0)))
+        # the library copies what it needs; these are only kept for introspection (cf. raycaster.py:271-272)
+        self.verts = verts.detach().to(torch.float32).contiguous()
+        self.tris = tris.detach().to(torch.int32).contiguous()
+        self.device = self.verts.device
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        handle = C.c_uint64(0)
+        check(self._lib.drp_build(self.verts.data_ptr(), self.tris.data_ptr(), len(self.verts), len(self.tris),
+                                  dev_index, _stream_ptr(self.device), C.byref(handle)), "drp_build")
+        self.handle = handle.value
+        check(self._lib.drp_set_epsilon(self.handle, float(config.get('epsilon', 1e-8))), "drp_set_epsilon")
+
+    @torch.no_grad()
+    def query(self, rays_o: torch.Tensor, rays_d: torch.Tensor, far: float) -> Tuple[torch.Tensor, torch.Tensor]:
+        rays_o = rays_o.to(torch.float32).contiguous()
+        rays_d = rays_d.to(torch.float32).contiguous()
+        n = rays_o.shape[0] if rays_o.ndim > 0 else 0
+        out_t = rays_o.new_empty([n])
+        out_i = rays_o.new_empty([n], dtype=torch.int32)
+        check(self._lib.drp_trace(self.handle, rays_o.data_ptr(), rays_d.data_ptr(), out_t.data_ptr(), out_i.data_ptr(),
+                                  float(far), n, _stream_ptr(rays_o.device)), "drp_trace")
+        return out_t, out_i
+
+    @torch.no_grad()
+    def query_bruteforce(self, rays_o: torch.Tensor, rays_d: torch.Tensor, far: float):
+        """Exhaustive O(R*F) query with the same triangle test / tie rule (validation aid)."""
+        rays_o = rays_o.to(torch.float32).contiguous()
+        rays_d = rays_d.to(torch.float32).contiguous()
+        out_t = rays_o.new_empty([len(rays_o)])
+        out_i = rays_o.new_empty([len(rays_o)], dtype=torch.int32)
+        check(self._lib.drp_trace_bruteforce(self.verts.data_ptr(), self.tris.data_ptr(), len(self.tris), rays_o.data_ptr(),
+                                             rays_d.data_ptr(), out_t.data_ptr(), out_i.data_ptr(), float(far),
+                                             float(self.config.get('epsilon', 1e-8)), len(rays_o),
+                                             _stream_ptr(rays_o.device)), "drp_trace_bruteforce")
+        return out_t, out_i
+
+    def stats(self) -> dict:
+        st = _abi.BVHStats()
+        check(self._lib.drp_bvh_stats(self.handle, C.byref(st)), "drp_bvh_stats")
+        return dict(n_tris=st.n_tris, n_nodes=st.n_nodes, n_leaves=st.n_leaves, node_bytes=st.node_bytes,
+                    tri_bytes=st.tri_bytes, sah_cost=st.sah_cost, bounds=list(st.bounds), max_depth=st.max_depth)
+
+    def release(self):
+        if getattr(self, 'handle', None) is not None and getattr(self, '_lib', None) is not None:
+            self._lib.drp_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        # guarded for interpreter teardown like the reference (raycaster.py:293-296)
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -17,6 +17,7 @@
  *                       NaivePBBVH.query              diffrp/utils/raycaster.py:226-260
  *                       BruteForceRaycaster.query     diffrp/utils/raycaster.py:86-97
  *   drp_release         torchoptix.release            called at diffrp/utils/raycaster.py:293-296
+ *   drp_set_epsilon     Raycaster.config['epsilon']   diffrp/utils/raycaster.py:91-92, path_tracing.py:144
  *   drp_render          PathTracingSession.trace_rays diffrp/rendering/path_tracing.py:310-347
  *                       (section x bounce loop with the built-in sampler_brdf, :250-279)
  *   drp_finalize        trace_rays epilogue           diffrp/rendering/path_tracing.py:348-352
@@ -148,10 +149,14 @@ int drp_trace(uint64_t handle, const float* rays_o, const float* rays_d, float* 
 
 /* O(R*F) exhaustive closest hit with the same triangle test and tie rule (validation aid). */
 int drp_trace_bruteforce(const float* verts, const int32_t* tris, int64_t n_tris, const float* rays_o,
-                         const float* rays_d, float* out_t, int32_t* out_i, float t_far, int64_t n_rays,
-                         void* stream);
+                         const float* rays_d, float* out_t, int32_t* out_i, float t_far, float epsilon,
+                         int64_t n_rays, void* stream);
 
 int drp_release(uint64_t handle);
+
+/* |det| rejection threshold of the Moller-Trumbore test: the `epsilon` entry of the Raycaster config
+ * (diffrp/utils/raycaster.py:91-92; PathTracingSessionOptions.raycaster_epsilon, default 1e-8). */
+int drp_set_epsilon(uint64_t handle, float epsilon);
 
 /* Statistics about a built structure (host-synchronous; for tests / bench reporting). */
 typedef struct drp_bvh_stats {

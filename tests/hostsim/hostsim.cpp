@@ -1,0 +1,121 @@
+// hostsim.cpp -- serial host build of the kernel logic in diffrp_b200/csrc/*.cuh (compiled with -DDRP_HOSTSIM).
+// TEST INFRASTRUCTURE ONLY: lets the `-m "not gpu"` tests exercise the exact per-thread code of the CUDA kernels
+// (LBVH phases, traversal, shading) in a container without a GPU.  It is never loaded by the product package.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <numeric>
+#include "../../diffrp_b200/csrc/common.cuh"
+#include "../../diffrp_b200/csrc/lbvh.cuh"
+#include "../../diffrp_b200/csrc/traverse.cuh"
+
+struct HsBvh {
+    int n;
+    std::vector<float4> nodes, packed;
+    float sah;
+    float bounds[6];
+};
+
+extern "C" HsBvh* hs_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris) {
+    (void)n_verts;
+    HsBvh* h = new HsBvh();
+    const int n = (int)n_tris;
+    const size_t nn = n > 0 ? n : 1;
+    h->n = n;
+    h->nodes.resize(4 * (n > 1 ? n - 1 : 1));
+    h->packed.resize(3 * nn);
+    std::vector<uint32_t> bounds(12);
+    for (int i = 0; i < 12; ++i) bounds[i] = ((i / 3) % 2 == 0) ? 0xffffffffu : 0u;
+    std::vector<float4> prim_lo(nn), prim_hi(nn), box_lo(2 * nn), box_hi(2 * nn);
+    std::vector<uint64_t> keys(nn);
+    std::vector<uint32_t> vals(nn);
+    std::vector<int> left(nn), right(nn), parent(2 * nn), rf(nn), rl(nn), arrive(nn, 0);
+    std::vector<uint8_t> collapsed(nn, 0);
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.verts = verts; b.tris = tris; b.n = n; b.bounds = bounds.data();
+    b.prim_lo = prim_lo.data(); b.prim_hi = prim_hi.data(); b.keys = keys.data(); b.vals = vals.data();
+    b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.range_first = rf.data(); b.range_last = rl.data();
+    b.box_lo = box_lo.data(); b.box_hi = box_hi.data(); b.arrive = arrive.data(); b.collapsed = collapsed.data();
+    b.nodes = h->nodes.data(); b.packed = h->packed.data();
+    for (int i = 0; i < n; ++i) {
+        Vec3 lo, hi;
+        lbvh_prim_bounds(b, i, lo, hi);
+        float v[12] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, 0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z), 0, 0, 0};
+        v[9] = v[6]; v[10] = v[7]; v[11] = v[8];
+        for (int k = 0; k < 12; ++k) {
+            bool is_min = (k / 3) % 2 == 0;
+            uint32_t o = f2ord(v[k]);
+            bounds[k] = is_min ? std::min(bounds[k], o) : std::max(bounds[k], o);
+        }
+    }
+    for (int i = 0; i < n; ++i) lbvh_morton(b, i);
+    {   // phase 3: stable sort by key (cub radix sort is stable as well)
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return keys[a] < keys[c]; });
+        std::vector<uint64_t> k2(nn);
+        std::vector<uint32_t> v2(nn);
+        for (int i = 0; i < n; ++i) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
+        keys.swap(k2); vals.swap(v2);
+        b.keys = keys.data(); b.vals = vals.data();
+    }
+    if (n > 1) {
+        for (int i = 0; i < n - 1; ++i) lbvh_karras(b, i);
+        for (int j = 0; j < n; ++j) lbvh_refit(b, j, [](int* p) { int o = *p; *p = o + 1; return o; }, []() {});
+        for (int i = 0; i < n - 1; ++i) lbvh_emit(b, i);
+        h->sah = box_lo[0].w / std::max(box_hi[0].w, 1e-30f);
+    } else {
+        lbvh_emit_tiny(b);
+        h->sah = 1.0f;
+    }
+    for (int j = 0; j < n; ++j) lbvh_pack_tri(b, j);
+    for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(bounds[k]);
+    return h;
+}
+
+extern "C" void hs_free(HsBvh* h) { delete h; }
+
+extern "C" int64_t hs_trace(const HsBvh* h, const float* ro, const float* rd, int64_t n, float t_far, float eps, float* out_t, int32_t* out_i) {
+    int64_t overflow = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : overflow)
+    for (int64_t r = 0; r < n; ++r) {
+        bool of = false;
+        RayHit hit = trace_one(h->nodes.data(), h->packed.data(), v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]),
+                               v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]), t_far, eps, of);
+        out_t[r] = hit.t;
+        out_i[r] = hit.id;
+        overflow += of;
+    }
+    return overflow;
+}
+
+// structure statistics: live nodes, leaves, max depth, triangles covered exactly once
+extern "C" void hs_stats(const HsBvh* h, int64_t* out /* [n_nodes, n_leaves, max_depth, tris_in_leaves, max_leaf] */, float* sah) {
+    std::vector<std::pair<int, int>> stack{{0, 1}};
+    int64_t nodes = 0, leaves = 0, tris = 0;
+    int md = 0, ml = 0;
+    std::vector<uint8_t> seen(h->n > 0 ? h->n : 1, 0);
+    bool dup = false;
+    while (!stack.empty()) {
+        auto [node, depth] = stack.back();
+        stack.pop_back();
+        md = std::max(md, depth);
+        if (node < 0) {
+            int first, count;
+            leaf_decode(node, first, count);
+            if (count > 0) ++leaves;
+            tris += count;
+            ml = std::max(ml, count);
+            for (int k = 0; k < count; ++k) { if (seen[first + k]) dup = true; seen[first + k] = 1; }
+            continue;
+        }
+        ++nodes;
+        float4 n3 = h->nodes[(size_t)node * 4 + 3];
+        stack.push_back({f2i(n3.x), depth + 1});
+        stack.push_back({f2i(n3.y), depth + 1});
+    }
+    out[0] = nodes; out[1] = leaves; out[2] = md; out[3] = dup ? -1 : tris; out[4] = ml;
+    *sah = h->sah;
+}
