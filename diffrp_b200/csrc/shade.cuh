@@ -1,0 +1,251 @@
+// shade.cuh -- per-ray device logic of the fused wavefront: primary-ray generation, surface attributes
+// (DefaultMaterial / GLTFMaterial), environment lookup and the metallic-roughness GGX sampler.
+// One DRP_HD function per reference op group (citations into eliphatfs/diffrp v0.2.7):
+//   gen_primary_ray   mixin.py:31-39, coordinates.py:6-10, path_tracing.py:329-331
+//   tex_fetch         shader_ops.py:198-221 (F.grid_sample, align_corners=False), gltf_material.py:15-22
+//   env_fetch         coordinates.py:60-71, path_tracing.py:238-248,267
+//   surface_attrs     path_tracing.py:158-187, geometry.py:94-110, interpolator.py:32-48, base_material.py:183-257,
+//                     default_material.py:21-24, gltf_material.py:48-67, mixin.py:115-128
+//   brdf_sample       path_tracing.py:189-236, light_transport.py:35-43,72-83,179-196, shader_ops.py:313-325
+#pragma once
+#include "common.cuh"
+#include "../../include/diffrp_b200.h"
+
+#define DRP_TAU 6.283185307179586f
+#define DRP_PI 3.141592653589793f
+
+struct SurfaceAttrs {  // the (R,12) g-buffer row of _super_collector, path_tracing.py:180-187
+    Vec3 albedo;
+    Vec3 normal;
+    float metal, smooth, alpha;
+    Vec3 emission;
+};
+
+struct BounceOut {
+    Vec3 radiance;  // emission + env
+    Vec3 transfer;
+    Vec3 hit_pos;   // o + d t   (extras['world_position'])
+    Vec3 next_d;
+};
+
+DRP_HD float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(x, lo)); }
+
+// ---- primary rays ---------------------------------------------------------------------------------------------
+DRP_HD void gen_primary_ray(const float* __restrict__ inv_vp, const float* __restrict__ cam_pos, float t_near, float gx, float gy,
+                            Vec3& o, Vec3& d) {
+    // grid = (gx, gy, -1, 1);  p = grid @ inv(VP)^T;  p.xyz / p.w;  d = normalize(p - cam);  o = cam + d * near.
+    // p - cam cancels ~5 digits (the near plane is 0.1 from the eye), so the rounding ORDER of the 4-term dot product
+    // shows up at 1e-5 in the hit position.  Explicitly rounded, left-to-right, unfused operations reproduce the
+    // oracle / CPU reference sequence bit for bit.
+    float q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        q[k] = x_add(x_sub(x_add(x_mul(gx, inv_vp[4 * k]), x_mul(gy, inv_vp[4 * k + 1])), inv_vp[4 * k + 2]), inv_vp[4 * k + 3]);
+    Vec3 c = v3(cam_pos[0], cam_pos[1], cam_pos[2]);
+    Vec3 v = x_sub3(v3(q[0] / q[3], q[1] / q[3], q[2] / q[3]), c);
+    float len = fmaxf(sqrtf(x_dot3(v, v)), 1e-12f);
+    d = v3(v.x / len, v.y / len, v.z / len);
+    o = v3(x_add(c.x, x_mul(d.x, t_near)), x_add(c.y, x_mul(d.y, t_near)), x_add(c.z, x_mul(d.z, t_near)));
+}
+
+// ---- textures -------------------------------------------------------------------------------------------------
+DRP_HD float reflect_coord(float in, int twice_low, int twice_high) {
+    if (twice_low == twice_high) return 0.0f;
+    float mn = (float)twice_low * 0.5f, span = (float)(twice_high - twice_low) * 0.5f;
+    in = fabsf(in - mn);
+    float extra = fmodf(in, span);
+    int flips = (int)floorf(in / span);
+    return (flips & 1) ? span - extra + mn : extra + mn;
+}
+DRP_HD float grid_coord(float g, int size, bool reflection) {
+    float c = ((g + 1.0f) * (float)size - 1.0f) * 0.5f;
+    if (reflection) c = reflect_coord(c, -1, 2 * size - 1);
+    return clampf(c, 0.0f, (float)(size - 1));
+}
+DRP_HD void texel_fetch(const drp_texture_t& t, int x, int y, float w, float out[4]) {
+    if (x < 0 || y < 0 || x >= t.w || y >= t.h) return;
+    const float* p = t.data + ((int64_t)y * t.w + x) * t.c;
+    if (t.c == 4) {
+        float4 v = ldg(reinterpret_cast<const float4*>(p));
+        out[0] += v.x * w; out[1] += v.y * w; out[2] += v.z * w; out[3] += v.w * w;
+    } else {
+        for (int c = 0; c < t.c; ++c) out[c] += ldg(p + c) * w;
+    }
+}
+// out[0..c) = sampled texel, channels >= c left at 0
+DRP_HD void tex_fetch(const drp_texture_t& t, float u, float v, float out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    if (t.wrap == DRP_WRAP_REPEAT) {  // uv.remainder(1.0)
+        u = u - floorf(u); v = v - floorf(v);
+        if (u >= 1.0f) u = 0.0f;
+        if (v >= 1.0f) v = 0.0f;
+    }
+    bool reflection = t.wrap != DRP_WRAP_CLAMP;
+    float ix = grid_coord(u * 2.0f - 1.0f, t.w, reflection);
+    float iy = grid_coord(-(v * 2.0f - 1.0f), t.h, reflection);
+    if (t.interp == DRP_INTERP_POINT) {
+        texel_fetch(t, (int)nearbyintf(ix), (int)nearbyintf(iy), 1.0f, out);
+        return;
+    }
+    float x0 = floorf(ix), y0 = floorf(iy);
+    float fx = ix - x0, fy = iy - y0, gx = (x0 + 1.0f) - ix, gy = (y0 + 1.0f) - iy;
+    int X = (int)x0, Y = (int)y0;
+    texel_fetch(t, X, Y, gx * gy, out);
+    texel_fetch(t, X + 1, Y, fx * gy, out);
+    texel_fetch(t, X, Y + 1, gx * fy, out);
+    texel_fetch(t, X + 1, Y + 1, fx * fy, out);
+}
+
+DRP_HD Vec3 env_fetch(const drp_texture_t& env, Vec3 d) {
+    if (!env.data) return v3(0.0f, 0.0f, 0.0f);  // black_tex, path_tracing.py:247
+    float a = atan2f(d.x, d.z) * (0.5f / DRP_PI);
+    a = a - floorf(a);
+    if (a >= 1.0f) a = 0.0f;
+    float v = (1.0f / DRP_PI) * asinf(clampf(d.y, -0.999999f, 0.999999f)) + 0.5f;
+    float rgb[4];
+    tex_fetch(env, a, v, rgb);  // env.wrap = CLAMP ('border'), env.interp = LINEAR set by the host
+    return v3(rgb[0], rgb[1], rgb[2]);
+}
+
+// ---- surface attributes -----------------------------------------------------------------------------------------
+DRP_HD Vec3 ld3(const float* __restrict__ p, int i) { return v3(ldg(p + 3 * (int64_t)i), ldg(p + 3 * (int64_t)i + 1), ldg(p + 3 * (int64_t)i + 2)); }
+DRP_HD float4 ld4(const float* __restrict__ p, int i) { return ldg(reinterpret_cast<const float4*>(p) + i); }
+DRP_HD float2 ld2(const float* __restrict__ p, int i) { return ldg(reinterpret_cast<const float2*>(p) + i); }
+// (v1 - v3) * u + ((v2 - v3) * v + v3), interpolator.py:32-48
+DRP_HD float lerp3(float a, float b, float c, float u, float v) { return (a - c) * u + ((b - c) * v + c); }
+DRP_HD Vec3 lerp3v(Vec3 a, Vec3 b, Vec3 c, float u, float v) { return v3(lerp3(a.x, b.x, c.x, u, v), lerp3(a.y, b.y, c.y, u, v), lerp3(a.z, b.z, c.z, u, v)); }
+
+DRP_HD void hit_barycentric(Vec3 a, Vec3 b, Vec3 c, Vec3 p, float& u, float& v) {  // geometry.py:94-110
+    Vec3 v0 = b - a, v1 = c - a, v2 = p - a;
+    float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+    float denom = d00 * d11 - d01 * d01;
+    float bv = (d11 * d20 - d01 * d21) / denom, bw = (d00 * d21 - d01 * d20) / denom;
+    if (bv != bv) bv = 0.0f;
+    if (bw != bw) bw = 0.0f;
+    bv = clampf(bv, 0.0f, 1.0f);
+    bw = clampf(bw, 0.0f, 1.0f);
+    u = 1.0f - bv - bw;
+    v = bv;
+}
+
+DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id) {
+    SurfaceAttrs s;
+    const int i0 = ldg(sc.tris + 3 * (int64_t)tri_id), i1 = ldg(sc.tris + 3 * (int64_t)tri_id + 1), i2 = ldg(sc.tris + 3 * (int64_t)tri_id + 2);
+    float u, v;
+    hit_barycentric(ld3(sc.world_pos, i0), ld3(sc.world_pos, i1), ld3(sc.world_pos, i2), hit_pos, u, v);
+    const drp_material_t& m = mats[ldg(sc.tri_material + tri_id)];
+    Vec3 nu = lerp3v(ld3(sc.world_nrm, i0), ld3(sc.world_nrm, i1), ld3(sc.world_nrm, i2), u, v);  // world_normal_unnormalized
+    float4 c0 = ld4(sc.color, i0), c1 = ld4(sc.color, i1), c2 = ld4(sc.color, i2);
+    float col[4] = {lerp3(c0.x, c1.x, c2.x, u, v), lerp3(c0.y, c1.y, c2.y, u, v), lerp3(c0.z, c1.z, c2.z, u, v), lerp3(c0.w, c1.w, c2.w, u, v)};
+    s.normal = normalize_ref(nu);
+    s.metal = 0.0f; s.smooth = 0.5f; s.alpha = 1.0f;  // path_tracing.py:183-186
+    s.emission = v3(0.0f, 0.0f, 0.0f);
+    if (m.kind == DRP_MAT_DEFAULT) {
+        s.albedo = v3(col[0] * m.tint[0], col[1] * m.tint[1], col[2] * m.tint[2]);
+        return s;
+    }
+    float2 t0 = ld2(sc.uv, i0), t1 = ld2(sc.uv, i1), t2 = ld2(sc.uv, i2);
+    float tu = lerp3(t0.x, t1.x, t2.x, u, v), tv = lerp3(t0.y, t1.y, t2.y, u, v);
+    float bc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, mr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (m.base_color_tex.data) {
+        tex_fetch(m.base_color_tex, tu, tv, bc);
+        if (m.base_color_tex.c < 4) bc[3] = 1.0f;
+    }
+    if (m.mr_tex.data) tex_fetch(m.mr_tex, tu, tv, mr);
+    float a = m.base_color_factor[3] * col[3] * bc[3];
+    s.albedo = v3(m.base_color_factor[0] * col[0] * bc[0], m.base_color_factor[1] * col[1] * bc[1], m.base_color_factor[2] * col[2] * bc[2]);
+    s.metal = m.metallic_factor * mr[2];
+    s.smooth = 1.0f + (-m.roughness_factor) * mr[1];
+    if (m.alpha_mode == DRP_ALPHA_MASK) s.alpha = a > m.alpha_cutoff ? 1.0f : 0.0f;
+    else if (m.alpha_mode == DRP_ALPHA_BLEND) s.alpha = a;
+    if (m.has_emissive) {
+        float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (m.emissive_tex.data) tex_fetch(m.emissive_tex, tu, tv, e);
+        s.emission = v3(m.emissive_factor[0] * e[0], m.emissive_factor[1] * e[1], m.emissive_factor[2] * e[2]);
+    }
+    if (m.has_normal_tex && m.normal_tex.data) {  // tangent-space normal map, mixin.py:118-123
+        float nt[4];
+        tex_fetch(m.normal_tex, tu, tv, nt);
+        float nx = 2.0f * nt[0] - 1.0f, ny = 2.0f * nt[1] - 1.0f, nz = 2.0f * nt[2] - 1.0f;
+        float4 g0 = ld4(sc.world_tan, i0), g1 = ld4(sc.world_tan, i1), g2 = ld4(sc.world_tan, i2);
+        Vec3 vt = v3(lerp3(g0.x, g1.x, g2.x, u, v), lerp3(g0.y, g1.y, g2.y, u, v), lerp3(g0.z, g1.z, g2.z, u, v));
+        float vs = lerp3(g0.w, g1.w, g2.w, u, v);
+        Vec3 vb = cross(nu, vt) * vs;
+        s.normal = normalize_ref(vt * nx + (vb * ny + nu * nz));
+    }
+    return s;
+}
+
+// ---- BRDF sampler -----------------------------------------------------------------------------------------------
+DRP_HD Vec3 tangent_combine(float x, float y, float z, Vec3 n) {  // light_transport.py:35-43
+    Vec3 up = n.y < 0.999f ? v3(0.0f, 1.0f, 0.0f) : v3(1.0f, 0.0f, 0.0f);
+    Vec3 right = normalize_ref(cross(up, n));
+    Vec3 up2 = cross(n, right);
+    return right * x + up2 * z + n * y;
+}
+DRP_HD float g_schlick(float ndv, float rough) {
+    float k = (rough * rough) * 0.5f;
+    return ndv / (ndv * (1.0f - k) + k);
+}
+
+// `s` must be all-zero for a miss (zero-initialised g-buffer, path_tracing.py:261-263)
+DRP_HD BounceOut brdf_sample(const SurfaceAttrs& s, float t, Vec3 o, Vec3 d, Vec3 env, const float u[6]) {
+    BounceOut r;
+    r.hit_pos = o + d * t;
+    r.radiance = s.emission + env;
+    float diel = 1.0f - s.metal;
+    Vec3 dc = s.albedo * diel;
+    float dm = fmaxf(fmaxf(dc.x, dc.y), dc.z);
+    float p_diff = diel * dm / (0.04f + dm);
+    float p_spec = 1.0f - p_diff;
+    if (u[0] >= s.alpha) {  // transmit
+        r.next_d = d;
+        r.transfer = v3(1.0f, 1.0f, 1.0f);
+    } else if (u[1] >= p_spec) {  // diffuse, cosine-weighted about n
+        float z2 = u[2], theta = u[3] * DRP_TAU, xy = sqrtf(1.0f - z2);
+        float sn, cs;
+        sincosf(theta, &sn, &cs);
+        r.next_d = tangent_combine(xy * cs, sqrtf(z2), xy * sn, s.normal);
+        float den = fmaxf(p_diff, 0.0001f);
+        r.transfer = v3(dc.x / den, dc.y / den, dc.z / den);
+    } else {  // GGX specular
+        float rough = fmaxf(1.0f - s.smooth, 1.0f / 512.0f);
+        float a = rough * rough;
+        float phi = DRP_TAU * u[4];
+        float ct = sqrtf((1.0f - u[5]) / (1.0f + (a * a - 1.0f) * u[5]));
+        float st = sqrtf(1.0f - ct * ct);
+        float sn, cs;
+        sincosf(phi, &sn, &cs);
+        Vec3 h = tangent_combine(cs * st, ct, sn * st, s.normal);
+        float hd = dot(h, d);
+        r.next_d = d + h * (-2.0f * hd);  // reflect
+        float vh = -hd;
+        float ndv = fmaxf(-dot(s.normal, d), 0.0f), ndl = fmaxf(dot(s.normal, r.next_d), 0.0f);
+        float G = g_schlick(ndl, rough) * g_schlick(ndv, rough);
+        float w1 = 1.0f - vh, w2 = w1 * w1, w5 = w2 * w2 * w1;
+        float geo = G * fmaxf(vh, 1e-6f) / (fmaxf(dot(s.normal, h), 1e-6f) * fmaxf(-dot(s.normal, d), 1e-6f));
+        float den = fmaxf(p_spec * s.alpha, 0.0001f);
+        float f0x = s.albedo.x * s.metal + 0.04f * diel, f0y = s.albedo.y * s.metal + 0.04f * diel, f0z = s.albedo.z * s.metal + 0.04f * diel;
+        r.transfer = v3((fmaxf(s.smooth - f0x, 0.0f) * w5 + f0x) * geo / den, (fmaxf(s.smooth - f0y, 0.0f) * w5 + f0y) * geo / den,
+                        (fmaxf(s.smooth - f0z, 0.0f) * w5 + f0z) * geo / den);
+    }
+    return r;
+}
+
+// does the ray (o, d), t in [0, inf), touch the (padded) scene box?  Used by the exact compaction rule: a ray that
+// missed everything and whose continuation cannot reach the scene box contributes nothing to any output again.
+DRP_HD bool ray_may_reach_box(Vec3 o, Vec3 d, const float* __restrict__ lo, const float* __restrict__ hi) {
+    float tn = 0.0f, tf = 3.0e38f;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (dd[a] == 0.0f) {
+            if (oo[a] < lo[a] || oo[a] > hi[a]) return false;
+        } else {
+            float t1 = (lo[a] - oo[a]) / dd[a], t2 = (hi[a] - oo[a]) / dd[a];
+            tn = fmaxf(tn, fminf(t1, t2));
+            tf = fminf(tf, fmaxf(t1, t2));
+        }
+    }
+    return tn <= tf;
+}

@@ -1,6 +1,376 @@
-// wavefront.cu -- fused wavefront path tracer (placeholder; filled in next)
+// wavefront.cu -- fused wavefront path tracer: drp_render / drp_finalize / drp_render_stats.
+//
+// Replaces the Python section x bounce loop of PathTracingSession.trace_rays with the built-in sampler_brdf
+// (diffrp/rendering/path_tracing.py:250-279, 310-352).  Per batch of samples and per bounce, two persistent kernels:
+//   k_extend : closest hit for every live ray (bounce 0 generates the primary ray from the ray index instead of
+//              reading it), writes (t, id)
+//   k_shade  : surface attributes + env lookup + BRDF sample + fp32 accumulation (RED.ADD) + next ray, appended to
+//              the output queue through a warp-aggregated atomic (stream compaction fused into the shade kernel)
+// Ray state lives in HBM as float4 SoA queues (coalesced 128-bit accesses):
+//   q_a[k] = (o.x, o.y, o.z, d.x)   q_b[k] = (d.y, d.z, bits(ray index), 0)   q_t[k] = (T.r, T.g, T.b, 0)   hit[k] = (t, bits(id))
+#include <vector>
+#include <algorithm>
+#include <string>
+#include <cstring>
+#include <cstdio>
 #include "internal.h"
-void drp_free_workspace(BvhHandle*) {}
-extern "C" int drp_render(uint64_t, const drp_scene_t*, const drp_render_params_t*, float*, void*) { drp_set_error("drp_render: not implemented"); return DRP_ERR_INVALID; }
-extern "C" int drp_finalize(const float*, int32_t, int32_t, int32_t, float*, float*, float*, float*, float*, float*, void*) { drp_set_error("drp_finalize: not implemented"); return DRP_ERR_INVALID; }
-extern "C" int drp_render_stats(uint64_t, drp_render_stats_t*) { return DRP_ERR_INVALID; }
+#include "common.cuh"
+#include "lbvh.cuh"
+#include "traverse.cuh"
+#include "shade.cuh"
+
+#define WF_BLOCK 128
+#define WF_FETCH 128  // rays fetched per warp per atomic
+
+struct RenderWorkspace {
+    int64_t capacity = 0;  // rays
+    float4 *qa[2] = {nullptr, nullptr}, *qb[2] = {nullptr, nullptr}, *qt[2] = {nullptr, nullptr};
+    float2* hit = nullptr;
+    int* counters = nullptr;  // [0..D] live counts per bounce, [64..64+2D) fetch cursors
+    int n_counters = 0;
+    drp_material_t* d_mats = nullptr;
+    int mats_capacity = 0;
+    std::vector<unsigned char> mats_host_copy;
+    unsigned long long* d_traced = nullptr;  // device: live rays traced by the last call (sum over batches and bounces)
+    int sm_count = 0;
+    int grid_extend[2] = {0, 0}, grid_shade[2] = {0, 0};
+    bool have_box = false;
+    float box_lo[3], box_hi[3];
+};
+
+struct WfConst {
+    drp_scene_t scene;        // device pointers (materials -> device copy)
+    drp_render_params_t p;
+    const float4* nodes;
+    const float4* tris;
+    float box_lo[3], box_hi[3];
+    float eps;
+    int HW;
+    int64_t R;          // rays in this batch
+    int64_t R_total;    // rays of the whole call (replay indexing)
+    int sample_base;    // first sample (within the call) of this batch
+    float* accum;
+    int* flags;
+};
+
+// ---- ray fetch: each warp claims WF_FETCH consecutive queue slots per atomic ------------------------------------
+struct WarpFetch {
+    int base, end;
+};
+
+template <bool PRIMARY>
+__device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restrict__ qa, const float4* __restrict__ qb, int k, Vec3& o,
+                                         Vec3& d, int& ray_index) {
+    if (PRIMARY) {
+        ray_index = k + c.sample_base * c.HW;  // index within the call: s_local * HW + pixel  (path_tracing.py:329-331)
+        int s = ray_index / c.HW, pix = ray_index - s * c.HW;
+        int y = pix / c.p.width, x = pix - y * c.p.width;
+        float gx = __ldg(c.p.ndc_x + x) + __ldg(c.p.jitter_x + s);
+        float gy = __ldg(c.p.ndc_y + y) + __ldg(c.p.jitter_y + s);
+        gen_primary_ray(c.p.inv_vp, c.p.cam_pos, c.p.t_near, gx, gy, o, d);
+    } else {
+        float4 a = __ldg(qa + k), b = __ldg(qb + k);
+        o = v3(a.x, a.y, a.z);
+        d = v3(a.w, b.x, b.y);
+        ray_index = __float_as_int(b.z);
+    }
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
+                                                     float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor) {
+    const int count = PRIMARY ? (int)c.R : *count_ptr;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+#pragma unroll 1
+        for (int j = 0; j < WF_FETCH; j += 32) {
+            int k = base + j + lane;
+            if (k < count) {
+                Vec3 o, d;
+                int ri;
+                load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
+                bool overflow = false;
+                RayHit h = trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow);
+                hit[k] = make_float2(h.t, __int_as_float(h.id));
+                if (overflow) atomicAdd(&c.flags[0], 1);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void accum_add4(float* p, float a, float b, float c, float d) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));  // RED.E.ADD.F32x4 (sm_90+)
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WF_BLOCK) k_shade(const __grid_constant__ WfConst c, int bounce, const float4* __restrict__ qa,
+                                                    const float4* __restrict__ qb, const float4* __restrict__ qt, const float2* __restrict__ hit,
+                                                    float4* __restrict__ oa, float4* __restrict__ ob, float4* __restrict__ ot,
+                                                    const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor) {
+    const int count = PRIMARY ? (int)c.R : *count_ptr;
+    const int lane = threadIdx.x & 31;
+    const bool last = bounce == c.p.ray_depth - 1;
+    const bool always_sky = last && c.p.last_bounce_skybox;  // path_tracing.py:260
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+#pragma unroll 1
+        for (int j = 0; j < WF_FETCH; j += 32) {
+            int k = base + j + lane;
+            bool alive = false;
+            Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
+            int ri = 0;
+            if (k < count) {
+                Vec3 o, d;
+                load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
+                if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
+                float2 h = __ldg(hit + k);
+                const float t = h.x;
+                const bool is_hit = t < c.p.t_far;
+                SurfaceAttrs s;
+                if (is_hit) {
+                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y));
+                } else {
+                    s.albedo = s.normal = s.emission = v3(0, 0, 0);
+                    s.metal = s.smooth = s.alpha = 0.0f;
+                }
+                Vec3 env = (always_sky || !is_hit) ? env_fetch(c.scene.env, d) : v3(0, 0, 0);  // path_tracing.py:267-269
+                float u[6];
+                const int pix = ri % c.HW;
+                if (c.p.rng_mode == DRP_RNG_REPLAY) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) u[q] = __ldg(c.p.replay_u + ((int64_t)bounce * 6 + q) * c.R_total + ri);
+                } else {
+                    philox_uniform6(c.p.seed, (uint32_t)pix, (uint32_t)__ldg(c.p.sample_ids + ri / c.HW), (uint32_t)bounce, u);
+                }
+                BounceOut r = brdf_sample(s, t, o, d, env, u);
+                float* acc = c.accum + (int64_t)DRP_ACCUM_CHANNELS * pix;
+                accum_add4(acc, T.x * r.radiance.x, T.y * r.radiance.y, T.z * r.radiance.z, s.alpha);  // path_tracing.py:336-337
+                if (PRIMARY) {  // extras on the first hit, path_tracing.py:340-347
+                    accum_add4(acc + 4, s.albedo.x, s.albedo.y, s.albedo.z, s.emission.x);
+                    accum_add4(acc + 8, s.emission.y, s.emission.z, s.normal.x, s.normal.y);
+                    accum_add4(acc + 12, s.normal.z, r.hit_pos.x, r.hit_pos.y, r.hit_pos.z);
+                }
+                if (!last) {
+                    T = is_hit ? T * r.transfer : v3(0, 0, 0);                 // path_tracing.py:338 with :275
+                    nd = r.next_d;
+                    no = r.hit_pos + nd * c.p.step_epsilon;                    // path_tracing.py:276
+                    alive = true;
+                    if (c.p.compaction && !is_hit) alive = ray_may_reach_box(no, nd, c.box_lo, c.box_hi);
+                }
+            }
+            // warp-aggregated append to the output queue
+            unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (m) {
+                int pos = 0;
+                if (lane == __ffs(m) - 1) pos = atomicAdd(out_count, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1);
+                if (alive) {
+                    int w = pos + __popc(m & ((1u << lane) - 1u));
+                    oa[w] = make_float4(no.x, no.y, no.z, nd.x);
+                    ob[w] = make_float4(nd.y, nd.z, __int_as_float(ri), 0.0f);
+                    ot[w] = make_float4(T.x, T.y, T.z, 0.0f);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_count_traced(const int* __restrict__ counts, int depth, unsigned long long R, unsigned long long* __restrict__ total) {
+    unsigned long long t = R;  // bounce 0 traces every ray of the batch
+    for (int b = 1; b < depth; ++b) t += (unsigned long long)counts[b];
+    *total += t;
+}
+
+__global__ void k_finalize(const float* __restrict__ accum, int H, int W, float spp, float* __restrict__ radiance, float* __restrict__ alpha,
+                           float* __restrict__ albedo, float* __restrict__ emission, float* __restrict__ normal, float* __restrict__ position) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    int y = i / W, x = i - y * W;
+    int src = (H - 1 - y) * W + x;  // flipud, path_tracing.py:348-352
+    const float4* a = reinterpret_cast<const float4*>(accum) + 4 * (int64_t)src;
+    float4 a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+    if (radiance) { radiance[3 * i] = a0.x / spp; radiance[3 * i + 1] = a0.y / spp; radiance[3 * i + 2] = a0.z / spp; }
+    if (alpha) alpha[i] = fminf(fmaxf(a0.w / spp, 0.0f), 1.0f);
+    if (albedo) { albedo[3 * i] = a1.x / spp; albedo[3 * i + 1] = a1.y / spp; albedo[3 * i + 2] = a1.z / spp; }
+    if (emission) { emission[3 * i] = a1.w / spp; emission[3 * i + 1] = a2.x / spp; emission[3 * i + 2] = a2.y / spp; }
+    if (normal) { normal[3 * i] = a2.z / spp; normal[3 * i + 1] = a2.w / spp; normal[3 * i + 2] = a3.x / spp; }
+    if (position) { position[3 * i] = a3.y / spp; position[3 * i + 1] = a3.z / spp; position[3 * i + 2] = a3.w / spp; }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+void drp_free_workspace(BvhHandle* h) {
+    RenderWorkspace* ws = h->ws;
+    if (!ws) return;
+    for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
+    cudaFree(ws->hit); cudaFree(ws->counters); cudaFree(ws->d_mats); cudaFree(ws->d_traced);
+    delete ws;
+    h->ws = nullptr;
+}
+
+static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
+    if (!h->ws) {
+        h->ws = new RenderWorkspace();
+        cudaDeviceProp prop;
+        DRP_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
+        h->ws->sm_count = prop.multiProcessorCount;
+        h->ws->n_counters = 256;
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 256));
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->d_traced, sizeof(unsigned long long)));
+        int nb = 0;
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true>, WF_BLOCK, 0));
+        h->ws->grid_extend[1] = std::max(1, nb) * h->ws->sm_count;
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false>, WF_BLOCK, 0));
+        h->ws->grid_extend[0] = std::max(1, nb) * h->ws->sm_count;
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true>, WF_BLOCK, 0));
+        h->ws->grid_shade[1] = std::max(1, nb) * h->ws->sm_count;
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<false>, WF_BLOCK, 0));
+        h->ws->grid_shade[0] = std::max(1, nb) * h->ws->sm_count;
+    }
+    RenderWorkspace* ws = h->ws;
+    if (rays > ws->capacity) {
+        for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
+        cudaFree(ws->hit);
+        ws->capacity = 0;
+        for (int k = 0; k < 2; ++k) {
+            DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qa[k], sizeof(float4) * rays));
+            DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qb[k], sizeof(float4) * rays));
+            DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qt[k], sizeof(float4) * rays));
+        }
+        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->hit, sizeof(float2) * rays));
+        ws->capacity = rays;
+    }
+    if (n_mats > ws->mats_capacity) {
+        cudaFree(ws->d_mats);
+        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->d_mats, sizeof(drp_material_t) * n_mats));
+        ws->mats_capacity = n_mats;
+        ws->mats_host_copy.clear();
+    }
+    return DRP_OK;
+}
+
+#define WF_MAX_BATCH_RAYS (int64_t(1) << 24)  // 16M rays per internal batch (~1.9 GB of queues)
+#define WF_MAX_DEPTH 60
+
+extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_render_params_t* params, float* accum, void* stream) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_render: unknown handle"); return DRP_ERR_HANDLE; }
+    if (!scene || !params || !accum) { drp_set_error("drp_render: null argument"); return DRP_ERR_INVALID; }
+    const drp_render_params_t& p = *params;
+    if (p.height <= 0 || p.width <= 0 || p.ray_depth <= 0 || p.ray_depth > WF_MAX_DEPTH || p.n_samples < 0) {
+        drp_set_error("drp_render: bad resolution / depth / sample count");
+        return DRP_ERR_INVALID;
+    }
+    if (scene->n_tris != h->n_tris) { drp_set_error("drp_render: scene does not match the built structure"); return DRP_ERR_INVALID; }
+    if (p.rng_mode == DRP_RNG_REPLAY && !p.replay_u) { drp_set_error("drp_render: replay mode without replay_u"); return DRP_ERR_INVALID; }
+    if (!p.ndc_x || !p.ndc_y || !p.jitter_x || !p.jitter_y || !p.sample_ids) { drp_set_error("drp_render: missing raygen tables"); return DRP_ERR_INVALID; }
+    if (scene->n_materials <= 0 || !scene->materials) { drp_set_error("drp_render: scene has no materials"); return DRP_ERR_INVALID; }
+    const int64_t HW = (int64_t)p.height * p.width;
+    if (HW > WF_MAX_BATCH_RAYS) { drp_set_error("drp_render: more than 2^24 pixels per frame not supported"); return DRP_ERR_INVALID; }
+    if (p.n_samples == 0) return DRP_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) { drp_set_error("drp_render: cannot select device"); return DRP_ERR_CUDA; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int spb = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
+    int rc = ensure_workspace(h, (int64_t)spb * HW, scene->n_materials);
+    if (rc != DRP_OK) return rc;
+    RenderWorkspace* ws = h->ws;
+    // material table -> device (skipped when unchanged since the previous call)
+    const size_t mbytes = sizeof(drp_material_t) * scene->n_materials;
+    if (ws->mats_host_copy.size() != mbytes || memcmp(ws->mats_host_copy.data(), scene->materials, mbytes) != 0) {
+        ws->mats_host_copy.assign((const unsigned char*)scene->materials, (const unsigned char*)scene->materials + mbytes);
+        DRP_CUDA_CHECK(cudaMemcpyAsync(ws->d_mats, ws->mats_host_copy.data(), mbytes, cudaMemcpyHostToDevice, s));
+    }
+    WfConst c;
+    memset(&c, 0, sizeof(c));
+    c.scene = *scene;
+    c.scene.materials = ws->d_mats;
+    c.p = p;
+    c.nodes = h->nodes;
+    c.tris = h->packed;
+    c.eps = h->eps;
+    c.HW = (int)HW;
+    c.R_total = HW * p.n_samples;
+    c.accum = accum;
+    c.flags = h->dev_flags;
+    if (!ws->have_box) {  // padded scene box for the exact compaction rule: one host read per handle, then cached
+        uint32_t ob[12];
+        DRP_CUDA_CHECK(cudaMemcpyAsync(ob, h->bounds, sizeof(ob), cudaMemcpyDeviceToHost, s));
+        DRP_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (int a = 0; a < 3; ++a) {
+            float lo = ord2f(ob[a]), hi = ord2f(ob[3 + a]);
+            float pad = 1e-5f * fmaxf(fmaxf(fabsf(lo), fabsf(hi)), 1e-30f) + 1e-5f * fmaxf(hi - lo, 0.0f);
+            ws->box_lo[a] = lo - pad; ws->box_hi[a] = hi + pad;
+        }
+        if (h->n_tris == 0) for (int a = 0; a < 3; ++a) { ws->box_lo[a] = 1.0f; ws->box_hi[a] = -1.0f; }
+        ws->have_box = true;
+    }
+    for (int a = 0; a < 3; ++a) { c.box_lo[a] = ws->box_lo[a]; c.box_hi[a] = ws->box_hi[a]; }
+    const int D = p.ray_depth;
+    int64_t launches = 0;
+    h->last_render.rays_nominal = HW * p.n_samples * D;
+    DRP_CUDA_CHECK(cudaMemsetAsync(ws->d_traced, 0, sizeof(unsigned long long), s));
+    for (int s0 = 0; s0 < p.n_samples; s0 += spb) {
+        const int ns = std::min(spb, p.n_samples - s0);
+        c.R = (int64_t)ns * HW;
+        c.sample_base = s0;
+        int* counts = ws->counters;       // [0..D]
+        int* cursors = ws->counters + 64; // [0..2D)
+        DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));
+        ++launches;
+        for (int b = 0; b < D; ++b) {
+            const int in = b & 1, out = in ^ 1;
+            if (b == 0) {
+                k_extend<true><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
+                k_shade<true><<<ws->grid_shade[1], WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, ws->hit, ws->qa[out], ws->qb[out], ws->qt[out], nullptr,
+                                                        counts + 1, cursors + 1);
+            } else {
+                k_extend<false><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
+                k_shade<false><<<ws->grid_shade[0], WF_BLOCK, 0, s>>>(c, b, ws->qa[in], ws->qb[in], ws->qt[in], ws->hit, ws->qa[out], ws->qb[out], ws->qt[out],
+                                                         counts + b, counts + b + 1, cursors + 2 * b + 1);
+            }
+            launches += 2;
+        }
+        k_count_traced<<<1, 1, 0, s>>>(counts, D, (unsigned long long)c.R, ws->d_traced);  // read lazily by drp_render_stats
+        ++launches;
+    }
+    DRP_CUDA_CHECK(cudaGetLastError());
+    h->last_render.kernel_launches = launches;
+    return DRP_OK;
+}
+
+extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h || !out) { drp_set_error("drp_render_stats: unknown handle"); return DRP_ERR_HANDLE; }
+    DeviceGuard guard(h->device);
+    DRP_CUDA_CHECK(cudaDeviceSynchronize());
+    *out = h->last_render;
+    if (h->ws) {
+        unsigned long long traced = 0;
+        DRP_CUDA_CHECK(cudaMemcpy(&traced, h->ws->d_traced, sizeof(traced), cudaMemcpyDeviceToHost));
+        out->rays_traced = (int64_t)traced;
+    }
+    int flags[4] = {0, 0, 0, 0};
+    DRP_CUDA_CHECK(cudaMemcpy(flags, h->dev_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[0] != 0) {
+        drp_set_error("traversal stack overflow on " + std::to_string(flags[0]) + " rays: results are invalid");
+        return DRP_ERR_INVALID;
+    }
+    return DRP_OK;
+}
+
+extern "C" int drp_finalize(const float* accum, int32_t height, int32_t width, int32_t spp_total, float* radiance, float* alpha, float* albedo,
+                            float* emission, float* world_normal, float* world_position, void* stream) {
+    if (!accum || height <= 0 || width <= 0 || spp_total <= 0) { drp_set_error("drp_finalize: invalid argument"); return DRP_ERR_INVALID; }
+    const int n = height * width;
+    k_finalize<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(accum, height, width, (float)spp_total, radiance, alpha, albedo, emission,
+                                                                 world_normal, world_position);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}

@@ -1,0 +1,89 @@
+"""
+Scene flattening: every object of a ``Scene`` concatenated into one set of vertex / index buffers, the way the
+reference's ``RenderSessionMixin.vertex_array_object`` does it (diffrp/rendering/mixin.py:74-113), plus the per-vertex
+world-space normals / tangents that ``SurfaceInput.interpolate_ex`` would compute per material
+(base_material.py:137-143: 'vectornor', 'vector3norex1') baked once for the fused kernel.
+
+Device-agnostic torch code (runs once per session; not the hot path).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from .ops import transform_point4x3, transform_vector3x3, normalized
+
+
+@dataclass
+class VertexArrayObject:
+    """Flattened scene buffers (base_material.py:12-34) + the baked world-space attributes the fused kernel reads."""
+    verts: torch.Tensor
+    normals: torch.Tensor
+    world_pos: torch.Tensor
+    tris: torch.Tensor
+    stencils: torch.Tensor
+    color: torch.Tensor
+    uv: torch.Tensor
+    tangents: torch.Tensor
+    custom_attrs: Dict[str, torch.Tensor]
+    world_nrm: torch.Tensor = None
+    world_tan: torch.Tensor = None
+    tri_material: torch.Tensor = None
+
+
+
+def flatten_scene(objs: List, dev) -> VertexArrayObject:
+    dev = torch.device(dev)
+    f32 = lambda t: t.to(dev, torch.float32, non_blocking=True)
+    keys = set().union(*(o.custom_attrs.keys() for o in objs)) if objs else set()
+    verts, nrms, wpos, tris, sts, cols, uvs, tans, wn, wt, tm = ([] for _ in range(11))
+    customs = {k: [] for k in keys}
+    sts.append(torch.zeros([1], dtype=torch.int32, device=dev))  # stencil 0 = miss (mixin.py:78)
+    offset = 0
+    for s, o in enumerate(objs):
+        assert o.tris.shape[-1] == 3, "Expected 3 vertices per triangle, got %d" % o.tris.shape[-1]
+        v, n, M = f32(o.verts), f32(o.normals), f32(o.M)
+        col, uv, tg = f32(o.color), f32(o.uv), f32(o.tangents)
+        for name, a, c in (("normals", n, 3), ("uv", uv, 2), ("tangents", tg, 4), ("color", col, None)):
+            assert a.shape[0] == v.shape[0], "attribute length not the same as number of vertices"
+            assert c is None or a.shape[-1] == c, "expected %s dims but got %d for vertex attribute %s" % (c, a.shape[-1], name)
+        if col.shape[-1] == 3:
+            col = torch.cat([col, torch.ones_like(col[:, :1])], -1)
+        verts.append(v); nrms.append(n); cols.append(col); uvs.append(uv); tans.append(tg)
+        wpos.append(transform_point4x3(v, M))
+        wn.append(normalized(transform_vector3x3(n, M)))                                     # 'vectornor'
+        wt.append(torch.cat([normalized(transform_vector3x3(tg[:, :3], M)), tg[:, 3:]], -1))  # 'vector3norex1'
+        t = o.tris.to(dev, torch.int32, non_blocking=True) + offset
+        tris.append(t)
+        sts.append(torch.full([len(t)], s + 1, dtype=torch.int32, device=dev))
+        tm.append(torch.full([len(t)], s, dtype=torch.int32, device=dev))
+        for k in keys:
+            if k in o.custom_attrs:
+                assert len(o.custom_attrs[k]) == len(o.verts), "Attribute length not the same as number of vertices: %s" % k
+                customs[k].append(f32(o.custom_attrs[k]))
+            else:
+                size = next(x.custom_attrs[k].shape[-1] for x in objs if k in x.custom_attrs)
+                customs[k].append(torch.zeros([len(v), size], device=dev))
+        offset += len(v)
+    cat = lambda xs, shape, dt=torch.float32: (torch.cat(xs).contiguous() if xs else torch.zeros(shape, dtype=dt, device=dev))
+    return VertexArrayObject(
+        cat(verts, [0, 3]), cat(nrms, [0, 3]), cat(wpos, [0, 3]), cat(tris, [0, 3], torch.int32), torch.cat(sts).contiguous(),
+        cat(cols, [0, 4]), cat(uvs, [0, 2]), cat(tans, [0, 4]), {k: torch.cat(v) for k, v in customs.items()},
+        cat(wn, [0, 3]), cat(wt, [0, 4]), cat(tm, [0], torch.int32))
+
+
+def material_descriptions(objs: List, dev) -> Optional[List[dict]]:
+    """Per-object drp_material_t descriptions (textures moved to ``dev``), or None if any material is Python-only."""
+    descs = []
+    for o in objs:
+        d = o.material.fused_description() if hasattr(o.material, 'fused_description') else None
+        if d is None:
+            return None
+        d = dict(d)
+        for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
+            if d.get(k) is not None:
+                d[k] = dict(d[k], image=d[k]['image'].to(dev, torch.float32).contiguous())
+        descs.append(d)
+    if not descs:
+        descs = [dict(kind='default', tint=None)]
+    return descs

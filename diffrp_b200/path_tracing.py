@@ -1,0 +1,317 @@
+"""
+``PathTracingSession`` / ``PathTracingSessionOptions`` / ``RayOutputs`` with the API of the reference
+(diffrp/rendering/path_tracing.py:23-367), driving the hand-written sm_100a kernels of ``libdiffrp_b200.so``.
+
+Two execution paths behind the same methods:
+
+* **fused** (``pbr()`` when every material is a built-in ``DefaultMaterial`` / ``GLTFMaterial``): the whole
+  section x bounce loop of ``trace_rays`` + ``sampler_brdf`` runs as CUDA kernels (``drp_render``); PyTorch only
+  allocates tensors and supplies the stream.
+* **generic** (``trace_rays(sampler)`` with a user sampler, or scenes with custom Python materials): the reference's
+  protocol is kept -- the sampler is called per bounce with ``(rays_o, rays_d, t, i, d)`` -- and only the
+  intersection runs in CUDA (``B200Raycaster``).  See ``diffrp_b200.generic``.
+
+There is no CPU fallback: without the CUDA library / a CUDA device the session raises.
+"""
+import math
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import _abi
+from ._lib import lib, check
+from .camera import Camera
+from .ops import small_matrix_inverse
+from .raycaster import B200Raycaster, _stream_ptr
+from .scene import Scene, ImageEnvironmentLight
+from .flatten import VertexArrayObject, flatten_scene, material_descriptions
+
+
+@dataclass
+class PathTracingSessionOptions:
+    """
+    Same fields, defaults and meaning as the reference's options (path_tracing.py:23-84), plus B200 extensions.
+
+    ``raycaster_impl``: ``'b200'`` (default).  The reference's names ``'torchoptix'``, ``'naive-pbbvh'`` and
+    ``'brute-force'`` are accepted so existing option objects keep working; all of them select the B200 LBVH
+    raycaster, whose closest-hit contract is the brute-force one (min t, then min primitive id).
+    ``raycaster_builder`` and ``optix_log_level`` are accepted (one builder exists; the level controls verbosity).
+
+    Extensions:
+        rng (str): ``'native'`` -- counter-based Philox4x32-10 keyed by (seed; pixel, sample, bounce), no RNG tensors
+            in HBM; ``'torch'`` -- draw the six ``torch.rand((R,1))`` tensors per bounce exactly like the reference's
+            sampler (path_tracing.py:205-223) and replay them in the kernel: with the same ``torch.manual_seed`` the image
+            reproduces the reference's within fp32 tolerance.
+        seed (int): key of the native RNG.
+        compaction (bool): drop rays that provably contribute nothing to any output (exact; the reference keeps
+            tracing them with zero throughput).
+        shard_rank / shard_world: this process renders global sample indices ``rank::world`` (scene replicated) and the
+            fp32 accumulators are summed with ``torch.distributed.all_reduce`` when a process group exists.
+    """
+    ray_depth: int = 3
+    ray_spp: int = 16
+    ray_split_size: int = 8 * 1024 * 1024
+    deterministic: bool = True
+    pbr_ray_step_epsilon: float = 1e-3
+    pbr_ray_last_bounce: str = 'void'
+    raycaster_impl: str = 'b200'
+    raycaster_epsilon: float = 1e-8
+    raycaster_builder: str = 'splitaxis'
+    optix_log_level: int = 3
+    rng: str = 'native'
+    seed: int = 0
+    compaction: bool = True
+    shard_rank: int = 0
+    shard_world: int = 1
+
+
+@dataclass
+class RayOutputs:
+    """Sampler protocol outputs (path_tracing.py:87-124)."""
+    radiance: torch.Tensor
+    transfer: torch.Tensor
+    next_rays_o: torch.Tensor
+    next_rays_d: torch.Tensor
+    alpha: torch.Tensor
+    extras: Dict[str, torch.Tensor]
+
+
+def _bit_reverse32(i: torch.Tensor) -> torch.Tensor:
+    """Van der Corput radical inverse numerator: reverse the low 32 bits of an int64 tensor (light_transport.py:10-17)."""
+    b = i
+    for shift, mask in ((16, 0x0000FFFF), (8, 0x00FF00FF), (4, 0x0F0F0F0F), (2, 0x33333333), (1, 0x55555555)):
+        b = ((b & mask) << shift) | ((b >> shift) & mask)
+    return b
+
+
+def hammersley(n: int, deterministic: bool = False, device=None):
+    """x_i = i/n, y_i = radical inverse of i; one global random shift when not deterministic (light_transport.py:20-32)."""
+    i = torch.arange(n, dtype=torch.int64, device=device)
+    x = i.float() * (1 / n)
+    y = _bit_reverse32(i).float() * 2.3283064365386963e-10
+    if not deterministic:
+        x = (x + torch.rand(1, dtype=x.dtype, device=x.device)) % 1.0
+        y = (y + torch.rand(1, dtype=x.dtype, device=x.device)) % 1.0
+    return x, y
+
+
+def raygen_tables(V: torch.Tensor, P: torch.Tensor, H: int, W: int, spp: int, deterministic: bool, device) -> dict:
+    """
+    Everything the primary-ray generator needs, computed with the same torch / numpy calls as the reference so the
+    values are identical: camera position and inv(VP) (mixin.py:31-39, host numpy inverse), far / near (mixin.py:38,44),
+    pixel-centre NDC ramps (coordinates.py:6-10) and the per-sample Hammersley offsets (path_tracing.py:317,329).
+    """
+    V, P = V.to(torch.float32), P.to(torch.float32)
+    inv = small_matrix_inverse(torch.stack([V, torch.mm(P, V)]))
+    qx, qy = hammersley(spp, deterministic, device)
+    return dict(
+        cam_pos=[float(x) for x in inv[0, :3, 3].cpu()],
+        inv_vp=[float(x) for x in inv[1].reshape(-1).cpu()],
+        t_far=(P[2, 3] / (P[2, 2] + 1)).item(),
+        t_near=(P[2, 3] / (P[2, 2] - 1)).item(),
+        ndc_x=torch.linspace(-1 + 1 / W, 1 - 1 / W, W, dtype=torch.float32, device=device),
+        ndc_y=torch.linspace(-1 + 1 / H, 1 - 1 / H, H, dtype=torch.float32, device=device),
+        jitter_x=((qx - 0.5) * (2 / W)).contiguous(),
+        jitter_y=((qy - 0.5) * (2 / H)).contiguous(),
+    )
+
+
+def _cached(fn):
+    name = fn.__name__
+
+    def wrapped(self):
+        cache = self.__dict__.setdefault('_cache', {})
+        if name not in cache:
+            cache[name] = fn(self)
+        return cache[name]
+    wrapped.__name__ = name
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+class PathTracingSession:
+    """Path tracing render session: single use, like the reference's sessions."""
+
+    def __init__(self, scene: Scene, camera: Camera, options: Optional[PathTracingSessionOptions] = None) -> None:
+        self.scene = scene
+        self.camera = camera
+        self.options = options if options is not None else PathTracingSessionOptions()
+        if not torch.cuda.is_available():
+            raise RuntimeError("diffrp_b200.PathTracingSession needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        #: rng='torch' only: callable(shape) -> uniforms; defaults to torch.rand on the CUDA device (what the reference's
+        #: rand_like draws).  Tests inject the CPU generator here to replay golden images made by the CPU reference.
+        self.uniform_source = None
+
+    # ---- camera (mixin.py:19-44) ---------------------------------------------------------------------------------
+    @_cached
+    def camera_V(self):
+        return self.camera.V().to(self.device, torch.float32)
+
+    @_cached
+    def camera_P(self):
+        return self.camera.P().to(self.device, torch.float32)
+
+    @_cached
+    def camera_VP(self):
+        return torch.mm(self.camera_P(), self.camera_V())
+
+    @_cached
+    def camera_far(self) -> float:
+        p = self.camera_P()
+        return (p[2, 3] / (p[2, 2] + 1)).item()
+
+    @_cached
+    def camera_near(self) -> float:
+        p = self.camera_P()
+        return (p[2, 3] / (p[2, 2] - 1)).item()
+
+    # ---- scene flattening (mixin.py:74-113) ------------------------------------------------------------------------
+    @_cached
+    def vertex_array_object(self) -> VertexArrayObject:
+        return flatten_scene(self.scene.objects, self.device)
+
+    # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
+    @_cached
+    def raycaster(self):
+        impl = self.options.raycaster_impl
+        if impl not in ('b200', 'torchoptix', 'naive-pbbvh', 'brute-force'):
+            raise ValueError("unknown raycaster_impl: %r" % (impl,))
+        vao = self.vertex_array_object()
+        cfg = {'epsilon': self.options.raycaster_epsilon, 'builder': self.options.raycaster_builder,
+               'optix_log_level': self.options.optix_log_level}
+        return B200Raycaster(vao.world_pos, vao.tris, cfg)
+
+    @_cached
+    def _single_env_light(self):
+        env = None
+        for light in self.scene.lights:
+            if isinstance(light, ImageEnvironmentLight):
+                if env is not None:
+                    raise ValueError("Only one environment light is supported in path tracing now.")
+                env = light.image_rh().to(self.device, torch.float32).contiguous()
+        return env  # None == the reference's 16x16 black texture
+
+    # ---- fused path ------------------------------------------------------------------------------------------------
+    @_cached
+    def _fused_scene(self):
+        """drp_scene_t for the fused kernels, or None when some material only exists as Python code."""
+        descs = material_descriptions(self.scene.objects, self.device)
+        if descs is None:
+            return None
+        vao = self.vertex_array_object()
+        arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
+                      tris=vao.tris, tri_material=vao.tri_material)
+        env = self._single_env_light()
+        return _abi.pack_scene(arrays, descs, None if env is None else dict(image=env), lambda t: t.data_ptr())
+
+    def _section_sample_ids(self, ids: torch.Tensor):
+        """Split like the reference: sections = min(spp, ceil(H*W*spp / ray_split_size)) (path_tracing.py:318-320)."""
+        H, W = self.camera.resolution()
+        n = len(ids)
+        if n == 0:
+            return []
+        sections = min(n, math.ceil((H * W * n) / self.options.ray_split_size))
+        return list(torch.tensor_split(ids, max(1, sections)))
+
+    def render_accumulators(self) -> torch.Tensor:
+        """Run the fused wavefront for this process' share of the samples; returns the (H*W, 16) fp32 sums."""
+        opt = self.options
+        fused = self._fused_scene()
+        if fused is None:
+            raise RuntimeError("scene contains custom Python materials: use pbr() / trace_rays() (generic path)")
+        scene_struct, _keep = fused
+        L = lib()
+        H, W = self.camera.resolution()
+        dev = self.device
+        rc = self.raycaster()
+        tab = raygen_tables(self.camera_V(), self.camera_P(), H, W, opt.ray_spp, opt.deterministic, dev)
+        ndc_x, ndc_y, jit_x, jit_y = tab['ndc_x'], tab['ndc_y'], tab['jitter_x'], tab['jitter_y']
+        all_ids = torch.arange(opt.ray_spp, dtype=torch.int32, device=dev)
+        my_ids = all_ids[opt.shard_rank::opt.shard_world] if opt.shard_world > 1 else all_ids
+        accum = torch.zeros([H * W, _abi.ACCUM_CHANNELS], dtype=torch.float32, device=dev)
+        p = _abi.RenderParams()
+        p.height, p.width, p.ray_depth = H, W, opt.ray_depth
+        p.last_bounce_skybox = int(opt.pbr_ray_last_bounce == 'skybox')
+        p.compaction = int(opt.compaction)
+        p.step_epsilon, p.t_far, p.t_near = opt.pbr_ray_step_epsilon, tab['t_far'], tab['t_near']
+        p.cam_pos[:3] = tab['cam_pos']
+        p.inv_vp[:] = tab['inv_vp']
+        p.seed = opt.seed
+        p.ndc_x, p.ndc_y = ndc_x.data_ptr(), ndc_y.data_ptr()
+        stream = _stream_ptr(dev)
+        self._launches = 0
+        if opt.rng == 'torch':
+            if opt.shard_world > 1:
+                raise ValueError("rng='torch' (reference replay) is a single-process mode")
+            chunks = self._section_sample_ids(my_ids)
+        elif opt.rng == 'native':
+            chunks = [my_ids] if len(my_ids) else []
+        else:
+            raise ValueError("rng must be 'native' or 'torch'")
+        for ids in chunks:
+            ids = ids.contiguous()
+            idl = ids.long()
+            jx, jy = jit_x[idl].contiguous(), jit_y[idl].contiguous()
+            p.n_samples = len(ids)
+            p.jitter_x, p.jitter_y, p.sample_ids = jx.data_ptr(), jy.data_ptr(), ids.data_ptr()
+            if opt.rng == 'torch':
+                R = len(ids) * H * W
+                # the reference draws six rand_like((R,1)) per bounce, bounce-major (path_tracing.py:205-223)
+                draw = self.uniform_source if self.uniform_source is not None else (lambda shape: torch.rand(shape, dtype=torch.float32, device=dev))
+                u = torch.stack([draw([R, 1]).to(dev, torch.float32) for _ in range(opt.ray_depth * 6)])
+                u = u.reshape(opt.ray_depth, 6, R).contiguous()
+                p.replay_u, p.rng_mode = u.data_ptr(), _abi.RNG_REPLAY
+            else:
+                p.replay_u, p.rng_mode = None, _abi.RNG_NATIVE
+            check(L.drp_render(rc.handle, C.byref(scene_struct), C.byref(p), accum.data_ptr(), stream), "drp_render")
+        return accum
+
+    def finalize(self, accum: torch.Tensor):
+        """Epilogue of trace_rays (path_tracing.py:348-352): /spp, saturate(alpha), flipud -- one kernel."""
+        H, W = self.camera.resolution()
+        dev = accum.device
+        outs = {k: torch.empty([H, W, 3], dtype=torch.float32, device=dev) for k in
+                ('radiance', 'albedo', 'emission', 'world_normal', 'world_position')}
+        alpha = torch.empty([H, W, 1], dtype=torch.float32, device=dev)
+        check(lib().drp_finalize(accum.data_ptr(), H, W, self.options.ray_spp, outs['radiance'].data_ptr(), alpha.data_ptr(),
+                                 outs['albedo'].data_ptr(), outs['emission'].data_ptr(), outs['world_normal'].data_ptr(),
+                                 outs['world_position'].data_ptr(), _stream_ptr(dev)), "drp_finalize")
+        radiance = outs.pop('radiance')
+        return radiance, alpha, outs
+
+    def render_stats(self) -> dict:
+        st = _abi.RenderStats()
+        check(lib().drp_render_stats(self.raycaster().handle, C.byref(st)), "drp_render_stats")
+        return dict(rays_traced=st.rays_traced, rays_nominal=st.rays_nominal, kernel_launches=st.kernel_launches)
+
+    @torch.no_grad()
+    def pbr(self):
+        """
+        Path-traced PBR rendering; returns ``(radiance (H,W,3), alpha (H,W,1), extras)`` with extras ``albedo``,
+        ``emission``, ``world_normal`` and ``world_position`` (H,W,3) -- same contract as path_tracing.py:354-367.
+        """
+        if self._fused_scene() is None:
+            return self.trace_rays(self.sampler_brdf)
+        accum = self.render_accumulators()
+        if self.options.shard_world > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(accum, op=dist.ReduceOp.SUM)  # NCCL over NVLink: one packed fp32 accumulator
+        return self.finalize(accum)
+
+    # ---- generic path (user samplers / Python materials): see diffrp_b200/generic.py -------------------------------
+    def layer_material_rays(self, rays_o, rays_d, t, i):
+        from . import generic
+        return generic.layer_material_rays(self, rays_o, rays_d, t, i)
+
+    def sampler_brdf(self, rays_o, rays_d, t, i, d: int) -> RayOutputs:
+        from . import generic
+        return generic.sampler_brdf(self, rays_o, rays_d, t, i, d)
+
+    @torch.no_grad()
+    def trace_rays(self, sampler: Callable, radiance_channels: int = 3):
+        from . import generic
+        return generic.trace_rays(self, sampler, radiance_channels)

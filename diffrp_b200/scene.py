@@ -1,0 +1,150 @@
+"""
+Scene description with the interface of the reference's ``diffrp.scene`` (scene.py:10-75, objects.py:11-98,
+lights.py:6-50): ``Scene``, ``MeshObject`` and the light dataclasses.  These are the *inputs* of the hot path.
+"""
+import collections
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+
+from .ops import normalized, transform_point4x3, transform_vector3x3, zeros_like_vec, ones_like_vec
+
+
+def face_normals(verts: torch.Tensor, tris: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """Per-face normals of CCW triangles (geometry.py:26-41)."""
+    t = tris.long()
+    n = torch.linalg.cross(verts[t[:, 1]] - verts[t[:, 0]], verts[t[:, 2]] - verts[t[:, 0]])
+    return normalized(n) if normalize else n
+
+
+def vertex_normals(verts: torch.Tensor, tris: torch.Tensor) -> torch.Tensor:
+    """Area-weighted smooth vertex normals (geometry.py:44-65)."""
+    fn = face_normals(verts, tris)
+    t = tris.long()
+    acc = torch.zeros_like(verts)
+    for k in range(3):
+        acc = acc.index_add(0, t[:, k], fn)
+    return normalized(acc)
+
+
+@dataclass
+class MeshObject:
+    """Triangle mesh + material + per-vertex attributes; same fields and defaults as objects.py:11-69."""
+    material: Any
+    verts: torch.Tensor
+    tris: torch.Tensor
+    normals: Union[str, torch.Tensor] = 'flat'
+    M: Optional[torch.Tensor] = None
+    color: Optional[torch.Tensor] = None
+    uv: Optional[torch.Tensor] = None
+    tangents: Optional[torch.Tensor] = None
+    custom_attrs: Optional[Dict[str, torch.Tensor]] = None
+    metadata: Optional[Dict[str, Any]] = None
+
+    def preprocess(self):
+        """Fill defaults; 'flat' normals turn the mesh into a face soup (objects.py:71-98)."""
+        v = self.verts
+        if self.M is None:
+            self.M = torch.eye(4, device=v.device, dtype=v.dtype)
+        if self.color is None:
+            self.color = ones_like_vec(v, 4)
+        if self.uv is None:
+            self.uv = zeros_like_vec(v, 2)
+        if self.tangents is None:
+            self.tangents = zeros_like_vec(v, 4)
+        if self.custom_attrs is None:
+            self.custom_attrs = {}
+        if self.metadata is None:
+            self.metadata = {}
+        if isinstance(self.normals, str):
+            if self.normals == 'smooth':
+                self.normals = vertex_normals(self.verts, self.tris)
+            elif self.normals == 'flat':
+                f = self.tris.long()
+                fn = face_normals(self.verts, self.tris, normalize=True)
+                self.verts = self.verts[f].reshape(-1, 3)
+                self.normals = fn[:, None, :].expand(-1, 3, -1).reshape(-1, 3)
+                self.tris = torch.arange(f.numel(), device=f.device, dtype=torch.int32).reshape(f.shape)
+                self.color = self.color[f].flatten(0, 1)
+                self.uv = self.uv[f].flatten(0, 1)
+                self.tangents = self.tangents[f].flatten(0, 1)
+                self.custom_attrs = {k: a[f].flatten(0, 1) for k, a in self.custom_attrs.items()}
+            else:
+                raise ValueError("normals must be 'flat', 'smooth' or a tensor, got %r" % (self.normals,))
+        return self
+
+
+@dataclass
+class Light:
+    intensity: Union[torch.Tensor, float]
+    color: torch.Tensor
+
+
+@dataclass
+class DirectionalLight(Light):
+    """Data only (not supported by the path tracer; lights.py:20-25)."""
+    direction: torch.Tensor
+
+
+@dataclass
+class PointLight(Light):
+    """Data only (not supported by the path tracer; lights.py:28-33)."""
+    position: torch.Tensor
+
+
+@dataclass
+class ImageEnvironmentLight(Light):
+    """Lat-long (H, 2H, 3) environment image (lights.py:36-50)."""
+    image: torch.Tensor
+    render_skybox: bool = True
+
+    def image_rh(self) -> torch.Tensor:
+        return torch.fliplr(self.image) * (self.intensity * self.color)
+
+
+class Scene:
+    """Container of objects and lights; ``add_*`` return the scene for chaining (scene.py:10-75)."""
+
+    def __init__(self) -> None:
+        self.lights: List[Light] = []
+        self.objects: List[MeshObject] = []
+        self.metadata = {}
+
+    def add_light(self, light: Light):
+        self.lights.append(light)
+        return self
+
+    def add_mesh_object(self, mesh_obj: MeshObject):
+        self.objects.append(mesh_obj.preprocess())
+        return self
+
+    def static_batching(self):
+        """Merge meshes that share a material object into one world-space mesh, in place (scene.py:33-75)."""
+        groups = collections.OrderedDict()
+        for mesh in self.objects:
+            groups.setdefault(id(mesh.material), []).append(mesh)
+        merged = []
+        for meshes in groups.values():
+            if len(meshes) == 1:
+                merged.append(meshes[0])
+                continue
+            tris, offset = [], 0
+            for m in meshes:
+                tris.append(m.tris + offset)
+                offset += len(m.verts)
+            last = meshes[-1]
+            merged.append(MeshObject(
+                last.material,
+                torch.cat([transform_point4x3(m.verts, m.M) for m in meshes]),
+                torch.cat(tris),
+                torch.cat([normalized(transform_vector3x3(m.normals, m.M)) for m in meshes]),
+                torch.eye(4, dtype=torch.float32, device=last.verts.device),
+                torch.cat([m.color for m in meshes]),
+                torch.cat([m.uv for m in meshes]),
+                torch.cat([torch.cat([normalized(transform_vector3x3(m.tangents[..., :3], m.M)), m.tangents[..., 3:]], -1) for m in meshes]),
+                {k: torch.cat([m.custom_attrs[k] for m in meshes]) for k in last.custom_attrs},
+                {},
+            ))
+        self.objects = merged
+        return self

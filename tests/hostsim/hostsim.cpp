@@ -119,3 +119,50 @@ extern "C" void hs_stats(const HsBvh* h, int64_t* out /* [n_nodes, n_leaves, max
     out[0] = nodes; out[1] = leaves; out[2] = md; out[3] = dup ? -1 : tris; out[4] = ml;
     *sah = h->sah;
 }
+
+// ---- shading: the per-ray body of k_extend + k_shade run serially, without compaction -------------------------
+#include "../../diffrp_b200/csrc/shade.cuh"
+
+extern "C" int64_t hs_render(const HsBvh* h, const drp_scene_t* scene, const drp_render_params_t* pp, float eps, float* accum) {
+    const drp_render_params_t& p = *pp;
+    const int HW = p.height * p.width;
+    const int64_t R_total = (int64_t)HW * p.n_samples;
+    int64_t traced = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : traced)
+    for (int pix = 0; pix < HW; ++pix) {
+        for (int s = 0; s < p.n_samples; ++s) {
+            const int ri = s * HW + pix;
+            int y = pix / p.width, x = pix - y * p.width;
+            Vec3 o, d, T = v3(1, 1, 1);
+            gen_primary_ray(p.inv_vp, p.cam_pos, p.t_near, p.ndc_x[x] + p.jitter_x[s], p.ndc_y[y] + p.jitter_y[s], o, d);
+            for (int b = 0; b < p.ray_depth; ++b) {
+                bool of = false;
+                RayHit hit = trace_one(h->nodes.data(), h->packed.data(), o, d, p.t_far, eps, of);
+                ++traced;
+                const bool is_hit = hit.t < p.t_far;
+                const bool last = b == p.ray_depth - 1;
+                const bool always_sky = last && p.last_bounce_skybox;
+                SurfaceAttrs sa;
+                if (is_hit) sa = surface_attrs(*scene, scene->materials, o + d * hit.t, hit.id);
+                else { sa.albedo = sa.normal = sa.emission = v3(0, 0, 0); sa.metal = sa.smooth = sa.alpha = 0.0f; }
+                Vec3 env = (always_sky || !is_hit) ? env_fetch(scene->env, d) : v3(0, 0, 0);
+                float u[6];
+                if (p.rng_mode == DRP_RNG_REPLAY) for (int q = 0; q < 6; ++q) u[q] = p.replay_u[((int64_t)b * 6 + q) * R_total + ri];
+                else philox_uniform6(p.seed, (uint32_t)pix, (uint32_t)p.sample_ids[s], (uint32_t)b, u);
+                BounceOut r = brdf_sample(sa, hit.t, o, d, env, u);
+                float* acc = accum + (int64_t)DRP_ACCUM_CHANNELS * pix;
+                acc[0] += T.x * r.radiance.x; acc[1] += T.y * r.radiance.y; acc[2] += T.z * r.radiance.z; acc[3] += sa.alpha;
+                if (b == 0) {
+                    acc[4] += sa.albedo.x; acc[5] += sa.albedo.y; acc[6] += sa.albedo.z;
+                    acc[7] += sa.emission.x; acc[8] += sa.emission.y; acc[9] += sa.emission.z;
+                    acc[10] += sa.normal.x; acc[11] += sa.normal.y; acc[12] += sa.normal.z;
+                    acc[13] += r.hit_pos.x; acc[14] += r.hit_pos.y; acc[15] += r.hit_pos.z;
+                }
+                T = is_hit ? T * r.transfer : v3(0, 0, 0);
+                d = r.next_d;
+                o = r.hit_pos + d * p.step_epsilon;
+            }
+        }
+    }
+    return traced;
+}

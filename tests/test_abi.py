@@ -1,0 +1,61 @@
+"""CPU checks of the C-ABI boundary: the library builds, loads, and exports every symbol include/diffrp_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from diffrp_b200 import _abi
+from diffrp_b200._lib import lib, DiffrpB200Error, check
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "diffrp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_abi.EXPORTED_SYMBOLS)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = lib()
+    assert L.drp_abi_version() == _abi.ABI_VERSION
+    for name in declared_symbols():
+        assert getattr(L, name) is not None
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed from the header's field lists (LP64)
+    assert ctypes.sizeof(_abi.Texture) == 32
+    assert ctypes.sizeof(_abi.Material) == 16 + 3 * 16 + 16 + 4 * 32
+    assert ctypes.sizeof(_abi.Scene) == 8 * 8 + 16 + 8 + 32
+    assert ctypes.sizeof(_abi.RenderParams) == 32 + 16 + 16 + 64 + 8 + 6 * 8
+    assert ctypes.sizeof(_abi.RenderStats) == 24
+
+
+def test_errors_are_reported_not_swallowed():
+    L = lib()
+    assert L.drp_release(123456789) != 0
+    assert b"unknown handle" in L.drp_last_error()
+    with pytest.raises(DiffrpB200Error):
+        check(L.drp_set_epsilon(987654321, 0.0), "drp_set_epsilon")
+
+
+def test_product_has_no_cpu_fallback():
+    import torch
+    import diffrp_b200 as drp
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        drp.PathTracingSession(drp.Scene(), drp.PerspectiveCamera(h=8, w=8))
+    with pytest.raises((ValueError, RuntimeError)):
+        drp.B200Raycaster(torch.zeros(3, 3), torch.zeros(1, 3, dtype=torch.int32))
+    # the product package never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "diffrp_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/", ""), f

@@ -1,0 +1,96 @@
+"""
+The per-thread logic of the CUDA kernels (diffrp_b200/csrc/*.cuh), compiled for the host by tests/hostsim, against the
+CPU oracle.  This is how kernel logic is debugged in the GPU-less build container; the GPU tests repeat the same
+comparisons through the real library.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import scenes
+import diffrp_b200 as drp
+from diffrp_b200 import _abi, synthetic as syn
+from test_oracle_golden import make_camera
+
+HS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    L = C.CDLL(os.path.join(HS_DIR, "libhostsim.so"))
+    vp = C.c_void_p
+    L.hs_build.restype = vp
+    L.hs_build.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.hs_free.argtypes = [vp]
+    L.hs_trace.restype = C.c_int64
+    L.hs_trace.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp]
+    L.hs_stats.argtypes = [vp, vp, vp]
+    L.hs_render.restype = C.c_int64
+    L.hs_render.argtypes = [vp, C.POINTER(_abi.Scene), C.POINTER(_abi.RenderParams), C.c_float, vp]
+    return L
+
+
+def hs_query(L, v, f, o, d, far=10.0, eps=1e-8):
+    v, f = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(f, np.int32)
+    h = L.hs_build(v.ctypes.data, f.ctypes.data, len(v), len(f))
+    st = np.zeros(5, np.int64)
+    sah = C.c_float()
+    L.hs_stats(h, st.ctypes.data, C.byref(sah))
+    t, i = np.empty(len(o), np.float32), np.empty(len(o), np.int32)
+    overflow = L.hs_trace(h, o.ctypes.data, d.ctypes.data, len(o), far, eps, t.ctypes.data, i.ctypes.data)
+    L.hs_free(h)
+    return t, i, st, overflow
+
+
+@pytest.mark.parametrize("n_tris", [0, 1, 2, 3, 5, 1280])
+def test_lbvh_and_traversal_equal_bruteforce(hs, n_tris):
+    v, f = syn.icosphere(3, 0.8)
+    f = f[:n_tris].copy()
+    o, d = syn.random_rays(30_000, seed=n_tris)
+    t, i, st, overflow = hs_query(hs, v, f, o, d)
+    assert overflow == 0 and st[3] == n_tris and st[4] <= 4  # every triangle in exactly one leaf, leaves <= 4 tris
+    if n_tris == 0:
+        assert (t == np.float32(10.0)).all() and (i == 0).all()
+        return
+    ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)
+    assert np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+
+
+def test_degenerate_and_duplicate_triangles(hs):
+    v, f = syn.uv_sphere(64, 32)  # pole rows are zero-area triangles
+    f = np.concatenate([f, f[:200]])  # exact duplicates: ties must resolve to the smaller id
+    o, d = syn.random_rays(50_000, seed=4)
+    t, i, st, overflow = hs_query(hs, v, f, o, d)
+    ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)
+    assert overflow == 0 and np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+
+
+def test_axis_aligned_rays_on_box_planes(hs):
+    """Reference defect B9 (NaN slab test) must not be reproduced: axis-parallel rays starting on box planes still hit."""
+    v = np.array([[0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    o = np.array([[0.0, 0.25, 2.0], [0.5, 0.0, 2.0], [0.25, 0.25, 2.0], [1.0, 0.5, 2.0]], np.float32)
+    d = np.tile(np.array([[0, 0, -1]], np.float32), (4, 1))
+    t, i, st, overflow = hs_query(hs, v, f, o, d)
+    ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)
+    assert np.array_equal(t, ot) and np.array_equal(i, oi)
+    assert (t == 1.0).all()
+
+
+@pytest.mark.parametrize("scene_name,last", [("ico", "void"), ("mixed", "void"), ("mixed", "skybox")])
+def test_shading_logic_matches_oracle(hs, scene_name, last):
+    scene = scenes.icosphere_scene() if scene_name == "ico" else scenes.mixed_scene()
+    cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
+    vao, hscene, p, keep = scenes.oracle_inputs(scene, cam, 3, 3, last_bounce=last, seed=123)
+    acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hscene, p)
+    wp, tr = hscene.arrays['world_pos'], hscene.arrays['tris']
+    h = hs.hs_build(wp.ctypes.data, tr.ctypes.data, len(wp), len(tr))
+    acc2 = np.zeros_like(acc)
+    hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc2.ctypes.data)
+    hs.hs_free(h)
+    np.testing.assert_allclose(acc2, acc, rtol=2e-5, atol=2e-5)
