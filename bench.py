@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the diffrp path-tracing hot path on B200 ("Measurement").
+
+Workload (BASELINE.json configs[2], the configuration the north-star metric is quoted on): synthetic 2,097,152-triangle
+textured PBR scene (49 objects, 8 GLTF materials with 1024^2 fp32 textures, HDR env), 1024x1024, 4 bounces,
+samples-per-pixel sharded across ranks.  A *step* is one section of `--spp-per-step` (default 8) samples of every pixel
+through all bounces = 8,388,608 paths = 33,554,432 nominal ray-bounces -- the reference's own section size
+(ray_split_size = 8M rays, path_tracing.py:74,318).  The default K = 128 steps is the full 1024-spp frame at N = 1.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm (CPU oracle port) on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+RES, DEPTH = 1024, 4
+METRIC, UNIT = "nominal_ray_bounces_per_second", "Mrays/s"
+
+
+def b_query(n_tris):  # ideal-descent bytes per traced ray
+    return 32 + 48 * int(np.ceil(np.log2(max(2, n_tris)))) + 36
+
+
+S_GLTF = 504  # shading bytes per ray-bounce, textured GLTF
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def scene_bytes(scene):
+    n = 0
+    seen = set()
+
+    def add(t):
+        nonlocal n
+        if isinstance(t, torch.Tensor) and t.data_ptr() not in seen:
+            seen.add(t.data_ptr())
+            n += t.numel() * t.element_size()
+    for o in scene.objects:
+        for t in (o.verts, o.tris, o.normals, o.M, o.color, o.uv, o.tangents):
+            add(t)
+        m = o.material
+        for k in ("base_color_texture", "metallic_roughness_texture", "normal_texture", "emissive_texture"):
+            s = getattr(m, k, None)
+            if s is not None:
+                add(s.image)
+    for l in scene.lights:
+        add(l.image)
+    return n
+
+
+def cpu_oracle_setup(tex):
+    """Scene flattened on the host + oracle BVH (the reference's algorithm restated in C, oracle/)."""
+    import oracle
+    from diffrp_b200 import synthetic as syn, ops
+    import diffrp_b200 as drp
+    scene, camkw = syn.teaser_scene('cpu', tex=tex)
+    ops.set_default_device('cpu')
+    try:
+        cam = drp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
+        cam._keep = (cam.V(), cam.P())
+        vao, hs, p, keep = oracle.inputs_from_scene(scene, cam, 1024, DEPTH, seed=1)
+    finally:
+        ops.set_default_device(None)
+    t0 = time.perf_counter()
+    bvh = oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy(), 'splitaxis')
+    build_s = time.perf_counter() - t0
+    return oracle, bvh, hs, p, keep, build_s, int(vao.tris.shape[0])
+
+
+def cpu_oracle_step(oracle, bvh, hs, p, keep, win, sample_ids):
+    """One bounded sample of the workload: central win x win window of the 1024^2 frame, given samples, 4 bounces."""
+    lo = RES // 2 - win // 2
+    p2, k2 = oracle.make_params(win, win, DEPTH, p.t_far, p.t_near, list(p.cam_pos)[:3], np.array(list(p.inv_vp), np.float32),
+                                keep['ndc_x'][lo:lo + win].copy(), keep['ndc_y'][lo:lo + win].copy(), keep['jitter_x_all'][sample_ids],
+                                keep['jitter_y_all'][sample_ids], sample_ids=sample_ids, seed=1)
+    t0 = time.perf_counter()
+    acc, n = oracle.render(bvh, hs, p2)
+    return time.perf_counter() - t0, n
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the reference's own algorithm for the path (CPU oracle port) on the box's host cores."""
+    if rank != 0:
+        return
+    oracle, bvh, hs, p, keep, build_s, n_tris = cpu_oracle_setup(args.tex)
+    cores = oracle.num_threads()
+    win, spp = args.ref_window, args.ref_spp
+    for w in range(min(args.warmup, 1)):
+        cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(spp))
+    tot_t, tot_n = 0.0, 0
+    for k in range(args.steps):
+        dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(k * spp, (k + 1) * spp) % 1024)
+        tot_t += dt
+        tot_n += n
+    val = tot_n / tot_t / 1e6
+    sample = "%dx%d central window of the %dx%d frame, %d spp, %d bounces per step (%d ray-bounces), 2,097,152-tri scene, CPU BVH build %.1f s excluded" % (
+        win, win, RES, RES, spp, DEPTH, win * win * spp * DEPTH, build_s)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_t / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(n_tris, args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(n_tris, args):
+    return {"workload": "configs[2]: synthetic %d-triangle textured PBR scene (49 objects, 8 GLTF materials, %d^2 fp32 textures, HDR env), "
+                        "%dx%d, %d bounces, %d spp per step, spp-sharded" % (n_tris, args.tex, RES, RES, DEPTH, args.spp_per_step),
+            "triangles": n_tris, "resolution": [RES, RES], "ray_depth": DEPTH, "spp_per_step": args.spp_per_step,
+            "rays_per_step": RES * RES * args.spp_per_step * DEPTH, "l2_policy": "working set (BVH 0.2 GB + attributes + 0.45 GB textures + 0.9 GB ray queues) exceeds the 126 MB L2",
+            "parallelism": "spp-shard x%d, scene replicated, NCCL all-reduce of the fp32 accumulators" % args.gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--tex", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--ref-window", type=int, default=128)
+    ap.add_argument("--ref-spp", type=int, default=8)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        return run_reference(args, world, rank)
+
+    import torch.distributed as dist
+    import diffrp_b200 as drp
+    from diffrp_b200 import synthetic as syn
+    from diffrp_b200._lib import loaded_path
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, K, W = args.spp_per_step, args.steps, max(args.warmup, 3)
+    HW = RES * RES
+
+    # ---- device-resident arm -------------------------------------------------------------------------------------
+    scene_host, camkw = syn.teaser_scene('cpu', tex=args.tex, pin=True)
+    scene = scene_host.to(dev)
+    cam = drp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
+    total_spp = max(1, world * K * S)
+    opts = drp.PathTracingSessionOptions(ray_spp=total_spp, ray_depth=DEPTH, rng='native', seed=1, shard_rank=rank, shard_world=world)
+    sess = drp.PathTracingSession(scene, cam, opts)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record(); rc = sess.raycaster(); e1.record(); torch.cuda.synchronize()
+    build_ms = e0.elapsed_time(e1)
+    n_tris = int(sess.vertex_array_object().tris.shape[0])
+    my_ids = torch.arange(total_spp, dtype=torch.int32, device=dev)[rank::world]  # global Hammersley indices of this rank
+    step_ids = [my_ids[j * S:(j + 1) * S] for j in range(K)]
+    scratch = sess.new_accumulators()
+    for j in range(W):
+        sess.render_samples(step_ids[j % K], scratch)
+    if world > 1:
+        dist.all_reduce(scratch)
+    torch.cuda.synchronize()
+    sess.get_profile()
+    sess.set_profiling(True)
+    launches0 = 0
+    accum = sess.new_accumulators()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for j in range(K):
+        sess.render_samples(step_ids[j], accum)
+    if world > 1:
+        dist.all_reduce(accum)  # the path's one exchange step: fp32 accumulators over NVLink
+    radiance, alpha, extras = sess.finalize(accum)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    prof = sess.get_profile()
+    sess.set_profiling(False)
+    stats = sess.render_stats()
+    launches_per_step = stats["kernel_launches"]
+    rays_nominal = world * K * S * HW * DEPTH
+    value = rays_nominal / (ms_max * 1e-3) / 1e6
+    assert torch.isfinite(radiance).all()
+
+    # ---- end-to-end arm: host scene -> public API -> host image, every step ----------------------------------------
+    E = max(1, min(args.e2e_steps, K))
+    out_host = torch.empty([RES, RES, 16], dtype=torch.float32).pin_memory()
+    h2d = scene_bytes(scene_host)
+    d2h = out_host.numel() * 4
+
+    def e2e_step(j):
+        o = drp.PathTracingSessionOptions(ray_spp=S, ray_depth=DEPTH, rng='native', seed=100 + j * world + rank)
+        s = drp.PathTracingSession(scene_host, cam, o)          # pinned host tensors: H2D of the whole scene inside
+        r, a, x = s.pbr()                                       # flatten + LBVH build + wavefront + finalize
+        out_host[..., 0:3].copy_(r, non_blocking=True)          # D2H of every output
+        out_host[..., 3:4].copy_(a, non_blocking=True)
+        for q, k in enumerate(("albedo", "emission", "world_normal", "world_position")):
+            out_host[..., 4 + 3 * q:7 + 3 * q].copy_(x[k], non_blocking=True)
+        torch.cuda.synchronize()
+        s.raycaster().release()
+    e2e_step(-1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for j in range(E):
+        e2e_step(j)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    t_e = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * S * HW * DEPTH / (float(t_e.item()) * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_extend, all bounces), from live CUDA events on the launch stream ---------
+    peak, peak_src = measured_peaks()
+    ext_s = prof["extend_ms"] * 1e-3
+    algo_bytes = prof["extend_rays"] * b_query(n_tris)
+    achieved = algo_bytes / ext_s / 1e9 if ext_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_extend (closest hit, all bounces)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": b_query(n_tris), "rays_per_launch_avg": prof["extend_rays"] / max(1, prof["extend_launches"]),
+                "launches": prof["extend_launches"], "avg_launch_ms": prof["extend_ms"] / max(1, prof["extend_launches"]),
+                "share_of_step": prof["extend_ms"] / ms, "shade_share_of_step": prof["shade_ms"] / ms,
+                "whole_path_frac": (stats_bytes(prof, n_tris) / (ms * 1e-3) / 1e9) / peak}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_k_extend.json")
+    if os.path.exists(traffic_file):
+        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        oracle, bvh, hs, p, keep, build_s, _ = cpu_oracle_setup(args.tex)
+        tt, nn = 0.0, 0
+        cpu_oracle_step(oracle, bvh, hs, p, keep, args.ref_window, np.arange(args.ref_spp))
+        for k in range(args.cpu_baseline_steps):
+            dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, args.ref_window, np.arange(k * args.ref_spp, (k + 1) * args.ref_spp))
+            tt += dt; nn += n
+        cpu_baseline = {"value": nn / tt / 1e6, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                        "sample": "%d steps of a %dx%d central window x %d spp x %d bounces of the same scene (%d ray-bounces, %.1f s); CPU BVH build %.1f s excluded"
+                                  % (args.cpu_baseline_steps, args.ref_window, args.ref_window, args.ref_spp, DEPTH, nn, tt, build_s)}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n_tris, args),
+        "spp_per_second": world * K * S / (ms_max * 1e-3),
+        "live_ray_fraction": prof["extend_rays"] / max(1, K * S * HW * DEPTH),
+        "bvh_build_ms": build_ms,
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": E,
+                "ms_per_step": float(t_e.item()) / E,
+                "what": "PathTracingSession(host-pinned scene, camera, options(ray_spp=%d)).pbr() + D2H of all outputs, per step: "
+                        "H2D scene upload, flatten, LBVH build, wavefront, finalize" % S},
+        "gpu_launches": int(launches_per_step * K + 1),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "native_library": loaded_path(),
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stats_bytes(prof, n_tris):
+    """Algorithmic bytes of the whole path: traced rays x B_query + shaded rays x S_gltf."""
+    return prof["extend_rays"] * b_query(n_tris) + prof["shade_rays"] * S_GLTF
+
+
+if __name__ == "__main__":
+    main()

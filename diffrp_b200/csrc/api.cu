@@ -179,7 +179,7 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
         *out_handle = g_next_handle++;
         g_handles[*out_handle] = h;
     }
-    if (g_drp_log_level >= 3) fprintf(stderr, "[diffrp_b200] built LBVH over %lld triangles (handle %llu)\n", (long long)n_tris, (unsigned long long)*out_handle);
+    if (g_drp_log_level >= 4) fprintf(stderr, "[diffrp_b200] built LBVH over %lld triangles (handle %llu)\n", (long long)n_tris, (unsigned long long)*out_handle);
     return DRP_OK;
 }
 

@@ -36,7 +36,25 @@ struct RenderWorkspace {
     int grid_extend[2] = {0, 0}, grid_shade[2] = {0, 0};
     bool have_box = false;
     float box_lo[3], box_hi[3];
+    // optional per-kernel timing (drp_set_profiling)
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int kind; int bounce; unsigned long long* traced_slot; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    unsigned long long* d_live = nullptr;  // device: per-launch live-ray counts while profiling
+    int live_capacity = 0, live_used = 0;
 };
+
+static cudaEvent_t wf_event(RenderWorkspace* ws) {
+    if (!ws->event_pool.empty()) { cudaEvent_t e = ws->event_pool.back(); ws->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+__global__ void k_record_live(const int* __restrict__ count_ptr, unsigned long long fixed, unsigned long long* __restrict__ slot) {
+    *slot = count_ptr ? (unsigned long long)*count_ptr : fixed;
+}
 
 struct WfConst {
     drp_scene_t scene;        // device pointers (materials -> device copy)
@@ -205,16 +223,37 @@ __global__ void k_finalize(const float* __restrict__ accum, int H, int W, float 
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
+// Workspaces (ray queues etc.) outlive handles: sessions are single-use (one handle per frame), so a released handle
+// parks its workspace in a per-process pool and the next handle on the same device adopts it instead of re-allocating.
+#include <mutex>
+static std::mutex g_ws_mutex;
+static std::vector<std::pair<int, RenderWorkspace*>> g_ws_pool;
+
 void drp_free_workspace(BvhHandle* h) {
     RenderWorkspace* ws = h->ws;
     if (!ws) return;
-    for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
-    cudaFree(ws->hit); cudaFree(ws->counters); cudaFree(ws->d_mats); cudaFree(ws->d_traced);
-    delete ws;
+    for (auto& sp : ws->spans) { ws->event_pool.push_back(sp.a); ws->event_pool.push_back(sp.b); }
+    ws->spans.clear();
+    ws->live_used = 0;
+    ws->profiling = false;
+    ws->have_box = false;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        g_ws_pool.push_back({h->device, ws});
+    }
     h->ws = nullptr;
 }
 
 static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
+    if (!h->ws) {
+        std::lock_guard<std::mutex> lk(g_ws_mutex);
+        for (size_t k = 0; k < g_ws_pool.size(); ++k)
+            if (g_ws_pool[k].first == h->device) {
+                h->ws = g_ws_pool[k].second;
+                g_ws_pool.erase(g_ws_pool.begin() + k);
+                break;
+            }
+    }
     if (!h->ws) {
         h->ws = new RenderWorkspace();
         cudaDeviceProp prop;
@@ -234,7 +273,7 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
         h->ws->grid_shade[0] = std::max(1, nb) * h->ws->sm_count;
     }
     RenderWorkspace* ws = h->ws;
-    if (rays > ws->capacity) {
+    if (rays > 0 && rays > ws->capacity) {
         for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
         cudaFree(ws->hit);
         ws->capacity = 0;
@@ -324,16 +363,35 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
         int* cursors = ws->counters + 64; // [0..2D)
         DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));
         ++launches;
+        auto span_begin = [&](int kind, int b, const int* count_ptr) -> int {
+            if (!ws->profiling || ws->live_used >= ws->live_capacity) return -1;
+            RenderWorkspace::Span sp;
+            sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
+            sp.traced_slot = ws->d_live + ws->live_used++;
+            k_record_live<<<1, 1, 0, s>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
+            cudaEventRecord(sp.a, s);
+            ws->spans.push_back(sp);
+            return (int)ws->spans.size() - 1;
+        };
+        auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, s); };
         for (int b = 0; b < D; ++b) {
             const int in = b & 1, out = in ^ 1;
             if (b == 0) {
+                int sp = span_begin(0, b, nullptr);
                 k_extend<true><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
+                span_end(sp);
+                sp = span_begin(1, b, nullptr);
                 k_shade<true><<<ws->grid_shade[1], WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, ws->hit, ws->qa[out], ws->qb[out], ws->qt[out], nullptr,
                                                         counts + 1, cursors + 1);
+                span_end(sp);
             } else {
+                int sp = span_begin(0, b, counts + b);
                 k_extend<false><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
+                span_end(sp);
+                sp = span_begin(1, b, counts + b);
                 k_shade<false><<<ws->grid_shade[0], WF_BLOCK, 0, s>>>(c, b, ws->qa[in], ws->qb[in], ws->qt[in], ws->hit, ws->qa[out], ws->qb[out], ws->qt[out],
                                                          counts + b, counts + b + 1, cursors + 2 * b + 1);
+                span_end(sp);
             }
             launches += 2;
         }
@@ -362,6 +420,45 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
         drp_set_error("traversal stack overflow on " + std::to_string(flags[0]) + " rays: results are invalid");
         return DRP_ERR_INVALID;
     }
+    return DRP_OK;
+}
+
+extern "C" int drp_set_profiling(uint64_t handle, int enable) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_set_profiling: unknown handle"); return DRP_ERR_HANDLE; }
+    DeviceGuard guard(h->device);
+    int rc = ensure_workspace(h, 0, 0);
+    if (rc != DRP_OK) return rc;
+    RenderWorkspace* ws = h->ws;
+    if (enable && !ws->d_live) {
+        ws->live_capacity = 1 << 16;
+        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->d_live, sizeof(unsigned long long) * ws->live_capacity));
+    }
+    ws->profiling = enable != 0;
+    return DRP_OK;
+}
+
+extern "C" int drp_get_profile(uint64_t handle, drp_profile_t* out) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h || !out) { drp_set_error("drp_get_profile: unknown handle"); return DRP_ERR_HANDLE; }
+    memset(out, 0, sizeof(*out));
+    if (!h->ws) return DRP_OK;
+    DeviceGuard guard(h->device);
+    RenderWorkspace* ws = h->ws;
+    DRP_CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> live(ws->live_used > 0 ? ws->live_used : 1);
+    if (ws->live_used > 0) DRP_CUDA_CHECK(cudaMemcpy(live.data(), ws->d_live, sizeof(unsigned long long) * ws->live_used, cudaMemcpyDeviceToHost));
+    for (auto& sp : ws->spans) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        unsigned long long rays = live[sp.traced_slot - ws->d_live];
+        if (sp.kind == 0) { out->extend_ms += ms; out->extend_launches++; out->extend_rays += (int64_t)rays; }
+        else { out->shade_ms += ms; out->shade_launches++; out->shade_rays += (int64_t)rays; }
+        ws->event_pool.push_back(sp.a);
+        ws->event_pool.push_back(sp.b);
+    }
+    ws->spans.clear();
+    ws->live_used = 0;
     return DRP_OK;
 }
 

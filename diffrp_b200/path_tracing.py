@@ -216,22 +216,15 @@ class PathTracingSession:
         sections = min(n, math.ceil((H * W * n) / self.options.ray_split_size))
         return list(torch.tensor_split(ids, max(1, sections)))
 
-    def render_accumulators(self) -> torch.Tensor:
-        """Run the fused wavefront for this process' share of the samples; returns the (H*W, 16) fp32 sums."""
+    @_cached
+    def _render_setup(self):
+        """Per-session constants of the fused path: scene struct, raygen tables, parameter block."""
         opt = self.options
         fused = self._fused_scene()
         if fused is None:
             raise RuntimeError("scene contains custom Python materials: use pbr() / trace_rays() (generic path)")
-        scene_struct, _keep = fused
-        L = lib()
         H, W = self.camera.resolution()
-        dev = self.device
-        rc = self.raycaster()
-        tab = raygen_tables(self.camera_V(), self.camera_P(), H, W, opt.ray_spp, opt.deterministic, dev)
-        ndc_x, ndc_y, jit_x, jit_y = tab['ndc_x'], tab['ndc_y'], tab['jitter_x'], tab['jitter_y']
-        all_ids = torch.arange(opt.ray_spp, dtype=torch.int32, device=dev)
-        my_ids = all_ids[opt.shard_rank::opt.shard_world] if opt.shard_world > 1 else all_ids
-        accum = torch.zeros([H * W, _abi.ACCUM_CHANNELS], dtype=torch.float32, device=dev)
+        tab = raygen_tables(self.camera_V(), self.camera_P(), H, W, opt.ray_spp, opt.deterministic, self.device)
         p = _abi.RenderParams()
         p.height, p.width, p.ray_depth = H, W, opt.ray_depth
         p.last_bounce_skybox = int(opt.pbr_ray_last_bounce == 'skybox')
@@ -240,21 +233,39 @@ class PathTracingSession:
         p.cam_pos[:3] = tab['cam_pos']
         p.inv_vp[:] = tab['inv_vp']
         p.seed = opt.seed
-        p.ndc_x, p.ndc_y = ndc_x.data_ptr(), ndc_y.data_ptr()
-        stream = _stream_ptr(dev)
-        self._launches = 0
+        p.ndc_x, p.ndc_y = tab['ndc_x'].data_ptr(), tab['ndc_y'].data_ptr()
+        return fused[0], tab, p, fused[1]
+
+    def new_accumulators(self) -> torch.Tensor:
+        H, W = self.camera.resolution()
+        return torch.zeros([H * W, _abi.ACCUM_CHANNELS], dtype=torch.float32, device=self.device)
+
+    def render_samples(self, sample_ids: torch.Tensor, accum: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """
+        Progressive entry point of the fused path: add the given GLOBAL sample indices (into the n = ``ray_spp``
+        Hammersley sequence) of every pixel to ``accum`` (H*W, 16) and return it.  Asynchronous on the current stream.
+        ``pbr()`` is ``finalize(all_reduce(render_samples(my share)))``.
+        """
+        opt, dev = self.options, self.device
+        scene_struct, tab, p, _keep = self._render_setup()
+        H, W = self.camera.resolution()
+        rc = self.raycaster()
+        if accum is None:
+            accum = self.new_accumulators()
+        ids = sample_ids.to(dev, torch.int32).contiguous()
+        if len(ids) == 0:
+            return accum
         if opt.rng == 'torch':
-            if opt.shard_world > 1:
-                raise ValueError("rng='torch' (reference replay) is a single-process mode")
-            chunks = self._section_sample_ids(my_ids)
+            chunks = self._section_sample_ids(ids)
         elif opt.rng == 'native':
-            chunks = [my_ids] if len(my_ids) else []
+            chunks = [ids]
         else:
             raise ValueError("rng must be 'native' or 'torch'")
+        L, stream = lib(), _stream_ptr(dev)
         for ids in chunks:
             ids = ids.contiguous()
             idl = ids.long()
-            jx, jy = jit_x[idl].contiguous(), jit_y[idl].contiguous()
+            jx, jy = tab['jitter_x'][idl].contiguous(), tab['jitter_y'][idl].contiguous()
             p.n_samples = len(ids)
             p.jitter_x, p.jitter_y, p.sample_ids = jx.data_ptr(), jy.data_ptr(), ids.data_ptr()
             if opt.rng == 'torch':
@@ -268,6 +279,15 @@ class PathTracingSession:
                 p.replay_u, p.rng_mode = None, _abi.RNG_NATIVE
             check(L.drp_render(rc.handle, C.byref(scene_struct), C.byref(p), accum.data_ptr(), stream), "drp_render")
         return accum
+
+    def render_accumulators(self) -> torch.Tensor:
+        """Run the fused wavefront for this process' share of the samples; returns the (H*W, 16) fp32 sums."""
+        opt = self.options
+        if opt.rng == 'torch' and opt.shard_world > 1:
+            raise ValueError("rng='torch' (reference replay) is a single-process mode")
+        all_ids = torch.arange(opt.ray_spp, dtype=torch.int32, device=self.device)
+        my_ids = all_ids[opt.shard_rank::opt.shard_world] if opt.shard_world > 1 else all_ids
+        return self.render_samples(my_ids)
 
     def finalize(self, accum: torch.Tensor):
         """Epilogue of trace_rays (path_tracing.py:348-352): /spp, saturate(alpha), flipud -- one kernel."""
@@ -286,6 +306,14 @@ class PathTracingSession:
         st = _abi.RenderStats()
         check(lib().drp_render_stats(self.raycaster().handle, C.byref(st)), "drp_render_stats")
         return dict(rays_traced=st.rays_traced, rays_nominal=st.rays_nominal, kernel_launches=st.kernel_launches)
+
+    def set_profiling(self, enable: bool = True):
+        check(lib().drp_set_profiling(self.raycaster().handle, int(enable)), "drp_set_profiling")
+
+    def get_profile(self) -> dict:
+        pr = _abi.Profile()
+        check(lib().drp_get_profile(self.raycaster().handle, C.byref(pr)), "drp_get_profile")
+        return {k: getattr(pr, k) for k, _ in _abi.Profile._fields_}
 
     @torch.no_grad()
     def pbr(self):

@@ -42,6 +42,13 @@ class MeshObject:
     custom_attrs: Optional[Dict[str, torch.Tensor]] = None
     metadata: Optional[Dict[str, Any]] = None
 
+    def to(self, device):
+        """Copy of this object with every tensor on ``device`` (the material object is shared)."""
+        mv = lambda x: x.to(device) if isinstance(x, torch.Tensor) else x
+        return MeshObject(self.material, mv(self.verts), mv(self.tris), mv(self.normals), mv(self.M), mv(self.color), mv(self.uv),
+                          mv(self.tangents), None if self.custom_attrs is None else {k: mv(v) for k, v in self.custom_attrs.items()},
+                          self.metadata)
+
     def preprocess(self):
         """Fill defaults; 'flat' normals turn the mesh into a face soup (objects.py:71-98)."""
         v = self.verts
@@ -118,6 +125,18 @@ class Scene:
     def add_mesh_object(self, mesh_obj: MeshObject):
         self.objects.append(mesh_obj.preprocess())
         return self
+
+    def to(self, device):
+        """Copy of the scene with geometry and light tensors on ``device`` (objects must already be preprocessed)."""
+        out = Scene()
+        out.objects = [o.to(device) for o in self.objects]
+        for l in self.lights:
+            if isinstance(l, ImageEnvironmentLight):
+                out.lights.append(ImageEnvironmentLight(l.intensity, l.color.to(device), l.image.to(device), l.render_skybox))
+            else:
+                out.lights.append(l)
+        out.metadata = dict(self.metadata)
+        return out
 
     def static_batching(self):
         """Merge meshes that share a material object into one world-space mesh, in place (scene.py:33-75)."""

@@ -109,3 +109,66 @@ def smooth_texture(h: int, w: int, c: int, seed: int, lo: float = 0.0, hi: float
 def gradient_env(h: int = 64, w: int = 128, top: float = 2.0):
     """Deterministic lat-long environment: linspace(0, top) ramp (config 1)."""
     return np.linspace(0.0, top, h * w * 3, dtype=np.float32).reshape(h, w, 3)
+
+
+# ---- benchmark scenes (SURVEY.md 8d) -------------------------------------------------------------------------------
+
+def torch_noise_texture(h, w, c, seed, lo=0.0, hi=1.0, octaves=5, device='cpu'):
+    """Seeded multi-octave value noise (bilinear-upsampled random grids) as an (h, w, c) fp32 torch tensor."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    acc = torch.zeros(1, c, h, w)
+    amp, tot = 1.0, 0.0
+    for o in range(octaves):
+        n = 4 * 2 ** o
+        grid = torch.rand(1, c, n, n, generator=g)
+        acc += amp * F.interpolate(grid, size=(h, w), mode='bilinear', align_corners=False)
+        tot += amp
+        amp *= 0.5
+    img = (acc / tot)[0].permute(1, 2, 0)
+    return (lo + (hi - lo) * img).contiguous().to(device)
+
+
+def teaser_scene(device='cpu', n_spheres=48, sphere_res=(160, 128), ground=256, tex=1024, n_materials=8, seed=0, pin=False):
+    """
+    Config 3: ground quad grid + ``n_spheres`` displaced UV spheres, ``n_materials`` GLTFMaterials with seeded
+    tex x tex fp32 textures (base RGBA, metallic-roughness, normal, emissive), analytic tangents, seeded HDR env.
+    Defaults give exactly 48*2*160*128 + 2*256^2 = 2,097,152 triangles.  Returns (Scene, orbit-camera kwargs).
+    """
+    import torch
+    from .scene import Scene, MeshObject, ImageEnvironmentLight
+    from .materials import GLTFMaterial, GLTFSampler
+    put = (lambda t: t.pin_memory()) if pin else (lambda t: t.to(device))
+    Tn = lambda a: put(torch.from_numpy(np.ascontiguousarray(a)))
+    mats = []
+    for k in range(n_materials):
+        nrm = torch_noise_texture(tex, tex, 3, seed * 100 + k * 10 + 3, 0.35, 0.65)
+        nrm[..., 2] = 0.92
+        mats.append(GLTFMaterial(
+            base_color_factor=put(torch.tensor([1.0, 1.0, 1.0, 1.0])),
+            base_color_texture=GLTFSampler(put(torch_noise_texture(tex, tex, 4, seed * 100 + k * 10 + 1, 0.15, 0.95))),
+            metallic_factor=0.2 + 0.1 * k, roughness_factor=0.9,
+            metallic_roughness_texture=GLTFSampler(put(torch_noise_texture(tex, tex, 3, seed * 100 + k * 10 + 2, 0.1, 0.9))),
+            normal_texture=GLTFSampler(put(nrm)), occlusion_texture=None,
+            emissive_factor=put(torch.tensor([0.3, 0.25, 0.2])) if k % 4 == 0 else None,
+            emissive_texture=GLTFSampler(put(torch_noise_texture(tex, tex, 3, seed * 100 + k * 10 + 4, 0.0, 0.5))),
+            alpha_cutoff=0.5, alpha_mode='OPAQUE'))
+    scene = Scene()
+    gv, gf, gn, guv, gt = ground_grid(ground, 2.2, -0.6)
+    scene.add_mesh_object(MeshObject(mats[0], Tn(gv), Tn(gf), normals=Tn(gn), uv=Tn(guv), tangents=Tn(gt)))
+    rng = np.random.default_rng(seed)
+    cols = int(np.ceil(np.sqrt(n_spheres * 4 / 3)))
+    rows = int(np.ceil(n_spheres / cols))
+    for k in range(n_spheres):
+        cx = (k % cols - (cols - 1) / 2) * (3.6 / cols)
+        cz = (k // cols - (rows - 1) / 2) * (3.0 / rows)
+        r = 0.16 + 0.06 * rng.random()
+        v, f, n, uv, tg = uv_sphere(sphere_res[0], sphere_res[1], radius=r, bump=0.012, noise=0.002, seed=seed + k,
+                                    center=(cx, -0.6 + r + 0.02 + 0.25 * rng.random(), cz), with_attrs=True)
+        scene.add_mesh_object(MeshObject(mats[k % n_materials], Tn(v), Tn(f), normals=Tn(n), uv=Tn(uv * 2.0), tangents=Tn(tg)))
+    env = torch_noise_texture(256, 512, 3, seed * 100 + 99, 0.0, 1.0)
+    env = env ** 3 * 6.0 + 0.05  # a few bright regions
+    scene.add_light(ImageEnvironmentLight(intensity=1.0, color=put(torch.ones(3)), image=put(env.contiguous())))
+    cam = dict(radius=4.6, azim=32.0, elev=24.0, origin=[0.0, -0.35, 0.0], fov=40.0, near=0.1, far=20.0)
+    return scene, cam

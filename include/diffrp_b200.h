@@ -190,6 +190,20 @@ typedef struct drp_render_stats {
 } drp_render_stats_t;
 int drp_render_stats(uint64_t handle, drp_render_stats_t* out);
 
+/* Optional per-kernel timing (measurement aid, no reference equivalent): when enabled, drp_render brackets every
+ * extend / shade launch with CUDA events on the launch stream; drp_get_profile synchronises, sums the elapsed times
+ * since the last call, and resets.  rays_* are the live rays those launches processed. */
+typedef struct drp_profile {
+    double extend_ms;
+    double shade_ms;
+    int64_t extend_launches;
+    int64_t shade_launches;
+    int64_t extend_rays;
+    int64_t shade_rays;
+} drp_profile_t;
+int drp_set_profiling(uint64_t handle, int enable);
+int drp_get_profile(uint64_t handle, drp_profile_t* out);
+
 #ifdef __cplusplus
 }
 #endif

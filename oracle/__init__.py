@@ -222,3 +222,32 @@ def finalize(accum, height, width, spp_total):
     a = accum.reshape(height, width, _abi.ACCUM_CHANNELS)[::-1] / np.float32(spp_total)
     return dict(radiance=a[..., 0:3].copy(), alpha=np.clip(a[..., 3:4], 0.0, 1.0), albedo=a[..., 4:7].copy(),
                 emission=a[..., 7:10].copy(), world_normal=a[..., 10:13].copy(), world_position=a[..., 13:16].copy())
+
+
+def inputs_from_scene(scene, camera, spp, depth, last_bounce='void', step_eps=1e-3, replay_u=None, seed=0, sample_ids=None):
+    """Flatten a diffrp_b200 ``Scene`` on the CPU and build the oracle's HostScene + host-pointer render params.
+    ``camera.V()`` / ``camera.P()`` must be CPU tensors (diffrp_b200.ops.set_default_device('cpu'))."""
+    from diffrp_b200.flatten import flatten_scene, material_descriptions
+    from diffrp_b200.path_tracing import raygen_tables
+    vao = flatten_scene(scene.objects, 'cpu')
+    mats = []
+    for d in material_descriptions(scene.objects, 'cpu'):
+        d = dict(d)
+        for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
+            if d.get(k) is not None:
+                d[k] = dict(d[k], image=d[k]['image'].numpy())
+        mats.append(d)
+    env = None
+    for l in scene.lights:
+        if hasattr(l, 'image_rh'):
+            env = l.image_rh().numpy()
+    hs = HostScene(vao.world_pos.numpy(), vao.world_nrm.numpy(), vao.color.numpy(), vao.uv.numpy(), vao.world_tan.numpy(),
+                   vao.tris.numpy(), vao.tri_material.numpy(), mats, env=env)
+    H, W = camera.resolution()
+    tab = raygen_tables(camera.V().cpu(), camera.P().cpu(), H, W, spp, True, 'cpu')
+    ids = np.arange(spp) if sample_ids is None else np.asarray(sample_ids)
+    p, keep = make_params(H, W, depth, tab['t_far'], tab['t_near'], tab['cam_pos'], tab['inv_vp'], tab['ndc_x'].numpy(),
+                          tab['ndc_y'].numpy(), tab['jitter_x'].numpy()[ids], tab['jitter_y'].numpy()[ids], sample_ids=ids,
+                          step_epsilon=step_eps, last_bounce_skybox=(last_bounce == 'skybox'), seed=seed, replay_u=replay_u)
+    keep['jitter_x_all'], keep['jitter_y_all'] = tab['jitter_x'].numpy(), tab['jitter_y'].numpy()
+    return vao, hs, p, keep

@@ -68,39 +68,9 @@ def mixed_scene(n_theta=48, n_phi=24):
 
 
 def to_device(scene, dev):
-    """Copy of the scene with every tensor on ``dev`` (the reference requires GPU tensors in MeshObject)."""
-    mv = lambda x: x.to(dev) if isinstance(x, torch.Tensor) else x
-    out = drp.Scene()
-    for o in scene.objects:
-        m = o.material
-        out.objects.append(drp.MeshObject(m, mv(o.verts), mv(o.tris), mv(o.normals), mv(o.M), mv(o.color), mv(o.uv), mv(o.tangents),
-                                          {k: mv(v) for k, v in o.custom_attrs.items()}, o.metadata))
-    for l in scene.lights:
-        out.lights.append(drp.ImageEnvironmentLight(l.intensity, mv(l.color), mv(l.image), l.render_skybox))
-    return out
+    return scene.to(dev)
 
 
-def oracle_inputs(scene, camera, spp, depth, last_bounce='void', step_eps=1e-3, replay_u=None, seed=0, sample_ids=None):
-    """Flatten on the CPU and build the oracle's HostScene + host-pointer render params."""
+def oracle_inputs(scene, camera, spp, depth, **kw):
     import oracle
-    vao = flatten_scene(scene.objects, 'cpu')
-    descs = material_descriptions(scene.objects, 'cpu')
-    mats = []
-    for d in descs:
-        d = dict(d)
-        for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
-            if d.get(k) is not None:
-                d[k] = dict(d[k], image=d[k]['image'].numpy())
-        mats.append(d)
-    env = None
-    for l in scene.lights:
-        env = l.image_rh().numpy()
-    hs = oracle.HostScene(vao.world_pos.numpy(), vao.world_nrm.numpy(), vao.color.numpy(), vao.uv.numpy(), vao.world_tan.numpy(),
-                          vao.tris.numpy(), vao.tri_material.numpy(), mats, env=env)
-    H, W = camera.resolution()
-    tab = raygen_tables(camera.V().cpu(), camera.P().cpu(), H, W, spp, True, 'cpu')
-    ids = np.arange(spp) if sample_ids is None else np.asarray(sample_ids)
-    p, keep = oracle.make_params(H, W, depth, tab['t_far'], tab['t_near'], tab['cam_pos'], tab['inv_vp'], tab['ndc_x'].numpy(),
-                                 tab['ndc_y'].numpy(), tab['jitter_x'].numpy()[ids], tab['jitter_y'].numpy()[ids], sample_ids=ids,
-                                 step_epsilon=step_eps, last_bounce_skybox=(last_bounce == 'skybox'), seed=seed, replay_u=replay_u)
-    return vao, hs, p, keep
+    return oracle.inputs_from_scene(scene, camera, spp, depth, **kw)

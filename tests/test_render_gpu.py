@@ -113,7 +113,8 @@ def test_custom_python_material_uses_generic_path():
     cam = drp.PerspectiveCamera(h=32, w=32)
     rad, alpha, extras = drp.PathTracingSession(scenes.to_device(scene, 'cuda'), cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2)).pbr()
     assert rad.shape == (32, 32, 3) and alpha.max() == 1.0 and set(extras) == {'albedo', 'emission', 'world_normal', 'world_position'}
-    assert torch.allclose(extras['albedo'][alpha[..., 0] == 1.0], torch.tensor(0.5, device='cuda'))
+    centre = extras['albedo'][12:20, 12:20]  # every sample of these pixels hits the sphere
+    assert (centre - 0.5).abs().max() < 1e-5 and extras['albedo'].max() <= 0.5 + 1e-5
 
 
 def test_generic_python_path_agrees_with_fused_kernels():
