@@ -49,7 +49,7 @@ class DefaultMaterial(SurfaceMaterial):
 
     def shade(self, su, si) -> SurfaceOutputStandard:
         rgb = si.color[..., :3]
-        return SurfaceOutputStandard(rgb * self.tint if self.tint is not None else rgb)
+        return SurfaceOutputStandard(rgb * torch.as_tensor(self.tint).to(rgb) if self.tint is not None else rgb)
 
     def fused_description(self) -> Optional[dict]:
         if type(self) is not DefaultMaterial:
@@ -68,7 +68,7 @@ class GLTFSampler:
     def sample(self, uv: torch.Tensor) -> torch.Tensor:
         if self.wrap_mode == 'repeat':
             uv = uv.remainder(1.0)
-        return sample2d(self.image, uv, wrap='border' if self.wrap_mode == 'clamp' else 'reflection',
+        return sample2d(self.image.to(uv), uv, wrap='border' if self.wrap_mode == 'clamp' else 'reflection',
                         mode='bilinear' if self.interpolation == 'linear' else 'nearest')
 
     def fused_description(self) -> dict:
@@ -92,7 +92,7 @@ class GLTFMaterial(SurfaceMaterial):
 
     def shade(self, su, si) -> SurfaceOutputStandard:
         uv = si.uv
-        rgba = self.base_color_factor * si.color * self.base_color_texture.sample(uv)
+        rgba = torch.as_tensor(self.base_color_factor).to(uv) * si.color * self.base_color_texture.sample(uv)
         mr = self.metallic_roughness_texture.sample(uv)
         if self.alpha_mode == 'OPAQUE':
             alpha = None
@@ -105,7 +105,7 @@ class GLTFMaterial(SurfaceMaterial):
         return SurfaceOutputStandard(
             albedo=rgba[..., :3],
             normal=torch.add(-1, self.normal_texture.sample(uv), alpha=2) if self.normal_texture is not None else None,
-            emission=self.emissive_factor * self.emissive_texture.sample(uv) if self.emissive_factor is not None else None,
+            emission=torch.as_tensor(self.emissive_factor).to(uv) * self.emissive_texture.sample(uv) if self.emissive_factor is not None else None,
             metallic=self.metallic_factor * mr[..., 2:3],
             smoothness=torch.add(1.0, mr[..., 1:2], alpha=-self.roughness_factor),
             occlusion=self.occlusion_texture.sample(uv)[..., 0:1] if self.occlusion_texture is not None else ones_like_vec(uv, 1),
