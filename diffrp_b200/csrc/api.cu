@@ -9,7 +9,9 @@
 #include "common.cuh"
 #include "lbvh.cuh"
 #include "traverse.cuh"
+#include "cwbvh.cuh"
 #include "trace_kernels.cuh"
+#include <cstdlib>
 
 // ---- error / handle plumbing ------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -95,6 +97,25 @@ __global__ void __launch_bounds__(256) k_pack(LbvhBuild b) {
     if (j < b.n) lbvh_pack_tri(b, j);
 }
 
+__global__ void k_cw_init(CwBuild cw) {
+    cw.counters[0] = 1;  // root allocated
+    cw.counters[1] = 0;
+    cw.counters[8] = 0;
+    cw.counters[9] = 1;
+    cw.work[0] = 0;
+}
+__global__ void __launch_bounds__(128) k_cw_collapse(CwBuild cw, int level, float* sah) {
+    const int begin = cw.counters[8 + level], end = cw.counters[9 + level];
+    if (cw.b.n < 2) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && level == 0) { cw_emit_tiny(cw); *sah = 1.0f; }
+        return;
+    }
+    for (int ni = begin + blockIdx.x * blockDim.x + threadIdx.x; ni < end; ni += gridDim.x * blockDim.x)
+        cw_collapse_node(cw, ni, [](int* p, int v) { return atomicAdd(p, v); });
+    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) *sah = cw.b.box_lo[0].w / fmaxf(cw.b.box_hi[0].w, 1e-30f);
+}
+__global__ void k_cw_advance(CwBuild cw, int level) { cw.counters[10 + level] = cw.counters[0]; }
+
 template <typename T>
 static cudaError_t alloc_async(T** p, size_t count, cudaStream_t s) {
     return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s);
@@ -118,14 +139,16 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     h->device = device;
     h->n_tris = n_tris;
     h->n_nodes = n > 1 ? n - 1 : 1;
+    const char* layout_env = getenv("DRP_LAYOUT");  // "bvh2" selects the binary layout (kept for A/B profiling)
+    h->wide = !(layout_env && strcmp(layout_env, "bvh2") == 0);
 
     LbvhBuild b;
     memset(&b, 0, sizeof(b));
-    b.verts = verts; b.tris = tris; b.n = n;
+    b.verts = verts; b.tris = tris; b.n = n; b.max_leaf = h->wide ? CW_MAX_LEAF : DRP_MAX_LEAF;
     uint64_t* keys_in = nullptr; uint32_t* vals_in = nullptr; void* sort_tmp = nullptr;
     size_t sort_bytes = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    DRP_CUDA_CHECK(cudaMalloc((void**)&h->nodes, sizeof(float4) * 4 * (size_t)h->n_nodes));
+    DRP_CUDA_CHECK(cudaMalloc((void**)&h->nodes, sizeof(float4) * (h->wide ? 5 : 4) * (size_t)h->n_nodes));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->packed, sizeof(float4) * 3 * nn));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->sah, sizeof(float)));
@@ -166,12 +189,40 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
             k_karras<<<G, T, 0, s>>>(b);
             k_refit<<<G, T, 0, s>>>(b);
         }
-        k_pack<<<G, T, 0, s>>>(b);
+        if (!h->wide) k_pack<<<G, T, 0, s>>>(b);
     }
-    k_emit<<<G, T, 0, s>>>(b, h->sah);
+    int* cw_work = nullptr; int* cw_counters = nullptr;
+    if (!h->wide) {
+        k_emit<<<G, T, 0, s>>>(b, h->sah);
+    } else {
+        CwBuild cw;
+        cw.b = b;
+        cw.cw_nodes = h->nodes; cw.cw_tris = h->packed; cw.capacity = (int)h->n_nodes;
+        DRP_CUDA_CHECK(alloc_async(&cw_work, (size_t)h->n_nodes, s));
+        DRP_CUDA_CHECK(alloc_async(&cw_counters, 160, s));
+        DRP_CUDA_CHECK(cudaMemsetAsync(cw_counters, 0, sizeof(int) * 160, s));
+        cw.work = cw_work; cw.counters = cw_counters;
+        k_cw_init<<<1, 1, 0, s>>>(cw);
+        // level-synchronous collapse: level L reads its node range from device counters written by level L-1.  The number
+        // of levels is bounded by the binary depth; ranges of exhausted levels are empty, so extra launches are no-ops.
+        const int grid = 148 * 8;
+        int levels_done = 0;
+        for (;;) {
+            for (int L = levels_done; L < levels_done + 24 && L < 128; ++L) {
+                k_cw_collapse<<<(n < 2 || L > 6) ? grid : (L < 3 ? 1 : 64), 128, 0, s>>>(cw, L, h->sah);
+                k_cw_advance<<<1, 1, 0, s>>>(cw, L);
+            }
+            levels_done += 24;
+            int hc[160];
+            DRP_CUDA_CHECK(cudaMemcpyAsync(hc, cw_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+            DRP_CUDA_CHECK(cudaStreamSynchronize(s));
+            h->n_nodes_used = n < 2 ? 1 : hc[0];
+            if (n < 2 || levels_done >= 128 || hc[8 + levels_done] >= hc[9 + levels_done]) break;
+        }
+    }
     DRP_CUDA_CHECK(cudaGetLastError());
     void* temps[] = {b.prim_lo, b.prim_hi, keys_in, vals_in, b.keys, b.vals, b.left, b.right, b.parent, b.range_first,
-                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp};
+                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters};
     for (void* p : temps)
         if (p) DRP_CUDA_CHECK(cudaFreeAsync(p, s));
     {
@@ -221,6 +272,34 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
     DRP_CUDA_CHECK(cudaMemcpy(ob, h->bounds, sizeof(ob), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 6; ++k) out->bounds[k] = ord2f(ob[k]);
     DRP_CUDA_CHECK(cudaMemcpy(&out->sah_cost, h->sah, sizeof(float), cudaMemcpyDeviceToHost));
+    if (h->wide) {
+        const int64_t used = h->n_nodes_used;
+        std::vector<float4> nodes((size_t)used * 5);
+        DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
+        out->n_nodes = used;
+        out->node_bytes = used * 80;
+        int64_t leaves = 0;
+        // depth by walking child links
+        std::vector<std::pair<int, int>> st;
+        st.push_back({0, 1});
+        int md = 0;
+        while (!st.empty()) {
+            auto [ni, depth] = st.back();
+            st.pop_back();
+            md = depth > md ? depth : md;
+            const float4* p = nodes.data() + (size_t)ni * 5;
+            uint32_t imask = f2u(p[0].w) >> 24, m[2] = {f2u(p[1].z), f2u(p[1].w)};
+            int base = f2i(p[1].x), rank = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                uint32_t meta = (m[sl / 4] >> (8 * (sl % 4))) & 0xffu;
+                if (imask & (1u << sl)) st.push_back({base + rank++, depth + 1});
+                else if (meta) ++leaves;
+            }
+        }
+        out->n_leaves = leaves;
+        out->max_depth = md;
+        return DRP_OK;
+    }
     // walk the emitted nodes on the host for leaf count / depth (debug-only path)
     std::vector<float4> nodes((size_t)h->n_nodes * 4);
     DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
@@ -256,6 +335,8 @@ extern "C" int drp_trace(uint64_t handle, const float* rays_o, const float* rays
     if (n_rays == 0) return DRP_OK;
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_trace: cannot select device"); return DRP_ERR_CUDA; }
+    static const bool simple = getenv("DRP_EXTEND") && strcmp(getenv("DRP_EXTEND"), "simple") == 0;  // A/B profiling switch
+    if (h->wide && !simple) return drp_trace_wide_persistent(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream);
     DRP_CUDA_CHECK(launch_trace_aos(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream));
     return DRP_OK;
 }

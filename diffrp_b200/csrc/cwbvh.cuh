@@ -1,0 +1,334 @@
+// cwbvh.cuh -- compressed 8-wide BVH ("CWBVH", after Ylitie, Karras, Laine 2017) built on the GPU by collapsing the
+// LBVH of lbvh.cuh, and its closest-hit traversal.
+//
+// Why (ncu evidence, profiles/README.md): the 64-byte two-child layout is issue/L1-bound at 6-10 active lanes per
+// instruction and ~45 node visits per ray.  An 8-wide node with 8-bit quantised child boxes is 80 bytes for 8 children
+// (10 B/child instead of 32 B/child), is tested with one FMA per slab plane, and the per-thread traversal state
+// (node group + triangle group bitmasks) postpones triangle tests so that lanes of a warp stay in the same phase.
+//
+// Node = 5 x float4 (80 B):
+//   n0 = (p.x, p.y, p.z, bits{ex, ey, ez, imask})          origin of the local grid, per-axis exponent, internal mask
+//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])     first child node / first triangle, per-slot meta byte
+//   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
+//   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
+//   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
+// meta byte: 0 = empty; internal child: 0b001'11sss (low 5 bits = 24 + slot); leaf child: unary triangle count (1..3) in
+// the top 3 bits, offset of its first triangle relative to tri_base in the low 5 bits.  Child boxes are
+// lo = p + qlo * 2^e, hi = p + qhi * 2^e (rounded outwards), and contain the padded boxes of lbvh.cuh, so the traversal is
+// conservative and the closest hit equals the exhaustive one (traverse.cuh contract).
+#pragma once
+#include "common.cuh"
+#include "lbvh.cuh"
+#include "traverse.cuh"
+
+#define CW_MAX_LEAF 3
+#define CW_STACK 48
+#define CW_SLACK 4.76837158203125e-07f  // 2^-21: relative widening of every slab distance
+#define CW_GRID_SLACK 0.0079f           // + this many grid steps: 256 * 2^-21 (FMA cancellation) + 2^-8 (bias folding, x2 margin)
+
+struct CwBuild {
+    LbvhBuild b;       // the binary hierarchy (left/right, boxes with area in box_hi.w, collapsed flags, ranges, vals)
+    float4* cw_nodes;  // (capacity, 5)
+    float4* cw_tris;   // (n, 3) triangles in node order: A, B, C, original id
+    int* work;         // (capacity) binary node collapsed into each wide node
+    int* counters;     // [0] wide nodes allocated, [1] triangles placed, [8 + L] first node of level L
+    int capacity;
+};
+
+DRP_HD bool cw_is_leaf_child(const LbvhBuild& b, int c) { return c >= b.n - 1 || b.collapsed[c]; }
+DRP_HD int cw_leaf_count(const LbvhBuild& b, int c) { return c >= b.n - 1 ? 1 : b.range_last[c] - b.range_first[c] + 1; }
+DRP_HD int cw_leaf_first(const LbvhBuild& b, int c) { return c >= b.n - 1 ? c - (b.n - 1) : b.range_first[c]; }
+
+DRP_HD uint32_t cw_pack4(const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
+
+// Collapse the binary subtree rooted at work[ni] into wide node ni.  `atomic_add(ptr, v)` returns the old value.
+template <typename AtomicAdd>
+DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
+    const LbvhBuild& b = cw.b;
+    const int root = cw.work[ni];
+    int child[8];
+    int k = 2;
+    child[0] = b.left[root];
+    child[1] = b.right[root];
+    while (k < 8) {  // open the child with the largest surface area until 8 children or nothing left to open
+        int best = -1;
+        float best_area = -1.0f;
+        for (int j = 0; j < k; ++j)
+            if (!cw_is_leaf_child(b, child[j])) {
+                float a = b.box_hi[child[j]].w;
+                if (a > best_area) { best_area = a; best = j; }
+            }
+        if (best < 0) break;
+        int c = child[best];
+        child[best] = b.left[c];
+        child[k++] = b.right[c];
+    }
+    // padded child boxes and the node box
+    float lo[8][3], hi[8][3], nlo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {-3e38f, -3e38f, -3e38f};
+    const float abs_pad = lbvh_abs_pad(b);
+    for (int j = 0; j < k; ++j) {
+        float4 l = b.box_lo[child[j]], h = b.box_hi[child[j]];
+        pad_box(l, h, abs_pad);
+        lo[j][0] = l.x; lo[j][1] = l.y; lo[j][2] = l.z;
+        hi[j][0] = h.x; hi[j][1] = h.y; hi[j][2] = h.z;
+        for (int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], lo[j][a]); nhi[a] = fmaxf(nhi[a], hi[j][a]); }
+    }
+    // slot assignment: slot s stands for the octant direction ((s&4)?+:-, (s&2)?+:-, (s&1)?+:-); greedily give each slot the
+    // child that lies furthest in that direction, so that (slot ^ octant) orders children front to back for any ray.
+    float cost[8][8];
+    for (int j = 0; j < k; ++j) {
+        float cx = 0.5f * (lo[j][0] + hi[j][0]) - 0.5f * (nlo[0] + nhi[0]);
+        float cy = 0.5f * (lo[j][1] + hi[j][1]) - 0.5f * (nlo[1] + nhi[1]);
+        float cz = 0.5f * (lo[j][2] + hi[j][2]) - 0.5f * (nlo[2] + nhi[2]);
+        for (int s = 0; s < 8; ++s) cost[j][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
+    }
+    int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    bool child_done[8] = {false, false, false, false, false, false, false, false};
+    for (int it = 0; it < k; ++it) {
+        float bc = -3e38f;
+        int bj = -1, bs = -1;
+        for (int j = 0; j < k; ++j) {
+            if (child_done[j]) continue;
+            for (int s = 0; s < 8; ++s)
+                if (slot_child[s] < 0 && cost[j][s] > bc) { bc = cost[j][s]; bj = j; bs = s; }
+        }
+        slot_child[bs] = bj;
+        child_done[bj] = true;
+    }
+    // per-axis exponent of the 8-bit grid
+    int e[3];
+    float scale[3], inv_scale[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext = nhi[a] - nlo[a];
+        int ea = (int)ceilf(log2f(fmaxf(ext, 1e-30f) / 255.0f));
+        ea = ea < -100 ? -100 : (ea > 100 ? 100 : ea);
+        while (ext > 255.0f * i2f((ea + 127) << 23) && ea < 100) ++ea;
+        e[a] = ea;
+        scale[a] = i2f((ea + 127) << 23);
+        inv_scale[a] = i2f((127 - ea) << 23);
+    }
+    uint32_t meta[8], q[6][8];
+    uint32_t imask = 0;
+    int n_inner = 0, n_tris = 0;
+    for (int s = 0; s < 8; ++s) {
+        int j = slot_child[s];
+        if (j < 0) {
+            meta[s] = 0;
+            for (int a = 0; a < 3; ++a) { q[a][s] = 255; q[3 + a][s] = 0; }
+            continue;
+        }
+        for (int a = 0; a < 3; ++a) {
+            float ql = floorf((lo[j][a] - nlo[a]) * inv_scale[a]);
+            float qh = ceilf((hi[j][a] - nlo[a]) * inv_scale[a]);
+            q[a][s] = (uint32_t)fminf(fmaxf(ql, 0.0f), 255.0f);
+            q[3 + a][s] = (uint32_t)fminf(fmaxf(qh, 0.0f), 255.0f);
+        }
+        int c = child[j];
+        if (cw_is_leaf_child(b, c)) {
+            int cnt = cw_leaf_count(b, c);
+            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)n_tris;
+            n_tris += cnt;
+        } else {
+            meta[s] = (1u << 5) | (24u + (uint32_t)s);
+            imask |= 1u << s;
+            ++n_inner;
+        }
+    }
+    const int child_base = n_inner ? atomic_add(&cw.counters[0], n_inner) : 0;
+    const int tri_base = n_tris ? atomic_add(&cw.counters[1], n_tris) : 0;
+    int rank = 0, toff = 0;
+    for (int s = 0; s < 8; ++s) {
+        int j = slot_child[s];
+        if (j < 0) continue;
+        int c = child[j];
+        if (imask & (1u << s)) {
+            if (child_base + rank < cw.capacity) cw.work[child_base + rank] = c;
+            ++rank;
+        } else {
+            int first = cw_leaf_first(b, c), cnt = cw_leaf_count(b, c);
+            for (int t = 0; t < cnt; ++t) {
+                int prim = (int)b.vals[first + t];
+                Vec3 A = load_vert(b.verts, b.tris[3 * (int64_t)prim]);
+                Vec3 B = load_vert(b.verts, b.tris[3 * (int64_t)prim + 1]);
+                Vec3 C = load_vert(b.verts, b.tris[3 * (int64_t)prim + 2]);
+                float4* o = cw.cw_tris + 3 * (int64_t)(tri_base + toff + t);
+                o[0] = make_float4(A.x, A.y, A.z, B.x);
+                o[1] = make_float4(B.y, B.z, C.x, C.y);
+                o[2] = make_float4(C.z, i2f(prim), 0.0f, 0.0f);
+            }
+            toff += cnt;
+        }
+    }
+    float4* o = cw.cw_nodes + 5 * (int64_t)ni;
+    uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16) | (imask << 24);
+    o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
+    o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(cw_pack4(meta)), u2f(cw_pack4(meta + 4)));
+    o[2] = make_float4(u2f(cw_pack4(q[0])), u2f(cw_pack4(q[0] + 4)), u2f(cw_pack4(q[1])), u2f(cw_pack4(q[1] + 4)));
+    o[3] = make_float4(u2f(cw_pack4(q[2])), u2f(cw_pack4(q[2] + 4)), u2f(cw_pack4(q[3])), u2f(cw_pack4(q[3] + 4)));
+    o[4] = make_float4(u2f(cw_pack4(q[4])), u2f(cw_pack4(q[4] + 4)), u2f(cw_pack4(q[5])), u2f(cw_pack4(q[5] + 4)));
+}
+
+// n < 2: one node whose slot 0 is a leaf with n triangles
+DRP_HD void cw_emit_tiny(const CwBuild& cw) {
+    const LbvhBuild& b = cw.b;
+    float4* o = cw.cw_nodes;
+    float4 lo = make_float4(0, 0, 0, 0), hi = make_float4(0, 0, 0, 0);
+    uint32_t meta0 = 0;
+    if (b.n == 1) {
+        lo = b.prim_lo[0]; hi = b.prim_hi[0];
+        pad_box(lo, hi, lbvh_abs_pad(b));
+        meta0 = 1u << 5;
+        Vec3 A = load_vert(b.verts, b.tris[0]), B = load_vert(b.verts, b.tris[1]), C = load_vert(b.verts, b.tris[2]);
+        cw.cw_tris[0] = make_float4(A.x, A.y, A.z, B.x);
+        cw.cw_tris[1] = make_float4(B.y, B.z, C.x, C.y);
+        cw.cw_tris[2] = make_float4(C.z, i2f(0), 0.0f, 0.0f);
+    }
+    int e[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext = a == 0 ? hi.x - lo.x : (a == 1 ? hi.y - lo.y : hi.z - lo.z);
+        int ea = (int)ceilf(log2f(fmaxf(ext, 1e-30f) / 255.0f));
+        ea = ea < -100 ? -100 : (ea > 100 ? 100 : ea);
+        while (ext > 255.0f * i2f((ea + 127) << 23) && ea < 100) ++ea;
+        e[a] = ea;
+    }
+    uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16);
+    o[0] = make_float4(lo.x, lo.y, lo.z, u2f(ebits));
+    o[1] = make_float4(i2f(0), i2f(0), u2f(meta0), u2f(0u));
+    const uint32_t lo_q = 0xffffff00u, hi_q = 0x000000ffu;  // slot 0 spans the grid, slots 1..7 are empty (lo 255 > hi 0)
+    o[2] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(lo_q), u2f(0xffffffffu));
+    o[3] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(hi_q), u2f(0u));
+    o[4] = make_float4(u2f(hi_q), u2f(0u), u2f(hi_q), u2f(0u));
+}
+
+// ---- traversal ----------------------------------------------------------------------------------------------------
+DRP_HD uint32_t cw_sign_extend_s8x4(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;  // prmt with selector bit 3 set replicates the sign bit of the selected byte (__byte_perm masks that bit off)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0x0000ba98u));
+    return r;
+#else
+    return ((x & 0x80u) ? 0xffu : 0u) | ((x & 0x8000u) ? 0xff00u : 0u) | ((x & 0x800000u) ? 0xff0000u : 0u) | ((x & 0x80000000u) ? 0xff000000u : 0u);
+#endif
+}
+// Byte i of x as the float 32768 + byte, without an I2F (quarter-rate XU pipe; 48 per node otherwise): one PRMT drops the
+// byte into mantissa bits 8..15 of 2^15.  The 32768 is folded into the FMA's addend (cw_node_hits), whose rounding then
+// costs at most 2^-9 of a grid step -- covered by the conservative slack.
+#define CW_BIAS 32768.0f
+DRP_HD float cw_byte_biased(uint32_t x, int i) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7504u + ((uint32_t)i << 4)));
+#else
+    return u2f(0x47000000u | (((x >> (8 * i)) & 0xffu) << 8));
+#endif
+}
+DRP_HD int cw_bfind(uint32_t x) { return 31 - clz32(x); }
+DRP_HD int cw_popc(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+struct CwRay {
+    Vec3 o, d, idir;
+    uint32_t octinv4;
+};
+DRP_HD float cw_safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+DRP_HD CwRay cw_make_ray(Vec3 o, Vec3 d) {
+    CwRay r;
+    r.o = o; r.d = d;
+    r.idir = v3(cw_safe_rcp(d.x), cw_safe_rcp(d.y), cw_safe_rcp(d.z));
+    uint32_t oct = (r.idir.x < 0.0f ? 4u : 0u) | (r.idir.y < 0.0f ? 2u : 0u) | (r.idir.z < 0.0f ? 1u : 0u);
+    r.octinv4 = (7u - oct) * 0x01010101u;
+    return r;
+}
+
+// intersect the 8 quantised child boxes of one node; returns the hit mask (internal children in bits 24..31 at their
+// traversal priority, triangles of leaf children in bits 0..23)
+DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4, float t_cull) {
+    const uint32_t ebits = f2u(n0.w);
+    const int ex = (int)(int8_t)(ebits & 0xffu), ey = (int)(int8_t)((ebits >> 8) & 0xffu), ez = (int)(int8_t)((ebits >> 16) & 0xffu);
+    const float ax = i2f((ex + 127) << 23) * r.idir.x, ay = i2f((ey + 127) << 23) * r.idir.y, az = i2f((ez + 127) << 23) * r.idir.z;
+    const float ox = (n0.x - r.o.x) * r.idir.x, oy = (n0.y - r.o.y) * r.idir.y, oz = (n0.z - r.o.z) * r.idir.z;
+    // conservative widening: the FMA form cancels, its error is relative to |origin term| + |grid term|
+    const float sx = CW_SLACK * fabsf(ox) + CW_GRID_SLACK * fabsf(ax), sy = CW_SLACK * fabsf(oy) + CW_GRID_SLACK * fabsf(ay),
+                sz = CW_SLACK * fabsf(oz) + CW_GRID_SLACK * fabsf(az);
+    // addends with the byte bias folded in: t = (32768 + q) * a + (o -+ slack - 32768 a)
+    const float bx = ox - CW_BIAS * ax, by = oy - CW_BIAS * ay, bz = oz - CW_BIAS * az;
+    const float oxl = bx - sx, oxh = bx + sx, oyl = by - sy, oyh = by + sy, ozl = bz - sz, ozh = bz + sz;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = cw_sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlx = f2u(half ? n2.y : n2.x), qly = f2u(half ? n2.w : n2.z), qlz = f2u(half ? n3.y : n3.x);
+        const uint32_t qhx = f2u(half ? n3.w : n3.z), qhy = f2u(half ? n4.y : n4.x), qhz = f2u(half ? n4.w : n4.z);
+        const uint32_t nx = r.idir.x < 0.0f ? qhx : qlx, fx = r.idir.x < 0.0f ? qlx : qhx;
+        const uint32_t ny = r.idir.y < 0.0f ? qhy : qly, fy = r.idir.y < 0.0f ? qly : qhy;
+        const uint32_t nz = r.idir.z < 0.0f ? qhz : qlz, fz = r.idir.z < 0.0f ? qlz : qhz;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float tnx = cw_byte_biased(nx, i) * ax + oxl, tny = cw_byte_biased(ny, i) * ay + oyl, tnz = cw_byte_biased(nz, i) * az + ozl;
+            float tfx = cw_byte_biased(fx, i) * ax + oxh, tfy = cw_byte_biased(fy, i) * ay + oyh, tfz = cw_byte_biased(fz, i) * az + ozh;
+            float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t_cull));
+            if (cmin <= cmax) hitmask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
+        }
+    }
+    return hitmask;
+}
+
+DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
+                           bool& overflow) {
+    const CwRay r = cw_make_ray(o, d);
+    uint32_t st_x[CW_STACK], st_y[CW_STACK];
+    int sp = 0;
+    float t_best = t_far;
+    int id_best = 0x7fffffff;
+    uint32_t ng_x = 0, ng_y = 0x80000000u;  // node group: (child base, hits in bits 24..31 | imask in bits 0..7); starts at the root
+    uint32_t tg_x = 0, tg_y = 0;            // triangle group: (triangle base, pending triangle bits)
+    for (;;) {
+        if (ng_y > 0x00ffffffu) {
+            const uint32_t hits = ng_y;
+            const int child_bit = cw_bfind(hits);
+            const uint32_t base = ng_x;
+            ng_y &= ~(1u << child_bit);
+            if (ng_y > 0x00ffffffu) {
+                if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
+                else overflow = true;
+            }
+            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = (uint32_t)cw_popc(hits & ~(0xffffffffu << slot));
+            const float4* p = nodes + 5 * (int64_t)(base + rel);
+            const float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3), n4 = ldg(p + 4);
+            DRP_COUNT_NODE();
+            const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
+            ng_x = f2u(n1.x);
+            ng_y = (hitmask & 0xff000000u) | (f2u(n0.w) >> 24);
+            tg_x = f2u(n1.y);
+            tg_y = hitmask & 0x00ffffffu;
+        } else {
+            tg_x = ng_x; tg_y = ng_y;
+            ng_x = 0; ng_y = 0;
+        }
+        while (tg_y != 0) {
+            const int ti = cw_bfind(tg_y);
+            tg_y &= ~(1u << ti);
+            leaf_intersect(tris, (int)tg_x + ti, 1, r.o, r.d, eps, t_best, id_best);
+        }
+        if (ng_y <= 0x00ffffffu) {
+            if (sp == 0) break;
+            --sp;
+            ng_x = st_x[sp]; ng_y = st_y[sp];
+        }
+    }
+    RayHit h;
+    const bool hit = t_best < t_far;
+    h.t = hit ? t_best : t_far;
+    h.id = hit ? id_best : 0;
+    return h;
+}

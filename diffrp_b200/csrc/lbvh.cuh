@@ -29,6 +29,7 @@ struct LbvhBuild {
     const float* verts;     // (V,3)
     const int32_t* tris;    // (F,3)
     int n;                  // F
+    int max_leaf;           // max triangles per collapsed leaf (<= 15); 4 for the binary layout, 3 for the wide layout
     // scene bounds as ordered uints: [0:3] min, [3:6] max of triangle boxes; [6:9] min, [9:12] max of centres
     uint32_t* bounds;
     // per primitive (original order)
@@ -163,7 +164,7 @@ DRP_HD void lbvh_refit(const LbvhBuild& b, int j, AtomicInc atomic_inc, Fence fe
         int count = b.range_last[p] - b.range_first[p] + 1;
         float c_split = DRP_SAH_CI * a + llo.w + rlo.w;
         float c_leaf = DRP_SAH_CT * a * (float)count;
-        bool make_leaf = (count <= DRP_MAX_LEAF) && (c_leaf <= c_split) && (p != 0);
+        bool make_leaf = (count <= b.max_leaf) && (c_leaf <= c_split) && (p != 0);
         b.collapsed[p] = make_leaf ? 1 : 0;
         plo.w = make_leaf ? c_leaf : c_split;
         phi.w = a;

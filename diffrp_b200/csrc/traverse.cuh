@@ -14,6 +14,17 @@
 #define DRP_T_SHRINK 0.99999905f  // 1 - 2^-20
 #define DRP_T_GROW 1.00000095f    // 1 + 2^-20
 
+// traversal statistics, compiled in only for the host simulator (tests/hostsim): nodes fetched / triangles tested
+#ifdef DRP_HOSTSIM
+struct TravStats { long long nodes, tris; };
+static thread_local TravStats g_trav = {0, 0};
+#define DRP_COUNT_NODE() (++g_trav.nodes)
+#define DRP_COUNT_TRI() (++g_trav.tris)
+#else
+#define DRP_COUNT_NODE()
+#define DRP_COUNT_TRI()
+#endif
+
 struct RayHit {
     float t;
     int id;
@@ -36,6 +47,7 @@ DRP_HD void leaf_intersect(const float4* __restrict__ tris, int first, int count
     for (int k = 0; k < count; ++k) {
         const float4* p = tris + 3 * (int64_t)(first + k);
         float4 a = ldg(p), b = ldg(p + 1), c = ldg(p + 2);
+        DRP_COUNT_TRI();
         float t;
         if (tri_test_mt(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t)) {
             int id = f2i(c.y);
@@ -58,6 +70,7 @@ DRP_HD RayHit trace_one(const float4* __restrict__ nodes, const float4* __restri
         if (node >= 0) {
             const float4* p = nodes + 4 * (int64_t)node;
             float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3);
+            DRP_COUNT_NODE();
             float tl, tr;
             bool hl = slab_test(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, idir, t_best, tl);
             bool hr = slab_test(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, idir, t_best, tr);

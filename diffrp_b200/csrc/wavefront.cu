@@ -13,10 +13,12 @@
 #include <string>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
 #include "lbvh.cuh"
 #include "traverse.cuh"
+#include "cwbvh.cuh"
 #include "shade.cuh"
 
 #define WF_BLOCK 128
@@ -94,7 +96,7 @@ __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restr
     }
 }
 
-template <bool PRIMARY>
+template <bool PRIMARY, bool WIDE>
 __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
                                                      float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor) {
     const int count = PRIMARY ? (int)c.R : *count_ptr;
@@ -112,12 +114,155 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
                 int ri;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
                 bool overflow = false;
-                RayHit h = trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow);
+                RayHit h = WIDE ? cw_trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow) : trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow);
                 hit[k] = make_float2(h.t, __int_as_float(h.id));
                 if (overflow) atomicAdd(&c.flags[0], 1);
             }
         }
     }
+}
+
+// ---- persistent-thread extend over the wide layout -----------------------------------------------------------------
+// Every lane owns one ray and walks the 8-wide hierarchy with the (node group, triangle group) state of cwbvh.cuh.
+//  * dynamic ray fetch (Aila & Laine 2009 / Ylitie et al. 2017): a lane whose ray terminated does not wait for the slowest
+//    ray of its warp -- when the accumulated number of idle lane-iterations exceeds CWK_NW the warp leaves the traversal
+//    loop, votes (ballot) which lanes need work and refills them from a warp-private chunk of the queue (one atomic per
+//    CWK_CHUNK rays);
+//  * triangle postponing: a triangle group is pushed back on the stack when fewer than CWK_POSTPONE of the warp's active
+//    lanes have triangles to test, so that the warp stays in the node phase.
+// Scheduling only: the closest hit found is the exhaustive one whatever the order (min t, then min id).
+#define CWK_CHUNK 256
+#define CWK_ND 4
+#define CWK_NW 16
+#define CWK_POSTPONE 0.2f
+
+#define SRC_QUEUE 0    // rays from the float4 queues, result to hit[]
+#define SRC_PRIMARY 1  // rays generated from the ray index, result to hit[]
+#define SRC_AOS 2      // standalone query: rays from two (R,3) arrays, results to separate t / id arrays (Raycaster.query)
+struct AosRays {
+    const float* ro;
+    const float* rd;
+    float* out_t;
+    int32_t* out_i;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(WF_BLOCK) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
+                                                        float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos) {
+    const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int chunk_next = 0, chunk_end = 0;  // warp-uniform: private range of queue slots
+    bool exhausted = false;             // warp-uniform: the queue has no more chunks
+    int k = -1;                         // queue slot of this lane's ray, -1 = idle
+    CwRay r;
+    float t_best = 0.0f;
+    int id_best = 0, sp = 0;
+    uint32_t ng_x = 0, ng_y = 0, tg_x = 0, tg_y = 0;
+    uint32_t st_x[CW_STACK], st_y[CW_STACK];
+    bool overflow = false;
+    for (;;) {
+        // ---- refill idle lanes --------------------------------------------------------------------------------
+        const unsigned need = __ballot_sync(0xffffffffu, k < 0);
+        if (need && !exhausted) {
+            int want = __popc(need);
+            if (chunk_end - chunk_next < want) {  // take a new chunk (rays left in the old one, at most 31, come first)
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cursor, CWK_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                // hand out the tail of the old chunk, then continue in the new one
+                const int left = chunk_end - chunk_next;
+                const int rank = __popc(need & lt_mask);
+                if (k < 0) {
+                    int kk = rank < left ? chunk_next + rank : base + (rank - left);
+                    k = kk < count ? kk : -1;
+                }
+                chunk_next = base + (want - left);
+                chunk_end = base + CWK_CHUNK;
+                if (base >= count) exhausted = true;
+            } else {
+                if (k < 0) k = chunk_next + __popc(need & lt_mask);
+                chunk_next += want;
+                if (k >= count) k = -1;
+            }
+            if (k >= 0 && (need >> lane & 1u)) {  // freshly assigned: load / generate the ray, reset the traversal state
+                Vec3 o, d;
+                int ri;
+                if (SRC == SRC_AOS) {
+                    o = v3(__ldg(aos.ro + 3 * (int64_t)k), __ldg(aos.ro + 3 * (int64_t)k + 1), __ldg(aos.ro + 3 * (int64_t)k + 2));
+                    d = v3(__ldg(aos.rd + 3 * (int64_t)k), __ldg(aos.rd + 3 * (int64_t)k + 1), __ldg(aos.rd + 3 * (int64_t)k + 2));
+                } else {
+                    load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
+                }
+                r = cw_make_ray(o, d);
+                t_best = c.p.t_far;
+                id_best = 0x7fffffff;
+                sp = 0;
+                ng_x = 0; ng_y = 0x80000000u;
+                tg_x = 0; tg_y = 0;
+            }
+        }
+        if (__all_sync(0xffffffffu, k < 0)) break;  // nothing left anywhere in this warp
+        // ---- traverse ---------------------------------------------------------------------------------------------
+        if (k >= 0) {
+            int lost = 0;
+            for (;;) {
+                if (ng_y > 0x00ffffffu) {
+                    const uint32_t hits = ng_y;
+                    const int child_bit = 31 - __clz(hits);
+                    const uint32_t base = ng_x;
+                    ng_y &= ~(1u << child_bit);
+                    if (ng_y > 0x00ffffffu) {
+                        if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
+                        else overflow = true;
+                    }
+                    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
+                    const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
+                    const float4* p = c.nodes + 5 * (int64_t)(base + rel);
+                    const float4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
+                    const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
+                    ng_x = __float_as_uint(n1.x);
+                    ng_y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
+                    tg_x = __float_as_uint(n1.y);
+                    tg_y = hitmask & 0x00ffffffu;
+                } else {
+                    tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
+                    ng_x = 0; ng_y = 0;
+                }
+                const int total_active = __popc(__activemask());
+                while (tg_y != 0) {
+                    if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
+                        st_x[sp] = tg_x; st_y[sp] = tg_y; ++sp;  // postpone: too few lanes have triangles
+                        break;
+                    }
+                    const int ti = 31 - __clz(tg_y);
+                    tg_y &= ~(1u << ti);
+                    leaf_intersect(c.tris, (int)tg_x + ti, 1, r.o, r.d, c.eps, t_best, id_best);
+                }
+                if (ng_y <= 0x00ffffffu) {
+                    if (sp > 0) {
+                        --sp;
+                        ng_x = st_x[sp]; ng_y = st_y[sp];
+                    } else {  // ray finished
+                        const bool is_hit = t_best < c.p.t_far;
+                        if (SRC == SRC_AOS) {
+                            aos.out_t[k] = is_hit ? t_best : c.p.t_far;
+                            aos.out_i[k] = is_hit ? id_best : 0;
+                        } else {
+                            hit[k] = make_float2(is_hit ? t_best : c.p.t_far, __int_as_float(is_hit ? id_best : 0));
+                        }
+                        k = -1;
+                        break;
+                    }
+                }
+                if (!exhausted) {  // dynamic fetch: leave when enough lane-iterations were lost to idle lanes
+                    lost += 32 - __popc(__activemask()) - CWK_ND;
+                    if (lost >= CWK_NW) break;
+                }
+            }
+        }
+    }
+    if (overflow) atomicAdd(&c.flags[0], 1);
 }
 
 __device__ __forceinline__ void accum_add4(float* p, float a, float b, float c, float d) {
@@ -263,9 +408,9 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 256));
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->d_traced, sizeof(unsigned long long)));
         int nb = 0;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, WF_BLOCK, 0));
         h->ws->grid_extend[1] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_QUEUE>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, WF_BLOCK, 0));
         h->ws->grid_extend[0] = std::max(1, nb) * h->ws->sm_count;
         DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true>, WF_BLOCK, 0));
         h->ws->grid_shade[1] = std::max(1, nb) * h->ws->sm_count;
@@ -352,6 +497,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     }
     for (int a = 0; a < 3; ++a) { c.box_lo[a] = ws->box_lo[a]; c.box_hi[a] = ws->box_hi[a]; }
     const int D = p.ray_depth;
+    static const bool simple_extend = getenv("DRP_EXTEND") && strcmp(getenv("DRP_EXTEND"), "simple") == 0;  // A/B profiling switch
     int64_t launches = 0;
     h->last_render.rays_nominal = HW * p.n_samples * D;
     DRP_CUDA_CHECK(cudaMemsetAsync(ws->d_traced, 0, sizeof(unsigned long long), s));
@@ -378,7 +524,9 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
             const int in = b & 1, out = in ^ 1;
             if (b == 0) {
                 int sp = span_begin(0, b, nullptr);
-                k_extend<true><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
+                if (h->wide && !simple_extend) k_extend_cw<SRC_PRIMARY><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0, AosRays());
+                else if (h->wide) k_extend<true, true><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
+                else k_extend<true, false><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
                 span_end(sp);
                 sp = span_begin(1, b, nullptr);
                 k_shade<true><<<ws->grid_shade[1], WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, ws->hit, ws->qa[out], ws->qb[out], ws->qt[out], nullptr,
@@ -386,7 +534,9 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
                 span_end(sp);
             } else {
                 int sp = span_begin(0, b, counts + b);
-                k_extend<false><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
+                if (h->wide && !simple_extend) k_extend_cw<SRC_QUEUE><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b, AosRays());
+                else if (h->wide) k_extend<false, true><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
+                else k_extend<false, false><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
                 span_end(sp);
                 sp = span_begin(1, b, counts + b);
                 k_shade<false><<<ws->grid_shade[0], WF_BLOCK, 0, s>>>(c, b, ws->qa[in], ws->qb[in], ws->qt[in], ws->hit, ws->qa[out], ws->qb[out], ws->qt[out],
@@ -400,6 +550,24 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     }
     DRP_CUDA_CHECK(cudaGetLastError());
     h->last_render.kernel_launches = launches;
+    return DRP_OK;
+}
+
+// Standalone Raycaster.query over the wide layout with the persistent kernel (called by drp_trace).
+int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, float* out_t, int32_t* out_i, float t_far, int64_t n, cudaStream_t s) {
+    int rc = ensure_workspace(h, 0, 0);
+    if (rc != DRP_OK) return rc;
+    RenderWorkspace* ws = h->ws;
+    if (n > 0x7fffff00) { drp_set_error("drp_trace: more than 2^31 rays per call"); return DRP_ERR_INVALID; }
+    WfConst c;
+    memset(&c, 0, sizeof(c));
+    c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.flags = h->dev_flags;
+    int* cursor = ws->counters + 250;
+    DRP_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int), s));
+    AosRays aos = {ro, rd, out_t, out_i};
+    int grid = ws->grid_extend[1];
+    k_extend_cw<SRC_AOS><<<grid, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, cursor, aos);
+    DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }
 

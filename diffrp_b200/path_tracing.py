@@ -118,6 +118,22 @@ def raygen_tables(V: torch.Tensor, P: torch.Tensor, H: int, W: int, spp: int, de
     )
 
 
+def shard_sample_ids(spp: int, rank: int, world: int, device=None) -> torch.Tensor:
+    """Global Hammersley indices rendered by ``rank`` of ``world``: a strided share, so the union over ranks is exactly
+    the single-process sample set and every rank sees the whole [0,1) range of the low-discrepancy sequence."""
+    ids = torch.arange(spp, dtype=torch.int32, device=device)
+    return ids[rank::world] if world > 1 else ids
+
+
+def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
+    """The path's one exchange step: sum the packed fp32 accumulators over all ranks (NCCL on GPUs, gloo in CPU tests)."""
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+    return accum
+
+
 def _cached(fn):
     name = fn.__name__
 
@@ -285,9 +301,7 @@ class PathTracingSession:
         opt = self.options
         if opt.rng == 'torch' and opt.shard_world > 1:
             raise ValueError("rng='torch' (reference replay) is a single-process mode")
-        all_ids = torch.arange(opt.ray_spp, dtype=torch.int32, device=self.device)
-        my_ids = all_ids[opt.shard_rank::opt.shard_world] if opt.shard_world > 1 else all_ids
-        return self.render_samples(my_ids)
+        return self.render_samples(shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device))
 
     def finalize(self, accum: torch.Tensor):
         """Epilogue of trace_rays (path_tracing.py:348-352): /spp, saturate(alpha), flipud -- one kernel."""
@@ -323,11 +337,7 @@ class PathTracingSession:
         """
         if self._fused_scene() is None:
             return self.trace_rays(self.sampler_brdf)
-        accum = self.render_accumulators()
-        if self.options.shard_world > 1:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(accum, op=dist.ReduceOp.SUM)  # NCCL over NVLink: one packed fp32 accumulator
+        accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
         return self.finalize(accum)
 
     # ---- generic path (user samplers / Python materials): see diffrp_b200/generic.py -------------------------------

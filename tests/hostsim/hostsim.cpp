@@ -9,16 +9,27 @@
 #include "../../diffrp_b200/csrc/common.cuh"
 #include "../../diffrp_b200/csrc/lbvh.cuh"
 #include "../../diffrp_b200/csrc/traverse.cuh"
+#include "../../diffrp_b200/csrc/cwbvh.cuh"
 
 struct HsBvh {
     int n;
     std::vector<float4> nodes, packed;
+    std::vector<float4> cw_nodes, cw_tris;  // wide layout (cwbvh.cuh)
+    int cw_count = 0, cw_levels = 0;
     float sah;
     float bounds[6];
 };
 
+static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_tris, int max_leaf, bool wide);
 extern "C" HsBvh* hs_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris) {
     (void)n_verts;
+    return hs_build_impl(verts, tris, n_tris, DRP_MAX_LEAF, false);
+}
+extern "C" HsBvh* hs_build_wide(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris) {
+    (void)n_verts;
+    return hs_build_impl(verts, tris, n_tris, CW_MAX_LEAF, true);
+}
+static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_tris, int max_leaf, bool wide) {
     HsBvh* h = new HsBvh();
     const int n = (int)n_tris;
     const size_t nn = n > 0 ? n : 1;
@@ -34,7 +45,7 @@ extern "C" HsBvh* hs_build(const float* verts, const int32_t* tris, int64_t n_ve
     std::vector<uint8_t> collapsed(nn, 0);
     LbvhBuild b;
     memset(&b, 0, sizeof(b));
-    b.verts = verts; b.tris = tris; b.n = n; b.bounds = bounds.data();
+    b.verts = verts; b.tris = tris; b.n = n; b.max_leaf = max_leaf; b.bounds = bounds.data();
     b.prim_lo = prim_lo.data(); b.prim_hi = prim_hi.data(); b.keys = keys.data(); b.vals = vals.data();
     b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.range_first = rf.data(); b.range_last = rl.data();
     b.box_lo = box_lo.data(); b.box_hi = box_hi.data(); b.arrive = arrive.data(); b.collapsed = collapsed.data();
@@ -72,7 +83,62 @@ extern "C" HsBvh* hs_build(const float* verts, const int32_t* tris, int64_t n_ve
     }
     for (int j = 0; j < n; ++j) lbvh_pack_tri(b, j);
     for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(bounds[k]);
+    if (wide) {
+        CwBuild cw;
+        cw.b = b;
+        cw.capacity = n > 1 ? n - 1 : 1;
+        h->cw_nodes.resize(5 * (size_t)cw.capacity);
+        h->cw_tris.resize(3 * nn);
+        std::vector<int> work(cw.capacity, 0), counters(128, 0);
+        cw.cw_nodes = h->cw_nodes.data(); cw.cw_tris = h->cw_tris.data(); cw.work = work.data(); cw.counters = counters.data();
+        if (n < 2) {
+            cw_emit_tiny(cw);
+            h->cw_count = 1;
+        } else {
+            counters[0] = 1;
+            int begin = 0, end = 1, levels = 0;
+            while (begin < end) {
+                for (int ni = begin; ni < end; ++ni) cw_collapse_node(cw, ni, [](int* p, int v) { int o = *p; *p = o + v; return o; });
+                begin = end; end = counters[0]; ++levels;
+            }
+            h->cw_count = counters[0];
+            h->cw_levels = levels;
+        }
+    }
     return h;
+}
+
+extern "C" int64_t hs_trace_wide(const HsBvh* h, const float* ro, const float* rd, int64_t n, float t_far, float eps, float* out_t, int32_t* out_i) {
+    int64_t overflow = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : overflow)
+    for (int64_t r = 0; r < n; ++r) {
+        bool of = false;
+        RayHit hit = cw_trace_one(h->cw_nodes.data(), h->cw_tris.data(), v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]),
+                                  v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]), t_far, eps, of);
+        out_t[r] = hit.t;
+        out_i[r] = hit.id;
+        overflow += of;
+    }
+    return overflow;
+}
+
+// wide-layout statistics: [nodes, levels, inner children, leaf children, triangles referenced, max tris per node]
+extern "C" void hs_stats_wide(const HsBvh* h, int64_t* out) {
+    int64_t inner = 0, leaf = 0, tris = 0, maxt = 0;
+    for (int ni = 0; ni < h->cw_count; ++ni) {
+        const float4* p = h->cw_nodes.data() + 5 * (size_t)ni;
+        uint32_t m[2] = {f2u(p[1].z), f2u(p[1].w)};
+        int64_t nt = 0;
+        for (int s = 0; s < 8; ++s) {
+            uint32_t meta = (m[s / 4] >> (8 * (s % 4))) & 0xffu;
+            if (meta == 0) continue;
+            if ((meta & 0x18u) == 0x18u && (meta >> 5) == 1u) ++inner;
+            else { ++leaf; nt += cw_popc(meta >> 5); }
+        }
+        tris += nt;
+        maxt = std::max(maxt, nt);
+    }
+    out[0] = h->cw_count; out[1] = h->cw_levels; out[2] = inner; out[3] = leaf; out[4] = tris; out[5] = maxt;
 }
 
 extern "C" void hs_free(HsBvh* h) { delete h; }
@@ -165,4 +231,17 @@ extern "C" int64_t hs_render(const HsBvh* h, const drp_scene_t* scene, const drp
         }
     }
     return traced;
+}
+
+// mean nodes fetched / triangles tested per ray (tree-quality probe; serial)
+extern "C" void hs_trav_stats(const HsBvh* h, int wide, const float* ro, const float* rd, int64_t n, float t_far, float eps, double* out) {
+    g_trav.nodes = g_trav.tris = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        bool of = false;
+        Vec3 o = v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]), d = v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]);
+        if (wide) cw_trace_one(h->cw_nodes.data(), h->cw_tris.data(), o, d, t_far, eps, of);
+        else trace_one(h->nodes.data(), h->packed.data(), o, d, t_far, eps, of);
+    }
+    out[0] = (double)g_trav.nodes / (double)n;
+    out[1] = (double)g_trav.tris / (double)n;
 }

@@ -1,0 +1,59 @@
+"""
+World-size-2 `gloo` test of the multi-process host logic (CPU): sample sharding + the one exchange step
+(all_reduce of the packed accumulators) + finalisation reproduce the single-process image.  The CPU oracle stands in for
+the CUDA renderer here (this file tests the plumbing around it; GPU sharding itself is covered in test_render_gpu.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPP, DEPTH, H, W = 6, 3, 24, 32
+
+
+def _render_shard(rank, world):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    import scenes
+    from test_oracle_golden import make_camera
+    from diffrp_b200.path_tracing import shard_sample_ids
+    cam = make_camera(dict(h=H, w=W), None)
+    ids = shard_sample_ids(SPP, rank, world).numpy()
+    vao, hs, p, keep = scenes.oracle_inputs(scenes.mixed_scene(24, 12), cam, SPP, DEPTH, seed=4, sample_ids=ids)
+    acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hs, p)
+    return acc, ids
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffrp_b200.path_tracing import reduce_accumulators
+    acc, ids = _render_shard(rank, world)
+    t = reduce_accumulators(torch.from_numpy(acc), world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ids.tolist())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum.npy"), t.numpy())
+        np.save(os.path.join(out_dir, "ids.npy"), np.array(sorted(sum(gathered, []))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sample_sharding_and_accumulator_reduce(tmp_path):
+    world, port = 2, 29000 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    summed = np.load(tmp_path / "sum.npy")
+    assert np.array_equal(np.load(tmp_path / "ids.npy"), np.arange(SPP))  # shards partition the sample set
+    whole, _ = _render_shard(0, 1)
+    np.testing.assert_allclose(summed, whole, rtol=1e-5, atol=1e-5)
+    sys.path.insert(0, ROOT)
+    import oracle
+    a, b = oracle.finalize(summed, H, W, SPP), oracle.finalize(whole, H, W, SPP)
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-5, atol=1e-5)
