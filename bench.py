@@ -203,7 +203,7 @@ def main():
     import torch.distributed as dist
     import diffrp_b200 as drp
     from diffrp_b200 import synthetic as syn
-    from diffrp_b200._lib import loaded_path
+    from diffrp_b200._lib import loaded_path, build_config
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -350,6 +350,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "native_library": loaded_path(),
+        "native_build": build_config(),
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -85,7 +85,7 @@ class Profile(C.Structure):
 
 #: every symbol declared in include/diffrp_b200.h (checked by tests/test_abi.py against the built library)
 EXPORTED_SYMBOLS = (
-    "drp_abi_version", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
+    "drp_abi_version", "drp_build_config", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
     "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
 )
 

@@ -19,6 +19,7 @@ def _declare(L):
     vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
     L.drp_abi_version.restype = C.c_int
     L.drp_last_error.restype = C.c_char_p
+    L.drp_build_config.restype = C.c_char_p
     L.drp_set_log_level.argtypes = [C.c_int]
     L.drp_build.argtypes = [vp, vp, i64, i64, C.c_int, vp, C.POINTER(u64)]
     L.drp_trace.argtypes = [u64, vp, vp, vp, vp, f32, i64, vp]
@@ -33,7 +34,7 @@ def _declare(L):
     L.drp_get_profile.argtypes = [u64, C.POINTER(_abi.Profile)]
     for name in _abi.EXPORTED_SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("drp_last_error",):
+        if name not in ("drp_last_error", "drp_build_config"):
             fn.restype = C.c_int
 
 
@@ -56,6 +57,10 @@ def check(status: int, what: str = ""):
     if status != 0:
         msg = lib().drp_last_error()
         raise DiffrpB200Error("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def build_config() -> str:
+    return lib().drp_build_config().decode()
 
 
 def loaded_path():

@@ -91,6 +91,16 @@ DRP_HD float x_fma(float a, float b, float c) { return fmaf(a, b, c); }
 DRP_HD float x_rcp(float a) { return 1.0f / a; }
 #endif
 
+// sin / cos of 2*pi*x for x in [0,1): the device uses sincospif (exact range reduction, compact code);
+// the host simulator evaluates the same quantity with libm.
+DRP_HD void sincos_2pi(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+    sincospif(2.0f * x, s, c);
+#else
+    sincosf(x * 6.283185307179586f, s, c);
+#endif
+}
+
 struct Vec3 {
     float x, y, z;
 };

@@ -21,6 +21,9 @@
 #include "lbvh.cuh"
 #include "traverse.cuh"
 
+#ifndef DRP_CW_HALFSKIP
+#define DRP_CW_HALFSKIP 1
+#endif
 #define CW_MAX_LEAF 3
 #define CW_STACK 48
 #define CW_SLACK 4.76837158203125e-07f  // 2^-21: relative widening of every slab distance
@@ -82,6 +85,19 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         float cz = 0.5f * (lo[j][2] + hi[j][2]) - 0.5f * (nlo[2] + nhi[2]);
         for (int s = 0; s < 8; ++s) cost[j][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
     }
+    // Nodes with <= 4 children use slots 0..3 only (ordered by the y/z octant bits), so the traversal can skip the empty
+    // half -- unless x is the axis along which the children are spread most, where losing the x ordering would cost more.
+    int n_slots = 8;
+    if (DRP_CW_HALFSKIP && k <= 4) {
+        float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
+        for (int j = 0; j < k; ++j)
+            for (int a = 0; a < 3; ++a) {
+                float cc = lo[j][a] + hi[j][a];
+                mn[a] = fminf(mn[a], cc); mx[a] = fmaxf(mx[a], cc);
+            }
+        float sx = mx[0] - mn[0], sy = mx[1] - mn[1], sz = mx[2] - mn[2];
+        if (!(sx > sy && sx > sz)) n_slots = 4;
+    }
     int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     bool child_done[8] = {false, false, false, false, false, false, false, false};
     for (int it = 0; it < k; ++it) {
@@ -89,7 +105,7 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         int bj = -1, bs = -1;
         for (int j = 0; j < k; ++j) {
             if (child_done[j]) continue;
-            for (int s = 0; s < 8; ++s)
+            for (int s = 0; s < n_slots; ++s)
                 if (slot_child[s] < 0 && cost[j][s] > bc) { bc = cost[j][s]; bj = j; bs = s; }
         }
         slot_child[bs] = bj;
@@ -214,10 +230,13 @@ DRP_HD uint32_t cw_sign_extend_s8x4(uint32_t x) {
 // byte into mantissa bits 8..15 of 2^15.  The 32768 is folded into the FMA's addend (cw_node_hits), whose rounding then
 // costs at most 2^-9 of a grid step -- covered by the conservative slack.
 #define CW_BIAS 32768.0f
-DRP_HD float cw_byte_biased(uint32_t x, int i) {
+// `bias` (= 0x47000000) is passed in as a runtime value so that PRMT takes the *selector* as its immediate operand and the
+// bias from a register / constant bank; with both compile-time constants ptxas spends an extra move per PRMT on the selector.
+DRP_HD float cw_byte_biased(uint32_t x, int i, uint32_t bias) {
 #ifdef __CUDA_ARCH__
-    return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7504u + ((uint32_t)i << 4)));
+    return __uint_as_float(__byte_perm(x, bias, 0x7504u + ((uint32_t)i << 4)));
 #else
+    (void)bias;
     return u2f(0x47000000u | (((x >> (8 * i)) & 0xffu) << 8));
 #endif
 }
@@ -233,10 +252,12 @@ DRP_HD int cw_popc(uint32_t x) {
 struct CwRay {
     Vec3 o, d, idir;
     uint32_t octinv4;
+    uint32_t bias;  // 0x47000000, see cw_byte_biased
 };
 DRP_HD float cw_safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
-DRP_HD CwRay cw_make_ray(Vec3 o, Vec3 d) {
+DRP_HD CwRay cw_make_ray(Vec3 o, Vec3 d, uint32_t bias = 0x47000000u) {
     CwRay r;
+    r.bias = bias;
     r.o = o; r.d = d;
     r.idir = v3(cw_safe_rcp(d.x), cw_safe_rcp(d.y), cw_safe_rcp(d.z));
     uint32_t oct = (r.idir.x < 0.0f ? 4u : 0u) | (r.idir.y < 0.0f ? 2u : 0u) | (r.idir.z < 0.0f ? 1u : 0u);
@@ -261,6 +282,9 @@ DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, fl
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+#if DRP_CW_HALFSKIP
+        if (half && meta4 == 0u) break;  // slots 4..7 empty: the builder packs nodes with <= 4 children into slots 0..3
+#endif
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
         const uint32_t inner_mask4 = cw_sign_extend_s8x4(is_inner4 << 3);
         const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
@@ -272,8 +296,8 @@ DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, fl
         const uint32_t nz = r.idir.z < 0.0f ? qhz : qlz, fz = r.idir.z < 0.0f ? qlz : qhz;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float tnx = cw_byte_biased(nx, i) * ax + oxl, tny = cw_byte_biased(ny, i) * ay + oyl, tnz = cw_byte_biased(nz, i) * az + ozl;
-            float tfx = cw_byte_biased(fx, i) * ax + oxh, tfy = cw_byte_biased(fy, i) * ay + oyh, tfz = cw_byte_biased(fz, i) * az + ozh;
+            float tnx = cw_byte_biased(nx, i, r.bias) * ax + oxl, tny = cw_byte_biased(ny, i, r.bias) * ay + oyl, tnz = cw_byte_biased(nz, i, r.bias) * az + ozl;
+            float tfx = cw_byte_biased(fx, i, r.bias) * ax + oxh, tfy = cw_byte_biased(fy, i, r.bias) * ay + oyh, tfz = cw_byte_biased(fz, i, r.bias) * az + ozh;
             float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t_cull));
             if (cmin <= cmax) hitmask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);

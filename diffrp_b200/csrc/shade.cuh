@@ -49,51 +49,79 @@ DRP_HD void gen_primary_ray(const float* __restrict__ inv_vp, const float* __res
 }
 
 // ---- textures -------------------------------------------------------------------------------------------------
-DRP_HD float reflect_coord(float in, int twice_low, int twice_high) {
-    if (twice_low == twice_high) return 0.0f;
-    float mn = (float)twice_low * 0.5f, span = (float)(twice_high - twice_low) * 0.5f;
+// F.grid_sample(align_corners=False) semantics.  The device path is split into a branch-free address stage (tex_taps:
+// four texel offsets + weights) and a load stage (one 128-bit load per tap on RGBA texels), so that the 16 texel loads of a
+// GLTF material are independent instructions the scheduler can keep in flight together (the shade kernel is
+// latency-bound: ncu long_scoreboard), and the address code exists once instead of being inlined per texture.
+struct TexTaps {
+    int off[4];   // texel index y * w + x of the four taps (always in range)
+    float wt[4];  // bilinear weight; 0 for taps outside the image
+};
+
+DRP_HD float reflect_coord(float in, float twice_low, float twice_high) {
+    // reflect `in` into [low, high] given 2*low and 2*high (ATen reflect_coordinates); span > 0 here
+    float mn = twice_low * 0.5f, span = (twice_high - twice_low) * 0.5f;
     in = fabsf(in - mn);
-    float extra = fmodf(in, span);
-    int flips = (int)floorf(in / span);
-    return (flips & 1) ? span - extra + mn : extra + mn;
+    float flips = floorf(in / span);
+    float extra = in - flips * span;
+    return (((int)flips) & 1) ? span - extra + mn : extra + mn;
 }
 DRP_HD float grid_coord(float g, int size, bool reflection) {
     float c = ((g + 1.0f) * (float)size - 1.0f) * 0.5f;
-    if (reflection) c = reflect_coord(c, -1, 2 * size - 1);
+    float r = reflect_coord(c, -1.0f, (float)(2 * size - 1));
+    c = reflection ? r : c;
     return clampf(c, 0.0f, (float)(size - 1));
 }
-DRP_HD void texel_fetch(const drp_texture_t& t, int x, int y, float w, float out[4]) {
-    if (x < 0 || y < 0 || x >= t.w || y >= t.h) return;
-    const float* p = t.data + ((int64_t)y * t.w + x) * t.c;
-    if (t.c == 4) {
-        float4 v = ldg(reinterpret_cast<const float4*>(p));
-        out[0] += v.x * w; out[1] += v.y * w; out[2] += v.z * w; out[3] += v.w * w;
-    } else {
-        for (int c = 0; c < t.c; ++c) out[c] += ldg(p + c) * w;
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+TexTaps tex_taps(int h, int w, int wrap, int interp, float u, float v) {
+    TexTaps t;
+    if (wrap == DRP_WRAP_REPEAT) {  // uv.remainder(1.0)
+        u = u - floorf(u); v = v - floorf(v);
+        u = u >= 1.0f ? 0.0f : u;
+        v = v >= 1.0f ? 0.0f : v;
     }
+    const bool reflection = wrap != DRP_WRAP_CLAMP;
+    float ix = grid_coord(u * 2.0f - 1.0f, w, reflection);
+    float iy = grid_coord(-(v * 2.0f - 1.0f), h, reflection);
+    if (interp == DRP_INTERP_POINT) { ix = nearbyintf(ix); iy = nearbyintf(iy); }
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float fx = ix - x0, fy = iy - y0, gx = (x0 + 1.0f) - ix, gy = (y0 + 1.0f) - iy;
+    const int X = (int)x0, Y = (int)y0;
+    const bool xin = X + 1 < w, yin = Y + 1 < h;  // X, Y themselves are in range after the clamp
+    const int X1 = xin ? X + 1 : X, Y1 = yin ? Y + 1 : Y;
+    t.off[0] = Y * w + X;   t.wt[0] = gx * gy;
+    t.off[1] = Y * w + X1;  t.wt[1] = xin ? fx * gy : 0.0f;
+    t.off[2] = Y1 * w + X;  t.wt[2] = yin ? gx * fy : 0.0f;
+    t.off[3] = Y1 * w + X1; t.wt[3] = (xin && yin) ? fx * fy : 0.0f;
+    return t;
 }
-// out[0..c) = sampled texel, channels >= c left at 0
+
+// generic-channel fetch (host oracle-compatible path; textures with c in {1,3,4})
 DRP_HD void tex_fetch(const drp_texture_t& t, float u, float v, float out[4]) {
     out[0] = out[1] = out[2] = out[3] = 0.0f;
-    if (t.wrap == DRP_WRAP_REPEAT) {  // uv.remainder(1.0)
-        u = u - floorf(u); v = v - floorf(v);
-        if (u >= 1.0f) u = 0.0f;
-        if (v >= 1.0f) v = 0.0f;
+    TexTaps tp = tex_taps(t.h, t.w, t.wrap, t.interp, u, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (t.c == 4) {
+            float4 x = ldg(reinterpret_cast<const float4*>(t.data) + tp.off[k]);
+            out[0] += x.x * tp.wt[k]; out[1] += x.y * tp.wt[k]; out[2] += x.z * tp.wt[k]; out[3] += x.w * tp.wt[k];
+        } else {
+            for (int c = 0; c < t.c; ++c) out[c] += ldg(t.data + (int64_t)tp.off[k] * t.c + c) * tp.wt[k];
+        }
     }
-    bool reflection = t.wrap != DRP_WRAP_CLAMP;
-    float ix = grid_coord(u * 2.0f - 1.0f, t.w, reflection);
-    float iy = grid_coord(-(v * 2.0f - 1.0f), t.h, reflection);
-    if (t.interp == DRP_INTERP_POINT) {
-        texel_fetch(t, (int)nearbyintf(ix), (int)nearbyintf(iy), 1.0f, out);
-        return;
-    }
-    float x0 = floorf(ix), y0 = floorf(iy);
-    float fx = ix - x0, fy = iy - y0, gx = (x0 + 1.0f) - ix, gy = (y0 + 1.0f) - iy;
-    int X = (int)x0, Y = (int)y0;
-    texel_fetch(t, X, Y, gx * gy, out);
-    texel_fetch(t, X + 1, Y, fx * gy, out);
-    texel_fetch(t, X, Y + 1, gx * fy, out);
-    texel_fetch(t, X + 1, Y + 1, fx * fy, out);
+}
+// RGBA-only fetch from precomputed taps: four independent 128-bit loads
+DRP_HD float4 tex_fetch4(const float* __restrict__ data, const TexTaps& tp) {
+    const float4* p = reinterpret_cast<const float4*>(data);
+    float4 a = ldg(p + tp.off[0]), b = ldg(p + tp.off[1]), c = ldg(p + tp.off[2]), d = ldg(p + tp.off[3]);
+    return make_float4(a.x * tp.wt[0] + b.x * tp.wt[1] + c.x * tp.wt[2] + d.x * tp.wt[3],
+                       a.y * tp.wt[0] + b.y * tp.wt[1] + c.y * tp.wt[2] + d.y * tp.wt[3],
+                       a.z * tp.wt[0] + b.z * tp.wt[1] + c.z * tp.wt[2] + d.z * tp.wt[3],
+                       a.w * tp.wt[0] + b.w * tp.wt[1] + c.w * tp.wt[2] + d.w * tp.wt[3]);
 }
 
 DRP_HD Vec3 env_fetch(const drp_texture_t& env, Vec3 d) {
@@ -102,9 +130,15 @@ DRP_HD Vec3 env_fetch(const drp_texture_t& env, Vec3 d) {
     a = a - floorf(a);
     if (a >= 1.0f) a = 0.0f;
     float v = (1.0f / DRP_PI) * asinf(clampf(d.y, -0.999999f, 0.999999f)) + 0.5f;
-    float rgb[4];
-    tex_fetch(env, a, v, rgb);  // env.wrap = CLAMP ('border'), env.interp = LINEAR set by the host
-    return v3(rgb[0], rgb[1], rgb[2]);
+#ifndef __CUDA_ARCH__
+    if (env.c != 4) {
+        float rgb[4];
+        tex_fetch(env, a, v, rgb);  // env.wrap = CLAMP ('border'), env.interp = LINEAR set by the host
+        return v3(rgb[0], rgb[1], rgb[2]);
+    }
+#endif
+    float4 r = tex_fetch4(env.data, tex_taps(env.h, env.w, DRP_WRAP_CLAMP, DRP_INTERP_LINEAR, a, v));  // device: RGBA-padded
+    return v3(r.x, r.y, r.z);
 }
 
 // ---- surface attributes -----------------------------------------------------------------------------------------
@@ -146,26 +180,44 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
     }
     float2 t0 = ld2(sc.uv, i0), t1 = ld2(sc.uv, i1), t2 = ld2(sc.uv, i2);
     float tu = lerp3(t0.x, t1.x, t2.x, u, v), tv = lerp3(t0.y, t1.y, t2.y, u, v);
-    float bc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, mr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (m.base_color_tex.data) {
-        tex_fetch(m.base_color_tex, tu, tv, bc);
-        if (m.base_color_tex.c < 4) bc[3] = 1.0f;
+    float bc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, mr[4] = {0.0f, 0.0f, 0.0f, 0.0f}, nt[4] = {0.0f, 0.0f, 0.0f, 0.0f}, em[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const bool use_nt = m.has_normal_tex && m.normal_tex.data, use_em = m.has_emissive && m.emissive_tex.data;
+#ifdef __CUDA_ARCH__
+    const bool rgba = true;  // drp_render only accepts RGBA-padded textures (validated on the host side)
+#else
+    const bool rgba = (!m.base_color_tex.data || m.base_color_tex.c == 4) && (!m.mr_tex.data || m.mr_tex.c == 4) &&
+                      (!use_nt || m.normal_tex.c == 4) && (!use_em || m.emissive_tex.c == 4);
+#endif
+    if (rgba) {  // device path: address stage for all textures first, then all loads back to back
+        TexTaps ta, tb, tc, td;
+        if (m.base_color_tex.data) ta = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
+        if (m.mr_tex.data) tb = tex_taps(m.mr_tex.h, m.mr_tex.w, m.mr_tex.wrap, m.mr_tex.interp, tu, tv);
+        if (use_nt) tc = tex_taps(m.normal_tex.h, m.normal_tex.w, m.normal_tex.wrap, m.normal_tex.interp, tu, tv);
+        if (use_em) td = tex_taps(m.emissive_tex.h, m.emissive_tex.w, m.emissive_tex.wrap, m.emissive_tex.interp, tu, tv);
+        if (m.base_color_tex.data) { float4 r = tex_fetch4(m.base_color_tex.data, ta); bc[0] = r.x; bc[1] = r.y; bc[2] = r.z; bc[3] = r.w; }
+        if (m.mr_tex.data) { float4 r = tex_fetch4(m.mr_tex.data, tb); mr[1] = r.y; mr[2] = r.z; }
+        if (use_nt) { float4 r = tex_fetch4(m.normal_tex.data, tc); nt[0] = r.x; nt[1] = r.y; nt[2] = r.z; }
+        if (use_em) { float4 r = tex_fetch4(m.emissive_tex.data, td); em[0] = r.x; em[1] = r.y; em[2] = r.z; }
     }
-    if (m.mr_tex.data) tex_fetch(m.mr_tex, tu, tv, mr);
+#ifndef __CUDA_ARCH__
+    else {
+        if (m.base_color_tex.data) {
+            tex_fetch(m.base_color_tex, tu, tv, bc);
+            if (m.base_color_tex.c < 4) bc[3] = 1.0f;
+        }
+        if (m.mr_tex.data) tex_fetch(m.mr_tex, tu, tv, mr);
+        if (use_nt) tex_fetch(m.normal_tex, tu, tv, nt);
+        if (use_em) tex_fetch(m.emissive_tex, tu, tv, em);
+    }
+#endif
     float a = m.base_color_factor[3] * col[3] * bc[3];
     s.albedo = v3(m.base_color_factor[0] * col[0] * bc[0], m.base_color_factor[1] * col[1] * bc[1], m.base_color_factor[2] * col[2] * bc[2]);
     s.metal = m.metallic_factor * mr[2];
     s.smooth = 1.0f + (-m.roughness_factor) * mr[1];
     if (m.alpha_mode == DRP_ALPHA_MASK) s.alpha = a > m.alpha_cutoff ? 1.0f : 0.0f;
     else if (m.alpha_mode == DRP_ALPHA_BLEND) s.alpha = a;
-    if (m.has_emissive) {
-        float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (m.emissive_tex.data) tex_fetch(m.emissive_tex, tu, tv, e);
-        s.emission = v3(m.emissive_factor[0] * e[0], m.emissive_factor[1] * e[1], m.emissive_factor[2] * e[2]);
-    }
-    if (m.has_normal_tex && m.normal_tex.data) {  // tangent-space normal map, mixin.py:118-123
-        float nt[4];
-        tex_fetch(m.normal_tex, tu, tv, nt);
+    if (m.has_emissive) s.emission = v3(m.emissive_factor[0] * em[0], m.emissive_factor[1] * em[1], m.emissive_factor[2] * em[2]);
+    if (use_nt) {  // tangent-space normal map, mixin.py:118-123
         float nx = 2.0f * nt[0] - 1.0f, ny = 2.0f * nt[1] - 1.0f, nz = 2.0f * nt[2] - 1.0f;
         float4 g0 = ld4(sc.world_tan, i0), g1 = ld4(sc.world_tan, i1), g2 = ld4(sc.world_tan, i2);
         Vec3 vt = v3(lerp3(g0.x, g1.x, g2.x, u, v), lerp3(g0.y, g1.y, g2.y, u, v), lerp3(g0.z, g1.z, g2.z, u, v));
@@ -202,20 +254,19 @@ DRP_HD BounceOut brdf_sample(const SurfaceAttrs& s, float t, Vec3 o, Vec3 d, Vec
         r.next_d = d;
         r.transfer = v3(1.0f, 1.0f, 1.0f);
     } else if (u[1] >= p_spec) {  // diffuse, cosine-weighted about n
-        float z2 = u[2], theta = u[3] * DRP_TAU, xy = sqrtf(1.0f - z2);
+        float z2 = u[2], xy = sqrtf(1.0f - z2);
         float sn, cs;
-        sincosf(theta, &sn, &cs);
+        sincos_2pi(u[3], &sn, &cs);
         r.next_d = tangent_combine(xy * cs, sqrtf(z2), xy * sn, s.normal);
         float den = fmaxf(p_diff, 0.0001f);
         r.transfer = v3(dc.x / den, dc.y / den, dc.z / den);
     } else {  // GGX specular
         float rough = fmaxf(1.0f - s.smooth, 1.0f / 512.0f);
         float a = rough * rough;
-        float phi = DRP_TAU * u[4];
         float ct = sqrtf((1.0f - u[5]) / (1.0f + (a * a - 1.0f) * u[5]));
         float st = sqrtf(1.0f - ct * ct);
         float sn, cs;
-        sincosf(phi, &sn, &cs);
+        sincos_2pi(u[4], &sn, &cs);
         Vec3 h = tangent_combine(cs * st, ct, sn * st, s.normal);
         float hd = dot(h, d);
         r.next_d = d + h * (-2.0f * hd);  // reflect

@@ -71,6 +71,7 @@ struct WfConst {
     int sample_base;    // first sample (within the call) of this batch
     float* accum;
     int* flags;
+    uint32_t cw_bias;   // 0x47000000 (cwbvh.cuh: cw_byte_biased), passed through the constant bank
 };
 
 // ---- ray fetch: each warp claims WF_FETCH consecutive queue slots per atomic ------------------------------------
@@ -146,8 +147,14 @@ struct AosRays {
     int32_t* out_i;
 };
 
+#ifndef DRP_EXTEND_MINBLOCKS
+#define DRP_EXTEND_MINBLOCKS 9
+#endif
+#ifndef DRP_SHADE_MINBLOCKS
+#define DRP_SHADE_MINBLOCKS 5
+#endif
 template <int SRC>
-__global__ void __launch_bounds__(WF_BLOCK) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
+__global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
                                                         float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos) {
     const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
     const int lane = threadIdx.x & 31;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend_cw(const __grid_constant__ 
                 } else {
                     load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
                 }
-                r = cw_make_ray(o, d);
+                r = cw_make_ray(o, d, c.cw_bias);
                 t_best = c.p.t_far;
                 id_best = 0x7fffffff;
                 sp = 0;
@@ -270,7 +277,7 @@ __device__ __forceinline__ void accum_add4(float* p, float a, float b, float c, 
 }
 
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_BLOCK) k_shade(const __grid_constant__ WfConst c, int bounce, const float4* __restrict__ qa,
+__global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WfConst c, int bounce, const float4* __restrict__ qa,
                                                     const float4* __restrict__ qb, const float4* __restrict__ qt, const float2* __restrict__ hit,
                                                     float4* __restrict__ oa, float4* __restrict__ ob, float4* __restrict__ ot,
                                                     const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor) {
@@ -455,6 +462,15 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     if (p.rng_mode == DRP_RNG_REPLAY && !p.replay_u) { drp_set_error("drp_render: replay mode without replay_u"); return DRP_ERR_INVALID; }
     if (!p.ndc_x || !p.ndc_y || !p.jitter_x || !p.jitter_y || !p.sample_ids) { drp_set_error("drp_render: missing raygen tables"); return DRP_ERR_INVALID; }
     if (scene->n_materials <= 0 || !scene->materials) { drp_set_error("drp_render: scene has no materials"); return DRP_ERR_INVALID; }
+    {   // the shade kernel fetches texels with one 128-bit load: every texture must be RGBA (diffrp_b200.flatten.pad_rgba)
+        auto ok = [](const drp_texture_t& t) { return t.data == nullptr || (t.c == 4 && t.h > 0 && t.w > 0); };
+        bool all = ok(scene->env);
+        for (int k = 0; k < scene->n_materials; ++k) {
+            const drp_material_t& m = scene->materials[k];
+            all = all && ok(m.base_color_tex) && ok(m.mr_tex) && ok(m.normal_tex) && ok(m.emissive_tex);
+        }
+        if (!all) { drp_set_error("drp_render: textures must be 4-channel (RGBA-padded) fp32 images"); return DRP_ERR_INVALID; }
+    }
     const int64_t HW = (int64_t)p.height * p.width;
     if (HW > WF_MAX_BATCH_RAYS) { drp_set_error("drp_render: more than 2^24 pixels per frame not supported"); return DRP_ERR_INVALID; }
     if (p.n_samples == 0) return DRP_OK;
@@ -483,6 +499,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     c.R_total = HW * p.n_samples;
     c.accum = accum;
     c.flags = h->dev_flags;
+    c.cw_bias = 0x47000000u;
     if (!ws->have_box) {  // padded scene box for the exact compaction rule: one host read per handle, then cached
         uint32_t ob[12];
         DRP_CUDA_CHECK(cudaMemcpyAsync(ob, h->bounds, sizeof(ob), cudaMemcpyDeviceToHost, s));
@@ -561,7 +578,7 @@ int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, fl
     if (n > 0x7fffff00) { drp_set_error("drp_trace: more than 2^31 rays per call"); return DRP_ERR_INVALID; }
     WfConst c;
     memset(&c, 0, sizeof(c));
-    c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.flags = h->dev_flags;
+    c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.flags = h->dev_flags; c.cw_bias = 0x47000000u;
     int* cursor = ws->counters + 250;
     DRP_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int), s));
     AosRays aos = {ro, rd, out_t, out_i};
@@ -589,6 +606,14 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
         return DRP_ERR_INVALID;
     }
     return DRP_OK;
+}
+
+#define DRP_STR2(x) #x
+#define DRP_STR(x) DRP_STR2(x)
+extern "C" const char* drp_build_config(void) {
+    return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
+           " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
+           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

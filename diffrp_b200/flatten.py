@@ -72,9 +72,23 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
         cat(wn, [0, 3]), cat(wt, [0, 4]), cat(tm, [0], torch.int32))
 
 
-def material_descriptions(objs: List, dev) -> Optional[List[dict]]:
-    """Per-object drp_material_t descriptions (textures moved to ``dev``), or None if any material is Python-only."""
+def pad_rgba(img: torch.Tensor) -> torch.Tensor:
+    """(H,W,1|3|4) -> (H,W,4): the fused kernel fetches every texel with one 128-bit load.  One channel broadcasts
+    (what ``factor * color * tex`` does in the reference), RGB gets alpha = 1."""
+    c = img.shape[-1]
+    if c == 4:
+        return img.contiguous()
+    if c == 1:
+        return img.expand(*img.shape[:-1], 4).contiguous()
+    assert c == 3, "textures must have 1, 3 or 4 channels"
+    return torch.cat([img, torch.ones_like(img[..., :1])], -1).contiguous()
+
+
+def material_descriptions(objs: List, dev, rgba: bool = False) -> Optional[List[dict]]:
+    """Per-object drp_material_t descriptions (textures moved to ``dev``, RGBA-padded for the CUDA path when ``rgba``),
+    or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
     descs = []
+    uploaded = {}
     for o in objs:
         d = o.material.fused_description() if hasattr(o.material, 'fused_description') else None
         if d is None:
@@ -82,7 +96,12 @@ def material_descriptions(objs: List, dev) -> Optional[List[dict]]:
         d = dict(d)
         for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
             if d.get(k) is not None:
-                d[k] = dict(d[k], image=d[k]['image'].to(dev, torch.float32).contiguous())
+                src = d[k]['image']
+                key = (src.data_ptr(), tuple(src.shape))
+                if key not in uploaded:
+                    img = src.to(dev, torch.float32, non_blocking=True)
+                    uploaded[key] = pad_rgba(img) if rgba else img.contiguous()
+                d[k] = dict(d[k], image=uploaded[key])
         descs.append(d)
     if not descs:
         descs = [dict(kind='default', tint=None)]

@@ -26,7 +26,7 @@ from .camera import Camera
 from .ops import small_matrix_inverse
 from .raycaster import B200Raycaster, _stream_ptr
 from .scene import Scene, ImageEnvironmentLight
-from .flatten import VertexArrayObject, flatten_scene, material_descriptions
+from .flatten import VertexArrayObject, flatten_scene, material_descriptions, pad_rgba
 
 
 @dataclass
@@ -214,14 +214,14 @@ class PathTracingSession:
     @_cached
     def _fused_scene(self):
         """drp_scene_t for the fused kernels, or None when some material only exists as Python code."""
-        descs = material_descriptions(self.scene.objects, self.device)
+        descs = material_descriptions(self.scene.objects, self.device, rgba=True)
         if descs is None:
             return None
         vao = self.vertex_array_object()
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
                       tris=vao.tris, tri_material=vao.tri_material)
         env = self._single_env_light()
-        return _abi.pack_scene(arrays, descs, None if env is None else dict(image=env), lambda t: t.data_ptr())
+        return _abi.pack_scene(arrays, descs, None if env is None else dict(image=pad_rgba(env)), lambda t: t.data_ptr())
 
     def _section_sample_ids(self, ids: torch.Tensor):
         """Split like the reference: sections = min(spp, ceil(H*W*spp / ray_split_size)) (path_tracing.py:318-320)."""

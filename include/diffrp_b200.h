@@ -52,7 +52,7 @@ extern "C" {
 
 typedef struct drp_texture {
     const float* data; /* (h, w, c) fp32, row 0 = top (v = 1)      */
-    int32_t h, w, c;   /* c in {1, 3, 4}; data == NULL => absent   */
+    int32_t h, w, c;   /* channels; drp_render requires c == 4 (RGBA-padded; RGB gets alpha 1); data == NULL => absent */
     int32_t wrap;      /* DRP_WRAP_*                               */
     int32_t interp;    /* DRP_INTERP_*                             */
     int32_t _pad;
@@ -134,6 +134,8 @@ typedef struct drp_render_params {
 /* ---- entry points -------------------------------------------------------------------------- */
 
 int drp_abi_version(void);
+/* build configuration string (compile-time tuning macros, compile date) -- for logs and A/B experiments */
+const char* drp_build_config(void);
 const char* drp_last_error(void);
 int drp_set_log_level(int level);
 
