@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -55,6 +55,7 @@ class RenderParams(C.Structure):
         ("ray_depth", C.c_int32), ("n_samples", C.c_int32),
         ("last_bounce_skybox", C.c_int32), ("rng_mode", C.c_int32),
         ("compaction", C.c_int32), ("_pad", C.c_int32),
+        ("tile_x0", C.c_int32), ("tile_y0", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
         ("step_epsilon", C.c_float), ("t_far", C.c_float), ("t_near", C.c_float), ("_padf", C.c_float),
         ("cam_pos", C.c_float * 4),
         ("inv_vp", C.c_float * 16),

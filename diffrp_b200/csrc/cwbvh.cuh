@@ -21,8 +21,10 @@
 #include "lbvh.cuh"
 #include "traverse.cuh"
 
+// A/B-measured on B200 (profiles/README.md): packing <= 4 children into slots 0..3 and skipping the empty half LOSES ~1-3 %
+// (worse front-to-back order, extra divergent branch), so it is off.
 #ifndef DRP_CW_HALFSKIP
-#define DRP_CW_HALFSKIP 1
+#define DRP_CW_HALFSKIP 0
 #endif
 #define CW_MAX_LEAF 3
 #define CW_STACK 48

@@ -65,7 +65,8 @@ struct WfConst {
     const float4* tris;
     float box_lo[3], box_hi[3];
     float eps;
-    int HW;
+    int HW;             // pixels rendered per sample (the tile's pixel count when tile sharding)
+    int tx0, ty0, tw;   // tile origin and width (tw == frame width, origin 0 for a full frame)
     int64_t R;          // rays in this batch
     int64_t R_total;    // rays of the whole call (replay indexing)
     int sample_base;    // first sample (within the call) of this batch
@@ -85,7 +86,8 @@ __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restr
     if (PRIMARY) {
         ray_index = k + c.sample_base * c.HW;  // index within the call: s_local * HW + pixel  (path_tracing.py:329-331)
         int s = ray_index / c.HW, pix = ray_index - s * c.HW;
-        int y = pix / c.p.width, x = pix - y * c.p.width;
+        int y = pix / c.tw, x = pix - y * c.tw;
+        x += c.tx0; y += c.ty0;
         float gx = __ldg(c.p.ndc_x + x) + __ldg(c.p.jitter_x + s);
         float gy = __ldg(c.p.ndc_y + y) + __ldg(c.p.jitter_y + s);
         gen_primary_ray(c.p.inv_vp, c.p.cam_pos, c.p.t_near, gx, gy, o, d);
@@ -132,10 +134,21 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 //  * triangle postponing: a triangle group is pushed back on the stack when fewer than CWK_POSTPONE of the warp's active
 //    lanes have triangles to test, so that the warp stays in the node phase.
 // Scheduling only: the closest hit found is the exhaustive one whatever the order (min t, then min id).
+#ifndef CWK_SMEM_STACK
+#define CWK_SMEM_STACK 8
+#endif
+#ifndef CWK_CHUNK
 #define CWK_CHUNK 256
+#endif
+#ifndef CWK_ND
 #define CWK_ND 4
+#endif
+#ifndef CWK_NW
 #define CWK_NW 16
+#endif
+#ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
+#endif
 
 #define SRC_QUEUE 0    // rays from the float4 queues, result to hit[]
 #define SRC_PRIMARY 1  // rays generated from the ray index, result to hit[]
@@ -166,8 +179,26 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     float t_best = 0.0f;
     int id_best = 0, sp = 0;
     uint32_t ng_x = 0, ng_y = 0, tg_x = 0, tg_y = 0;
-    uint32_t st_x[CW_STACK], st_y[CW_STACK];
+    // traversal stack: the first CWK_SMEM_STACK entries of every thread live in shared memory (conflict-free 64-bit
+    // accesses, [entry][thread]), deeper entries spill to local memory.  ncu: the local-memory stack of the first
+    // version was ~40 % of the kernel's L1 wavefronts.
+    __shared__ uint2 s_stack[CWK_SMEM_STACK][WF_BLOCK];
+    uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
+    const int tid = threadIdx.x;
     bool overflow = false;
+#define CWK_PUSH(X, Y)                                                                   \
+    do {                                                                                 \
+        if (sp < CWK_SMEM_STACK) s_stack[sp][tid] = make_uint2((X), (Y));                \
+        else if (sp < CW_STACK) { st_x[sp - CWK_SMEM_STACK] = (X); st_y[sp - CWK_SMEM_STACK] = (Y); } \
+        else overflow = true;                                                            \
+        if (sp < CW_STACK) ++sp;                                                         \
+    } while (0)
+#define CWK_POP(X, Y)                                                                    \
+    do {                                                                                 \
+        --sp;                                                                            \
+        if (sp < CWK_SMEM_STACK) { uint2 _v = s_stack[sp][tid]; (X) = _v.x; (Y) = _v.y; } \
+        else { (X) = st_x[sp - CWK_SMEM_STACK]; (Y) = st_y[sp - CWK_SMEM_STACK]; }       \
+    } while (0)
     for (;;) {
         // ---- refill idle lanes --------------------------------------------------------------------------------
         const unsigned need = __ballot_sync(0xffffffffu, k < 0);
@@ -219,10 +250,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     const int child_bit = 31 - __clz(hits);
                     const uint32_t base = ng_x;
                     ng_y &= ~(1u << child_bit);
-                    if (ng_y > 0x00ffffffu) {
-                        if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
-                        else overflow = true;
-                    }
+                    if (ng_y > 0x00ffffffu) CWK_PUSH(ng_x, ng_y);
                     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
                     const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
                     const float4* p = c.nodes + 5 * (int64_t)(base + rel);
@@ -239,7 +267,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                 const int total_active = __popc(__activemask());
                 while (tg_y != 0) {
                     if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
-                        st_x[sp] = tg_x; st_y[sp] = tg_y; ++sp;  // postpone: too few lanes have triangles
+                        CWK_PUSH(tg_x, tg_y);  // postpone: too few lanes have triangles
                         break;
                     }
                     const int ti = 31 - __clz(tg_y);
@@ -248,8 +276,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                 }
                 if (ng_y <= 0x00ffffffu) {
                     if (sp > 0) {
-                        --sp;
-                        ng_x = st_x[sp]; ng_y = st_y[sp];
+                        CWK_POP(ng_x, ng_y);
                     } else {  // ray finished
                         const bool is_hit = t_best < c.p.t_far;
                         if (SRC == SRC_AOS) {
@@ -312,7 +339,8 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                 }
                 Vec3 env = (always_sky || !is_hit) ? env_fetch(c.scene.env, d) : v3(0, 0, 0);  // path_tracing.py:267-269
                 float u[6];
-                const int pix = ri % c.HW;
+                const int lpix = ri % c.HW, ly = lpix / c.tw;
+                const int pix = (c.ty0 + ly) * c.p.width + c.tx0 + (lpix - ly * c.tw);  // global pixel: accumulator row and RNG key
                 if (c.p.rng_mode == DRP_RNG_REPLAY) {
 #pragma unroll
                     for (int q = 0; q < 6; ++q) u[q] = __ldg(c.p.replay_u + ((int64_t)bounce * 6 + q) * c.R_total + ri);
@@ -471,7 +499,12 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
         }
         if (!all) { drp_set_error("drp_render: textures must be 4-channel (RGBA-padded) fp32 images"); return DRP_ERR_INVALID; }
     }
-    const int64_t HW = (int64_t)p.height * p.width;
+    const bool tiled = p.tile_w > 0 && p.tile_h > 0;
+    if (tiled && (p.tile_x0 < 0 || p.tile_y0 < 0 || p.tile_x0 + p.tile_w > p.width || p.tile_y0 + p.tile_h > p.height)) {
+        drp_set_error("drp_render: tile outside the frame");
+        return DRP_ERR_INVALID;
+    }
+    const int64_t HW = tiled ? (int64_t)p.tile_w * p.tile_h : (int64_t)p.height * p.width;
     if (HW > WF_MAX_BATCH_RAYS) { drp_set_error("drp_render: more than 2^24 pixels per frame not supported"); return DRP_ERR_INVALID; }
     if (p.n_samples == 0) return DRP_OK;
     DeviceGuard guard(h->device);
@@ -496,6 +529,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     c.tris = h->packed;
     c.eps = h->eps;
     c.HW = (int)HW;
+    c.tx0 = tiled ? p.tile_x0 : 0; c.ty0 = tiled ? p.tile_y0 : 0; c.tw = tiled ? p.tile_w : p.width;
     c.R_total = HW * p.n_samples;
     c.accum = accum;
     c.flags = h->dev_flags;
@@ -613,7 +647,7 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
 extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
-           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE);
+           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

@@ -47,8 +47,10 @@ class PathTracingSessionOptions:
         seed (int): key of the native RNG.
         compaction (bool): drop rays that provably contribute nothing to any output (exact; the reference keeps
             tracing them with zero throughput).
-        shard_rank / shard_world: this process renders global sample indices ``rank::world`` (scene replicated) and the
-            fp32 accumulators are summed with ``torch.distributed.all_reduce`` when a process group exists.
+        shard_rank / shard_world: this process renders its share of the frame (scene replicated) and the fp32 accumulators
+            are summed with ``torch.distributed.all_reduce`` when a process group exists.  ``shard_mode='spp'``: global
+            sample indices ``rank::world`` of every pixel; ``shard_mode='tile'``: every sample of the ``tile_size``^2 tiles
+            ``rank::world`` (row-major tile order), the rest of the accumulator stays zero.
     """
     ray_depth: int = 3
     ray_spp: int = 16
@@ -65,6 +67,8 @@ class PathTracingSessionOptions:
     compaction: bool = True
     shard_rank: int = 0
     shard_world: int = 1
+    shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
+    tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
 
 
 @dataclass
@@ -256,11 +260,18 @@ class PathTracingSession:
         H, W = self.camera.resolution()
         return torch.zeros([H * W, _abi.ACCUM_CHANNELS], dtype=torch.float32, device=self.device)
 
-    def render_samples(self, sample_ids: torch.Tensor, accum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def tiles(self):
+        """Row-major list of (x0, y0, w, h) tiles of the frame (y counted from the bottom row, like the accumulator)."""
+        H, W = self.camera.resolution()
+        T = max(1, int(self.options.tile_size))
+        return [(x, y, min(T, W - x), min(T, H - y)) for y in range(0, H, T) for x in range(0, W, T)]
+
+    def render_samples(self, sample_ids: torch.Tensor, accum: Optional[torch.Tensor] = None, tile=None) -> torch.Tensor:
         """
         Progressive entry point of the fused path: add the given GLOBAL sample indices (into the n = ``ray_spp``
         Hammersley sequence) of every pixel to ``accum`` (H*W, 16) and return it.  Asynchronous on the current stream.
-        ``pbr()`` is ``finalize(all_reduce(render_samples(my share)))``.
+        ``pbr()`` is ``finalize(all_reduce(render_samples(my share)))``.  ``tile=(x0, y0, w, h)`` restricts the call to a
+        pixel rectangle (tile sharding); RNG streams and accumulator rows are keyed by the global pixel either way.
         """
         opt, dev = self.options, self.device
         scene_struct, tab, p, _keep = self._render_setup()
@@ -278,6 +289,9 @@ class PathTracingSession:
         else:
             raise ValueError("rng must be 'native' or 'torch'")
         L, stream = lib(), _stream_ptr(dev)
+        p.tile_x0, p.tile_y0, p.tile_w, p.tile_h = tile if tile is not None else (0, 0, 0, 0)
+        if tile is not None and opt.rng == 'torch':
+            raise ValueError("rng='torch' (reference replay) renders whole frames only")
         for ids in chunks:
             ids = ids.contiguous()
             idl = ids.long()
@@ -301,6 +315,14 @@ class PathTracingSession:
         opt = self.options
         if opt.rng == 'torch' and opt.shard_world > 1:
             raise ValueError("rng='torch' (reference replay) is a single-process mode")
+        if opt.shard_mode == 'tile' and opt.shard_world > 1:
+            accum = self.new_accumulators()
+            ids = torch.arange(opt.ray_spp, dtype=torch.int32, device=self.device)
+            for tile in self.tiles()[opt.shard_rank::opt.shard_world]:
+                self.render_samples(ids, accum, tile=tile)
+            return accum
+        if opt.shard_mode not in ('spp', 'tile'):
+            raise ValueError("shard_mode must be 'spp' or 'tile'")
         return self.render_samples(shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device))
 
     def finalize(self, accum: torch.Tensor):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 1
+#define DRP_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -112,6 +112,8 @@ typedef struct drp_render_params {
     int32_t rng_mode;           /* DRP_RNG_*                                                */
     int32_t compaction;         /* 1: drop rays that provably contribute nothing (default)  */
     int32_t _pad;
+    int32_t tile_x0, tile_y0;   /* tile sharding: render only the pixel rectangle [x0, x0+w) x [y0, y0+h) (y counted  */
+    int32_t tile_w, tile_h;     /* from the bottom row, like ndc_y); w == 0 or h == 0 means the whole frame            */
     float step_epsilon;         /* pbr_ray_step_epsilon                                     */
     float t_far;                /* camera_far()  (mixin.py:41-44)                           */
     float t_near;               /* P[2,3]/(P[2,2]-1) (mixin.py:38)                          */

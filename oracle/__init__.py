@@ -176,7 +176,7 @@ def sampler_brdf(attrs, t, rays_o, rays_d, env_radiance, u6):
 
 
 def make_params(height, width, ray_depth, t_far, t_near, cam_pos, inv_vp, ndc_x, ndc_y, jitter_x, jitter_y,
-                sample_ids=None, step_epsilon=1e-3, last_bounce_skybox=False, seed=0, replay_u=None):
+                sample_ids=None, step_epsilon=1e-3, last_bounce_skybox=False, seed=0, replay_u=None, tile=None):
     """Host-pointer drp_render_params_t + keepalive."""
     p = _abi.RenderParams()
     keep = dict(ndc_x=_f32(ndc_x), ndc_y=_f32(ndc_y), jitter_x=_f32(jitter_x), jitter_y=_f32(jitter_y))
@@ -189,11 +189,13 @@ def make_params(height, width, ray_depth, t_far, t_near, cam_pos, inv_vp, ndc_x,
     p.cam_pos[:3] = [float(x) for x in cam_pos]
     p.inv_vp[:] = [float(x) for x in np.asarray(inv_vp, np.float32).reshape(-1)]
     p.seed = seed
+    if tile is not None:
+        p.tile_x0, p.tile_y0, p.tile_w, p.tile_h = [int(x) for x in tile]
     for k in ('ndc_x', 'ndc_y', 'jitter_x', 'jitter_y', 'sample_ids'):
         setattr(p, k, _p(keep[k]))
     if replay_u is not None:
         keep['replay_u'] = _f32(replay_u)
-        assert keep['replay_u'].size == ray_depth * 6 * n * height * width
+        assert keep['replay_u'].size == ray_depth * 6 * n * (height * width if tile is None else tile[2] * tile[3])
         p.replay_u = _p(keep['replay_u'])
         p.rng_mode = _abi.RNG_REPLAY
     else:

@@ -122,12 +122,15 @@ void orc_env_lookup(const drp_texture_t* env, const float* rays_d, int64_t n, fl
 /* ---- primary rays -------------------------------------------------------------------------------------- */
 void orc_raygen(const drp_render_params_t* p, float jx, float jy, const float* ndc_x, const float* ndc_y, float* o,
                 float* d) {
-    const int H = p->height, W = p->width;
+    /* whole frame, or the tile [x0, x0+w) x [y0, y0+h) when tile sharding (rays stored tile-locally) */
+    const int tiled = p->tile_w > 0 && p->tile_h > 0;
+    const int H = tiled ? p->tile_h : p->height, W = tiled ? p->tile_w : p->width;
+    const int x0 = tiled ? p->tile_x0 : 0, y0 = tiled ? p->tile_y0 : 0;
     const float* m = p->inv_vp;
 #pragma omp parallel for
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
-            float g[4] = {ndc_x[x] + jx, ndc_y[y] + jy, -1.0f, 1.0f};
+            float g[4] = {ndc_x[x0 + x] + jx, ndc_y[y0 + y] + jy, -1.0f, 1.0f};
             float q[4];
             for (int k = 0; k < 4; ++k) q[k] = g[0] * m[4 * k] + g[1] * m[4 * k + 1] + g[2] * m[4 * k + 2] + g[3] * m[4 * k + 3];
             float dir[3] = {q[0] / q[3] - p->cam_pos[0], q[1] / q[3] - p->cam_pos[1], q[2] / q[3] - p->cam_pos[2]};
@@ -293,7 +296,9 @@ void orc_sampler_brdf(const float* attrs, const float* t, const float* rays_o, c
 
 /* ---- bounce loop ------------------------------------------------------------------------------------------ */
 int64_t orc_render(const orc_bvh_t* bvh, const drp_scene_t* scene, const drp_render_params_t* p, float* accum) {
-    const int64_t HW = (int64_t)p->height * p->width;
+    const int tiled = p->tile_w > 0 && p->tile_h > 0;
+    const int TW = tiled ? p->tile_w : p->width, TX0 = tiled ? p->tile_x0 : 0, TY0 = tiled ? p->tile_y0 : 0;
+    const int64_t HW = tiled ? (int64_t)p->tile_w * p->tile_h : (int64_t)p->height * p->width;
     const int64_t R_total = HW * p->n_samples;
     float* o = (float*)malloc(sizeof(float) * 3 * HW);
     float* d = (float*)malloc(sizeof(float) * 3 * HW);
@@ -313,17 +318,18 @@ int64_t orc_render(const orc_bvh_t* bvh, const drp_scene_t* scene, const drp_ren
 #pragma omp parallel for schedule(static)
             for (int64_t px = 0; px < HW; ++px) {
                 const int hit = t[px] < p->t_far;
+                const int64_t gpx = (int64_t)(TY0 + px / TW) * p->width + TX0 + px % TW; /* global pixel (accumulator row, RNG key) */
                 float env[3], u[6], rad[3], tr[3], no[3], nd[3];
                 env_fetch(&scene->env, d + 3 * px, env);
                 if (!always_sky && hit) env[0] = env[1] = env[2] = 0.0f; /* path_tracing.py:268-269 */
                 if (p->rng_mode == DRP_RNG_REPLAY) {
                     for (int k = 0; k < 6; ++k) u[k] = p->replay_u[((int64_t)b * 6 + k) * R_total + (int64_t)s * HW + px];
                 } else {
-                    orc_philox_uniform6(p->seed, (uint32_t)px, (uint32_t)p->sample_ids[s], (uint32_t)b, u);
+                    orc_philox_uniform6(p->seed, (uint32_t)gpx, (uint32_t)p->sample_ids[s], (uint32_t)b, u);
                 }
                 const float* at = attrs + 12 * px;
                 brdf_one(at, t[px], o + 3 * px, d + 3 * px, env, u, rad, tr, no, nd);
-                float* acc = accum + DRP_ACCUM_CHANNELS * px;
+                float* acc = accum + DRP_ACCUM_CHANNELS * gpx;
                 for (int k = 0; k < 3; ++k) acc[k] += T[3 * px + k] * rad[k]; /* path_tracing.py:336 */
                 acc[3] += at[8];                                             /* :337 */
                 if (b == 0) {                                                /* :340-347, extras at :278 */

@@ -191,14 +191,17 @@ extern "C" void hs_stats(const HsBvh* h, int64_t* out /* [n_nodes, n_leaves, max
 
 extern "C" int64_t hs_render(const HsBvh* h, const drp_scene_t* scene, const drp_render_params_t* pp, float eps, float* accum) {
     const drp_render_params_t& p = *pp;
-    const int HW = p.height * p.width;
+    const bool tiled = p.tile_w > 0 && p.tile_h > 0;
+    const int tw = tiled ? p.tile_w : p.width, th = tiled ? p.tile_h : p.height, tx0 = tiled ? p.tile_x0 : 0, ty0 = tiled ? p.tile_y0 : 0;
+    const int HW = tw * th;
     const int64_t R_total = (int64_t)HW * p.n_samples;
     int64_t traced = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : traced)
-    for (int pix = 0; pix < HW; ++pix) {
+    for (int lpix = 0; lpix < HW; ++lpix) {
         for (int s = 0; s < p.n_samples; ++s) {
-            const int ri = s * HW + pix;
-            int y = pix / p.width, x = pix - y * p.width;
+            const int ri = s * HW + lpix;
+            int y = ty0 + lpix / tw, x = tx0 + lpix % tw;
+            const int pix = y * p.width + x;
             Vec3 o, d, T = v3(1, 1, 1);
             gen_primary_ray(p.inv_vp, p.cam_pos, p.t_near, p.ndc_x[x] + p.jitter_x[s], p.ndc_y[y] + p.jitter_y[s], o, d);
             for (int b = 0; b < p.ray_depth; ++b) {

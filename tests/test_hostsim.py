@@ -94,3 +94,23 @@ def test_shading_logic_matches_oracle(hs, scene_name, last):
     hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc2.ctypes.data)
     hs.hs_free(h)
     np.testing.assert_allclose(acc2, acc, rtol=2e-5, atol=2e-5)
+
+
+def test_tile_render_matches_oracle_tile(hs):
+    scene = scenes.mixed_scene()
+    cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
+    vao, hscene, p, keep = scenes.oracle_inputs(scene, cam, 2, 3, seed=5)
+    bvh = oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy())
+    whole, _ = oracle.render(bvh, hscene, p)
+    p.tile_x0, p.tile_y0, p.tile_w, p.tile_h = 16, 8, 24, 20
+    tile, _ = oracle.render(bvh, hscene, p)
+    img_w, img_t = whole.reshape(40, 56, 16), tile.reshape(40, 56, 16)
+    np.testing.assert_allclose(img_t[8:28, 16:40], img_w[8:28, 16:40], rtol=1e-6, atol=1e-6)  # same pixels, same RNG keys
+    mask = np.ones((40, 56), bool); mask[8:28, 16:40] = False
+    assert (img_t[mask] == 0).all()
+    wp, tr = hscene.arrays['world_pos'], hscene.arrays['tris']
+    h = hs.hs_build(wp.ctypes.data, tr.ctypes.data, len(wp), len(tr))
+    acc2 = np.zeros_like(tile)
+    hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc2.ctypes.data)
+    hs.hs_free(h)
+    np.testing.assert_allclose(acc2, tile, rtol=2e-5, atol=2e-5)

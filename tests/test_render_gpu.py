@@ -130,3 +130,16 @@ def test_generic_python_path_agrees_with_fused_kernels():
     errs = image_errors(fused, generic)
     for k, (emax, emean, frac) in errs.items():
         assert frac <= OUTLIER_FRAC and emean <= INLIER_MEAN, (k, errs[k])
+
+
+def test_tile_sharding_equals_whole_frame():
+    """shard_mode='tile': every tile rendered separately (two ranks' shares) sums to the whole-frame accumulator."""
+    scene = scenes.mixed_scene()
+    cam = drp.PerspectiveCamera.from_orbit(h=80, w=112, radius=3.0, azim=10, elev=12, origin=[0.0, -0.1, 0.0], fov=32)
+    base = dict(ray_spp=4, ray_depth=3, rng='native', seed=8)
+    whole = run_session(scene, cam, **base).render_accumulators()
+    parts = [run_session(scene, cam, shard_rank=r, shard_world=2, shard_mode='tile', tile_size=48, **base).render_accumulators() for r in range(2)]
+    assert (parts[0] != 0).any() and (parts[1] != 0).any()
+    # disjoint support: a pixel belongs to exactly one rank
+    assert not ((parts[0].abs().sum(-1) > 0) & (parts[1].abs().sum(-1) > 0)).any()
+    torch.testing.assert_close(parts[0] + parts[1], whole, rtol=1e-5, atol=1e-5)
