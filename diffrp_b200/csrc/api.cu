@@ -170,6 +170,12 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     DRP_CUDA_CHECK(alloc_async(&b.box_hi, 2 * nn, s));
     DRP_CUDA_CHECK(alloc_async(&b.arrive, nn, s));
     DRP_CUDA_CHECK(alloc_async(&b.collapsed, nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.count, 2 * nn, s));
+    static const bool greedy = getenv("DRP_COLLAPSE") && strcmp(getenv("DRP_COLLAPSE"), "greedy") == 0;  // A/B switch; default = optimal (DP)
+    if (h->wide && !greedy) {
+        DRP_CUDA_CHECK(alloc_async(&b.dp_cost, 16 * nn, s));
+        DRP_CUDA_CHECK(alloc_async(&b.dp_dec, 16 * nn, s));
+    }
     DRP_CUDA_CHECK(cudaMemsetAsync(b.arrive, 0, sizeof(int) * nn, s));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.collapsed, 0, nn, s));
 
@@ -222,7 +228,7 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     }
     DRP_CUDA_CHECK(cudaGetLastError());
     void* temps[] = {b.prim_lo, b.prim_hi, keys_in, vals_in, b.keys, b.vals, b.left, b.right, b.parent, b.range_first,
-                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters};
+                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters, b.count, b.dp_cost, b.dp_dec};
     for (void* p : temps)
         if (p) DRP_CUDA_CHECK(cudaFreeAsync(p, s));
     {

@@ -11,6 +11,7 @@
 
 #ifdef DRP_HOSTSIM
 #include <cmath>
+#include <cstdlib>
 #define DRP_HD inline
 #define DRP_D inline
 struct float2 { float x, y; };

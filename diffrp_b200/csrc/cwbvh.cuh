@@ -41,8 +41,19 @@ struct CwBuild {
 };
 
 DRP_HD bool cw_is_leaf_child(const LbvhBuild& b, int c) { return c >= b.n - 1 || b.collapsed[c]; }
-DRP_HD int cw_leaf_count(const LbvhBuild& b, int c) { return c >= b.n - 1 ? 1 : b.range_last[c] - b.range_first[c] + 1; }
-DRP_HD int cw_leaf_first(const LbvhBuild& b, int c) { return c >= b.n - 1 ? c - (b.n - 1) : b.range_first[c]; }
+DRP_HD int cw_leaf_count(const LbvhBuild& b, int c) { return b.count[c]; }
+// sorted positions of the (<= CW_MAX_LEAF) primitives under binary node c, by walking the subtree (the PLOC tree does not
+// keep primitives of a subtree contiguous in Morton order)
+DRP_HD int cw_leaf_gather(const LbvhBuild& b, int c, int* out) {
+    int stack[8], sp = 0, k = 0;
+    stack[sp++] = c;
+    while (sp > 0) {
+        int nd = stack[--sp];
+        if (nd >= b.n - 1) { if (k < CW_MAX_LEAF) out[k] = nd - (b.n - 1); ++k; }
+        else { stack[sp++] = b.right[nd]; stack[sp++] = b.left[nd]; }
+    }
+    return k;
+}
 
 DRP_HD uint32_t cw_pack4(const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
 
@@ -52,21 +63,42 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
     const LbvhBuild& b = cw.b;
     const int root = cw.work[ni];
     int child[8];
-    int k = 2;
-    child[0] = b.left[root];
-    child[1] = b.right[root];
-    while (k < 8) {  // open the child with the largest surface area until 8 children or nothing left to open
-        int best = -1;
-        float best_area = -1.0f;
-        for (int j = 0; j < k; ++j)
-            if (!cw_is_leaf_child(b, child[j])) {
-                float a = b.box_hi[child[j]].w;
-                if (a > best_area) { best_area = a; best = j; }
-            }
-        if (best < 0) break;
-        int c = child[best];
-        child[best] = b.left[c];
-        child[k++] = b.right[c];
+    int k = 0;
+    if (b.dp_dec) {
+        // children chosen by the optimal collapse (lbvh_dp_node): split the 8 slots between the two binary children as
+        // decided bottom-up, then resolve each share recursively
+        int st_node[16], st_i[16], sp = 0;
+        const int kl = b.dp_dec[8 * (int64_t)root];
+        st_node[sp] = b.right[root]; st_i[sp] = 8 - kl; ++sp;
+        st_node[sp] = b.left[root]; st_i[sp] = kl; ++sp;
+        while (sp > 0) {
+            --sp;
+            int nd = st_node[sp], i = st_i[sp];
+            if (nd >= b.n - 1) { child[k++] = nd; continue; }  // a single primitive
+            const uint8_t* dec = b.dp_dec + 8 * (int64_t)nd;
+            while (i > 1 && dec[i] == 0) --i;                  // "same as i-1"
+            if (i == 1) { child[k++] = nd; continue; }         // one slot: leaf or internal wide node (collapsed flag)
+            const int kk = dec[i];
+            st_node[sp] = b.right[nd]; st_i[sp] = i - kk; ++sp;
+            st_node[sp] = b.left[nd]; st_i[sp] = kk; ++sp;
+        }
+    } else {
+        k = 2;
+        child[0] = b.left[root];
+        child[1] = b.right[root];
+        while (k < 8) {  // greedy: open the child with the largest surface area until 8 children or nothing left to open
+            int best = -1;
+            float best_area = -1.0f;
+            for (int j = 0; j < k; ++j)
+                if (!cw_is_leaf_child(b, child[j])) {
+                    float a = b.box_hi[child[j]].w;
+                    if (a > best_area) { best_area = a; best = j; }
+                }
+            if (best < 0) break;
+            int c = child[best];
+            child[best] = b.left[c];
+            child[k++] = b.right[c];
+        }
     }
     // padded child boxes and the node box
     float lo[8][3], hi[8][3], nlo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {-3e38f, -3e38f, -3e38f};
@@ -163,9 +195,10 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
             if (child_base + rank < cw.capacity) cw.work[child_base + rank] = c;
             ++rank;
         } else {
-            int first = cw_leaf_first(b, c), cnt = cw_leaf_count(b, c);
+            int pos[CW_MAX_LEAF];
+            const int cnt = cw_leaf_gather(b, c, pos);
             for (int t = 0; t < cnt; ++t) {
-                int prim = (int)b.vals[first + t];
+                int prim = (int)b.vals[pos[t]];
                 Vec3 A = load_vert(b.verts, b.tris[3 * (int64_t)prim]);
                 Vec3 B = load_vert(b.verts, b.tris[3 * (int64_t)prim + 1]);
                 Vec3 C = load_vert(b.verts, b.tris[3 * (int64_t)prim + 2]);

@@ -48,6 +48,10 @@ struct LbvhBuild {
     float4* box_hi;         // (2n-1) xyz = max, w = surface area
     int* arrive;            // (n-1) arrival counters, zero-initialised
     uint8_t* collapsed;     // (n-1)
+    int* count;             // (2n-1) primitives under each node
+    // wide-layout collapse by dynamic programming (cwbvh.cuh); null for the binary layout
+    float* dp_cost;         // (2n-1, 8): [i] = optimal SAH cost of the subtree as a forest of at most i wide-node children, i = 1..7
+    uint8_t* dp_dec;        // (2n-1, 8): [0] = left share of the 8-way split; [1] = 0 leaf / 1 internal; [i>=2] = 0 "same as i-1" or left share
     // outputs
     float4* nodes;          // (max(n-1,1), 4)
     float4* packed;         // (n, 3)
@@ -134,6 +138,52 @@ DRP_HD float box_area(float4 lo, float4 hi) {
     float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
     return 2.0f * (dx * dy + dy * dz + dz * dx);
 }
+// Optimal collapse into 8-wide nodes (Ylitie, Karras, Laine 2017, section 4.2), evaluated bottom-up inside the refit walk.
+// C(n,i): minimum SAH cost of subtree n when it may occupy at most i child slots of a wide node.
+//   C(n,1) = min(leaf: A P Cprim if P <= max_leaf, internal: A Cnode + D(n,8));  C(n,i) = min(D(n,i), C(n,i-1))
+//   D(n,j) = min over 0<k<j of C(left,k) + C(right,j-k)
+// Returns whether n taken as ONE slot is a leaf.
+#define DRP_DP_CNODE 1.0f
+#define DRP_DP_CPRIM 0.3f
+DRP_HD bool lbvh_dp_node(const LbvhBuild& b, int p, int lc, int rc, float area, int count) {
+    float cl[8], cr[8];
+    for (int i = 1; i < 8; ++i) {
+#ifdef __CUDA_ARCH__
+        cl[i] = __ldcg(&b.dp_cost[8 * (int64_t)lc + i]);
+        cr[i] = __ldcg(&b.dp_cost[8 * (int64_t)rc + i]);
+#else
+        cl[i] = b.dp_cost[8 * (int64_t)lc + i];
+        cr[i] = b.dp_cost[8 * (int64_t)rc + i];
+#endif
+    }
+    float dist[9];
+    uint8_t argk[9];
+    for (int j = 2; j <= 8; ++j) {
+        float best = 3e38f;
+        int bk = 1;
+        for (int k = 1; k < j; ++k) {
+            if (k > 7 || j - k > 7) continue;
+            float c = cl[k] + cr[j - k];
+            if (c < best) { best = c; bk = k; }
+        }
+        dist[j] = best;
+        argk[j] = (uint8_t)bk;
+    }
+    float* cost = b.dp_cost + 8 * (int64_t)p;
+    uint8_t* dec = b.dp_dec + 8 * (int64_t)p;
+    const float c_leaf = count <= b.max_leaf ? area * (float)count * DRP_DP_CPRIM : 3e38f;
+    const float c_int = dist[8] + area * DRP_DP_CNODE;
+    const bool leaf = (c_leaf <= c_int) && (p != 0);
+    cost[1] = leaf ? c_leaf : c_int;
+    dec[0] = argk[8];
+    dec[1] = leaf ? 0 : 1;
+    for (int i = 2; i < 8; ++i) {
+        if (dist[i] < cost[i - 1]) { cost[i] = dist[i]; dec[i] = argk[i]; }
+        else { cost[i] = cost[i - 1]; dec[i] = 0; }
+    }
+    return leaf;
+}
+
 // `atomic_inc(ptr)` returns the previous value; `fence()` orders the box stores before the counter update.
 template <typename AtomicInc, typename Fence>
 DRP_HD void lbvh_refit(const LbvhBuild& b, int j, AtomicInc atomic_inc, Fence fence) {
@@ -146,6 +196,11 @@ DRP_HD void lbvh_refit(const LbvhBuild& b, int j, AtomicInc atomic_inc, Fence fe
     int node = n - 1 + j;
     b.box_lo[node] = lo;
     b.box_hi[node] = hi;
+    if (b.count) b.count[node] = 1;
+    if (b.dp_cost) {
+        for (int i = 1; i < 8; ++i) { b.dp_cost[8 * (int64_t)node + i] = DRP_DP_CPRIM * area; b.dp_dec[8 * (int64_t)node + i] = 0; }
+        b.dp_dec[8 * (int64_t)node] = 0;
+    }
     int p = b.parent[node];
     while (p >= 0) {
         fence();
@@ -162,9 +217,11 @@ DRP_HD void lbvh_refit(const LbvhBuild& b, int j, AtomicInc atomic_inc, Fence fe
         float4 phi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
         float a = box_area(plo, phi);
         int count = b.range_last[p] - b.range_first[p] + 1;
+        if (b.count) b.count[p] = count;
         float c_split = DRP_SAH_CI * a + llo.w + rlo.w;
         float c_leaf = DRP_SAH_CT * a * (float)count;
         bool make_leaf = (count <= b.max_leaf) && (c_leaf <= c_split) && (p != 0);
+        if (b.dp_cost) make_leaf = lbvh_dp_node(b, p, lc, rc, a, count);
         b.collapsed[p] = make_leaf ? 1 : 0;
         plo.w = make_leaf ? c_leaf : c_split;
         phi.w = a;

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 //    lanes have triangles to test, so that the warp stays in the node phase.
 // Scheduling only: the closest hit found is the exhaustive one whatever the order (min t, then min id).
 #ifndef CWK_SMEM_STACK
-#define CWK_SMEM_STACK 8
+#define CWK_SMEM_STACK 0
 #endif
 #ifndef CWK_CHUNK
 #define CWK_CHUNK 256
@@ -179,13 +179,23 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     float t_best = 0.0f;
     int id_best = 0, sp = 0;
     uint32_t ng_x = 0, ng_y = 0, tg_x = 0, tg_y = 0;
-    // traversal stack: the first CWK_SMEM_STACK entries of every thread live in shared memory (conflict-free 64-bit
-    // accesses, [entry][thread]), deeper entries spill to local memory.  ncu: the local-memory stack of the first
-    // version was ~40 % of the kernel's L1 wavefronts.
+    // Traversal stack.  CWK_SMEM_STACK > 0 keeps the first entries of every thread in shared memory ([entry][thread],
+    // conflict-free 64-bit accesses) and spills deeper ones to local memory.  A/B on B200 (profiles/README.md): the
+    // all-local stack (L1-resident, no extra branch per push/pop) is ~5 % FASTER than 8 shared entries, so the default is 0.
+#if CWK_SMEM_STACK > 0
     __shared__ uint2 s_stack[CWK_SMEM_STACK][WF_BLOCK];
-    uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
     const int tid = threadIdx.x;
+#endif
+    uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
     bool overflow = false;
+#if CWK_SMEM_STACK == 0
+#define CWK_PUSH(X, Y)                                                 \
+    do {                                                               \
+        if (sp < CW_STACK) { st_x[sp] = (X); st_y[sp] = (Y); ++sp; }   \
+        else overflow = true;                                          \
+    } while (0)
+#define CWK_POP(X, Y) do { --sp; (X) = st_x[sp]; (Y) = st_y[sp]; } while (0)
+#else
 #define CWK_PUSH(X, Y)                                                                   \
     do {                                                                                 \
         if (sp < CWK_SMEM_STACK) s_stack[sp][tid] = make_uint2((X), (Y));                \
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
         if (sp < CWK_SMEM_STACK) { uint2 _v = s_stack[sp][tid]; (X) = _v.x; (Y) = _v.y; } \
         else { (X) = st_x[sp - CWK_SMEM_STACK]; (Y) = st_y[sp - CWK_SMEM_STACK]; }       \
     } while (0)
+#endif
     for (;;) {
         // ---- refill idle lanes --------------------------------------------------------------------------------
         const unsigned need = __ballot_sync(0xffffffffu, k < 0);

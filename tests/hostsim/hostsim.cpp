@@ -50,6 +50,12 @@ static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_t
     b.left = left.data(); b.right = right.data(); b.parent = parent.data(); b.range_first = rf.data(); b.range_last = rl.data();
     b.box_lo = box_lo.data(); b.box_hi = box_hi.data(); b.arrive = arrive.data(); b.collapsed = collapsed.data();
     b.nodes = h->nodes.data(); b.packed = h->packed.data();
+    std::vector<float> dp_cost;
+    std::vector<uint8_t> dp_dec;
+    if (wide && getenv("HS_GREEDY") == nullptr) {
+        dp_cost.assign(16 * nn, 0.0f); dp_dec.assign(16 * nn, 0);
+        b.dp_cost = dp_cost.data(); b.dp_dec = dp_dec.data();
+    }
     for (int i = 0; i < n; ++i) {
         Vec3 lo, hi;
         lbvh_prim_bounds(b, i, lo, hi);
@@ -72,16 +78,18 @@ static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_t
         keys.swap(k2); vals.swap(v2);
         b.keys = keys.data(); b.vals = vals.data();
     }
+    std::vector<int> count(2 * nn, 0);
+    b.count = count.data();
     if (n > 1) {
         for (int i = 0; i < n - 1; ++i) lbvh_karras(b, i);
         for (int j = 0; j < n; ++j) lbvh_refit(b, j, [](int* p) { int o = *p; *p = o + 1; return o; }, []() {});
-        for (int i = 0; i < n - 1; ++i) lbvh_emit(b, i);
+        if (!wide) for (int i = 0; i < n - 1; ++i) lbvh_emit(b, i);
         h->sah = box_lo[0].w / std::max(box_hi[0].w, 1e-30f);
     } else {
         lbvh_emit_tiny(b);
         h->sah = 1.0f;
     }
-    for (int j = 0; j < n; ++j) lbvh_pack_tri(b, j);
+    if (!wide) for (int j = 0; j < n; ++j) lbvh_pack_tri(b, j);
     for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(bounds[k]);
     if (wide) {
         CwBuild cw;
