@@ -12,6 +12,7 @@
 #include "cwbvh.cuh"
 #include "trace_kernels.cuh"
 #include <cstdlib>
+#include <chrono>
 
 // ---- error / handle plumbing ------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -135,6 +136,23 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     if (!guard.ok) { drp_set_error("drp_build: cannot select device"); return DRP_ERR_CUDA; }
     cudaStream_t s = (cudaStream_t)stream;
     const int n = (int)n_tris;
+    {   // build scratch comes from the device's default stream-ordered pool; keep freed blocks cached across builds instead of
+        // returning them to the driver at every synchronisation (sessions are single-use: one build per frame)
+        static std::mutex pool_mutex;
+        static bool pool_ready[64] = {false};
+        std::lock_guard<std::mutex> lk(pool_mutex);
+        if (device >= 0 && device < 64 && !pool_ready[device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t threshold = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+            }
+            pool_ready[device] = true;
+        }
+    }
+    static const bool timing = getenv("DRP_BUILD_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     BvhHandle* h = new BvhHandle();
     h->device = device;
     h->n_tris = n_tris;
@@ -148,8 +166,8 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     uint64_t* keys_in = nullptr; uint32_t* vals_in = nullptr; void* sort_tmp = nullptr;
     size_t sort_bytes = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    DRP_CUDA_CHECK(cudaMalloc((void**)&h->nodes, sizeof(float4) * (h->wide ? 5 : 4) * (size_t)h->n_nodes));
-    DRP_CUDA_CHECK(cudaMalloc((void**)&h->packed, sizeof(float4) * 3 * nn));
+    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * (h->wide ? 5 : 4) * (size_t)h->n_nodes, s));
+    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->packed, sizeof(float4) * 3 * nn, s));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->sah, sizeof(float)));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->dev_flags, sizeof(int) * 4));
@@ -179,6 +197,7 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     DRP_CUDA_CHECK(cudaMemsetAsync(b.arrive, 0, sizeof(int) * nn, s));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.collapsed, 0, nn, s));
 
+    const double t_alloc = now();
     const int T = 256;
     const int G = (int)((nn + T - 1) / T);
     k_init_bounds<<<1, 32, 0, s>>>(h->bounds);
@@ -227,6 +246,7 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
         }
     }
     DRP_CUDA_CHECK(cudaGetLastError());
+    const double t_launch = now();
     void* temps[] = {b.prim_lo, b.prim_hi, keys_in, vals_in, b.keys, b.vals, b.left, b.right, b.parent, b.range_first,
                      b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters, b.count, b.dp_cost, b.dp_dec};
     for (void* p : temps)
@@ -236,6 +256,8 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
         *out_handle = g_next_handle++;
         g_handles[*out_handle] = h;
     }
+    if (timing) fprintf(stderr, "[diffrp_b200] drp_build n=%d: alloc %.2f ms, launch+collapse-sync %.2f ms, free+register %.2f ms\n", n, t_alloc - t_begin,
+                        t_launch - t_alloc, now() - t_launch);
     if (g_drp_log_level >= 4) fprintf(stderr, "[diffrp_b200] built LBVH over %lld triangles (handle %llu)\n", (long long)n_tris, (unsigned long long)*out_handle);
     return DRP_OK;
 }
@@ -252,7 +274,7 @@ extern "C" int drp_release(uint64_t handle) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     drp_free_workspace(h);
-    cudaFree(h->nodes); cudaFree(h->packed); cudaFree(h->bounds); cudaFree(h->sah); cudaFree(h->dev_flags);
+    cudaFreeAsync(h->nodes, 0); cudaFreeAsync(h->packed, 0); cudaFree(h->bounds); cudaFree(h->sah); cudaFree(h->dev_flags);
     delete h;
     return DRP_OK;
 }

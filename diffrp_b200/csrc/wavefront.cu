@@ -138,13 +138,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 #define CWK_SMEM_STACK 0
 #endif
 #ifndef CWK_CHUNK
-#define CWK_CHUNK 256
+#define CWK_CHUNK 64   // B200 sweep (profiles/README.md): 32-128 within 1 %, 256 -4 %, 1024 -35 %
 #endif
 #ifndef CWK_ND
-#define CWK_ND 4
+#define CWK_ND 2
 #endif
 #ifndef CWK_NW
-#define CWK_NW 16
+#define CWK_NW 8
 #endif
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
