@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -43,6 +43,7 @@ class Scene(C.Structure):
         ("world_pos", C.c_void_p), ("world_nrm", C.c_void_p), ("color", C.c_void_p), ("uv", C.c_void_p),
         ("world_tan", C.c_void_p), ("tris", C.c_void_p), ("tri_material", C.c_void_p),
         ("materials", C.POINTER(Material)),
+        ("vertex_records", C.c_void_p),
         ("n_verts", C.c_int64), ("n_tris", C.c_int64),
         ("n_materials", C.c_int32), ("_pad", C.c_int32),
         ("env", Texture),
@@ -150,6 +151,9 @@ def pack_scene(arrays, materials, env, ptr_of):
         a = arrays[k]
         keep.append(a)
         setattr(s, k, ptr_of(a))
+    if arrays.get("vertex_records") is not None:
+        keep.append(arrays["vertex_records"])
+        s.vertex_records = ptr_of(arrays["vertex_records"])
     s.n_verts = int(arrays["world_pos"].shape[0])
     s.n_tris = int(arrays["tris"].shape[0])
     mats = (Material * max(1, len(materials)))()

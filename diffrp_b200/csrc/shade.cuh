@@ -162,14 +162,41 @@ DRP_HD void hit_barycentric(Vec3 a, Vec3 b, Vec3 c, Vec3 p, float& u, float& v) 
     v = bv;
 }
 
+// per-vertex shading inputs, from the interleaved 64-byte record when the scene has one, else from the five arrays
+struct VertexIn {
+    Vec3 pos, nrm;
+    float2 uv;
+    float4 color, tan;
+};
+DRP_HD VertexIn load_vertex(const drp_scene_t& sc, int i) {
+    VertexIn v;
+    if (sc.vertex_records) {
+        const float4* r = reinterpret_cast<const float4*>(sc.vertex_records) + 4 * (int64_t)i;
+        const float4 a = ldg(r), b = ldg(r + 1);
+        v.pos = v3(a.x, a.y, a.z);
+        v.nrm = v3(a.w, b.x, b.y);
+        v.uv = make_float2(b.z, b.w);
+        v.color = ldg(r + 2);
+        v.tan = ldg(r + 3);
+    } else {
+        v.pos = ld3(sc.world_pos, i);
+        v.nrm = ld3(sc.world_nrm, i);
+        v.uv = ld2(sc.uv, i);
+        v.color = ld4(sc.color, i);
+        v.tan = ld4(sc.world_tan, i);
+    }
+    return v;
+}
+
 DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id) {
     SurfaceAttrs s;
     const int i0 = ldg(sc.tris + 3 * (int64_t)tri_id), i1 = ldg(sc.tris + 3 * (int64_t)tri_id + 1), i2 = ldg(sc.tris + 3 * (int64_t)tri_id + 2);
+    const VertexIn q0 = load_vertex(sc, i0), q1 = load_vertex(sc, i1), q2 = load_vertex(sc, i2);
     float u, v;
-    hit_barycentric(ld3(sc.world_pos, i0), ld3(sc.world_pos, i1), ld3(sc.world_pos, i2), hit_pos, u, v);
+    hit_barycentric(q0.pos, q1.pos, q2.pos, hit_pos, u, v);
     const drp_material_t& m = mats[ldg(sc.tri_material + tri_id)];
-    Vec3 nu = lerp3v(ld3(sc.world_nrm, i0), ld3(sc.world_nrm, i1), ld3(sc.world_nrm, i2), u, v);  // world_normal_unnormalized
-    float4 c0 = ld4(sc.color, i0), c1 = ld4(sc.color, i1), c2 = ld4(sc.color, i2);
+    Vec3 nu = lerp3v(q0.nrm, q1.nrm, q2.nrm, u, v);  // world_normal_unnormalized
+    const float4 c0 = q0.color, c1 = q1.color, c2 = q2.color;
     float col[4] = {lerp3(c0.x, c1.x, c2.x, u, v), lerp3(c0.y, c1.y, c2.y, u, v), lerp3(c0.z, c1.z, c2.z, u, v), lerp3(c0.w, c1.w, c2.w, u, v)};
     s.normal = normalize_ref(nu);
     s.metal = 0.0f; s.smooth = 0.5f; s.alpha = 1.0f;  // path_tracing.py:183-186
@@ -178,7 +205,7 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
         s.albedo = v3(col[0] * m.tint[0], col[1] * m.tint[1], col[2] * m.tint[2]);
         return s;
     }
-    float2 t0 = ld2(sc.uv, i0), t1 = ld2(sc.uv, i1), t2 = ld2(sc.uv, i2);
+    const float2 t0 = q0.uv, t1 = q1.uv, t2 = q2.uv;
     float tu = lerp3(t0.x, t1.x, t2.x, u, v), tv = lerp3(t0.y, t1.y, t2.y, u, v);
     float bc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, mr[4] = {0.0f, 0.0f, 0.0f, 0.0f}, nt[4] = {0.0f, 0.0f, 0.0f, 0.0f}, em[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const bool use_nt = m.has_normal_tex && m.normal_tex.data, use_em = m.has_emissive && m.emissive_tex.data;
@@ -219,7 +246,7 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
     if (m.has_emissive) s.emission = v3(m.emissive_factor[0] * em[0], m.emissive_factor[1] * em[1], m.emissive_factor[2] * em[2]);
     if (use_nt) {  // tangent-space normal map, mixin.py:118-123
         float nx = 2.0f * nt[0] - 1.0f, ny = 2.0f * nt[1] - 1.0f, nz = 2.0f * nt[2] - 1.0f;
-        float4 g0 = ld4(sc.world_tan, i0), g1 = ld4(sc.world_tan, i1), g2 = ld4(sc.world_tan, i2);
+        const float4 g0 = q0.tan, g1 = q1.tan, g2 = q2.tan;
         Vec3 vt = v3(lerp3(g0.x, g1.x, g2.x, u, v), lerp3(g0.y, g1.y, g2.y, u, v), lerp3(g0.z, g1.z, g2.z, u, v));
         float vs = lerp3(g0.w, g1.w, g2.w, u, v);
         Vec3 vb = cross(nu, vt) * vs;

@@ -222,8 +222,9 @@ class PathTracingSession:
         if descs is None:
             return None
         vao = self.vertex_array_object()
+        records = torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
-                      tris=vao.tris, tri_material=vao.tri_material)
+                      tris=vao.tris, tri_material=vao.tri_material, vertex_records=records)
         env = self._single_env_light()
         return _abi.pack_scene(arrays, descs, None if env is None else dict(image=pad_rgba(env)), lambda t: t.data_ptr())
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 2
+#define DRP_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -94,6 +94,8 @@ typedef struct drp_scene {
     const int32_t* tris;         /* (F,3)                                              */
     const int32_t* tri_material; /* (F,)  index into materials (= stencil - 1)         */
     const drp_material_t* materials; /* HOST pointer, n_materials entries (copied)      */
+    const float* vertex_records; /* optional (V,16): [pos3 nrm3 uv2 | color4 tan4] interleaved copy of the five arrays above;
+                                    64 B per vertex = 2 sectors instead of 5 scattered ones (drp_render prefers it)          */
     int64_t n_verts;
     int64_t n_tris;
     int32_t n_materials;

@@ -82,13 +82,18 @@ def test_axis_aligned_rays_on_box_planes(hs):
     assert (t == 1.0).all()
 
 
-@pytest.mark.parametrize("scene_name,last", [("ico", "void"), ("mixed", "void"), ("mixed", "skybox")])
-def test_shading_logic_matches_oracle(hs, scene_name, last):
+@pytest.mark.parametrize("scene_name,last,records", [("ico", "void", False), ("mixed", "void", False), ("mixed", "skybox", True)])
+def test_shading_logic_matches_oracle(hs, scene_name, last, records):
     scene = scenes.icosphere_scene() if scene_name == "ico" else scenes.mixed_scene()
     cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
     vao, hscene, p, keep = scenes.oracle_inputs(scene, cam, 3, 3, last_bounce=last, seed=123)
     acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hscene, p)
     wp, tr = hscene.arrays['world_pos'], hscene.arrays['tris']
+    if records:  # the interleaved 64-byte vertex records the CUDA path prefers must give the same result as the five arrays
+        a = hscene.arrays
+        rec = np.ascontiguousarray(np.concatenate([a['world_pos'], a['world_nrm'], a['uv'], a['color'], a['world_tan']], 1), np.float32)
+        assert rec.shape[1] == 16
+        hscene.struct.vertex_records = rec.ctypes.data
     h = hs.hs_build(wp.ctypes.data, tr.ctypes.data, len(wp), len(tr))
     acc2 = np.zeros_like(acc)
     hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc2.ctypes.data)
