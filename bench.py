@@ -330,8 +330,13 @@ def main():
                 "share_of_step": prof["extend_ms"] / ms, "shade_share_of_step": prof["shade_ms"] / ms,
                 "whole_path_frac": (stats_bytes(prof, n_tris) / (ms * 1e-3) / 1e9) / peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_k_extend.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file):  # one `ncu --set full` capture of the same command, committed under profiles/
         roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
+    roofline["algorithmic_bytes_per_launch"] = roofline["rays_per_launch_avg"] * b_query(n_tris)
+    roofline["note"] = ("algorithmic bytes = live rays x B_query (SURVEY 8d ideal-descent model, every level re-read from memory); measured DRAM "
+                        "traffic is ~10x lower because the upper BVH levels stay in L1/L2 -- the kernel is issue-bound (ncu: math-pipe throttle, "
+                        "~0.7 inst/cycle/SMSP, 19-21 of 32 lanes active), see profiles/README.md")
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

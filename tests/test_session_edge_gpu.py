@@ -1,0 +1,82 @@
+"""Edge cases of the session API on the GPU: empty scene, no light, depth 1, odd sizes, spp = 1, options compatibility."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import scenes
+import diffrp_b200 as drp
+from test_oracle_golden import make_camera, image_errors
+
+pytestmark = pytest.mark.gpu
+
+
+def render(scene, cam, **opt):
+    s = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**opt))
+    rad, alpha, extras = s.pbr()
+    out = {k: v.cpu().numpy() for k, v in extras.items()}
+    out['radiance'], out['alpha'] = rad.cpu().numpy(), alpha.cpu().numpy()
+    return s, out
+
+
+def test_empty_scene_renders_the_environment_only():
+    scene = drp.Scene().add_light(drp.ImageEnvironmentLight(1.0, torch.ones(3), scenes.T(drp.synthetic.gradient_env())))
+    s, out = render(scene, drp.PerspectiveCamera(h=16, w=24), ray_spp=2, ray_depth=2)
+    assert out['alpha'].max() == 0.0 and out['radiance'].min() >= 0.0 and out['radiance'].max() > 0.0
+    assert np.abs(out['albedo']).max() == 0.0
+    assert s.render_stats()['rays_traced'] == 16 * 24 * 2  # every ray is dropped after the first (provable) miss
+
+
+def test_no_light_gives_black_radiance_and_correct_alpha():
+    scene = scenes.icosphere_scene(env=False)
+    cam = drp.PerspectiveCamera(h=33, w=47)  # odd, non-square
+    s, out = render(scene, cam, ray_spp=3, ray_depth=1)
+    assert out['radiance'].shape == (33, 47, 3) and np.abs(out['radiance']).max() == 0.0
+    cpu_cam = make_camera(dict(h=33, w=47), None)
+    vao, hs, p, keep = scenes.oracle_inputs(scene, cpu_cam, 3, 1)
+    acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hs, p)
+    ref = oracle.finalize(acc, 33, 47, 3)
+    errs = image_errors(out, ref)
+    for k, (emax, emean, frac) in errs.items():
+        assert frac <= 0.005 and emean <= 2e-5, (k, errs[k])
+
+
+def test_reference_option_names_are_accepted():
+    scene = scenes.icosphere_scene()
+    cam = drp.PerspectiveCamera(h=16, w=16)
+    outs = []
+    for impl in ('torchoptix', 'naive-pbbvh', 'brute-force', 'b200'):
+        s, out = render(scene, cam, ray_spp=2, ray_depth=2, raycaster_impl=impl, raycaster_builder='morton', optix_log_level=0, seed=1)
+        outs.append(out['radiance'])
+    for o in outs[1:]:
+        np.testing.assert_allclose(o, outs[0], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        render(scene, cam, raycaster_impl='embree')
+
+
+def test_nondeterministic_hammersley_shift_uses_torch_rng():
+    scene = scenes.icosphere_scene()
+    cam = drp.PerspectiveCamera(h=16, w=16)
+    torch.manual_seed(3)
+    _, a = render(scene, cam, ray_spp=2, ray_depth=1, deterministic=False)
+    torch.manual_seed(3)
+    _, b = render(scene, cam, ray_spp=2, ray_depth=1, deterministic=False)
+    torch.manual_seed(4)
+    _, c = render(scene, cam, ray_spp=2, ray_depth=1, deterministic=False)
+    np.testing.assert_allclose(a['world_position'], b['world_position'], rtol=0, atol=1e-6)
+    assert np.abs(a['world_position'] - c['world_position']).max() > 1e-4
+
+
+def test_many_samples_split_into_internal_batches():
+    """More rays than one internal batch (2^24): the result must equal the sum of two half renders."""
+    scene = scenes.icosphere_scene()
+    cam = drp.PerspectiveCamera(h=512, w=512)
+    base = dict(ray_spp=96, ray_depth=2, seed=6)  # 512*512*96 = 25.2M rays > 16.8M
+    s = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**base))
+    whole = s.render_accumulators()
+    assert s.render_stats()['rays_nominal'] == 512 * 512 * 96 * 2
+    ids = torch.arange(96, dtype=torch.int32, device='cuda')
+    s2 = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**base))
+    parts = s2.render_samples(ids[:40])
+    parts = s2.render_samples(ids[40:], parts)
+    torch.testing.assert_close(parts, whole, rtol=2e-5, atol=2e-4)
