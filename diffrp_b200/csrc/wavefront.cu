@@ -38,6 +38,8 @@ struct RenderWorkspace {
     int grid_extend[2] = {0, 0}, grid_shade[2] = {0, 0};
     bool have_box = false;
     float box_lo[3], box_hi[3];
+    cudaStream_t streams[2] = {nullptr, nullptr};  // DRP_OVERLAP: one internal stream per ray group
+    cudaEvent_t sync_events[4] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing (drp_set_profiling)
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int kind; int bounce; unsigned long long* traced_slot; };
@@ -69,7 +71,7 @@ struct WfConst {
     int tx0, ty0, tw;   // tile origin and width (tw == frame width, origin 0 for a full frame)
     int64_t R;          // rays in this batch
     int64_t R_total;    // rays of the whole call (replay indexing)
-    int sample_base;    // first sample (within the call) of this batch
+    int64_t ray_base;   // index (within the call) of this launch group's first ray: s_local * HW + pixel of queue slot 0 at bounce 0
     float* accum;
     int* flags;
     uint32_t cw_bias;   // 0x47000000 (cwbvh.cuh: cw_byte_biased), passed through the constant bank
@@ -84,7 +86,7 @@ template <bool PRIMARY>
 __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restrict__ qa, const float4* __restrict__ qb, int k, Vec3& o,
                                          Vec3& d, int& ray_index) {
     if (PRIMARY) {
-        ray_index = k + c.sample_base * c.HW;  // index within the call: s_local * HW + pixel  (path_tracing.py:329-331)
+        ray_index = k + (int)c.ray_base;  // index within the call: s_local * HW + pixel  (path_tracing.py:329-331)
         int s = ray_index / c.HW, pix = ray_index - s * c.HW;
         int y = pix / c.tw, x = pix - y * c.tw;
         x += c.tx0; y += c.ty0;
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
 __global__ void k_count_traced(const int* __restrict__ counts, int depth, unsigned long long R, unsigned long long* __restrict__ total) {
     unsigned long long t = R;  // bounce 0 traces every ray of the batch
     for (int b = 1; b < depth; ++b) t += (unsigned long long)counts[b];
-    *total += t;
+    atomicAdd(total, t);
 }
 
 __global__ void k_finalize(const float* __restrict__ accum, int H, int W, float spp, float* __restrict__ radiance, float* __restrict__ alpha,
@@ -450,8 +452,8 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
         cudaDeviceProp prop;
         DRP_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
         h->ws->sm_count = prop.multiProcessorCount;
-        h->ws->n_counters = 256;
-        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 256));
+        h->ws->n_counters = 512;  // two launch groups x (64 live counts + 128 fetch cursors + spare)
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 512));
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->d_traced, sizeof(unsigned long long)));
         int nb = 0;
         DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, WF_BLOCK, 0));
@@ -518,11 +520,12 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     const int64_t HW = tiled ? (int64_t)p.tile_w * p.tile_h : (int64_t)p.height * p.width;
     if (HW > WF_MAX_BATCH_RAYS) { drp_set_error("drp_render: more than 2^24 pixels per frame not supported"); return DRP_ERR_INVALID; }
     if (p.n_samples == 0) return DRP_OK;
+    if (HW * p.n_samples >= (int64_t(1) << 31)) { drp_set_error("drp_render: more than 2^31 rays per call; render the samples in several calls"); return DRP_ERR_INVALID; }
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_render: cannot select device"); return DRP_ERR_CUDA; }
     cudaStream_t s = (cudaStream_t)stream;
     const int spb = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
-    int rc = ensure_workspace(h, (int64_t)spb * HW, scene->n_materials);
+    int rc = ensure_workspace(h, (((int64_t)spb * HW + 1) / 2) * 2 + 64, scene->n_materials);
     if (rc != DRP_OK) return rc;
     RenderWorkspace* ws = h->ws;
     // material table -> device (skipped when unchanged since the previous call)
@@ -563,52 +566,85 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     int64_t launches = 0;
     h->last_render.rays_nominal = HW * p.n_samples * D;
     DRP_CUDA_CHECK(cudaMemsetAsync(ws->d_traced, 0, sizeof(unsigned long long), s));
+    // Overlap (DRP_OVERLAP=1, experimental): every batch is split into two ray groups that run as independent kernel chains on two
+    // internal streams, the second one bounce-phase behind the first, with grids sized so that an (ALU-bound) extend kernel
+    // of one group and a (DRAM-latency-bound) shade kernel of the other are co-resident on every SM.
+    static const bool overlap_env = getenv("DRP_OVERLAP") && atoi(getenv("DRP_OVERLAP")) != 0;
+    static const int ovl_e = getenv("DRP_OVL_E") ? atoi(getenv("DRP_OVL_E")) : 5, ovl_s = getenv("DRP_OVL_S") ? atoi(getenv("DRP_OVL_S")) : 2;
+    const bool overlap = overlap_env && h->wide && !simple_extend;
+    if (overlap && !ws->streams[0]) {
+        for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamCreateWithFlags(&ws->streams[g], cudaStreamNonBlocking));
+        for (int g = 0; g < 4; ++g) DRP_CUDA_CHECK(cudaEventCreateWithFlags(&ws->sync_events[g], cudaEventDisableTiming));
+    }
     for (int s0 = 0; s0 < p.n_samples; s0 += spb) {
         const int ns = std::min(spb, p.n_samples - s0);
-        c.R = (int64_t)ns * HW;
-        c.sample_base = s0;
-        int* counts = ws->counters;       // [0..D]
-        int* cursors = ws->counters + 64; // [0..2D)
+        const int64_t R_batch = (int64_t)ns * HW;
+        const int G = (overlap && R_batch >= (1 << 18)) ? 2 : 1;
         DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));
         ++launches;
-        auto span_begin = [&](int kind, int b, const int* count_ptr) -> int {
-            if (!ws->profiling || ws->live_used >= ws->live_capacity) return -1;
-            RenderWorkspace::Span sp;
-            sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
-            sp.traced_slot = ws->d_live + ws->live_used++;
-            k_record_live<<<1, 1, 0, s>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
-            cudaEventRecord(sp.a, s);
-            ws->spans.push_back(sp);
-            return (int)ws->spans.size() - 1;
-        };
-        auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, s); };
-        for (int b = 0; b < D; ++b) {
-            const int in = b & 1, out = in ^ 1;
-            if (b == 0) {
-                int sp = span_begin(0, b, nullptr);
-                if (h->wide && !simple_extend) k_extend_cw<SRC_PRIMARY><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0, AosRays());
-                else if (h->wide) k_extend<true, true><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
-                else k_extend<true, false><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, ws->hit, nullptr, cursors + 0);
-                span_end(sp);
-                sp = span_begin(1, b, nullptr);
-                k_shade<true><<<ws->grid_shade[1], WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, ws->hit, ws->qa[out], ws->qb[out], ws->qt[out], nullptr,
-                                                        counts + 1, cursors + 1);
-                span_end(sp);
-            } else {
-                int sp = span_begin(0, b, counts + b);
-                if (h->wide && !simple_extend) k_extend_cw<SRC_QUEUE><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b, AosRays());
-                else if (h->wide) k_extend<false, true><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
-                else k_extend<false, false><<<ws->grid_extend[0], WF_BLOCK, 0, s>>>(c, ws->qa[in], ws->qb[in], ws->hit, counts + b, cursors + 2 * b);
-                span_end(sp);
-                sp = span_begin(1, b, counts + b);
-                k_shade<false><<<ws->grid_shade[0], WF_BLOCK, 0, s>>>(c, b, ws->qa[in], ws->qb[in], ws->qt[in], ws->hit, ws->qa[out], ws->qb[out], ws->qt[out],
-                                                         counts + b, counts + b + 1, cursors + 2 * b + 1);
-                span_end(sp);
-            }
-            launches += 2;
+        if (G == 2) {  // fork: both internal streams start after everything already queued on the caller's stream
+            DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[0], s));
+            for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamWaitEvent(ws->streams[g], ws->sync_events[0], 0));
         }
-        k_count_traced<<<1, 1, 0, s>>>(counts, D, (unsigned long long)c.R, ws->d_traced);  // read lazily by drp_render_stats
-        ++launches;
+        for (int b = 0; b < D; ++b) {
+            for (int g = 0; g < G; ++g) {
+                cudaStream_t sg = G == 2 ? ws->streams[g] : s;
+                const int64_t r0 = R_batch * g / G, r1 = R_batch * (g + 1) / G;
+                const int64_t qoff = (int64_t)g * (ws->capacity / 2);  // each group owns one half of every queue
+                c.R = r1 - r0;
+                c.ray_base = (int64_t)s0 * HW + r0;
+                int* counts = ws->counters + 256 * g;        // [0..D]
+                int* cursors = ws->counters + 256 * g + 64;  // [0..2D)
+                float2* hit = ws->hit + qoff;
+                const int in = b & 1, out = in ^ 1;
+                float4 *qa_in = ws->qa[in] + qoff, *qb_in = ws->qb[in] + qoff, *qt_in = ws->qt[in] + qoff;
+                float4 *qa_out = ws->qa[out] + qoff, *qb_out = ws->qb[out] + qoff, *qt_out = ws->qt[out] + qoff;
+                const int ge = G == 2 ? ws->sm_count * ovl_e : ws->grid_extend[b == 0], gs = G == 2 ? ws->sm_count * ovl_s : ws->grid_shade[b == 0];
+                if (G == 2 && g == 1 && b == 0) DRP_CUDA_CHECK(cudaStreamWaitEvent(sg, ws->sync_events[1], 0));  // phase offset: after group 0's first extend
+                auto span_begin = [&](int kind, const int* count_ptr) -> int {
+                    if (!ws->profiling || ws->live_used >= ws->live_capacity) return -1;
+                    RenderWorkspace::Span sp;
+                    sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
+                    sp.traced_slot = ws->d_live + ws->live_used++;
+                    k_record_live<<<1, 1, 0, sg>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
+                    cudaEventRecord(sp.a, sg);
+                    ws->spans.push_back(sp);
+                    return (int)ws->spans.size() - 1;
+                };
+                auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, sg); };
+                if (b == 0) {
+                    int sp = span_begin(0, nullptr);
+                    if (h->wide && !simple_extend) k_extend_cw<SRC_PRIMARY><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays());
+                    else if (h->wide) k_extend<true, true><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
+                    else k_extend<true, false><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
+                    span_end(sp);
+                    if (G == 2 && g == 0) DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[1], sg));
+                    sp = span_begin(1, nullptr);
+                    k_shade<true><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1);
+                    span_end(sp);
+                } else {
+                    int sp = span_begin(0, counts + b);
+                    if (h->wide && !simple_extend) k_extend_cw<SRC_QUEUE><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays());
+                    else if (h->wide) k_extend<false, true><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
+                    else k_extend<false, false><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
+                    span_end(sp);
+                    sp = span_begin(1, counts + b);
+                    k_shade<false><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, counts + b, counts + b + 1, cursors + 2 * b + 1);
+                    span_end(sp);
+                }
+                launches += 2;
+                if (b == D - 1) {
+                    k_count_traced<<<1, 1, 0, sg>>>(counts, D, (unsigned long long)c.R, ws->d_traced);  // read lazily by drp_render_stats
+                    ++launches;
+                }
+            }
+        }
+        if (G == 2) {  // join: the caller's stream continues after both chains
+            for (int g = 0; g < 2; ++g) {
+                DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[2 + g], ws->streams[g]));
+                DRP_CUDA_CHECK(cudaStreamWaitEvent(s, ws->sync_events[2 + g], 0));
+            }
+        }
     }
     DRP_CUDA_CHECK(cudaGetLastError());
     h->last_render.kernel_launches = launches;
