@@ -69,6 +69,7 @@ struct WfConst {
     float eps;
     int HW;             // pixels rendered per sample (the tile's pixel count when tile sharding)
     int tx0, ty0, tw;   // tile origin and width (tw == frame width, origin 0 for a full frame)
+    int tiled8x4;       // primary rays enumerated in 8x4 pixel blocks (rectangle width % 8 == 0 and height % 4 == 0)
     int64_t R;          // rays in this batch
     int64_t R_total;    // rays of the whole call (replay indexing)
     int64_t ray_base;   // index (within the call) of this launch group's first ray: s_local * HW + pixel of queue slot 0 at bounce 0
@@ -86,8 +87,19 @@ template <bool PRIMARY>
 __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restrict__ qa, const float4* __restrict__ qb, int k, Vec3& o,
                                          Vec3& d, int& ray_index) {
     if (PRIMARY) {
-        ray_index = k + (int)c.ray_base;  // index within the call: s_local * HW + pixel  (path_tracing.py:329-331)
-        int s = ray_index / c.HW, pix = ray_index - s * c.HW;
+        // Queue slot -> (sample, pixel).  Scanline order by default; DRP_PRIMARY_ORDER=tiled enumerates 8x4-pixel blocks so that a
+        // warp starts on a compact screen tile instead of a 32x1 strip (measured: no gain, see drp_render).
+        // The ray index (RNG key, replay index, accumulator row) is the reference's s * HW + y * W + x either way.
+        const int kk = k + (int)c.ray_base;
+        const int s = kk / c.HW;
+        int pix = kk - s * c.HW;
+        if (c.tiled8x4) {
+            const int blocks_x = c.tw >> 3;
+            const int blk = pix >> 5, in = pix & 31;
+            const int by = blk / blocks_x, bx = blk - by * blocks_x;
+            pix = ((by << 2) + (in >> 3)) * c.tw + (bx << 3) + (in & 7);
+        }
+        ray_index = s * c.HW + pix;
         int y = pix / c.tw, x = pix - y * c.tw;
         x += c.tx0; y += c.ty0;
         float gx = __ldg(c.p.ndc_x + x) + __ldg(c.p.jitter_x + s);
@@ -138,6 +150,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 // Scheduling only: the closest hit found is the exhaustive one whatever the order (min t, then min id).
 #ifndef CWK_SMEM_STACK
 #define CWK_SMEM_STACK 0
+#endif
+#ifndef CWK_PREFETCH
+#define CWK_PREFETCH 0
 #endif
 #ifndef CWK_CHUNK
 #define CWK_CHUNK 64   // B200 sweep (profiles/README.md): 32-128 within 1 %, 256 -4 %, 1024 -35 %
@@ -273,6 +288,14 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     ng_y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
                     tg_x = __float_as_uint(n1.y);
                     tg_y = hitmask & 0x00ffffffu;
+#if CWK_PREFETCH
+                    if (ng_y > 0x00ffffffu) {  // the child visited next is already known: pull its two cache lines towards L1 while triangles are tested
+                        const uint32_t nslot = (uint32_t)(31 - __clz(ng_y) - 24) ^ (r.octinv4 & 0xffu);
+                        const float4* np = c.nodes + 5 * (int64_t)(ng_x + __popc(ng_y & ~(0xffffffffu << nslot)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 4));
+                    }
+#endif
                 } else {
                     tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
                     ng_x = 0; ng_y = 0;
@@ -544,6 +567,12 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     c.eps = h->eps;
     c.HW = (int)HW;
     c.tx0 = tiled ? p.tile_x0 : 0; c.ty0 = tiled ? p.tile_y0 : 0; c.tw = tiled ? p.tile_w : p.width;
+    {
+        const int rect_h = tiled ? p.tile_h : p.height;
+        // A/B on B200: 8x4 blocks leave extend unchanged and make shade 5 % slower (accumulator RED rows less contiguous) -> off by default
+        static const bool blocks = getenv("DRP_PRIMARY_ORDER") && strcmp(getenv("DRP_PRIMARY_ORDER"), "tiled") == 0;
+        c.tiled8x4 = (blocks && c.tw % 8 == 0 && rect_h % 4 == 0) ? 1 : 0;
+    }
     c.R_total = HW * p.n_samples;
     c.accum = accum;
     c.flags = h->dev_flags;
@@ -694,7 +723,7 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
 extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
-           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK);
+           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {
