@@ -281,7 +281,7 @@ def main():
     d2h = out_host.numel() * 4
 
     def e2e_call(spp_total, seed, sharded):
-        o = drp.PathTracingSessionOptions(ray_spp=spp_total, ray_depth=DEPTH, rng='native', seed=seed,
+        o = drp.PathTracingSessionOptions(ray_spp=spp_total, ray_depth=DEPTH, rng='native', seed=seed, reuse_scene=False,  # nothing cached between calls
                                           shard_rank=rank if sharded else 0, shard_world=world if sharded else 1)
         s = drp.PathTracingSession(scene_host, cam, o)          # pinned host tensors: H2D of the whole scene happens inside
         r, a, x = s.pbr()                                       # flatten + LBVH build + wavefront (+ all-reduce) + finalize

@@ -45,6 +45,9 @@ class PathTracingSessionOptions:
             sampler (path_tracing.py:205-223) and replay them in the kernel: with the same ``torch.manual_seed`` the image
             reproduces the reference's within fp32 tolerance.
         seed (int): key of the native RNG.
+        reuse_scene (bool): sessions are single-use like the reference's, but the flattened buffers, uploaded textures and the BVH
+            of a ``Scene`` are kept (one entry per scene, keyed by the identity, shape and in-place version counter of every tensor)
+            and adopted by the next session over the same unmodified scene -- multi-view rendering builds once, not per view.
         compaction (bool): drop rays that provably contribute nothing to any output (exact; the reference keeps
             tracing them with zero throughput).
         shard_rank / shard_world: this process renders its share of the frame (scene replicated) and the fp32 accumulators
@@ -69,6 +72,7 @@ class PathTracingSessionOptions:
     shard_world: int = 1
     shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
+    reuse_scene: bool = True  # share the flattened scene + BVH between sessions over the same, unmodified Scene
 
 
 @dataclass
@@ -138,6 +142,44 @@ def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
     return accum
 
 
+def _scene_signature(scene: Scene, device) -> tuple:
+    """Changes whenever an object, a tensor (identity, shape or in-place version), a material or a light of the scene changes."""
+    sig = [str(device)]
+
+    def t(x):
+        return (x.data_ptr(), tuple(x.shape), x._version, str(x.device)) if isinstance(x, torch.Tensor) else repr(x)
+    for o in scene.objects:
+        sig.append((id(o), id(o.material), t(o.verts), t(o.tris), t(o.normals), t(o.M), t(o.color), t(o.uv), t(o.tangents),
+                    tuple(sorted((k, t(v)) for k, v in (o.custom_attrs or {}).items()))))
+        m = o.material
+        for name in ('tint', 'base_color_factor', 'emissive_factor', 'metallic_factor', 'roughness_factor', 'alpha_cutoff', 'alpha_mode'):
+            if hasattr(m, name):
+                sig.append(t(getattr(m, name)))
+        for name in ('base_color_texture', 'metallic_roughness_texture', 'normal_texture', 'emissive_texture'):
+            smp = getattr(m, name, None)
+            if smp is not None:
+                sig.append((t(smp.image), smp.wrap_mode, smp.interpolation))
+    for l in scene.lights:
+        sig.append((id(l), t(getattr(l, 'image', None)), t(l.color), repr(l.intensity) if not isinstance(l.intensity, torch.Tensor) else t(l.intensity)))
+    return tuple(sig)
+
+
+#: id(scene) -> (weakref to the scene, signature, {cache key: value}); one entry per live Scene object
+_SCENE_CACHE: Dict[int, tuple] = {}
+
+
+def _shared_scene_cache(scene: Scene, device, epsilon: float) -> dict:
+    import weakref
+    sig = _scene_signature(scene, device) + (float(epsilon),)
+    key = id(scene)
+    ent = _SCENE_CACHE.get(key)
+    if ent is not None and ent[0]() is scene and ent[1] == sig:
+        return ent[2]
+    store: dict = {}
+    _SCENE_CACHE[key] = (weakref.ref(scene, lambda _r, k=key: _SCENE_CACHE.pop(k, None)), sig, store)
+    return store
+
+
 def _cached(fn):
     name = fn.__name__
 
@@ -189,23 +231,40 @@ class PathTracingSession:
         return (p[2, 3] / (p[2, 2] - 1)).item()
 
     # ---- scene flattening (mixin.py:74-113) ------------------------------------------------------------------------
-    @_cached
+    def _scene_store(self) -> dict:
+        """Per-scene cache shared between sessions (options.reuse_scene), else private to this session."""
+        if '_store' not in self.__dict__:
+            self._store = (_shared_scene_cache(self.scene, self.device, self.options.raycaster_epsilon)
+                           if self.options.reuse_scene else {})
+        return self._store
+
     def vertex_array_object(self) -> VertexArrayObject:
-        return flatten_scene(self.scene.objects, self.device)
+        st = self._scene_store()
+        if 'vao' not in st:
+            st['vao'] = flatten_scene(self.scene.objects, self.device)
+        return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
-    @_cached
     def raycaster(self):
         impl = self.options.raycaster_impl
         if impl not in ('b200', 'torchoptix', 'naive-pbbvh', 'brute-force'):
             raise ValueError("unknown raycaster_impl: %r" % (impl,))
-        vao = self.vertex_array_object()
-        cfg = {'epsilon': self.options.raycaster_epsilon, 'builder': self.options.raycaster_builder,
-               'optix_log_level': self.options.optix_log_level}
-        return B200Raycaster(vao.world_pos, vao.tris, cfg)
+        st = self._scene_store()
+        rc = st.get('raycaster')
+        if rc is None or rc.handle is None:
+            vao = self.vertex_array_object()
+            cfg = {'epsilon': self.options.raycaster_epsilon, 'builder': self.options.raycaster_builder,
+                   'optix_log_level': self.options.optix_log_level}
+            rc = st['raycaster'] = B200Raycaster(vao.world_pos, vao.tris, cfg)
+        return rc
 
-    @_cached
     def _single_env_light(self):
+        st = self._scene_store()
+        if 'env' not in st:
+            st['env'] = self._load_env_light()
+        return st['env']
+
+    def _load_env_light(self):
         env = None
         for light in self.scene.lights:
             if isinstance(light, ImageEnvironmentLight):
@@ -215,8 +274,13 @@ class PathTracingSession:
         return env  # None == the reference's 16x16 black texture
 
     # ---- fused path ------------------------------------------------------------------------------------------------
-    @_cached
     def _fused_scene(self):
+        st = self._scene_store()
+        if 'fused' not in st:
+            st['fused'] = self._build_fused_scene()
+        return st['fused']
+
+    def _build_fused_scene(self):
         """drp_scene_t for the fused kernels, or None when some material only exists as Python code."""
         descs = material_descriptions(self.scene.objects, self.device, rgba=True)
         if descs is None:

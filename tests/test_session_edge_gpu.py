@@ -80,3 +80,22 @@ def test_many_samples_split_into_internal_batches():
     parts = s2.render_samples(ids[:40])
     parts = s2.render_samples(ids[40:], parts)
     torch.testing.assert_close(parts, whole, rtol=2e-5, atol=2e-4)
+
+
+def test_scene_cache_is_shared_between_sessions_and_invalidated_by_in_place_edits():
+    scene = scenes.to_device(scenes.mixed_scene(), 'cuda')
+    cam = drp.PerspectiveCamera.from_orbit(h=32, w=48, radius=3.0, azim=5, elev=10, origin=[0.0, -0.1, 0.0], fov=32)
+    a = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1))
+    ra = a.pbr()[0]
+    b = drp.PathTracingSession(scene, drp.PerspectiveCamera.from_orbit(h=32, w=48, radius=3.0, azim=90, elev=10, origin=[0.0, -0.1, 0.0], fov=32),
+                               drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1))
+    assert b.raycaster() is a.raycaster() and b.vertex_array_object() is a.vertex_array_object()  # built once, used by both views
+    rb = b.pbr()[0]
+    assert (ra - rb).abs().max() > 1e-3  # a different view, really rendered
+    private = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1, reuse_scene=False))
+    assert private.raycaster() is not a.raycaster()
+    torch.testing.assert_close(private.pbr()[0], ra, rtol=1e-5, atol=1e-6)
+    scene.objects[1].verts.mul_(0.5)  # in-place edit bumps the tensor version -> the cache entry is stale
+    c = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1))
+    assert c.raycaster() is not a.raycaster()
+    assert (c.pbr()[0] - ra).abs().max() > 1e-3

@@ -17,7 +17,7 @@ def timed(label, fn):
 for it in range(3):
     print("--- iteration", it)
     t_all = time.perf_counter()
-    s = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=8, ray_depth=4, seed=it))
+    s = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=8, ray_depth=4, seed=it, reuse_scene=False))
     vao = timed("flatten (H2D geometry)", s.vertex_array_object)
     timed("raycaster (LBVH build)", s.raycaster)
     timed("fused scene (H2D textures)", s._fused_scene)

@@ -20,6 +20,7 @@ from diffrp_b200 import synthetic as syn
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, required=True, choices=[4, 5])
 ap.add_argument("--scale", type=float, default=1.0, help="scale spp (and views for config 4) for quick runs")
+ap.add_argument("--no-reuse", action="store_true", help="config 4: rebuild the BVH for every view (the reference's behaviour)")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -50,10 +51,9 @@ if args.config == 4:
     outs, traced = [], 0
     for k in views:
         cam = drp.PerspectiveCamera.from_orbit(h=512, w=512, radius=3.0, azim=360.0 * k / n_views, elev=20.0 * np.sin(2 * np.pi * k / n_views), origin=[0, 0, 0])
-        sess = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=k))
-        rad, alpha, extras = sess.pbr()  # a session per view: flatten + LBVH build + render (sessions are single-use)
+        sess = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=k, reuse_scene=not args.no_reuse))
+        rad, alpha, extras = sess.pbr()  # a session per view (single-use, like the reference); the scene cache keeps flatten + BVH
         outs.append(torch.cat([rad, extras['albedo'], extras['world_normal']], -1))
-        sess.raycaster().release()
     ev1.record(); torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
