@@ -147,6 +147,18 @@ def hit_barycentric(a, b, c, p):
     return torch.stack([1 - v - w, v, w], -1)
 
 
+def triidx_to_float(ids: torch.Tensor) -> torch.Tensor:
+    """1-based triangle id -> float channel of the raster record: exact float up to 2^24, bit-packed into the float's
+    mantissa beyond (interpolator.py:28-29), so ids never lose precision in ``vi_data``."""
+    ids = ids.int()
+    return torch.where(ids <= 0x01000000, ids.float(), (ids + 0x4a800000).view(torch.float32))
+
+
+def float_to_triidx(x: torch.Tensor) -> torch.Tensor:
+    """Inverse of triidx_to_float (interpolator.py:24-25)."""
+    return torch.where(x <= 16777216, x.int(), x.view(torch.int32) - 0x4a800000)
+
+
 def layer_material_rays(sess, rays_o, rays_d, t, i) -> List[Tuple[SurfaceInput, SurfaceOutputStandard]]:
     """Evaluate every object's material on the rays that hit it (path_tracing.py:158-178)."""
     V, P, far = sess.camera_V(), sess.camera_P(), sess.camera_far()
@@ -154,7 +166,7 @@ def layer_material_rays(sess, rays_o, rays_d, t, i) -> List[Tuple[SurfaceInput, 
     ids = torch.where(t < far, i.int() + 1, 0)  # 1-based, 0 = miss; int32 (the reference's int64 ids break here)
     corners = vao.world_pos[vao.tris[(ids - 1).long()].long()]
     bary = hit_barycentric(corners[:, 0], corners[:, 1], corners[:, 2], rays_o + rays_d * t[..., None])
-    vi_data = torch.cat([bary[:, :2], t[..., None], ids[..., None].float()], -1)
+    vi_data = torch.cat([bary[:, :2], t[..., None], triidx_to_float(ids[..., None])], -1)
     stencil = vao.stencils[ids.long()]
     mats = []
     for k, obj in enumerate(sess.scene.objects):

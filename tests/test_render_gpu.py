@@ -81,8 +81,10 @@ def test_compaction_is_exact_and_sharding_sums_to_the_whole():
     base = dict(ray_spp=8, ray_depth=4, rng='native', seed=5)
     a = run_session(scene, cam, compaction=True, **base)
     b = run_session(scene, cam, compaction=False, **base)
-    acc_a, acc_b = a.render_accumulators(), b.render_accumulators()
-    sa, sb = a.render_stats(), b.render_stats()
+    acc_a = a.render_accumulators()
+    sa = a.render_stats()  # per BVH handle = per shared scene cache entry: read before the next session renders
+    acc_b = b.render_accumulators()
+    sb = b.render_stats()
     assert sb['rays_traced'] == sb['rays_nominal'] and sa['rays_traced'] < sb['rays_traced']
     torch.testing.assert_close(acc_a, acc_b, rtol=1e-5, atol=1e-5)  # fp32 atomics reorder only
     parts = [run_session(scene, cam, shard_rank=r, shard_world=2, **base).render_accumulators() for r in range(2)]

@@ -99,3 +99,27 @@ def test_scene_cache_is_shared_between_sessions_and_invalidated_by_in_place_edit
     c = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1))
     assert c.raycaster() is not a.raycaster()
     assert (c.pbr()[0] - ra).abs().max() > 1e-3
+
+
+def test_torchoptix_shaped_module_drives_raw_pointers():
+    """diffrp_b200.optix_compat has the call surface diffrp's TorchOptiX wrapper uses (raycaster.py:267-296)."""
+    import diffrp_b200.optix_compat as optix
+    from diffrp_b200 import synthetic as syn
+    v, f = syn.icosphere(3, 0.8)
+    o, d = syn.random_rays(30_000, seed=2)
+    V, F, O, D = (torch.from_numpy(x).cuda() for x in (v, f, o, d))
+    optix.set_log_level(0)
+    handle = optix.build(V.data_ptr(), F.data_ptr(), len(V), len(F))
+    out_t = O.new_empty([len(O)])
+    out_i = O.new_empty([len(O)], dtype=torch.int32)
+    optix.trace_rays(handle, O.data_ptr(), D.data_ptr(), out_t.data_ptr(), out_i.data_ptr(), 10.0, len(O))
+    torch.cuda.synchronize()
+    optix.release(handle)
+    ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)
+    assert np.array_equal(out_t.cpu().numpy().view(np.int32), ot.view(np.int32)) and np.array_equal(out_i.cpu().numpy(), oi)
+
+
+def test_triangle_id_float_packing_round_trips():
+    from diffrp_b200.generic import triidx_to_float, float_to_triidx
+    ids = torch.tensor([0, 1, 5, 2 ** 24 - 1, 2 ** 24, 2 ** 24 + 1, 2 ** 24 + 12345, 2 ** 26 + 7], dtype=torch.int32, device='cuda')
+    assert torch.equal(float_to_triidx(triidx_to_float(ids)), ids)
