@@ -366,7 +366,8 @@ def main():
                 "single_section_session": {"value": e2e_sec_value, "unit": UNIT, "ms_per_call": e2e_sec_ms, "calls": E,
                                            "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
                                            "what": "same call with ray_spp=%d: scene upload + build paid per section" % S}},
-        "gpu_launches": int(launches_per_step * K + 1),
+        "gpu_launches": int(launches_per_step * K + 1),  # kernels of libdiffrp_b200.so in the timed region: per step 4 x (k_extend_cw + k_shade)
+                                                          # + k_count_traced + 8 x k_record_live (profiling spans); + 1 k_finalize
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "native_library": loaded_path(),

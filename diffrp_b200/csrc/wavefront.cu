@@ -609,8 +609,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
         const int ns = std::min(spb, p.n_samples - s0);
         const int64_t R_batch = (int64_t)ns * HW;
         const int G = (overlap && R_batch >= (1 << 18)) ? 2 : 1;
-        DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));
-        ++launches;
+        DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));  // (a memset node, not counted as a kernel launch)
         if (G == 2) {  // fork: both internal streams start after everything already queued on the caller's stream
             DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[0], s));
             for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamWaitEvent(ws->streams[g], ws->sync_events[0], 0));
@@ -636,6 +635,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
                     sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
                     sp.traced_slot = ws->d_live + ws->live_used++;
                     k_record_live<<<1, 1, 0, sg>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
+                    ++launches;
                     cudaEventRecord(sp.a, sg);
                     ws->spans.push_back(sp);
                     return (int)ws->spans.size() - 1;
