@@ -28,6 +28,8 @@ struct RenderWorkspace {
     int64_t capacity = 0;  // rays
     float4 *qa[2] = {nullptr, nullptr}, *qb[2] = {nullptr, nullptr}, *qt[2] = {nullptr, nullptr};
     float2* hit = nullptr;
+    int* hit_list = nullptr;   // queue slots of the rays that hit / missed in the last extend (partitioned shading)
+    int* miss_list = nullptr;
     int* counters = nullptr;  // [0..D] live counts per bounce, [64..64+2D) fetch cursors
     int n_counters = 0;
     drp_material_t* d_mats = nullptr;
@@ -176,6 +178,13 @@ struct AosRays {
     float* out_t;
     int32_t* out_i;
 };
+// optional hit / miss partition of the finished rays (queue slots), consumed by k_shade<., SHADE_HITS / SHADE_MISSES>
+struct Partition {
+    int* hit_list;
+    int* miss_list;
+    int* hit_count;
+    int* miss_count;
+};
 
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
@@ -183,9 +192,10 @@ struct AosRays {
 #ifndef DRP_SHADE_MINBLOCKS
 #define DRP_SHADE_MINBLOCKS 5
 #endif
-template <int SRC>
+template <int SRC, bool PART>
 __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
-                                                        float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos) {
+                                                        float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos,
+                                                        Partition part) {
     const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -320,6 +330,16 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                             aos.out_i[k] = is_hit ? id_best : 0;
                         } else {
                             hit[k] = make_float2(is_hit ? t_best : c.p.t_far, __int_as_float(is_hit ? id_best : 0));
+                            if (PART) {  // warp-aggregated append of this iteration's finished rays to the hit / miss lists
+                                const unsigned fin = __activemask();
+                                const unsigned hm = __ballot_sync(fin, is_hit), mm = fin & ~hm;
+                                const unsigned mine = is_hit ? hm : mm;
+                                const int leader = __ffs(mine) - 1;
+                                int pos = 0;
+                                if (lane == leader) pos = atomicAdd(is_hit ? part.hit_count : part.miss_count, __popc(mine));
+                                pos = __shfl_sync(mine, pos, leader);
+                                (is_hit ? part.hit_list : part.miss_list)[pos + __popc(mine & lt_mask)] = k;
+                            }
                         }
                         k = -1;
                         break;
@@ -339,12 +359,19 @@ __device__ __forceinline__ void accum_add4(float* p, float a, float b, float c, 
     atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));  // RED.E.ADD.F32x4 (sm_90+)
 }
 
-template <bool PRIMARY>
+// MODE: SHADE_ALL walks the queue itself (hits and misses mixed in one warp); SHADE_HITS / SHADE_MISSES walk the index lists the
+// extend kernel partitions finished rays into, so a warp runs either the surface + BRDF path or the environment path, not both
+// serialised (ncu: 14-16 of 32 lanes active on bounces >= 1 with the mixed kernel).
+#define SHADE_ALL 0
+#define SHADE_HITS 1
+#define SHADE_MISSES 2
+template <bool PRIMARY, int MODE>
 __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WfConst c, int bounce, const float4* __restrict__ qa,
                                                     const float4* __restrict__ qb, const float4* __restrict__ qt, const float2* __restrict__ hit,
                                                     float4* __restrict__ oa, float4* __restrict__ ob, float4* __restrict__ ot,
-                                                    const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor) {
-    const int count = PRIMARY ? (int)c.R : *count_ptr;
+                                                    const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor,
+                                                    const int* __restrict__ index_list) {
+    const int count = (PRIMARY && MODE == SHADE_ALL) ? (int)c.R : *count_ptr;
     const int lane = threadIdx.x & 31;
     const bool last = bounce == c.p.ray_depth - 1;
     const bool always_sky = last && c.p.last_bounce_skybox;  // path_tracing.py:260
@@ -355,17 +382,18 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
         if (base >= count) break;
 #pragma unroll 1
         for (int j = 0; j < WF_FETCH; j += 32) {
-            int k = base + j + lane;
+            const int slot = base + j + lane;
             bool alive = false;
             Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
             int ri = 0;
-            if (k < count) {
+            if (slot < count) {
+                const int k = MODE == SHADE_ALL ? slot : __ldg(index_list + slot);  // queue slot of the ray
                 Vec3 o, d;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
                 if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
-                float2 h = __ldg(hit + k);
+                float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : __ldg(hit + k);
                 const float t = h.x;
-                const bool is_hit = t < c.p.t_far;
+                const bool is_hit = MODE == SHADE_HITS ? true : (MODE == SHADE_MISSES ? false : t < c.p.t_far);
                 SurfaceAttrs s;
                 if (is_hit) {
                     s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y));
@@ -475,23 +503,23 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
         cudaDeviceProp prop;
         DRP_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
         h->ws->sm_count = prop.multiProcessorCount;
-        h->ws->n_counters = 512;  // two launch groups x (64 live counts + 128 fetch cursors + spare)
-        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 512));
+        h->ws->n_counters = 1024;  // two launch groups x (64 live counts, 128 fetch cursors, 4 x 64 partition counters / cursors)
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 1024));
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->d_traced, sizeof(unsigned long long)));
         int nb = 0;
-        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY, false>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, WF_BLOCK, 0));
         h->ws->grid_extend[1] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_QUEUE>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_QUEUE, false>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, WF_BLOCK, 0));
         h->ws->grid_extend[0] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true, SHADE_ALL>, WF_BLOCK, 0));
         h->ws->grid_shade[1] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<false, SHADE_ALL>, WF_BLOCK, 0));
         h->ws->grid_shade[0] = std::max(1, nb) * h->ws->sm_count;
     }
     RenderWorkspace* ws = h->ws;
     if (rays > 0 && rays > ws->capacity) {
         for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
-        cudaFree(ws->hit);
+        cudaFree(ws->hit); cudaFree(ws->hit_list); cudaFree(ws->miss_list);
         ws->capacity = 0;
         for (int k = 0; k < 2; ++k) {
             DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qa[k], sizeof(float4) * rays));
@@ -499,6 +527,8 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
             DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qt[k], sizeof(float4) * rays));
         }
         DRP_CUDA_CHECK(cudaMalloc((void**)&ws->hit, sizeof(float2) * rays));
+        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->hit_list, sizeof(int) * rays));
+        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->miss_list, sizeof(int) * rays));
         ws->capacity = rays;
     }
     if (n_mats > ws->mats_capacity) {
@@ -601,6 +631,10 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     static const bool overlap_env = getenv("DRP_OVERLAP") && atoi(getenv("DRP_OVERLAP")) != 0;
     static const int ovl_e = getenv("DRP_OVL_E") ? atoi(getenv("DRP_OVL_E")) : 5, ovl_s = getenv("DRP_OVL_S") ? atoi(getenv("DRP_OVL_S")) : 2;
     const bool overlap = overlap_env && h->wide && !simple_extend;
+    // A/B on B200: partitioned shading is 5 % SLOWER on config 3 (shade 3.36 vs 3.04 ms / step: the indirect, finish-ordered ray reads cost
+    // more than the hit/miss divergence they remove) -> off unless DRP_PARTITION=1
+    static const bool partition_env = getenv("DRP_PARTITION") && atoi(getenv("DRP_PARTITION")) != 0;
+    const bool partition = partition_env && h->wide && !simple_extend;
     if (overlap && !ws->streams[0]) {
         for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamCreateWithFlags(&ws->streams[g], cudaStreamNonBlocking));
         for (int g = 0; g < 4; ++g) DRP_CUDA_CHECK(cudaEventCreateWithFlags(&ws->sync_events[g], cudaEventDisableTiming));
@@ -621,8 +655,11 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
                 const int64_t qoff = (int64_t)g * (ws->capacity / 2);  // each group owns one half of every queue
                 c.R = r1 - r0;
                 c.ray_base = (int64_t)s0 * HW + r0;
-                int* counts = ws->counters + 256 * g;        // [0..D]
-                int* cursors = ws->counters + 256 * g + 64;  // [0..2D)
+                int* counts = ws->counters + 512 * g;        // [0..D]
+                int* cursors = ws->counters + 512 * g + 64;  // [0..2D)
+                int* pc = ws->counters + 512 * g + 192;      // partition: hit counts [0..63], miss counts [64..127], hit cursors [128..191], miss cursors [192..255]
+                Partition part = {nullptr, nullptr, nullptr, nullptr};
+                if (partition) part = Partition{ws->hit_list + qoff, ws->miss_list + qoff, pc + b, pc + 64 + b};
                 float2* hit = ws->hit + qoff;
                 const int in = b & 1, out = in ^ 1;
                 float4 *qa_in = ws->qa[in] + qoff, *qb_in = ws->qb[in] + qoff, *qt_in = ws->qt[in] + qoff;
@@ -643,22 +680,36 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
                 auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, sg); };
                 if (b == 0) {
                     int sp = span_begin(0, nullptr);
-                    if (h->wide && !simple_extend) k_extend_cw<SRC_PRIMARY><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays());
+                    if (h->wide && !simple_extend) { if (partition) k_extend_cw<SRC_PRIMARY, true><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), part);
+                      else k_extend_cw<SRC_PRIMARY, false><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), part); }
                     else if (h->wide) k_extend<true, true><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
                     else k_extend<true, false><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
                     span_end(sp);
                     if (G == 2 && g == 0) DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[1], sg));
                     sp = span_begin(1, nullptr);
-                    k_shade<true><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1);
+                    if (partition) {
+                        k_shade<true, SHADE_HITS><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, pc + b, counts + 1, pc + 128 + b, part.hit_list);
+                        k_shade<true, SHADE_MISSES><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, pc + 64 + b, counts + 1, pc + 192 + b, part.miss_list);
+                        ++launches;
+                    } else {
+                        k_shade<true, SHADE_ALL><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1, nullptr);
+                    }
                     span_end(sp);
                 } else {
                     int sp = span_begin(0, counts + b);
-                    if (h->wide && !simple_extend) k_extend_cw<SRC_QUEUE><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays());
+                    if (h->wide && !simple_extend) { if (partition) k_extend_cw<SRC_QUEUE, true><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays(), part);
+                      else k_extend_cw<SRC_QUEUE, false><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays(), part); }
                     else if (h->wide) k_extend<false, true><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
                     else k_extend<false, false><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
                     span_end(sp);
                     sp = span_begin(1, counts + b);
-                    k_shade<false><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, counts + b, counts + b + 1, cursors + 2 * b + 1);
+                    if (partition) {
+                        k_shade<false, SHADE_HITS><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, pc + b, counts + b + 1, pc + 128 + b, part.hit_list);
+                        k_shade<false, SHADE_MISSES><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, pc + 64 + b, counts + b + 1, pc + 192 + b, part.miss_list);
+                        ++launches;
+                    } else {
+                        k_shade<false, SHADE_ALL><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, counts + b, counts + b + 1, cursors + 2 * b + 1, nullptr);
+                    }
                     span_end(sp);
                 }
                 launches += 2;
@@ -689,11 +740,11 @@ int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, fl
     WfConst c;
     memset(&c, 0, sizeof(c));
     c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.flags = h->dev_flags; c.cw_bias = 0x47000000u;
-    int* cursor = ws->counters + 250;
+    int* cursor = ws->counters + 1020;
     DRP_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int), s));
     AosRays aos = {ro, rd, out_t, out_i};
     int grid = ws->grid_extend[1];
-    k_extend_cw<SRC_AOS><<<grid, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, cursor, aos);
+    k_extend_cw<SRC_AOS, false><<<grid, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, cursor, aos, Partition{nullptr, nullptr, nullptr, nullptr});
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }
