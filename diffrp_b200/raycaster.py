@@ -48,8 +48,12 @@ class B200Raycaster(Raycaster):
     def build(self, verts: torch.Tensor, tris: torch.IntTensor, config: dict) -> None:
         self.handle = None
         self._lib = lib()
-        if not verts.is_cuda:
+        if not verts.is_cuda or not tris.is_cuda:
             raise ValueError("B200Raycaster needs CUDA tensors (there is no CPU path)")
+        if verts.ndim != 2 or verts.shape[-1] != 3 or tris.ndim != 2 or tris.shape[-1] != 3:
+            raise ValueError("verts must be (V, 3) and tris (F, 3)")
+        if len(tris) and (int(tris.min()) < 0 or int(tris.max()) >= len(verts)):
+            raise ValueError("triangle indices out of range")
         self._lib.drp_set_log_level(int(config.get('optix_log_level', 0)))
         # the library copies what it needs; these are only kept for introspection (cf. raycaster.py:271-272)
         self.verts = verts.detach().to(torch.float32).contiguous()
@@ -62,8 +66,19 @@ class B200Raycaster(Raycaster):
         self.handle = handle.value
         check(self._lib.drp_set_epsilon(self.handle, float(config.get('epsilon', 1e-8))), "drp_set_epsilon")
 
+    def _check_rays(self, rays_o: torch.Tensor, rays_d: torch.Tensor):
+        if not (rays_o.is_cuda and rays_d.is_cuda):
+            raise ValueError("B200Raycaster.query needs CUDA tensors (there is no CPU path)")
+        if rays_o.device != self.device or rays_d.device != self.device:
+            raise ValueError("rays live on %s but the structure was built on %s" % (rays_o.device, self.device))
+        if rays_o.shape != rays_d.shape or rays_o.ndim != 2 or rays_o.shape[-1] != 3:
+            raise ValueError("rays_o and rays_d must both have shape (R, 3)")
+        if self.handle is None:
+            raise RuntimeError("raycaster has been released")
+
     @torch.no_grad()
     def query(self, rays_o: torch.Tensor, rays_d: torch.Tensor, far: float) -> Tuple[torch.Tensor, torch.Tensor]:
+        self._check_rays(rays_o, rays_d)
         rays_o = rays_o.to(torch.float32).contiguous()
         rays_d = rays_d.to(torch.float32).contiguous()
         n = rays_o.shape[0] if rays_o.ndim > 0 else 0
@@ -76,6 +91,7 @@ class B200Raycaster(Raycaster):
     @torch.no_grad()
     def query_bruteforce(self, rays_o: torch.Tensor, rays_d: torch.Tensor, far: float):
         """Exhaustive O(R*F) query with the same triangle test / tie rule (validation aid)."""
+        self._check_rays(rays_o, rays_d)
         rays_o = rays_o.to(torch.float32).contiguous()
         rays_d = rays_d.to(torch.float32).contiguous()
         out_t = rays_o.new_empty([len(rays_o)])

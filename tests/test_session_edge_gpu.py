@@ -123,3 +123,19 @@ def test_triangle_id_float_packing_round_trips():
     from diffrp_b200.generic import triidx_to_float, float_to_triidx
     ids = torch.tensor([0, 1, 5, 2 ** 24 - 1, 2 ** 24, 2 ** 24 + 1, 2 ** 24 + 12345, 2 ** 26 + 7], dtype=torch.int32, device='cuda')
     assert torch.equal(float_to_triidx(triidx_to_float(ids)), ids)
+
+
+def test_raycaster_rejects_bad_inputs():
+    from diffrp_b200 import synthetic as syn
+    v, f = syn.icosphere(1, 0.8)
+    V, F = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
+    rc = drp.B200Raycaster(V, F)
+    with pytest.raises(ValueError):
+        rc.query(torch.zeros(4, 3), torch.zeros(4, 3), 1.0)            # CPU rays
+    with pytest.raises(ValueError):
+        rc.query(torch.zeros(4, 3).cuda(), torch.zeros(5, 3).cuda(), 1.0)  # shape mismatch
+    with pytest.raises(ValueError):
+        drp.B200Raycaster(V, (F + 1000))                                # indices out of range
+    rc.release()
+    with pytest.raises(RuntimeError):
+        rc.query(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda(), 1.0)
