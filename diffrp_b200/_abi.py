@@ -55,7 +55,7 @@ class RenderParams(C.Structure):
         ("height", C.c_int32), ("width", C.c_int32),
         ("ray_depth", C.c_int32), ("n_samples", C.c_int32),
         ("last_bounce_skybox", C.c_int32), ("rng_mode", C.c_int32),
-        ("compaction", C.c_int32), ("_pad", C.c_int32),
+        ("compaction", C.c_int32), ("reproducible", C.c_int32),
         ("tile_x0", C.c_int32), ("tile_y0", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
         ("step_epsilon", C.c_float), ("t_far", C.c_float), ("t_near", C.c_float), ("_padf", C.c_float),
         ("cam_pos", C.c_float * 4),

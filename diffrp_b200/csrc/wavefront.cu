@@ -577,7 +577,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_render: cannot select device"); return DRP_ERR_CUDA; }
     cudaStream_t s = (cudaStream_t)stream;
-    const int spb = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
+    const int spb = p.reproducible ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
     int rc = ensure_workspace(h, (((int64_t)spb * HW + 1) / 2) * 2 + 64, scene->n_materials);
     if (rc != DRP_OK) return rc;
     RenderWorkspace* ws = h->ws;

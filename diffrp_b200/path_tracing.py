@@ -45,6 +45,9 @@ class PathTracingSessionOptions:
             sampler (path_tracing.py:205-223) and replay them in the kernel: with the same ``torch.manual_seed`` the image
             reproduces the reference's within fp32 tolerance.
         seed (int): key of the native RNG.
+        reproducible (bool): the accumulators are updated with fp32 atomic adds, so the low bits of an image depend on the order in
+            which rays of the same pixel retire.  With ``reproducible=True`` every launch batch holds one sample per pixel, which fixes the
+            order (bounce by bounce, sample by sample) at the price of smaller launches.
         reuse_scene (bool): sessions are single-use like the reference's, but the flattened buffers, uploaded textures and the BVH
             of a ``Scene`` are kept (one entry per scene, keyed by the identity, shape and in-place version counter of every tensor)
             and adopted by the next session over the same unmodified scene -- multi-view rendering builds once, not per view.
@@ -73,6 +76,7 @@ class PathTracingSessionOptions:
     shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
     reuse_scene: bool = True  # share the flattened scene + BVH between sessions over the same, unmodified Scene
+    reproducible: bool = False  # bit-identical images run to run: one sample per launch batch, fixed fp32 accumulation order
 
 
 @dataclass
@@ -314,6 +318,7 @@ class PathTracingSession:
         p.height, p.width, p.ray_depth = H, W, opt.ray_depth
         p.last_bounce_skybox = int(opt.pbr_ray_last_bounce == 'skybox')
         p.compaction = int(opt.compaction)
+        p.reproducible = int(opt.reproducible)
         p.step_epsilon, p.t_far, p.t_near = opt.pbr_ray_step_epsilon, tab['t_far'], tab['t_near']
         p.cam_pos[:3] = tab['cam_pos']
         p.inv_vp[:] = tab['inv_vp']

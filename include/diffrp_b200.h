@@ -113,7 +113,8 @@ typedef struct drp_render_params {
     int32_t last_bounce_skybox; /* pbr_ray_last_bounce == 'skybox'                          */
     int32_t rng_mode;           /* DRP_RNG_*                                                */
     int32_t compaction;         /* 1: drop rays that provably contribute nothing (default)  */
-    int32_t _pad;
+    int32_t reproducible;       /* 1: one sample per internal batch, so every accumulator row receives its fp32 adds in a fixed
+                                      (kernel) order and the image is bit-identical from run to run (slower: smaller launches)   */
     int32_t tile_x0, tile_y0;   /* tile sharding: render only the pixel rectangle [x0, x0+w) x [y0, y0+h) (y counted  */
     int32_t tile_w, tile_h;     /* from the bottom row, like ndc_y); w == 0 or h == 0 means the whole frame            */
     float step_epsilon;         /* pbr_ray_step_epsilon                                     */

@@ -139,3 +139,14 @@ def test_raycaster_rejects_bad_inputs():
     rc.release()
     with pytest.raises(RuntimeError):
         rc.query(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda(), 1.0)
+
+
+def test_reproducible_mode_is_bit_identical_run_to_run():
+    scene = scenes.mixed_scene()
+    cam = drp.PerspectiveCamera.from_orbit(h=64, w=96, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32)
+    opt = dict(ray_spp=6, ray_depth=4, seed=3, reproducible=True)
+    a = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**opt)).render_accumulators()
+    b = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**opt)).render_accumulators()
+    assert torch.equal(a, b)
+    c = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**dict(opt, reproducible=False))).render_accumulators()
+    torch.testing.assert_close(a, c, rtol=1e-5, atol=1e-5)
