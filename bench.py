@@ -293,7 +293,7 @@ def main():
         s.raycaster().release()
 
     def timed_calls(n_calls, spp_total, sharded):
-        e2e_call(spp_total if spp_total <= 4 * S else S, 99, sharded)  # warm-up (allocator pools, workspace)
+        e2e_call(min(spp_total, 2 * S * (world if sharded else 1)), 99, sharded)  # warm-up: allocator pools, ray-queue workspace at its full (2^24-ray) size
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
