@@ -80,6 +80,14 @@ class RenderStats(C.Structure):
     _fields_ = [("rays_traced", C.c_int64), ("rays_nominal", C.c_int64), ("kernel_launches", C.c_int64)]
 
 
+class Object(C.Structure):
+    _fields_ = [
+        ("verts", C.c_void_p), ("normals", C.c_void_p), ("color", C.c_void_p), ("uv", C.c_void_p), ("tangents", C.c_void_p),
+        ("tris", C.c_void_p), ("M", C.c_float * 16), ("n_verts", C.c_int64), ("n_tris", C.c_int64),
+        ("color_channels", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 class Profile(C.Structure):
     _fields_ = [("extend_ms", C.c_double), ("shade_ms", C.c_double), ("extend_launches", C.c_int64), ("shade_launches", C.c_int64),
                 ("extend_rays", C.c_int64), ("shade_rays", C.c_int64)]
@@ -88,7 +96,7 @@ class Profile(C.Structure):
 #: every symbol declared in include/diffrp_b200.h (checked by tests/test_abi.py against the built library)
 EXPORTED_SYMBOLS = (
     "drp_abi_version", "drp_build_config", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
-    "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
+    "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_flatten", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
 )
 
 

@@ -30,6 +30,7 @@ def _declare(L):
     L.drp_render.argtypes = [u64, C.POINTER(_abi.Scene), C.POINTER(_abi.RenderParams), vp, vp]
     L.drp_finalize.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.drp_render_stats.argtypes = [u64, C.POINTER(_abi.RenderStats)]
+    L.drp_flatten.argtypes = [C.POINTER(_abi.Object), i32] + [vp] * 13
     L.drp_set_profiling.argtypes = [u64, C.c_int]
     L.drp_get_profile.argtypes = [u64, C.POINTER(_abi.Profile)]
     for name in _abi.EXPORTED_SYMBOLS:

@@ -1,13 +1,16 @@
-// wavefront.cu -- fused wavefront path tracer: drp_render / drp_finalize / drp_render_stats.
+// wavefront.cu -- fused wavefront path tracer: drp_render / drp_finalize / drp_render_stats / profiling.
 //
 // Replaces the Python section x bounce loop of PathTracingSession.trace_rays with the built-in sampler_brdf
 // (diffrp/rendering/path_tracing.py:250-279, 310-352).  Per batch of samples and per bounce, two persistent kernels:
-//   k_extend : closest hit for every live ray (bounce 0 generates the primary ray from the ray index instead of
-//              reading it), writes (t, id)
-//   k_shade  : surface attributes + env lookup + BRDF sample + fp32 accumulation (RED.ADD) + next ray, appended to
-//              the output queue through a warp-aggregated atomic (stream compaction fused into the shade kernel)
+//   k_extend_cw : closest hit for every live ray over the compressed 8-wide BVH (cwbvh.cuh): one ray per lane, dynamic ray
+//                 fetch by warp ballot, triangle postponing; bounce 0 generates the primary ray from the ray index instead
+//                 of reading it; writes (t, id).  (k_extend: the simple one-warp-batch kernel, kept for the binary layout.)
+//   k_shade     : surface attributes + env lookup + BRDF sample + fp32 accumulation (RED.ADD.F32x4) + next ray, appended to
+//                 the output queue through a warp-aggregated atomic (stream compaction fused into the shade kernel)
 // Ray state lives in HBM as float4 SoA queues (coalesced 128-bit accesses):
 //   q_a[k] = (o.x, o.y, o.z, d.x)   q_b[k] = (d.y, d.z, bits(ray index), 0)   q_t[k] = (T.r, T.g, T.b, 0)   hit[k] = (t, bits(id))
+// Compile-time / environment switches exist for every design alternative that was measured (see profiles/README.md and
+// drp_build_config()); the defaults are the fastest measured configuration.
 #include <vector>
 #include <algorithm>
 #include <string>
@@ -78,11 +81,6 @@ struct WfConst {
     float* accum;
     int* flags;
     uint32_t cw_bias;   // 0x47000000 (cwbvh.cuh: cw_byte_biased), passed through the constant bank
-};
-
-// ---- ray fetch: each warp claims WF_FETCH consecutive queue slots per atomic ------------------------------------
-struct WarpFetch {
-    int base, end;
 };
 
 template <bool PRIMARY>

@@ -29,6 +29,7 @@ class VertexArrayObject:
     world_nrm: torch.Tensor = None
     world_tan: torch.Tensor = None
     tri_material: torch.Tensor = None
+    records: torch.Tensor = None  # (V,16) interleaved [pos3 nrm3 uv2 | color4 tan4] shading records (CUDA path)
 
 
 
@@ -70,6 +71,70 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
         cat(verts, [0, 3]), cat(nrms, [0, 3]), cat(wpos, [0, 3]), cat(tris, [0, 3], torch.int32), torch.cat(sts).contiguous(),
         cat(cols, [0, 4]), cat(uvs, [0, 2]), cat(tans, [0, 4]), {k: torch.cat(v) for k, v in customs.items()},
         cat(wn, [0, 3]), cat(wt, [0, 4]), cat(tm, [0], torch.int32))
+
+
+def flatten_scene_cuda(objs: List, dev) -> VertexArrayObject:
+    """
+    ``flatten_scene`` in one CUDA pass (``drp_flatten``): sources that already live on ``dev`` or in pinned host memory are
+    read in place (for a pinned host scene the kernel's read over PCIe is the upload); anything else is moved with torch first.
+    Custom vertex attributes (only visible to Python materials) are still concatenated with torch.
+    """
+    import ctypes as C
+    from . import _abi
+    from ._lib import lib, check
+    dev = torch.device(dev)
+    keep = []
+
+    def src(t, dtype):
+        ok = t.dtype == dtype and t.is_contiguous() and ((t.is_cuda and t.device == dev) or (not t.is_cuda and t.is_pinned()))
+        if not ok:
+            t = t.to(dev, dtype, non_blocking=True).contiguous()
+        keep.append(t)
+        return t
+
+    descs = (_abi.Object * max(1, len(objs)))()
+    V = F = 0
+    for k, o in enumerate(objs):
+        assert o.tris.shape[-1] == 3, "Expected 3 vertices per triangle, got %d" % o.tris.shape[-1]
+        v, n, col, uv, tg, tr = (src(o.verts, torch.float32), src(o.normals, torch.float32), src(o.color, torch.float32),
+                                 src(o.uv, torch.float32), src(o.tangents, torch.float32), src(o.tris, torch.int32))
+        nv = v.shape[0]
+        for name, a, c in (("normals", n, 3), ("uv", uv, 2), ("tangents", tg, 4), ("color", col, None)):
+            assert a.shape[0] == nv, "attribute length not the same as number of vertices"
+            assert c is None or a.shape[-1] == c, "expected %s dims but got %d for vertex attribute %s" % (c, a.shape[-1], name)
+        assert col.shape[-1] in (3, 4), "vertex colours must have 3 or 4 channels"
+        d = descs[k]
+        d.verts, d.normals, d.color, d.uv, d.tangents, d.tris = (v.data_ptr(), n.data_ptr(), col.data_ptr(), uv.data_ptr(),
+                                                                 tg.data_ptr(), tr.data_ptr())
+        d.M[:] = [float(x) for x in o.M.detach().to('cpu', torch.float32).reshape(-1)]
+        d.n_verts, d.n_tris, d.color_channels = nv, tr.shape[0], col.shape[-1]
+        V += nv
+        F += tr.shape[0]
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    i = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+    out = dict(world_pos=f(V, 3), world_nrm=f(V, 3), color=f(V, 4), uv=f(V, 2), world_tan=f(V, 4), tris=i(F, 3), tri_material=i(F),
+               stencils=i(F + 1), records=f(V, 16), verts=f(V, 3), normals=f(V, 3), tangents=f(V, 4))
+    check(lib().drp_flatten(descs, len(objs), out['world_pos'].data_ptr(), out['world_nrm'].data_ptr(), out['color'].data_ptr(),
+                            out['uv'].data_ptr(), out['world_tan'].data_ptr(), out['tris'].data_ptr(), out['tri_material'].data_ptr(),
+                            out['stencils'].data_ptr(), out['records'].data_ptr(), out['verts'].data_ptr(), out['normals'].data_ptr(),
+                            out['tangents'].data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "drp_flatten")
+    keys = set().union(*(o.custom_attrs.keys() for o in objs)) if objs else set()
+    customs = {}
+    for key in keys:
+        size = next(x.custom_attrs[key].shape[-1] for x in objs if key in x.custom_attrs)
+        parts = []
+        for o in objs:
+            if key in o.custom_attrs:
+                assert len(o.custom_attrs[key]) == len(o.verts), "Attribute length not the same as number of vertices: %s" % key
+                parts.append(o.custom_attrs[key].to(dev, torch.float32))
+            else:
+                parts.append(torch.zeros([len(o.verts), size], device=dev))
+        customs[key] = torch.cat(parts)
+    vao = VertexArrayObject(out['verts'], out['normals'], out['world_pos'], out['tris'], out['stencils'], out['color'], out['uv'],
+                            out['tangents'], customs, out['world_nrm'], out['world_tan'], out['tri_material'])
+    vao.records = out['records']
+    vao._sources = keep  # pinned / converted sources stay alive until the stream has consumed them
+    return vao
 
 
 def pad_rgba(img: torch.Tensor) -> torch.Tensor:

@@ -26,7 +26,7 @@ from .camera import Camera
 from .ops import small_matrix_inverse
 from .raycaster import B200Raycaster, _stream_ptr
 from .scene import Scene, ImageEnvironmentLight
-from .flatten import VertexArrayObject, flatten_scene, material_descriptions, pad_rgba
+from .flatten import VertexArrayObject, flatten_scene, flatten_scene_cuda, material_descriptions, pad_rgba
 
 
 @dataclass
@@ -245,7 +245,7 @@ class PathTracingSession:
     def vertex_array_object(self) -> VertexArrayObject:
         st = self._scene_store()
         if 'vao' not in st:
-            st['vao'] = flatten_scene(self.scene.objects, self.device)
+            st['vao'] = flatten_scene_cuda(self.scene.objects, self.device)  # one drp_flatten pass (flatten_scene = torch twin for CPU tests)
         return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
@@ -290,7 +290,7 @@ class PathTracingSession:
         if descs is None:
             return None
         vao = self.vertex_array_object()
-        records = torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
+        records = vao.records if vao.records is not None else torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
                       tris=vao.tris, tri_material=vao.tri_material, vertex_records=records)
         env = self._single_env_light()

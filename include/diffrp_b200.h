@@ -18,6 +18,7 @@
  *                       BruteForceRaycaster.query     diffrp/utils/raycaster.py:86-97
  *   drp_release         torchoptix.release            called at diffrp/utils/raycaster.py:293-296
  *   drp_set_epsilon     Raycaster.config['epsilon']   diffrp/utils/raycaster.py:91-92, path_tracing.py:144
+ *   drp_flatten         RenderSessionMixin.vertex_array_object  diffrp/rendering/mixin.py:74-113
  *   drp_render          PathTracingSession.trace_rays diffrp/rendering/path_tracing.py:310-347
  *                       (section x bounce loop with the built-in sampler_brdf, :250-279)
  *   drp_finalize        trace_rays epilogue           diffrp/rendering/path_tracing.py:348-352
@@ -136,6 +137,21 @@ typedef struct drp_render_params {
  *   [0:3] radiance  [3] alpha  [4:7] albedo  [7:10] emission  [10:13] world_normal  [13:16] world_position */
 #define DRP_ACCUM_CHANNELS 16
 
+/* One MeshObject as drp_flatten reads it (diffrp/scene/objects.py:11-69, after preprocess()).  The attribute pointers may be
+ * device memory or PINNED host memory (read through unified addressing: for host scenes the read is the upload). */
+typedef struct drp_object {
+    const float* verts;     /* (n_verts, 3)               */
+    const float* normals;   /* (n_verts, 3)               */
+    const float* color;     /* (n_verts, color_channels)  */
+    const float* uv;        /* (n_verts, 2)               */
+    const float* tangents;  /* (n_verts, 4)               */
+    const int32_t* tris;    /* (n_tris, 3)                */
+    float M[16];            /* model matrix, row-major    */
+    int64_t n_verts, n_tris;
+    int32_t color_channels; /* 3 or 4                     */
+    int32_t _pad;
+} drp_object_t;
+
 /* ---- entry points -------------------------------------------------------------------------- */
 
 int drp_abi_version(void);
@@ -177,6 +193,14 @@ typedef struct drp_bvh_stats {
     int32_t max_depth;
 } drp_bvh_stats_t;
 int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out);
+
+/* Scene flattening in one pass (RenderSessionMixin.vertex_array_object, diffrp/rendering/mixin.py:74-113, + the per-material
+ * world transforms of base_material.py:137-143): world positions, normalised world normals / tangents, RGBA colours, uv, offset
+ * indices, per-triangle material index, stencils (F+1, leading 0), optional interleaved (V,16) shading records and optional raw
+ * concatenations.  `objects` is a HOST array; outputs are device buffers sized from the descriptor totals. */
+int drp_flatten(const drp_object_t* objects, int32_t n_objects, float* world_pos, float* world_nrm, float* color4, float* uv,
+                float* world_tan, int32_t* tris, int32_t* tri_material, int32_t* stencils, float* records, float* verts_raw,
+                float* normals_raw, float* tangents_raw, void* stream);
 
 /* Fused wavefront: raygen -> [extend -> shade/sample/accumulate/compact] x ray_depth over
  * n_samples samples of every pixel, added into accum (H*W, 16).  `handle` must have been built over

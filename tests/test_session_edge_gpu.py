@@ -150,3 +150,25 @@ def test_reproducible_mode_is_bit_identical_run_to_run():
     assert torch.equal(a, b)
     c = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**dict(opt, reproducible=False))).render_accumulators()
     torch.testing.assert_close(a, c, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("where", ["pinned", "device", "pageable"])
+def test_cuda_flatten_matches_torch_flatten(where):
+    """drp_flatten (one pass, zero-copy reads of pinned host sources) vs the torch twin used by the CPU tests."""
+    from diffrp_b200.flatten import flatten_scene, flatten_scene_cuda
+    scene = scenes.mixed_scene()
+    if where == "device":
+        scene = scenes.to_device(scene, 'cuda')
+    elif where == "pinned":
+        for o in scene.objects:
+            for name in ("verts", "tris", "normals", "M", "color", "uv", "tangents"):
+                setattr(o, name, getattr(o, name).contiguous().pin_memory())
+    a = flatten_scene_cuda(scene.objects, 'cuda')
+    b = flatten_scene(scene.objects, 'cuda')
+    torch.cuda.synchronize()
+    for k in ("verts", "normals", "world_pos", "color", "uv", "tangents", "world_nrm", "world_tan"):
+        torch.testing.assert_close(getattr(a, k), getattr(b, k), rtol=1e-6, atol=1e-6, msg=k)
+    for k in ("tris", "stencils", "tri_material"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    rec = torch.cat([b.world_pos, b.world_nrm, b.uv, b.color, b.world_tan], 1)
+    torch.testing.assert_close(a.records, rec, rtol=1e-6, atol=1e-6)
