@@ -171,5 +171,7 @@ if __name__ == "__main__":
     orbit = dict(h=48, w=64, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32, near=0.1, far=10.0)
     pbr_fixture("pbr_mixed_void", scenes.mixed_scene(), None, 4, 3, 'void', 2, orbit=orbit)
     pbr_fixture("pbr_mixed_skybox", scenes.mixed_scene(), None, 2, 4, 'skybox', 3, orbit=orbit)
+    # high-spp image for the statistical (PSNR) comparison of the native counter-based RNG against the reference's torch RNG
+    pbr_fixture("pbr_mixed_256spp", scenes.mixed_scene(), None, 256, 3, 'skybox', 5, orbit=dict(orbit, h=36, w=48), impl='naive-pbbvh')
     # config 1 in full: icosphere, 64x64, 16 spp, 2 bounces (reference on CPU)
     pbr_fixture("pbr_config1", scenes.icosphere_scene(rotate=False, colors=False), dict(h=64, w=64), 16, 2, 'void', 0, impl='naive-pbbvh')

@@ -145,3 +145,12 @@ def test_tile_sharding_equals_whole_frame():
     # disjoint support: a pixel belongs to exactly one rank
     assert not ((parts[0].abs().sum(-1) > 0) & (parts[1].abs().sum(-1) > 0)).any()
     torch.testing.assert_close(parts[0] + parts[1], whole, rtol=1e-5, atol=1e-5)
+
+
+def test_native_rng_high_spp_matches_reference_image_by_psnr():
+    """No replay: the kernel's own Philox stream at 256 spp against the reference's 256-spp image (torch RNG)."""
+    from test_oracle_golden import HI_ORBIT, check_statistical_parity
+    g = load("pbr_mixed_256spp")
+    sess = run_session(scenes.mixed_scene(), drp.PerspectiveCamera.from_orbit(**HI_ORBIT), ray_spp=256, ray_depth=3, rng='native', seed=11,
+                       pbr_ray_last_bounce='skybox')
+    check_statistical_parity(as_numpy(*sess.pbr()), g)
