@@ -119,3 +119,48 @@ def test_tile_render_matches_oracle_tile(hs):
     hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc2.ctypes.data)
     hs.hs_free(h)
     np.testing.assert_allclose(acc2, tile, rtol=2e-5, atol=2e-5)
+
+
+def hs_query_wide(L, v, f, o, d, far, eps=1e-8):
+    vp = C.c_void_p
+    L.hs_build_wide.restype = vp
+    L.hs_build_wide.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.hs_trace_wide.restype = C.c_int64
+    L.hs_trace_wide.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp]
+    v, f = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(f, np.int32)
+    h = L.hs_build_wide(v.ctypes.data, f.ctypes.data, len(v), len(f))
+    t, i = np.empty(len(o), np.float32), np.empty(len(o), np.int32)
+    overflow = L.hs_trace_wide(h, o.ctypes.data, d.ctypes.data, len(o), far, eps, t.ctypes.data, i.ctypes.data)
+    L.hs_free(h)
+    return t, i, overflow
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e-3, 0.0), (1e3, 0.0), (1.0, 100.0), (1.0, 1e4), (1e-2, 37.5)])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_triangle_soups_all_layouts_equal_bruteforce(hs, scale, offset, seed):
+    """Conservativeness of the padded / quantised slab tests under extreme coordinates: random soups (sliver, degenerate and
+    duplicate triangles included) scaled by 1e-3..1e3 and translated up to 1e4 from the origin -- where fp32 spacing is ~1e-3
+    and every slab distance cancels catastrophically -- must still reproduce the exhaustive search bit for bit."""
+    rng = np.random.default_rng(seed)
+    n = 600
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    tri = c + rng.normal(0, 0.08, (n, 3, 3)) * rng.uniform(0.02, 1.0, (n, 1, 1))
+    tri[:20, 2] = tri[:20, 1]                      # degenerate (zero area)
+    tri[20:40] = tri[40:60]                        # exact duplicates
+    tri[60:80, :, 1] = tri[60:80, :1, 1]           # axis-aligned (flat in y): zero-thickness boxes
+    v = ((tri.reshape(-1, 3) * scale) + offset).astype(np.float32)
+    f = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    m = 20000
+    org = (rng.uniform(-3, 3, (m, 3)) * scale + offset).astype(np.float32)
+    tgt = (rng.uniform(-1, 1, (m, 3)) * scale + offset).astype(np.float32)
+    d = tgt - org
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    d[:200, 0] = 0.0                               # axis-parallel components
+    d[200:400, 1] = 0.0
+    d[:400] /= np.maximum(np.linalg.norm(d[:400], axis=-1, keepdims=True), 1e-20)
+    far = np.float32(20.0 * scale)
+    ot, oi = oracle.bruteforce(v, f, org, d, float(far), 0.0)
+    for name, (t, i, overflow) in (("binary", hs_query(hs, v, f, org, d, float(far), 0.0)[:2] + (0,)), ("wide", hs_query_wide(hs, v, f, org, d, float(far), 0.0))):
+        assert overflow == 0
+        bad = np.nonzero((t.view(np.int32) != ot.view(np.int32)) | (i != oi))[0]
+        assert len(bad) == 0, "%s layout: %d rays differ from the exhaustive search (first: %s)" % (name, len(bad), bad[:5])

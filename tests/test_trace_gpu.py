@@ -116,3 +116,30 @@ def test_noncontiguous_inputs_and_far_contract():
     ot, oi = oracle.bruteforce(v, f, o, d, 2.5, 1e-8)
     _assert_same(t.cpu().numpy(), i.cpu().numpy(), ot, oi)
     assert i.dtype == torch.int32 and t.dtype == torch.float32
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e-3, 0.0), (1e3, 0.0), (1.0, 1e4), (1e-2, 37.5)])
+def test_random_triangle_soups_extreme_coordinates(scale, offset):
+    """Same stress as tests/test_hostsim.py on the real kernels: sliver / degenerate / duplicate / flat triangles, axis-parallel
+    rays, coordinates scaled by 1e-3..1e3 and translated up to 1e4: t and ids bit-identical to the exhaustive oracle."""
+    rng = np.random.default_rng(3)
+    n = 2000
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    tri = c + rng.normal(0, 0.08, (n, 3, 3)) * rng.uniform(0.02, 1.0, (n, 1, 1))
+    tri[:20, 2] = tri[:20, 1]
+    tri[20:40] = tri[40:60]
+    tri[60:80, :, 1] = tri[60:80, :1, 1]
+    v = ((tri.reshape(-1, 3) * scale) + offset).astype(np.float32)
+    f = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    m = 200_000
+    org = (rng.uniform(-3, 3, (m, 3)) * scale + offset).astype(np.float32)
+    tgt = (rng.uniform(-1, 1, (m, 3)) * scale + offset).astype(np.float32)
+    d = tgt - org
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    d[:500, 0] = 0.0
+    d[500:1000, 1] = 0.0
+    d[:1000] /= np.maximum(np.linalg.norm(d[:1000], axis=-1, keepdims=True), 1e-20)
+    far = float(np.float32(20.0 * scale))
+    rc, t, i = _query(v, f, org, d, far=far, eps=0.0)
+    ot, oi = oracle.bruteforce(v, f, org, d, far, 0.0)
+    _assert_same(t, i, ot, oi)
