@@ -162,8 +162,34 @@ def pbr_fixture(name, scene, cam_kwargs, spp, depth, last_bounce, seed, orbit=No
          last_bounce=last_bounce, H=H, W=W, u_crc=crc(u.numpy()), far=np.float32(sess.camera_far()))
 
 
+def scene_api_fixture():
+    """MeshObject.preprocess ('flat' face soup / 'smooth' normals, objects.py:71-98) and Scene.static_batching (scene.py:33-75)."""
+    v, f = syn.icosphere(1, 0.5)
+    V, F = torch.from_numpy(v), torch.from_numpy(f)
+    rnd = lambda c, s: torch.rand(len(v), c, generator=torch.Generator().manual_seed(s))  # noqa: E731
+    out = {}
+    for mode in ('flat', 'smooth'):
+        o = diffrp.MeshObject(diffrp.DefaultMaterial(), V.clone(), F.clone(), normals=mode, color=rnd(4, 2), uv=rnd(2, 3), tangents=rnd(4, 4),
+                              custom_attrs={'w': rnd(2, 5)}).preprocess()
+        for k in ('verts', 'tris', 'normals', 'color', 'uv', 'tangents', 'M'):
+            out['%s_%s' % (mode, k)] = getattr(o, k).numpy()
+        out['%s_custom_w' % mode] = o.custom_attrs['w'].numpy()
+    m1, m2 = diffrp.DefaultMaterial(), diffrp.DefaultMaterial(torch.tensor([0.5, 0.6, 0.7]))
+    sc = diffrp.Scene()
+    for k, (mat, seed) in enumerate([(m1, 10), (m2, 11), (m1, 12)]):
+        sc.add_mesh_object(diffrp.MeshObject(mat, V.clone() * (1 + 0.1 * k), F.clone(), normals='smooth', M=scenes.rigid(seed, 1.0 + 0.2 * k, (k * 0.3, 0, 0)),
+                                             tangents=rnd(4, 20 + k)))
+    sc.static_batching()
+    out['batched_n'] = np.int32(len(sc.objects))
+    for j, o in enumerate(sc.objects):
+        for k in ('verts', 'tris', 'normals', 'color', 'uv', 'tangents', 'M'):
+            out['batched%d_%s' % (j, k)] = getattr(o, k).numpy()
+    save("scene_api", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    scene_api_fixture()
     raycast_fixtures()
     function_fixtures()
     pbr_fixture("pbr_icosphere", scenes.icosphere_scene(), dict(h=32, w=32), 4, 2, 'void', 0)

@@ -227,3 +227,30 @@ def test_oracle_native_rng_matches_reference_statistically():
     vao, hs, p, keep = scenes.oracle_inputs(scenes.mixed_scene(), cam, 256, 3, last_bounce='skybox', seed=11)
     acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hs, p)
     check_statistical_parity(oracle.finalize(acc, 36, 48, 256), g)
+
+
+# ---- scene API (inputs of the path): preprocess and static batching vs the reference's own results ---------------------
+def test_mesh_preprocess_and_static_batching_match_reference():
+    from diffrp_b200 import synthetic as syn
+    g = load("scene_api")
+    v, f = syn.icosphere(1, 0.5)
+    V, F = torch.from_numpy(v), torch.from_numpy(f)
+    rnd = lambda c, s: torch.rand(len(v), c, generator=torch.Generator().manual_seed(s))  # noqa: E731
+    for mode in ('flat', 'smooth'):
+        o = drp.MeshObject(drp.DefaultMaterial(), V.clone(), F.clone(), normals=mode, color=rnd(4, 2), uv=rnd(2, 3), tangents=rnd(4, 4),
+                           custom_attrs={'w': rnd(2, 5)}).preprocess()
+        for k in ('verts', 'normals', 'color', 'uv', 'tangents', 'M'):
+            np.testing.assert_allclose(getattr(o, k).numpy(), g['%s_%s' % (mode, k)], rtol=1e-6, atol=1e-7, err_msg="%s %s" % (mode, k))
+        assert np.array_equal(o.tris.numpy(), g['%s_tris' % mode]) and o.tris.dtype == torch.int32
+        np.testing.assert_allclose(o.custom_attrs['w'].numpy(), g['%s_custom_w' % mode], rtol=1e-6)
+    m1, m2 = drp.DefaultMaterial(), drp.DefaultMaterial(torch.tensor([0.5, 0.6, 0.7]))
+    sc = drp.Scene()
+    for k, (mat, seed) in enumerate([(m1, 10), (m2, 11), (m1, 12)]):
+        sc.add_mesh_object(drp.MeshObject(mat, V.clone() * (1 + 0.1 * k), F.clone(), normals='smooth', M=scenes.rigid(seed, 1.0 + 0.2 * k, (k * 0.3, 0, 0)),
+                                          tangents=rnd(4, 20 + k)))
+    sc.static_batching()
+    assert len(sc.objects) == int(g['batched_n']) == 2
+    for j, o in enumerate(sc.objects):
+        for k in ('verts', 'normals', 'color', 'uv', 'tangents', 'M'):
+            np.testing.assert_allclose(getattr(o, k).numpy(), g['batched%d_%s' % (j, k)], rtol=1e-5, atol=1e-6, err_msg="batched %d %s" % (j, k))
+        assert np.array_equal(o.tris.numpy(), g['batched%d_tris' % j])
