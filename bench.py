@@ -333,6 +333,12 @@ def main():
     if os.path.exists(traffic_file):  # one `ncu --set full` capture of the same command, committed under profiles/
         roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
+        tj = json.load(open(traffic_file))
+        if tj.get("l2_bytes_per_launch") and tj.get("l2_read_peak_gbs") and roofline["avg_launch_ms"] > 0:
+            # L2-level view (SURVEY 8d asks for % of the L2 roofline too): ncu L2 sector bytes per launch / live launch time / measured L2 peak
+            l2_gbs = tj["l2_bytes_per_launch"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9
+            roofline["l2"] = {"achieved": l2_gbs, "peak": tj["l2_read_peak_gbs"], "unit": "GB/s", "frac": l2_gbs / tj["l2_read_peak_gbs"],
+                              "bytes_per_launch": tj["l2_bytes_per_launch"], "peak_source": tj.get("l2_peak_source")}
     roofline["algorithmic_bytes_per_launch"] = roofline["rays_per_launch_avg"] * b_query(n_tris)
     roofline["note"] = ("algorithmic bytes = live rays x B_query (SURVEY 8d ideal-descent model, every level re-read from memory); measured DRAM "
                         "traffic is ~10x lower because the upper BVH levels stay in L1/L2 -- the kernel is issue-bound (ncu: math-pipe throttle, "

@@ -10,6 +10,6 @@ from .raycaster import Raycaster, B200Raycaster
 from .path_tracing import PathTracingSession, PathTracingSessionOptions, RayOutputs, hammersley
 from .flatten import VertexArrayObject
 from .generic import SurfaceInput, SurfaceUniform, MaskedSparseInterpolator
-from . import synthetic
+from . import synthetic, tonemap
 
 __version__ = "0.1.0"

@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -88,6 +88,14 @@ class Object(C.Structure):
     ]
 
 
+class TonemapParams(C.Structure):
+    _fields_ = [("tone", C.c_int32), ("lut_n", C.c_int32), ("lut", C.c_void_p), ("in_stride", C.c_int32), ("alpha_offset", C.c_int32),
+                ("flip_rows", C.c_int32), ("scale", C.c_float)]
+
+
+TONE_LINEAR, TONE_SRGB, TONE_AGX = 0, 1, 2
+
+
 class Profile(C.Structure):
     _fields_ = [("extend_ms", C.c_double), ("shade_ms", C.c_double), ("extend_launches", C.c_int64), ("shade_launches", C.c_int64),
                 ("extend_rays", C.c_int64), ("shade_rays", C.c_int64)]
@@ -97,6 +105,7 @@ class Profile(C.Structure):
 EXPORTED_SYMBOLS = (
     "drp_abi_version", "drp_build_config", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
     "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_flatten", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
+    "drp_tonemap",
 )
 
 

@@ -47,3 +47,10 @@ def install(diffrp_module):
     session.raycaster = raycaster
     session._b200_installed = True
     return cls
+
+
+def agx_lut(diffrp_module, variant: str = "base-contrast"):
+    """The AgX LUT of an installed diffrp, as its own loader returns it (tone_mapping.py:9-18: fliplr'd, z y x 3, on the GPU) --
+    the ``lut`` argument of ``diffrp_b200.tonemap.agx_base_contrast`` / ``PathTracingSession.pbr_image``."""
+    from importlib import import_module
+    return import_module(diffrp_module.__name__ + ".utils.tone_mapping").agx_lut_loader.load(variant)

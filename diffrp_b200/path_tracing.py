@@ -432,6 +432,22 @@ class PathTracingSession:
         accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
         return self.finalize(accum)
 
+    @torch.no_grad()
+    def pbr_image(self, tone='agx', lut: torch.Tensor = None):
+        """
+        ``pbr()`` followed by the documented display chain -- ``to_pil(cat([agx_base_contrast(radiance), alpha]))``
+        (tone_mapping.py:21-35, exchange.py:7-18) -- with normalisation, flipud, tone mapping, sRGB and quantisation fused into one pass
+        over the reduced accumulator (``drp_tonemap``): returns a (H, W, 4) uint8 CUDA tensor, 4 B/pixel to read back instead of 64.
+        ``tone``: 'agx' (needs ``lut``, see diffrp_b200.tonemap), 'srgb' or 'linear'.
+        """
+        from .tonemap import tonemap
+        if self._fused_scene() is None:
+            radiance, alpha, _ = self.trace_rays(self.sampler_brdf)
+            return tonemap(torch.cat([radiance, alpha], -1), tone, lut=lut, alpha_offset=3)[1]
+        accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
+        H, W = self.camera.resolution()
+        return tonemap(accum.view(H, W, _abi.ACCUM_CHANNELS), tone, lut=lut, scale=1.0 / self.options.ray_spp, alpha_offset=3, flip_rows=True)[1]
+
     # ---- generic path (user samplers / Python materials): see diffrp_b200/generic.py -------------------------------
     def layer_material_rays(self, rays_o, rays_d, t, i):
         from . import generic

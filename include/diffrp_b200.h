@@ -22,6 +22,11 @@
  *   drp_render          PathTracingSession.trace_rays diffrp/rendering/path_tracing.py:310-347
  *                       (section x bounce loop with the built-in sampler_brdf, :250-279)
  *   drp_finalize        trace_rays epilogue           diffrp/rendering/path_tracing.py:348-352
+ *   drp_tonemap         agx_base_contrast             diffrp/utils/tone_mapping.py:21-35
+ *                       linear_to_srgb                diffrp/utils/colors.py:33-42
+ *                       linear_to_alexa_logc_ei1000   diffrp/utils/colors.py:94-102
+ *                       sample3d (LUT lookup)         diffrp/utils/shader_ops.py:262-310
+ *                       to_pil byte conversion        diffrp/utils/exchange.py:7-18
  *   drp_trace_bruteforce (validation aid)             BruteForceRaycaster semantics on the GPU
  */
 #ifndef DIFFRP_B200_H
@@ -33,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 3
+#define DRP_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -212,6 +217,32 @@ int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_render_param
  * world_position (H,W,3) each; all divided by spp_total and flipped vertically (row 0 = top). */
 int drp_finalize(const float* accum, int32_t height, int32_t width, int32_t spp_total, float* radiance, float* alpha,
                  float* albedo, float* emission, float* world_normal, float* world_position, void* stream);
+
+/* Colour epilogue, one streaming pass instead of the reference's ~12 full-frame torch ops + fp32 D2H:
+ *   v   = src[pixel*in_stride + 0..2] * scale                     (scale = 1/spp when src is the accumulator)
+ *   rgb = tone == DRP_TONE_AGX  ? linear_to_srgb(sample3d(lut, linear_to_alexa_logc_ei1000(v)))   tone_mapping.py:21-35
+ *       : tone == DRP_TONE_SRGB ? linear_to_srgb(v)                                               colors.py:33-42
+ *       :                         v
+ *   a   = alpha_offset >= 0 ? src[pixel*in_stride + alpha_offset] * scale : absent
+ *   out_f32 (H,W,C) = (rgb, a) unclamped (what the reference's functions return); C = 3, or 4 with alpha
+ *   out_u8  (H,W,C) = trunc(clamp((rgb, a), 0, 1) * 255)          to_pil, exchange.py:17
+ * lut: (n,n,n,3) fp32, laid out as AgxLutLoader.load returns it (z y x 3, fliplr already applied); border-clamped
+ * trilinear lookup with grid_sample(align_corners=False) arithmetic.  flip_rows != 0 writes row r to H-1-r (trace_rays'
+ * flipud).  Either output may be NULL.  All pointers are device addresses. */
+#define DRP_TONE_LINEAR 0
+#define DRP_TONE_SRGB 1
+#define DRP_TONE_AGX 2
+typedef struct drp_tonemap_params {
+    int32_t tone;
+    int32_t lut_n;
+    const float* lut;
+    int32_t in_stride;    /* floats per source pixel (16 for the accumulator, 3 for an (N,3) tensor) */
+    int32_t alpha_offset; /* -1: no alpha channel */
+    int32_t flip_rows;
+    float scale;
+} drp_tonemap_params_t;
+int drp_tonemap(const float* src, int64_t height, int64_t width, const drp_tonemap_params_t* params, uint8_t* out_u8,
+                float* out_f32, void* stream);
 
 /* Counters of the last drp_render call on this handle (host-synchronous). */
 typedef struct drp_render_stats {

@@ -23,7 +23,7 @@ _BUILDER = {'splitaxis': BUILD_SPLITAXIS, 'morton': BUILD_MORTON}
 def build(force: bool = False) -> str:
     """Compile oracle/liborc.so with the committed Makefile (gcc, OpenMP)."""
     so = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orc_raycast.c", "orc_shade.c", "orc.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("orc_raycast.c", "orc_shade.c", "orc_tonemap.c", "orc.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "diffrp_b200.h"))
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
@@ -52,6 +52,7 @@ def lib():
         L.orc_render.argtypes = [vp, C.POINTER(_abi.Scene), C.POINTER(_abi.RenderParams), vp]
         L.orc_render.restype = i64
         L.orc_philox_uniform6.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+        L.orc_tonemap.argtypes = [vp, i64, i64, C.POINTER(_abi.TonemapParams), vp, vp]
         _LIB = L
     return _LIB
 
@@ -224,6 +225,24 @@ def finalize(accum, height, width, spp_total):
     a = accum.reshape(height, width, _abi.ACCUM_CHANNELS)[::-1] / np.float32(spp_total)
     return dict(radiance=a[..., 0:3].copy(), alpha=np.clip(a[..., 3:4], 0.0, 1.0), albedo=a[..., 4:7].copy(),
                 emission=a[..., 7:10].copy(), world_normal=a[..., 10:13].copy(), world_position=a[..., 13:16].copy())
+
+
+_TONES = {None: _abi.TONE_LINEAR, 'linear': _abi.TONE_LINEAR, 'srgb': _abi.TONE_SRGB, 'agx': _abi.TONE_AGX}
+
+
+def tonemap(src, tone='agx', lut=None, scale=1.0, alpha_offset=-1, flip_rows=False):
+    """orc_tonemap: src (H,W,S) or (N,S) fp32 -> (f32 (..,C), u8 (..,C)), C = 3 or 4 (with alpha).  tone_mapping.py:21-35,
+    colors.py:33-42, exchange.py:17."""
+    src = _f32(src)
+    shape = src.shape[:-1]
+    h, w = (shape if len(shape) == 2 else (1, int(np.prod(shape))))
+    lut = None if lut is None else _f32(lut)
+    p = _abi.TonemapParams(_TONES[tone], 0 if lut is None else lut.shape[0], None if lut is None else lut.ctypes.data, src.shape[-1],
+                           alpha_offset, int(flip_rows), scale)
+    c = 4 if alpha_offset >= 0 else 3
+    out_f, out_b = np.empty(shape + (c,), np.float32), np.empty(shape + (c,), np.uint8)
+    lib().orc_tonemap(_p(src), h, w, C.byref(p), _p(out_b), _p(out_f))
+    return out_f, out_b
 
 
 def inputs_from_scene(scene, camera, spp, depth, last_bounce='void', step_eps=1e-3, replay_u=None, seed=0, sample_ids=None):

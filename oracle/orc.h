@@ -81,6 +81,12 @@ int64_t orc_render(const orc_bvh_t* bvh, const drp_scene_t* scene, const drp_ren
 /* native RNG (shared definition with the CUDA kernels): Philox4x32-10 */
 void orc_philox_uniform6(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, float out6[6]);
 
+/* ---- colour epilogue (orc_tonemap.c): drp_tonemap's contract with host pointers ------------------------------ */
+float orc_logc(float x);
+float orc_srgb(float x);
+void orc_lut3d(const float* lut, int n, const float c[3], float out[3]);
+void orc_tonemap(const float* src, int64_t height, int64_t width, const drp_tonemap_params_t* p, uint8_t* out_u8, float* out_f32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,8 +187,42 @@ def scene_api_fixture():
     save("scene_api", **out)
 
 
+def tonemap_fixture():
+    """Colour epilogue: linear_to_srgb (colors.py:33-42), linear_to_alexa_logc_ei1000 (colors.py:94-102),
+    agx_base_contrast (tone_mapping.py:21-35) run unmodified with its LUT loader swapped for a synthetic LUT (the shipped LUT is a
+    data resource of the reference and is not copied), to_pil's byte conversion (exchange.py:7-18)."""
+    from diffrp.utils import tone_mapping
+    from diffrp.utils.colors import linear_to_srgb, linear_to_alexa_logc_ei1000
+    from diffrp.utils.shader_ops import saturate
+    g = torch.Generator().manual_seed(77)
+    n = 6000
+    rgb = torch.exp(torch.randn(n, 3, generator=g) * 2.5 - 1.5)                     # HDR, log-normal
+    rgb[:64] = torch.tensor([0.0, 0.0031308, 0.0031307, 0.010591, 0.010592, 1.0, 1e-8, 65504.0]).repeat(8)[:, None]
+    rgb[64:128] = -torch.rand(64, 3, generator=g) * 0.01                           # slightly negative (fireflies after filtering)
+    rgb[128:192] = torch.rand(64, 3, generator=g) * 0.02                           # around both cuts
+    # smooth synthetic LUT, stored the way AgxLutLoader.load returns it (fliplr already applied), z y x 3
+    N = 16
+    zz, yy, xx = torch.meshgrid(*(torch.linspace(0, 1, N),) * 3, indexing='ij')
+    lut_file = torch.stack([xx ** 1.5 * (1 - 0.2 * yy), 0.9 * yy + 0.1 * zz * xx, zz ** 0.7 * (0.5 + 0.5 * yy)], -1).contiguous()
+    lut_loaded = torch.fliplr(lut_file).contiguous()
+
+    class Loader:
+        def load(self, variant):
+            assert variant == "base-contrast"
+            return lut_loaded
+    tone_mapping.agx_lut_loader = Loader()
+    agx = tone_mapping.agx_base_contrast(rgb)
+    alpha = torch.rand(n, 1, generator=g) * 1.2 - 0.1
+    srgb = linear_to_srgb(rgb)
+    byte_agx = (saturate(torch.cat([agx, alpha], -1).float()) * 255).byte()
+    byte_srgb = (saturate(torch.cat([srgb, alpha], -1).float()) * 255).byte()
+    save("tonemap", rgb=rgb.numpy(), alpha=alpha.numpy(), lut=lut_loaded.numpy(), logc=linear_to_alexa_logc_ei1000(rgb).numpy(),
+         srgb=srgb.numpy(), agx=agx.numpy(), byte_agx=byte_agx.numpy(), byte_srgb=byte_srgb.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    tonemap_fixture()
     scene_api_fixture()
     raycast_fixtures()
     function_fixtures()

@@ -10,6 +10,7 @@
 #include "../../diffrp_b200/csrc/lbvh.cuh"
 #include "../../diffrp_b200/csrc/traverse.cuh"
 #include "../../diffrp_b200/csrc/cwbvh.cuh"
+#include "../../diffrp_b200/csrc/tonemap.cuh"
 
 struct HsBvh {
     int n;
@@ -255,4 +256,20 @@ extern "C" void hs_trav_stats(const HsBvh* h, int wide, const float* ro, const f
     }
     out[0] = (double)g_trav.nodes / (double)n;
     out[1] = (double)g_trav.tris / (double)n;
+}
+
+// colour epilogue: the per-pixel function of k_tonemap (csrc/tonemap.cuh), same output contract as drp_tonemap
+extern "C" void hs_tonemap(const float* src, int64_t height, int64_t width, const drp_tonemap_params_t* pp, uint8_t* out_u8, float* out_f32) {
+    const drp_tonemap_params_t p = *pp;
+    const int C = p.alpha_offset >= 0 ? 4 : 3;
+    for (int64_t i = 0; i < height * width; ++i) {
+        const int64_t row = i / width, col = i - row * width;
+        const int64_t o = (p.flip_rows ? height - 1 - row : row) * width + col;
+        float v[4];
+        tm_pixel(src + i * p.in_stride, p, v);
+        for (int ch = 0; ch < C; ++ch) {
+            if (out_f32) out_f32[C * o + ch] = v[ch];
+            if (out_u8) out_u8[C * o + ch] = tm_byte(v[ch]);
+        }
+    }
 }

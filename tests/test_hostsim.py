@@ -164,3 +164,20 @@ def test_random_triangle_soups_all_layouts_equal_bruteforce(hs, scale, offset, s
         assert overflow == 0
         bad = np.nonzero((t.view(np.int32) != ot.view(np.int32)) | (i != oi))[0]
         assert len(bad) == 0, "%s layout: %d rays differ from the exhaustive search (first: %s)" % (name, len(bad), bad[:5])
+
+
+def test_tonemap_pixel_function_equals_oracle(hs):
+    """csrc/tonemap.cuh (host build) vs oracle/orc_tonemap.c on the golden inputs: both use libm here, so floats are bit-identical."""
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tonemap.npz")))
+    hs.hs_tonemap.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(_abi.TonemapParams), C.c_void_p, C.c_void_p]
+    rgba = np.ascontiguousarray(np.concatenate([g['rgb'], g['alpha']], -1))
+    lut = np.ascontiguousarray(g['lut'])
+    for tone, name in ((_abi.TONE_AGX, 'agx'), (_abi.TONE_SRGB, 'srgb'), (_abi.TONE_LINEAR, 'linear')):
+        for alpha_offset in (3, -1):
+            c = 4 if alpha_offset >= 0 else 3
+            p = _abi.TonemapParams(tone, lut.shape[0], lut.ctypes.data, 4, alpha_offset, 0, 0.5)
+            f, b = np.empty((len(rgba), c), np.float32), np.empty((len(rgba), c), np.uint8)
+            hs.hs_tonemap(rgba.ctypes.data, 1, len(rgba), C.byref(p), b.ctypes.data, f.ctypes.data)
+            fo, bo = oracle.tonemap(rgba, name, lut=lut, scale=0.5, alpha_offset=alpha_offset)
+            assert np.array_equal(f.view(np.uint32), fo.view(np.uint32)), (name, alpha_offset, np.abs(f - fo).max())
+            assert np.array_equal(b, bo)

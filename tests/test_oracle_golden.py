@@ -254,3 +254,32 @@ def test_mesh_preprocess_and_static_batching_match_reference():
         for k in ('verts', 'normals', 'color', 'uv', 'tangents', 'M'):
             np.testing.assert_allclose(getattr(o, k).numpy(), g['batched%d_%s' % (j, k)], rtol=1e-5, atol=1e-6, err_msg="batched %d %s" % (j, k))
         assert np.array_equal(o.tris.numpy(), g['batched%d_tris' % j])
+
+
+# ---- colour epilogue: oracle vs the reference's agx_base_contrast / linear_to_srgb / to_pil -------------
+BYTE_FLIP_FRACTION = 2e-3   # trunc(x*255) flips by one when x*255 sits within an ulp of an integer (libm vs SLEEF pow/log10)
+
+
+def check_bytes(got, want):
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() <= BYTE_FLIP_FRACTION, (d.max(), (d > 0).mean())
+
+
+def test_oracle_tonemap_matches_reference():
+    g = load("tonemap")
+    rgba = np.concatenate([g['rgb'], g['alpha']], -1)
+    # stated tolerance (fp32 transcendental functions): 2e-6 absolute + 2e-6 relative
+    f, b = oracle.tonemap(rgba, 'srgb', alpha_offset=3)
+    np.testing.assert_allclose(f[:, :3], g['srgb'], rtol=2e-6, atol=2e-6)
+    assert np.array_equal(f[:, 3:], g['alpha'])
+    check_bytes(b, g['byte_srgb'])
+    f, b = oracle.tonemap(rgba, 'agx', lut=g['lut'], alpha_offset=3)
+    np.testing.assert_allclose(f[:, :3], g['agx'], rtol=2e-6, atol=2e-6)
+    check_bytes(b, g['byte_agx'])
+    # accumulator form: stride 16, /spp and flipud folded in
+    H, W, spp = 60, 100, 7
+    acc = np.zeros((H * W, 16), np.float32)
+    acc[:, :4] = rgba * spp
+    f2, b2 = oracle.tonemap(acc.reshape(H, W, 16), 'agx', lut=g['lut'], scale=1.0 / spp, alpha_offset=3, flip_rows=True)
+    np.testing.assert_allclose(f2[::-1].reshape(-1, 4)[:, :3], g['agx'], rtol=1e-5, atol=1e-5)
+    check_bytes(b2[::-1].reshape(-1, 4), g['byte_agx'])
