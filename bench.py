@@ -147,6 +147,54 @@ def cpu_oracle_step(oracle, bvh, hs, p, keep, win, sample_ids):
     return time.perf_counter() - t0, n
 
 
+def gpu_torch_baseline(scene, camkw, dev, args):
+    """The reference's torch-level GPU path, timed on this GPU in this run (north_star: "next to the reference timed in the same
+    run: its OptiX/torch GPU path"): the reference is a Python package that cannot travel to the box and torchoptix is not in the
+    image, so this is a PORT -- oracle/torch_pbbvh.py (NaivePBBVH restated as whole-array torch ops, checked against the reference's
+    own outputs in tests/test_oracle_golden.py) for intersection + the per-bounce torch shading ops of diffrp_b200/generic.py (the
+    restatement of path_tracing.py:158-352 that the parity tests compare with the fused kernels).  BVH build excluded, like `value`."""
+    import diffrp_b200 as drp
+    from oracle.torch_pbbvh import TorchPBBVHRaycaster
+    res, spp = args.torch_baseline_res, args.torch_baseline_spp
+    cam = drp.PerspectiveCamera.from_orbit(h=res, w=res, **camkw)
+    holder = {}
+
+    class TorchPathSession(drp.PathTracingSession):
+        def _fused_scene(self):
+            return None                                  # force the per-bounce torch path
+
+        def raycaster(self):
+            if 'rc' not in holder:
+                vao = self.vertex_array_object()
+                holder['rc'] = TorchPBBVHRaycaster(vao.world_pos, vao.tris, {'builder': 'splitaxis'})
+            return holder['rc']
+
+    def one(seed):
+        o = drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=DEPTH, rng='native', seed=seed)
+        r, a, x = TorchPathSession(scene, cam, o).pbr()
+        return r
+
+    t0 = time.perf_counter()
+    TorchPathSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=1, ray_depth=1)).raycaster()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    one(0)                                               # warm-up (jit, allocator)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, ms = 0, 0.0
+    while n < args.torch_baseline_steps or ms < 3000.0:
+        e0.record(); r = one(1 + n); e1.record(); torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1); n += 1
+        if n >= 16:
+            break
+    assert torch.isfinite(r).all()
+    rays = n * res * res * spp * DEPTH
+    return {"value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "kind": "port", "device": "same B200, same run",
+            "what": "torch-level NaivePBBVH (splitaxis) + per-bounce torch shading, the reference's fallback GPU path restated (oracle/torch_pbbvh.py + diffrp_b200/generic.py)",
+            "sample": "%d frames of %dx%d x %d spp x %d bounces, same scene and camera (%d nominal ray-bounces, %.1f s); torch BVH build %.1f s excluded"
+                      % (n, res, res, spp, DEPTH, rays, ms * 1e-3, build_s)}
+
+
 def run_reference(args, world, rank):
     """--impl reference: the reference's own algorithm for the path (CPU oracle port) on the box's host cores."""
     if rank != 0:
@@ -195,6 +243,10 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=8)
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-baseline-res", type=int, default=256)
+    ap.add_argument("--torch-baseline-spp", type=int, default=4)
+    ap.add_argument("--torch-baseline-steps", type=int, default=2)
+    ap.add_argument("--no-torch-baseline", action="store_true")
     args = ap.parse_args()
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
@@ -356,6 +408,13 @@ def main():
                         "sample": "%d steps of a %dx%d central window x %d spp x %d bounces of the same scene (%d ray-bounces, %.1f s); CPU BVH build %.1f s excluded"
                                   % (args.cpu_baseline_steps, args.ref_window, args.ref_window, args.ref_spp, DEPTH, nn, tt, build_s)}
 
+    torch_baseline = None
+    if world == 1 and not args.no_torch_baseline:
+        try:
+            torch_baseline = gpu_torch_baseline(scene, camkw, dev, args)
+        except Exception as exc:  # a baseline must never take the product's line down
+            torch_baseline = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -376,6 +435,7 @@ def main():
                                                           # + k_count_traced + 8 x k_record_live (profiling spans); + 1 k_finalize
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "gpu_torch_baseline": torch_baseline,
         "native_library": loaded_path(),
         "native_build": build_config(),
     }))

@@ -61,6 +61,23 @@ def test_bvh_reference_mode_matches_naive_pbbvh(builder):
     assert np.max(np.abs(t[hit] - rt[hit]) / rt[hit]) < 1e-5
 
 
+@pytest.mark.parametrize("builder", ['splitaxis', 'morton'])
+def test_torch_pbbvh_port_matches_naive_pbbvh(builder):
+    """oracle/torch_pbbvh.py (the torch-level program bench.py times on the GPU as the reference's fallback path) against the
+    reference's own NaivePBBVH outputs: same hit/miss, same ids on every hit, t to rounding."""
+    from oracle.torch_pbbvh import TorchPBBVH
+    g = load("raycast_icosphere")
+    far = float(g['far'])
+    bvh = TorchPBBVH(torch.from_numpy(g['verts']), torch.from_numpy(g['tris']), builder)
+    t, i = bvh.query(torch.from_numpy(g['rays_o']), torch.from_numpy(g['rays_d']), far)
+    t, i = t.numpy(), i.numpy()
+    rt, ri = g['bvh_%s_t' % builder], g['bvh_%s_i' % builder]
+    hit = rt < far
+    assert np.array_equal(t < far, hit)
+    assert np.array_equal(i[hit], ri[hit])
+    assert np.max(np.abs(t[hit] - rt[hit]) / rt[hit]) < 1e-5
+
+
 def _referee_explains(g, ids_a, t_a, ids_b, t_b, far):
     """Every ray on which two raycasters disagree must be a certified fp tie / edge case."""
     bad = np.nonzero((ids_a != ids_b) & ((t_a < far) | (t_b < far)) | ((t_a < far) != (t_b < far)))[0]
