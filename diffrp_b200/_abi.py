@@ -96,6 +96,15 @@ class TonemapParams(C.Structure):
 TONE_LINEAR, TONE_SRGB, TONE_AGX = 0, 1, 2
 
 
+class Conv3x3Params(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("height", C.c_int32), ("width", C.c_int32),
+                ("cin", C.c_int32), ("in_stride", C.c_int32), ("in_offset", C.c_int32), ("cout_pad", C.c_int32), ("cout_store", C.c_int32),
+                ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("mode", C.c_int32), ("relu", C.c_int32)]
+
+
+CONV_PLAIN, CONV_POOL2, CONV_UPSAMPLE2 = 0, 1, 2
+
+
 class Profile(C.Structure):
     _fields_ = [("extend_ms", C.c_double), ("shade_ms", C.c_double), ("extend_launches", C.c_int64), ("shade_launches", C.c_int64),
                 ("extend_rays", C.c_int64), ("shade_rays", C.c_int64)]
@@ -105,7 +114,7 @@ class Profile(C.Structure):
 EXPORTED_SYMBOLS = (
     "drp_abi_version", "drp_build_config", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
     "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_flatten", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
-    "drp_tonemap",
+    "drp_tonemap", "drp_conv3x3",
 )
 
 

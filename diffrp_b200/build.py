@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdiffrp_b200.so")
-SOURCES = ["api.cu", "wavefront.cu", "flatten.cu", "epilogue.cu"]
+SOURCES = ["api.cu", "wavefront.cu", "flatten.cu", "epilogue.cu", "conv3x3.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--extended-lambda",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",

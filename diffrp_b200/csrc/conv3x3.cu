@@ -1,0 +1,295 @@
+// conv3x3.cu -- drp_conv3x3: 3x3 convolution (padding 1) + bias + ReLU + {identity | 2x2 max-pool | 2x nearest upsample} as one
+// implicit-GEMM kernel on the 5th-generation tensor cores (tcgen05, TF32 operands, fp32 accumulators in TMEM).
+// Replaces the layers of the reference's OIDN-style U-Net denoiser, diffrp/rendering/denoiser.py:42-66 (Conv, relu, pool, upsample,
+// concat) as used by UNet.forward (:117-173); see include/diffrp_b200.h for the tensor layout contract.
+//
+// GEMM view per CTA:  D[128 pixels, cout_pad] = sum over 9 taps x (cin/16) channel chunks of  A[128, 16] * B[cout_pad, 16]^T
+//   * M tile = 8 rows x 16 columns of output pixels.  For tap (ky,kx) the A operand is the same 8x16 pixel box shifted by (ky-1,kx-1):
+//     ONE 3-D TMA box load (16 channels, 16 x, 8 y) per k-step; pixels outside the image are zero-filled by TMA (= padding 1).
+//   * B operand = 16 consecutive k of every output channel: one 2-D TMA box (16, cout_pad) of the [cout_pad][9*cin] weight matrix.
+//   * both tiles are K-major rows of 64 B -> SWIZZLE_64B on the TMA side and in the UMMA shared-memory descriptors;
+//     two tcgen05.mma.kind::tf32 (K = 8) per k-step, issued by one thread; tcgen05.commit releases the stage / signals the epilogue.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp % 4):
+//     tcgen05.ld 32x32b.x16 -> bias, ReLU -> pool via two shuffles (a 2x2 window lives in one warp) or 4-way replicated store.
+//   * STAGES-deep mbarrier ring between producer and MMA; several CTAs per SM overlap one tile's epilogue with another's main loop.
+#include <cuda.h>
+#include <cstdint>
+#include <mutex>
+#include "internal.h"
+
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 output pixels per CTA = UMMA M
+constexpr int KC = 16;                                         // fp32 per k-step row = 64 B (SWIZZLE_64B span)
+constexpr int STAGES = 6;
+constexpr int A_STAGE_BYTES = BM * KC * 4;                     // 8 KB
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;                      // a wedged pipeline traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO); version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)(512u >> 4) << 32;                // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version
+    d |= (uint64_t)4 << 61;                          // layout type SWIZZLE_64B
+    return d;
+}
+// instruction descriptor: D fp32, A/B TF32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct ConvArgs {
+    const float* bias;
+    float* out;
+    int height, width, k_steps, chunks;  // chunks = cin / 16, k_steps = 9 * chunks
+    int cout_pad, cout_store, out_stride, out_offset, mode, relu;
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                              const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage_bytes = a.cout_pad * KC * 4;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + STAGES * b_stage_bytes);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_ready = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer ----
+            const uint32_t stage_bytes = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+            for (int kb = 0; kb < a.k_steps; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty[s], phase ^ 1u);
+                mbar_expect_tx(&full[s], stage_bytes);
+                const int tap = kb / a.chunks, chunk = kb - tap * a.chunks;
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                tma_load_3d(&map_a, &full[s], smem_a + s * A_STAGE_BYTES, chunk * KC, x0 + dx, y0 + dy);
+                tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes, kb * KC, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            const uint32_t idesc = umma_idesc_tf32(a.cout_pad);
+            for (int kb = 0; kb < a.k_steps; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full[s], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t pa = smem_u32(smem_a + s * A_STAGE_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
+#pragma unroll
+                for (int k = 0; k < KC / 8; ++k)  // UMMA K = 8 TF32 = 32 B along the row
+                    umma_tf32(tmem_base, umma_desc_sw64(pa + k * 32), umma_desc_sw64(pb + k * 32), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
+            }
+            umma_commit(acc_ready);               // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;           // accumulator row = pixel of the tile
+        const int ty = m >> 4, tx = m & 15;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool inside = y < a.height && x < a.width;
+        mbar_wait(acc_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int c0 = 0; c0 < a.cout_pad; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also lanes outside the image
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] += __ldg(a.bias + c0 + i);
+                if (a.relu) v[i] = fmaxf(v[i], 0.0f);
+            }
+            if (a.mode == DRP_CONV_POOL2) {       // rows 2q, 2q+1 of the tile sit in this warp: lanes l, l^1, l^16, l^17
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+                }
+            }
+            if (!inside || c0 >= a.cout_store) continue;
+            const int n_store = min(16, a.cout_store - c0);
+            if (a.mode == DRP_CONV_PLAIN) {
+                float* o = a.out + ((int64_t)y * a.width + x) * a.out_stride + a.out_offset + c0;
+                if (n_store == 16) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
+                    for (int i = 0; i < n_store; ++i) o[i] = v[i];
+                }
+            } else if (a.mode == DRP_CONV_POOL2) {
+                if ((lane & 17) == 0) {           // lane 2j of the even row owns the window
+                    float* o = a.out + ((int64_t)(y >> 1) * (a.width >> 1) + (x >> 1)) * a.out_stride + a.out_offset + c0;
+                    if (n_store == 16) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < n_store; ++i) o[i] = v[i];
+                    }
+                }
+            } else {                              // DRP_CONV_UPSAMPLE2: nearest-neighbour 2x, written straight into the concat buffer
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float* o = a.out + ((int64_t)(2 * y + (r >> 1)) * (2 * a.width) + 2 * x + (r & 1)) * a.out_stride + a.out_offset + c0;
+                    if (n_store == 16) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < n_store; ++i) o[i] = v[i];
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+}  // namespace
+
+extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
+    if (!pp) { drp_set_error("drp_conv3x3: params is NULL"); return DRP_ERR_INVALID; }
+    const drp_conv3x3_params_t p = *pp;
+    if (p.height <= 0 || p.width <= 0) { drp_set_error("drp_conv3x3: empty image"); return DRP_ERR_INVALID; }
+    if (!p.in || !p.weight || !p.bias || !p.out) { drp_set_error("drp_conv3x3: NULL tensor"); return DRP_ERR_INVALID; }
+    if (p.cin < 16 || p.cin % 16 || p.in_stride % 16 || p.in_offset % 16 || p.in_offset + p.cin > p.in_stride) {
+        drp_set_error("drp_conv3x3: cin / in_stride / in_offset must be multiples of 16 with in_offset + cin <= in_stride"); return DRP_ERR_INVALID; }
+    if (p.cout_pad < 16 || p.cout_pad > 256 || p.cout_pad % 16 || p.cout_store < 1 || p.cout_store > p.cout_pad) {
+        drp_set_error("drp_conv3x3: cout_pad must be a multiple of 16 in [16, 256] and 1 <= cout_store <= cout_pad"); return DRP_ERR_INVALID; }
+    if (p.out_stride % 4 || p.out_offset % 4 || p.out_offset + p.cout_store > p.out_stride) {
+        drp_set_error("drp_conv3x3: out_stride / out_offset must be multiples of 4 with out_offset + cout_store <= out_stride"); return DRP_ERR_INVALID; }
+    if (p.mode < DRP_CONV_PLAIN || p.mode > DRP_CONV_UPSAMPLE2) { drp_set_error("drp_conv3x3: unknown mode"); return DRP_ERR_INVALID; }
+    if (p.mode == DRP_CONV_POOL2 && ((p.height | p.width) & 1)) { drp_set_error("drp_conv3x3: pooling needs even height and width"); return DRP_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.weight) | reinterpret_cast<uintptr_t>(p.out)) & 15) {
+        drp_set_error("drp_conv3x3: tensors must be 16-byte aligned"); return DRP_ERR_INVALID; }
+    EncodeTiledFn encode = encode_tiled();
+    if (!encode) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled is unavailable in this driver"); return DRP_ERR_CUDA; }
+
+    CUtensorMap map_a, map_b;
+    {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, 8), zero fill outside = padding 1
+        const cuuint64_t dims[3] = {(cuuint64_t)p.cin, (cuuint64_t)p.width, (cuuint64_t)p.height};
+        const cuuint64_t strides[2] = {(cuuint64_t)p.in_stride * 4, (cuuint64_t)p.in_stride * 4 * (cuuint64_t)p.width};
+        const cuuint32_t box[3] = {KC, TILE_W, TILE_H}, estr[3] = {1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.in + p.in_offset), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
+    }
+    {   // weights: (K = 9*cin, cout_pad), box (16, cout_pad)
+        const cuuint64_t dims[2] = {(cuuint64_t)9 * p.cin, (cuuint64_t)p.cout_pad};
+        const cuuint64_t strides[1] = {(cuuint64_t)9 * p.cin * 4};
+        const cuuint32_t box[2] = {KC, (cuuint32_t)p.cout_pad}, estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.weight), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
+    }
+    ConvArgs a;
+    a.bias = p.bias; a.out = p.out; a.height = p.height; a.width = p.width;
+    a.chunks = p.cin / KC; a.k_steps = 9 * a.chunks;
+    a.cout_pad = p.cout_pad; a.cout_store = p.cout_store; a.out_stride = p.out_stride; a.out_offset = p.out_offset; a.mode = p.mode; a.relu = p.relu;
+    a.tmem_cols = p.cout_pad <= 32 ? 32 : p.cout_pad <= 64 ? 64 : p.cout_pad <= 128 ? 128 : 256;
+    const size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + (size_t)p.cout_pad * KC * 4) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] { attr_err = cudaFuncSetAttribute(k_conv3x3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    DRP_CUDA_CHECK(attr_err);
+    const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + TILE_H - 1) / TILE_H));
+    k_conv3x3_tf32<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}

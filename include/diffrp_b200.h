@@ -27,6 +27,7 @@
  *                       linear_to_alexa_logc_ei1000   diffrp/utils/colors.py:94-102
  *                       sample3d (LUT lookup)         diffrp/utils/shader_ops.py:262-310
  *                       to_pil byte conversion        diffrp/utils/exchange.py:7-18
+ *   drp_conv3x3         Conv(...) + relu / pool / upsample / concat  diffrp/rendering/denoiser.py:42-66,117-173
  *   drp_trace_bruteforce (validation aid)             BruteForceRaycaster semantics on the GPU
  */
 #ifndef DIFFRP_B200_H
@@ -243,6 +244,33 @@ typedef struct drp_tonemap_params {
 } drp_tonemap_params_t;
 int drp_tonemap(const float* src, int64_t height, int64_t width, const drp_tonemap_params_t* params, uint8_t* out_u8,
                 float* out_f32, void* stream);
+
+/* ---- denoiser: the 3x3 convolutions of the OIDN-style U-Net the reference runs after pbr() -------------------
+ * Replaces nn.Conv2d(cin, cout, 3, padding=1) + F.relu (+ F.max_pool2d(x, 2, 2) | F.interpolate(scale_factor=2, 'nearest') +
+ * torch.cat) of diffrp/rendering/denoiser.py:42-66,117-173 with one tcgen05 (TF32, fp32 accumulate in TMEM) implicit-GEMM kernel per
+ * layer; cuDNN runs the reference's fp32 convolutions in TF32 as well (torch.backends.cudnn.allow_tf32 defaults to True).
+ * Activations are NHWC fp32 with a pixel stride, so a layer can read / write a channel slice of a wider (concatenation) buffer:
+ *   in  : pixel (y,x) channel c at in [(y*width + x)*in_stride  + in_offset  + c],  c < cin   (cin  % 16 == 0)
+ *   w   : [cout_pad][9*cin] fp32, k = (ky*3 + kx)*cin + c   (cout_pad % 16 == 0, 16..256; rows >= the real cout are zero)
+ *   bias: [cout_pad]
+ *   out : mode DRP_CONV_PLAIN     (y,x)        -> out[(y*width + x)*out_stride + out_offset + c], c < cout_store
+ *         mode DRP_CONV_POOL2     max over 2x2 -> out[((y/2)*(width/2) + x/2)*out_stride + ...]       (height, width even)
+ *         mode DRP_CONV_UPSAMPLE2 replicated   -> out[((2y+a)*(2*width) + 2x+b)*out_stride + ...], a,b in {0,1}
+ * All strides / offsets in floats, multiples of 4 (16 for the input side).  relu != 0 applies max(.,0) before pooling / replication. */
+#define DRP_CONV_PLAIN 0
+#define DRP_CONV_POOL2 1
+#define DRP_CONV_UPSAMPLE2 2
+typedef struct drp_conv3x3_params {
+    const float* in;
+    const float* weight;
+    const float* bias;
+    float* out;
+    int32_t height, width;
+    int32_t cin, in_stride, in_offset;
+    int32_t cout_pad, cout_store, out_stride, out_offset;
+    int32_t mode, relu;
+} drp_conv3x3_params_t;
+int drp_conv3x3(const drp_conv3x3_params_t* params, void* stream);
 
 /* Counters of the last drp_render call on this handle (host-synchronous). */
 typedef struct drp_render_stats {
