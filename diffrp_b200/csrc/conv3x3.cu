@@ -293,3 +293,80 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }
+
+// ---- network input / output transforms of run_denoiser (diffrp/rendering/denoiser.py:24-35) ------------------------------------
+// PU transfer function, diffrp/utils/colors.py:5-31
+namespace {
+constexpr float PU_A = 1.41283765e+03f, PU_B = 1.64593172e+00f, PU_C = 4.31384981e-01f, PU_D = -2.94139609e-03f, PU_E = 1.92653254e-01f,
+                PU_F = 6.26026094e-03f, PU_G = 9.98620152e-01f, PU_Y0 = 1.57945760e-06f, PU_Y1 = 3.22087631e-02f, PU_X0 = 2.23151711e-03f,
+                PU_X1 = 3.70974749e-01f;
+__host__ __device__ inline float linear_to_pu(float y) {
+    return y <= PU_Y0 ? PU_A * y : (y <= PU_Y1 ? PU_B * powf(y, PU_C) + PU_D : PU_E * logf(y + PU_F) + PU_G);
+}
+__host__ __device__ inline float pu_to_linear(float x) {
+    return x <= PU_X0 ? x / PU_A : (x <= PU_X1 ? powf((x - PU_D) / PU_B, 1.0f / PU_C) : expf((x - PU_G) / PU_E) - PU_F);
+}
+__device__ __forceinline__ int reflect_index(int i, int n) {  // nn.ReflectionPad2d: mirror without repeating the border sample
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return min(max(i, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256) k_denoise_pack(const float* __restrict__ hdr, const float* __restrict__ albedo, const float* __restrict__ normal,
+                                                      int h, int w, float* __restrict__ dst, int H, int W, int stride, int offset, float pu_scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)H * W) return;
+    const int Y = (int)(i / W), X = (int)(i - (int64_t)Y * W);
+    const int top = (H - h) / 2, left = (W - w) / 2;          // dh // 2, dw // 2
+    const int64_t s = ((int64_t)reflect_index(Y - top, h) * w + reflect_index(X - left, w)) * 3;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v[c] = linear_to_pu(__ldg(hdr + s + c)) * pu_scale;
+        v[3 + c] = __ldg(albedo + s + c);
+        v[6 + c] = __ldg(normal + s + c) * 0.5f + 0.5f;
+    }
+#pragma unroll
+    for (int c = 9; c < 16; ++c) v[c] = 0.0f;
+    float4* o = reinterpret_cast<float4*>(dst + i * stride + offset);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+__global__ void __launch_bounds__(256) k_denoise_unpack(const float* __restrict__ src, int H, int W, int stride, float* __restrict__ out, int h, int w,
+                                                        float inv_pu_scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)h * w) return;
+    const int y = (int)(i / w), x = (int)(i - (int64_t)y * w);
+    const int top = (H - h) / 2, left = (W - w) / 2;
+    const float* s = src + ((int64_t)(y + top) * W + (x + left)) * stride;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[3 * i + c] = pu_to_linear(__ldg(s + c) * inv_pu_scale);
+}
+}  // namespace
+
+extern "C" int drp_denoise_pack(const float* hdr, const float* albedo_srgb, const float* normal, int32_t height, int32_t width, float* dst,
+                                int32_t padded_height, int32_t padded_width, int32_t dst_stride, int32_t dst_offset, void* stream) {
+    if (!hdr || !albedo_srgb || !normal || !dst || height < 1 || width < 1 || padded_height < height || padded_width < width ||
+        dst_stride % 4 || dst_offset % 4 || dst_offset + 16 > dst_stride) {
+        drp_set_error("drp_denoise_pack: invalid argument"); return DRP_ERR_INVALID; }
+    if ((padded_height - height + 1) / 2 >= height || (padded_width - width + 1) / 2 >= width) {
+        drp_set_error("drp_denoise_pack: reflection padding must be smaller than the image"); return DRP_ERR_INVALID; }
+    const float pu_scale = 1.0f / linear_to_pu(65504.0f);
+    const int64_t n = (int64_t)padded_height * padded_width;
+    k_denoise_pack<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hdr, albedo_srgb, normal, height, width, dst, padded_height, padded_width,
+                                                                                   dst_stride, dst_offset, pu_scale);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}
+
+extern "C" int drp_denoise_unpack(const float* src, int32_t padded_height, int32_t padded_width, int32_t src_stride, float* out, int32_t height,
+                                  int32_t width, void* stream) {
+    if (!src || !out || height < 1 || width < 1 || padded_height < height || padded_width < width || src_stride < 3) {
+        drp_set_error("drp_denoise_unpack: invalid argument"); return DRP_ERR_INVALID; }
+    const float inv = linear_to_pu(65504.0f);
+    const int64_t n = (int64_t)height * width;
+    k_denoise_unpack<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, padded_height, padded_width, src_stride, out, height, width, inv);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}

@@ -63,3 +63,110 @@ def conv3x3(inp: torch.Tensor, in_offset: int, cin: int, weight: torch.Tensor, b
     p = _abi.Conv3x3Params(inp.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), H, W, cin, in_stride, in_offset, bias.shape[0], cout_store,
                            out.shape[2], out_offset, mode, int(relu))
     check(lib().drp_conv3x3(C.byref(p), _stream_ptr(inp.device)), "drp_conv3x3")
+
+
+class UNetWeights:
+    """Parameters of the reference's ``UNet(9, 3)`` (denoiser.py:72-115), packed for ``drp_conv3x3``."""
+
+    def __init__(self, state_dict, device='cuda'):
+        self.device = torch.device(device)
+        self.raw = {}
+        for name, cin, cout in LAYERS:
+            w, b = state_dict[name + ".weight"], state_dict[name + ".bias"]
+            if tuple(w.shape) != (cout, cin, 3, 3) or tuple(b.shape) != (cout,):
+                raise ValueError("%s: expected weight (%d, %d, 3, 3)" % (name, cout, cin))
+            self.raw[name] = (w.detach().to(self.device, torch.float32), b.detach().to(self.device, torch.float32))
+        ident = lambda n: list(range(n))  # noqa: E731
+        # buffer channel that holds each input channel of the layer, and the channel count of the slice the layer reads
+        maps = {name: (ident(cin), _pad16(cin)) for name, cin, _ in LAYERS}
+        maps["dec_conv1a"] = (ident(_DC2B + _IC), _DC2B + _pad16(_IC))      # [upsampled dec_conv2b | input padded to 16]
+        self.packed = {name: pack_weight(*self.raw[name], *maps[name]) for name, _, _ in LAYERS}
+
+    @staticmethod
+    def random(seed: int = 0, device='cuda'):
+        """Deterministic He-initialised parameters (CPU generator, so the same on every machine) -- stand-in for the OIDN weights file."""
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        for name, cin, cout in LAYERS:
+            sd[name + ".weight"] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (9 * cin))
+            sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.05
+        return UNetWeights(sd, device), sd
+
+
+class UNet:
+    """``UNet.forward`` of the reference (denoiser.py:117-173) as 16 ``drp_conv3x3`` launches over preallocated NHWC buffers."""
+
+    def __init__(self, weights: UNetWeights):
+        self.w = weights
+        self._bufs = {}
+
+    def _buffers(self, H, W):
+        key = (H, W)
+        if key not in self._bufs:
+            dev = self.w.device
+            z = lambda h, w, c: torch.zeros(h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
+            self._bufs = {key: dict(
+                cat1=z(H, W, _DC2B + 16), e0=z(H, W, _EC1), cat2=z(H // 2, W // 2, _DC3 + _EC1), cat3=z(H // 4, W // 4, _DC4 + _EC2),
+                cat4=z(H // 8, W // 8, _EC5 + _EC3), p4=z(H // 16, W // 16, _EC4), b5=z(H // 16, W // 16, _EC5), d4=z(H // 8, W // 8, _DC4),
+                d3=z(H // 4, W // 4, _DC3), d2=z(H // 2, W // 2, _DC2A), d1a=z(H, W, _DC1A), d1b=z(H, W, _DC1B), out=z(H, W, 4))}
+        return self._bufs[key]
+
+    def input_slice(self, H, W):
+        """(buffer, channel offset): where the (H, W, 16) network input (9 channels + zero padding) has to be written."""
+        return self._buffers(H, W)['cat1'], _DC2B
+
+    def forward(self, H, W):
+        """Runs the net on the input previously written to ``input_slice``; returns the (H, W, 4) output buffer (3 channels used)."""
+        if H % 16 or W % 16:
+            raise ValueError("the U-Net needs height and width to be multiples of 16 (run_denoiser pads)")
+        B, P = self._buffers(H, W), self.w.packed
+        PL, PO, UP = _abi.CONV_PLAIN, _abi.CONV_POOL2, _abi.CONV_UPSAMPLE2
+
+        def L(name, src, s_off, cin, dst, d_off, cout, mode=PL, relu=True):
+            conv3x3(B[src], s_off, cin, *P[name], B[dst], d_off, cout, mode, relu)
+        L("enc_conv0", 'cat1', _DC2B, 16, 'e0', 0, _EC1)
+        L("enc_conv1", 'e0', 0, _EC1, 'cat2', _DC3, _EC1, PO)            # pool1 -> skip slice of concat2
+        L("enc_conv2", 'cat2', _DC3, _EC1, 'cat3', _DC4, _EC2, PO)       # pool2 -> concat3
+        L("enc_conv3", 'cat3', _DC4, _EC2, 'cat4', _EC5, _EC3, PO)       # pool3 -> concat4
+        L("enc_conv4", 'cat4', _EC5, _EC3, 'p4', 0, _EC4, PO)
+        L("enc_conv5a", 'p4', 0, _EC4, 'b5', 0, _EC5)
+        L("enc_conv5b", 'b5', 0, _EC5, 'cat4', 0, _EC5, UP)              # upsample4 -> concat4
+        L("dec_conv4a", 'cat4', 0, _EC5 + _EC3, 'd4', 0, _DC4)
+        L("dec_conv4b", 'd4', 0, _DC4, 'cat3', 0, _DC4, UP)
+        L("dec_conv3a", 'cat3', 0, _DC4 + _EC2, 'd3', 0, _DC3)
+        L("dec_conv3b", 'd3', 0, _DC3, 'cat2', 0, _DC3, UP)
+        L("dec_conv2a", 'cat2', 0, _DC3 + _EC1, 'd2', 0, _DC2A)
+        L("dec_conv2b", 'd2', 0, _DC2A, 'cat1', 0, _DC2B, UP)
+        L("dec_conv1a", 'cat1', 0, _DC2B + 16, 'd1a', 0, _DC1A)
+        L("dec_conv1b", 'd1a', 0, _DC1A, 'd1b', 0, _DC1B)
+        L("dec_conv0", 'd1b', 0, _DC1B, 'out', 0, _OC, PL, False)
+        return B['out']
+
+
+# PU transfer function constants of the reference (utils/colors.py:5-15)
+_PU = dict(A=1.41283765e+03, B=1.64593172e+00, C=4.31384981e-01, D=-2.94139609e-03, E=1.92653254e-01, F=6.26026094e-03, G=9.98620152e-01,
+           Y0=1.57945760e-06, Y1=3.22087631e-02, X0=2.23151711e-03, X1=3.70974749e-01)
+
+
+def get_denoiser(state_dict=None, seed: int = 0) -> UNet:
+    """``get_denoiser`` (denoiser.py:16-21).  ``state_dict``: the reference's OIDN parameters; None -> seeded random stand-in."""
+    return UNet(UNetWeights(state_dict) if state_dict is not None else UNetWeights.random(seed)[0])
+
+
+def run_denoiser(denoiser: UNet, pbr_hdr: torch.Tensor, albedo_srgb: torch.Tensor, normal: torch.Tensor, alignment: int = 16) -> torch.Tensor:
+    """``run_denoiser`` (denoiser.py:24-35): (H, W, 3) HDR radiance + sRGB albedo + world normal -> denoised (H, W, 3) radiance.
+    PU-encode + concatenate + reflection-pad in one kernel, 16 tensor-core layers, crop + PU-decode in one kernel."""
+    if alignment != 16:
+        raise ValueError("alignment is fixed to 16 by the network's four pooling levels")
+    h, w = pbr_hdr.shape[:2]
+    for t in (pbr_hdr, albedo_srgb, normal):
+        if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != (h, w, 3):
+            raise ValueError("run_denoiser: three (H, W, 3) fp32 CUDA tensors are required")
+    H, W = math.ceil(h / 16) * 16, math.ceil(w / 16) * 16
+    buf, off = denoiser.input_slice(H, W)
+    check(lib().drp_denoise_pack(pbr_hdr.contiguous().data_ptr(), albedo_srgb.contiguous().data_ptr(), normal.contiguous().data_ptr(), h, w,
+                                 buf.data_ptr(), H, W, buf.shape[2], off, _stream_ptr(buf.device)), "drp_denoise_pack")
+    out = denoiser.forward(H, W)
+    res = torch.empty(h, w, 3, dtype=torch.float32, device=buf.device)
+    check(lib().drp_denoise_unpack(out.data_ptr(), H, W, out.shape[2], res.data_ptr(), h, w, _stream_ptr(buf.device)), "drp_denoise_unpack")
+    return res

@@ -28,6 +28,7 @@
  *                       sample3d (LUT lookup)         diffrp/utils/shader_ops.py:262-310
  *                       to_pil byte conversion        diffrp/utils/exchange.py:7-18
  *   drp_conv3x3         Conv(...) + relu / pool / upsample / concat  diffrp/rendering/denoiser.py:42-66,117-173
+ *   drp_denoise_pack / drp_denoise_unpack   run_denoiser pre/post   diffrp/rendering/denoiser.py:24-35
  *   drp_trace_bruteforce (validation aid)             BruteForceRaycaster semantics on the GPU
  */
 #ifndef DIFFRP_B200_H
@@ -271,6 +272,16 @@ typedef struct drp_conv3x3_params {
     int32_t mode, relu;
 } drp_conv3x3_params_t;
 int drp_conv3x3(const drp_conv3x3_params_t* params, void* stream);
+
+/* Network input / output of run_denoiser (diffrp/rendering/denoiser.py:24-35), one kernel each:
+ * pack:   cat([linear_to_pu(hdr) / linear_to_pu(65504), albedo_srgb, normal*0.5+0.5]) (utils/colors.py:18-23), reflection-padded
+ *         (nn.ReflectionPad2d, dh//2 rows on top, dw//2 columns on the left) to (padded_height, padded_width), written as 16 channels
+ *         (9 + 7 zeros) at dst[(y*padded_width + x)*dst_stride + dst_offset + c];
+ * unpack: crop of the 3 output channels + pu_to_linear(x * linear_to_pu(65504)) (utils/colors.py:25-30) -> out (height, width, 3). */
+int drp_denoise_pack(const float* hdr, const float* albedo_srgb, const float* normal, int32_t height, int32_t width, float* dst,
+                     int32_t padded_height, int32_t padded_width, int32_t dst_stride, int32_t dst_offset, void* stream);
+int drp_denoise_unpack(const float* src, int32_t padded_height, int32_t padded_width, int32_t src_stride, float* out, int32_t height,
+                       int32_t width, void* stream);
 
 /* Counters of the last drp_render call on this handle (host-synchronous). */
 typedef struct drp_render_stats {

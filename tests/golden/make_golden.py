@@ -220,8 +220,30 @@ def tonemap_fixture():
          srgb=srgb.numpy(), agx=agx.numpy(), byte_agx=byte_agx.numpy(), byte_srgb=byte_srgb.numpy())
 
 
+def denoiser_fixture():
+    """run_denoiser + UNet(9, 3) of the reference (rendering/denoiser.py:24-35, 72-173), unmodified, on the CPU in fp32, with the seeded
+    stand-in parameters of diffrp_b200.denoiser.UNetWeights.random (the OIDN weight file is a data resource and is not copied).
+    Odd image size so that the reflection padding (3 / 4 rows, 5 / 6 columns) is exercised."""
+    from diffrp.rendering import denoiser as rd
+    from diffrp_b200.denoiser import UNetWeights
+    _, sd = UNetWeights.random(seed=11, device='cpu')
+    net = rd.UNet(9, 3)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(12)
+    h, w = 41, 53
+    hdr = torch.exp(torch.randn(h, w, 3, generator=g) * 1.5 - 1.0)
+    hdr[:2] = 0.0
+    hdr[2, :8] = torch.tensor([1e-7, 1e-6, 1e-3, 0.03, 0.04, 1.0, 100.0, 60000.0])[:, None]
+    albedo = torch.rand(h, w, 3, generator=g)
+    normal = torch.nn.functional.normalize(torch.randn(h, w, 3, generator=g), dim=-1)
+    with torch.no_grad():
+        out = rd.run_denoiser(net.float(), hdr, albedo, normal)
+    save("denoiser", hdr=hdr.numpy(), albedo=albedo.numpy(), normal=normal.numpy(), out=out.numpy(), seed=np.int32(11))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    denoiser_fixture()
     tonemap_fixture()
     scene_api_fixture()
     raycast_fixtures()

@@ -65,3 +65,85 @@ def test_single_layer_matches_torch(H, W, cin, cout, mode, relu):
 
 def math_sqrt(v):
     return float(np.sqrt(v))
+
+
+# ---- whole network ------------------------------------------------------------------------------------------------------------
+def torch_unet(sd, x, trunc=False):
+    """Plain torch restatement of UNet.forward (denoiser.py:117-173), NCHW fp32; ``trunc`` rounds every conv operand to TF32 like the MMA."""
+    q = tf32_trunc if trunc else (lambda v: v)
+
+    def conv(name, v, relu=True):
+        v = F.conv2d(q(v.contiguous()), q(sd[name + ".weight"].contiguous()), sd[name + ".bias"], padding=1)
+        return F.relu(v) if relu else v
+    pool = lambda v: F.max_pool2d(v, 2, 2)                                     # noqa: E731
+    up = lambda v: F.interpolate(v, scale_factor=2.0, mode="nearest")         # noqa: E731
+    inp = x
+    x = conv("enc_conv0", inp)
+    x = p1 = pool(conv("enc_conv1", x))
+    x = p2 = pool(conv("enc_conv2", x))
+    x = p3 = pool(conv("enc_conv3", x))
+    x = pool(conv("enc_conv4", x))
+    x = conv("enc_conv5b", conv("enc_conv5a", x))
+    x = conv("dec_conv4b", conv("dec_conv4a", torch.cat([up(x), p3], 1)))
+    x = conv("dec_conv3b", conv("dec_conv3a", torch.cat([up(x), p2], 1)))
+    x = conv("dec_conv2b", conv("dec_conv2a", torch.cat([up(x), p1], 1)))
+    x = conv("dec_conv1b", conv("dec_conv1a", torch.cat([up(x), inp], 1)))
+    return conv("dec_conv0", x, relu=False)
+
+
+# stated tolerance for the whole net: 16 chained TF32 layers, relative to max|output|
+NET_TOL_FP32 = 1.5e-2
+NET_TOL_TF32_EMULATED = 3e-3   # re-truncation after every layer amplifies accumulation-order differences
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (64, 96), (128, 80)])
+def test_unet_matches_torch(H, W):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    weights, sd = dn.UNetWeights.random(seed=3)
+    sd = {k: v.cuda() for k, v in sd.items()}
+    net = dn.UNet(weights)
+    g = torch.Generator(device='cuda').manual_seed(H + W)
+    x = torch.rand(H, W, 9, device='cuda', generator=g)
+    buf, off = net.input_slice(H, W)
+    buf[..., off:off + 9] = x
+    out = net.forward(H, W)[..., :3]
+    ref = torch_unet(sd, x.permute(2, 0, 1)[None])[0].permute(1, 2, 0)
+    ref_t = torch_unet(sd, x.permute(2, 0, 1)[None], trunc=True)[0].permute(1, 2, 0)
+    scale = ref.abs().max().item()
+    e32, et = (out - ref).abs().max().item() / scale, (out - ref_t).abs().max().item() / scale
+    print("UNet %dx%d: rel err vs fp32 %.3e, vs TF32-emulated %.3e" % (H, W, e32, et))
+    assert e32 <= NET_TOL_FP32 and et <= NET_TOL_TF32_EMULATED
+    # a second forward on the same buffers (stale upsample / skip slices are fully overwritten) gives the same result
+    out2 = net.forward(H, W)[..., :3]
+    assert torch.equal(out, out2)
+
+
+def test_run_denoiser_matches_reference_golden():
+    """Against the reference's own run_denoiser + UNet (CPU, fp32; tests/golden/make_golden.py:denoiser_fixture)."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "denoiser.npz")))
+    net = dn.get_denoiser(seed=int(g['seed']))
+    cu = lambda a: torch.from_numpy(a).cuda()                                  # noqa: E731
+    out = dn.run_denoiser(net, cu(g['hdr']), cu(g['albedo']), cu(g['normal']))
+    assert out.shape == (41, 53, 3)
+
+    def to_pu(o):                                                              # compare in the network's output domain
+        P = dn._PU
+        o = o.double()
+        return torch.where(o <= P['Y0'], P['A'] * o, torch.where(o <= P['Y1'], P['B'] * o.clamp_min(1e-30) ** P['C'] + P['D'], P['E'] * torch.log(o.clamp_min(0) + P['F']) + P['G']))
+    a, b = to_pu(out.cpu()), to_pu(torch.from_numpy(g['out']))
+    rel = ((a - b).abs().max() / b.abs().max()).item()
+    print("run_denoiser vs reference golden: rel err in the PU domain %.3e" % rel)
+    assert rel <= NET_TOL_FP32
+
+
+def test_denoiser_argument_errors():
+    net = dn.get_denoiser(seed=0)
+    x = torch.rand(8, 8, 3, device='cuda')
+    with pytest.raises(ValueError):
+        dn.run_denoiser(net, x.cpu(), x, x)
+    with pytest.raises(ValueError):
+        dn.run_denoiser(net, x, x, x, alignment=32)
+    with pytest.raises(ValueError):
+        net.forward(24, 40)
