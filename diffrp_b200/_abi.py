@@ -99,7 +99,7 @@ TONE_LINEAR, TONE_SRGB, TONE_AGX = 0, 1, 2
 class Conv3x3Params(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("height", C.c_int32), ("width", C.c_int32),
                 ("cin", C.c_int32), ("in_stride", C.c_int32), ("in_offset", C.c_int32), ("cout_pad", C.c_int32), ("cout_store", C.c_int32),
-                ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("mode", C.c_int32), ("relu", C.c_int32)]
+                ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("mode", C.c_int32), ("relu", C.c_int32), ("round_tf32", C.c_int32)]
 
 
 CONV_PLAIN, CONV_POOL2, CONV_UPSAMPLE2 = 0, 1, 2

@@ -15,14 +15,16 @@
 #include <cuda.h>
 #include <cstdint>
 #include <mutex>
+#include <algorithm>
+#include <cstdlib>
+#include <string>
 #include "internal.h"
 
 namespace {
 
 constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 output pixels per CTA = UMMA M
 constexpr int KC = 16;                                         // fp32 per k-step row = 64 B (SWIZZLE_64B span)
-constexpr int STAGES = 6;
-constexpr int A_STAGE_BYTES = BM * KC * 4;                     // 8 KB
+constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;                      // a wedged pipeline traps instead of hanging the GPU
 
@@ -92,30 +94,53 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 struct ConvArgs {
     const float* bias;
     float* out;
-    int height, width, k_steps, chunks;  // chunks = cin / 16, k_steps = 9 * chunks
-    int cout_pad, cout_store, out_stride, out_offset, mode, relu;
-    int tmem_cols;
+    int height, width, k_steps, chunks;  // chunks = cin / 16, k_steps = 3 * chunks (one per filter column and channel chunk)
+    int cin, cout_pad, cout_store, out_stride, out_offset, mode, relu, round_tf32;
+    int tmem_cols, stages;
 };
 
+__device__ __forceinline__ float round_tf32(float v) {  // round-to-nearest on the 10-bit TF32 mantissa: the MMA then truncates nothing
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void store16(float* o, const float v[16], int n_store) {
+    if (n_store == 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < n_store) o[i] = v[i];
+    }
+}
+
+// TR = output rows per CTA (8 or 16): the M = 128 accumulator(s) cover 8 rows x 16 columns each.
+// Per k-step (filter column kx, 16-channel chunk) ONE activation box of TR+2 rows is loaded; the three filter rows are the same
+// shared-memory tile read at row offsets 0 / 1 / 2 (a row of 16 pixels = 1024 B, a multiple of the swizzle period), so every
+// activation element crosses L2 -> SM 3 (TR+2)/TR times per layer instead of 9, and the weights once per TR*16 pixels.
+template <int TR>
 __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                               const ConvArgs a) {
+    constexpr int HALVES = TR / 8;
+    constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;     // (TR+2) KB, 1024-aligned
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_stage_bytes = a.cout_pad * KC * 4;
+    const int b_tap_bytes = a.cout_pad * KC * 4;
+    const int b_stage_bytes = 3 * b_tap_bytes;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + STAGES * b_stage_bytes);
-    uint64_t* empty = full + STAGES;
-    uint64_t* acc_ready = empty + STAGES;
+    uint8_t* smem_b = smem + a.stages * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + a.stages * b_stage_bytes);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* acc_ready = empty + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TR;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -130,89 +155,80 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA producer ----
-            const uint32_t stage_bytes = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+            const uint32_t stage_bytes = (uint32_t)(A_BYTES + b_stage_bytes);
+            int s = 0; uint32_t phase = 0;
             for (int kb = 0; kb < a.k_steps; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(&empty[s], phase ^ 1u);
                 mbar_expect_tx(&full[s], stage_bytes);
-                const int tap = kb / a.chunks, chunk = kb - tap * a.chunks;
-                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                tma_load_3d(&map_a, &full[s], smem_a + s * A_STAGE_BYTES, chunk * KC, x0 + dx, y0 + dy);
-                tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes, kb * KC, 0);
+                const int kx = kb / a.chunks, chunk = kb - kx * a.chunks;
+                tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KC, x0 + kx - 1, y0 - 1);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+                    tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KC, 0);
+                if (++s == a.stages) { s = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
             const uint32_t idesc = umma_idesc_tf32(a.cout_pad);
+            int s = 0; uint32_t phase = 0;
             for (int kb = 0; kb < a.k_steps; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(&full[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t pa = smem_u32(smem_a + s * A_STAGE_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
+                const uint32_t pa = smem_u32(smem_a + s * A_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k)  // UMMA K = 8 TF32 = 32 B along the row
-                    umma_tf32(tmem_base, umma_desc_sw64(pa + k * 32), umma_desc_sw64(pb + k * 32), idesc, (kb | k) != 0);
+                for (int half = 0; half < HALVES; ++half)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int k = 0; k < KC / 8; ++k)  // UMMA K = 8 TF32 = 32 B along the row
+                            umma_tf32(tmem_base + (uint32_t)(half * a.cout_pad), umma_desc_sw64(pa + (half * 8 + ky) * (TILE_W * KC * 4) + k * 32),
+                                      umma_desc_sw64(pb + ky * b_tap_bytes + k * 32), idesc, (kb | ky | k) != 0);
                 umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
+                if (++s == a.stages) { s = 0; phase ^= 1u; }
             }
-            umma_commit(acc_ready);               // accumulator complete
+            umma_commit(acc_ready);               // accumulators complete
         }
     } else {
         // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;           // accumulator row = pixel of the tile
+        const int m = quad * 32 + lane;           // accumulator row = pixel of the 8 x 16 half tile
         const int ty = m >> 4, tx = m & 15;
-        const int y = y0 + ty, x = x0 + tx;
-        const bool inside = y < a.height && x < a.width;
+        const int x = x0 + tx;
         mbar_wait(acc_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int c0 = 0; c0 < a.cout_pad; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also lanes outside the image
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                v[i] += __ldg(a.bias + c0 + i);
-                if (a.relu) v[i] = fmaxf(v[i], 0.0f);
-            }
-            if (a.mode == DRP_CONV_POOL2) {       // rows 2q, 2q+1 of the tile sit in this warp: lanes l, l^1, l^16, l^17
+        for (int half = 0; half < HALVES; ++half) {
+            const int y = y0 + half * 8 + ty;
+            const bool inside = y < a.height && x < a.width;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * a.cout_pad);
+            for (int c0 = 0; c0 < a.cout_pad; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also lanes outside the image
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+                    v[i] += __ldg(a.bias + c0 + i);
+                    if (a.relu) v[i] = fmaxf(v[i], 0.0f);
+                    if (a.round_tf32) v[i] = round_tf32(v[i]);
                 }
-            }
-            if (!inside || c0 >= a.cout_store) continue;
-            const int n_store = min(16, a.cout_store - c0);
-            if (a.mode == DRP_CONV_PLAIN) {
-                float* o = a.out + ((int64_t)y * a.width + x) * a.out_stride + a.out_offset + c0;
-                if (n_store == 16) {
+                if (a.mode == DRP_CONV_POOL2) {       // rows 2q, 2q+1 of the half tile sit in this warp: lanes l, l^1, l^16, l^17
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                } else {
-                    for (int i = 0; i < n_store; ++i) o[i] = v[i];
-                }
-            } else if (a.mode == DRP_CONV_POOL2) {
-                if ((lane & 17) == 0) {           // lane 2j of the even row owns the window
-                    float* o = a.out + ((int64_t)(y >> 1) * (a.width >> 1) + (x >> 1)) * a.out_stride + a.out_offset + c0;
-                    if (n_store == 16) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        for (int i = 0; i < n_store; ++i) o[i] = v[i];
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
                     }
                 }
-            } else {                              // DRP_CONV_UPSAMPLE2: nearest-neighbour 2x, written straight into the concat buffer
+                if (!inside || c0 >= a.cout_store) continue;
+                const int n_store = min(16, a.cout_store - c0);
+                if (a.mode == DRP_CONV_PLAIN) {
+                    store16(a.out + ((int64_t)y * a.width + x) * a.out_stride + a.out_offset + c0, v, n_store);
+                } else if (a.mode == DRP_CONV_POOL2) {
+                    if ((lane & 17) == 0)             // lane 2j of the even row owns the window
+                        store16(a.out + ((int64_t)(y >> 1) * (a.width >> 1) + (x >> 1)) * a.out_stride + a.out_offset + c0, v, n_store);
+                } else {                              // DRP_CONV_UPSAMPLE2: nearest-neighbour 2x, written straight into the concat buffer
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float* o = a.out + ((int64_t)(2 * y + (r >> 1)) * (2 * a.width) + 2 * x + (r & 1)) * a.out_stride + a.out_offset + c0;
-                    if (n_store == 16) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        for (int i = 0; i < n_store; ++i) o[i] = v[i];
-                    }
+                    for (int r = 0; r < 4; ++r)
+                        store16(a.out + ((int64_t)(2 * y + (r >> 1)) * (2 * a.width) + 2 * x + (r & 1)) * a.out_stride + a.out_offset + c0, v, n_store);
                 }
             }
         }
@@ -261,11 +277,15 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     EncodeTiledFn encode = encode_tiled();
     if (!encode) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled is unavailable in this driver"); return DRP_ERR_CUDA; }
 
+    // rows per CTA: 16 halves the weight traffic and the halo overhead, 8 keeps every SM busy on the small (deep) levels
+    const int64_t tiles16 = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + 15) / 16);
+    int tr = tiles16 >= 2 * 148 && p.cout_pad <= 128 ? 16 : 8;
+    if (const char* e = getenv("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
     CUtensorMap map_a, map_b;
-    {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, 8), zero fill outside = padding 1
+    {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, tr + 2), zero fill outside = padding 1
         const cuuint64_t dims[3] = {(cuuint64_t)p.cin, (cuuint64_t)p.width, (cuuint64_t)p.height};
         const cuuint64_t strides[2] = {(cuuint64_t)p.in_stride * 4, (cuuint64_t)p.in_stride * 4 * (cuuint64_t)p.width};
-        const cuuint32_t box[3] = {KC, TILE_W, TILE_H}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {KC, TILE_W, (cuuint32_t)(tr + 2)}, estr[3] = {1, 1, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.in + p.in_offset), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
@@ -280,16 +300,28 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     }
     ConvArgs a;
     a.bias = p.bias; a.out = p.out; a.height = p.height; a.width = p.width;
-    a.chunks = p.cin / KC; a.k_steps = 9 * a.chunks;
+    a.chunks = p.cin / KC; a.k_steps = 3 * a.chunks; a.cin = p.cin;
     a.cout_pad = p.cout_pad; a.cout_store = p.cout_store; a.out_stride = p.out_stride; a.out_offset = p.out_offset; a.mode = p.mode; a.relu = p.relu;
-    a.tmem_cols = p.cout_pad <= 32 ? 32 : p.cout_pad <= 64 ? 64 : p.cout_pad <= 128 ? 128 : 256;
-    const size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + (size_t)p.cout_pad * KC * 4) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+    a.round_tf32 = p.round_tf32;
+    const int acc_cols = (tr / 8) * p.cout_pad;
+    a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+    const size_t stage_bytes = (size_t)(tr + 2) * TILE_W * KC * 4 + 3 * (size_t)p.cout_pad * KC * 4;
+    size_t budget = 72 * 1024;                                    // ~3 CTAs per SM: one tile's epilogue overlaps the others' main loops
+    if (const char* e = getenv("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+    a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, budget / stage_bytes));
+    a.stages = std::min(a.stages, std::max(2, a.k_steps));
+    const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] { attr_err = cudaFuncSetAttribute(k_conv3x3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(k_conv3x3_tf32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv3x3_tf32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
     DRP_CUDA_CHECK(attr_err);
-    const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + TILE_H - 1) / TILE_H));
-    k_conv3x3_tf32<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+    if (smem > 220 * 1024) { drp_set_error("drp_conv3x3: tile does not fit in shared memory"); return DRP_ERR_INVALID; }
+    const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + tr - 1) / tr));
+    if (tr == 16) k_conv3x3_tf32<16><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+    else k_conv3x3_tf32<8><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }
@@ -326,6 +358,8 @@ __global__ void __launch_bounds__(256) k_denoise_pack(const float* __restrict__ 
         v[3 + c] = __ldg(albedo + s + c);
         v[6 + c] = __ldg(normal + s + c) * 0.5f + 0.5f;
     }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = round_tf32(v[c]);      // network input: convolution operand only
 #pragma unroll
     for (int c = 9; c < 16; ++c) v[c] = 0.0f;
     float4* o = reinterpret_cast<float4*>(dst + i * stride + offset);

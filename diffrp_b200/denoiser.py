@@ -36,20 +36,26 @@ def _stream_ptr(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def pack_weight(w: torch.Tensor, b: torch.Tensor, channel_map, cin_buf: int):
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32), kept in fp32 storage."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+def pack_weight(w: torch.Tensor, b: torch.Tensor, channel_map, cin_buf: int, round_weights: bool = False):
     """(cout, cin, 3, 3) + (cout,) -> ([cout_pad][9*cin_buf] with k = tap*cin_buf + buffer channel, [cout_pad]); ``channel_map[c]`` is the
     buffer channel that holds the convolution's input channel c (padding channels of the buffer get zero weights)."""
     cout, cin = w.shape[0], w.shape[1]
     cout_pad = _pad16(cout)
     m = torch.zeros(cout_pad, 9, cin_buf, dtype=torch.float32, device=w.device)
-    m[:cout, :, torch.as_tensor(channel_map, device=w.device)] = w.float().permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    wf = round_tf32(w.float()) if round_weights else w.float()
+    m[:cout, :, torch.as_tensor(channel_map, device=w.device)] = wf.permute(0, 2, 3, 1).reshape(cout, 9, cin)
     bias = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
     bias[:cout] = b.float()
     return m.reshape(cout_pad, 9 * cin_buf).contiguous(), bias
 
 
 def conv3x3(inp: torch.Tensor, in_offset: int, cin: int, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, out_offset: int, cout_store: int,
-            mode: int = _abi.CONV_PLAIN, relu: bool = True):
+            mode: int = _abi.CONV_PLAIN, relu: bool = True, round_tf32: bool = False):
     """One ``drp_conv3x3`` launch.  ``inp`` (H, W, in_stride) and ``out`` (H', W', out_stride) are NHWC fp32 CUDA buffers; the layer reads
     channels [in_offset, in_offset+cin) and writes [out_offset, out_offset+cout_store)."""
     if not (inp.is_cuda and out.is_cuda and weight.is_cuda and bias.is_cuda):
@@ -61,7 +67,7 @@ def conv3x3(inp: torch.Tensor, in_offset: int, cin: int, weight: torch.Tensor, b
     if weight.shape != (bias.shape[0], 9 * cin):
         raise ValueError("weight matrix must be [cout_pad][9*cin]")
     p = _abi.Conv3x3Params(inp.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), H, W, cin, in_stride, in_offset, bias.shape[0], cout_store,
-                           out.shape[2], out_offset, mode, int(relu))
+                           out.shape[2], out_offset, mode, int(relu), int(round_tf32))
     check(lib().drp_conv3x3(C.byref(p), _stream_ptr(inp.device)), "drp_conv3x3")
 
 
@@ -80,7 +86,8 @@ class UNetWeights:
         # buffer channel that holds each input channel of the layer, and the channel count of the slice the layer reads
         maps = {name: (ident(cin), _pad16(cin)) for name, cin, _ in LAYERS}
         maps["dec_conv1a"] = (ident(_DC2B + _IC), _DC2B + _pad16(_IC))      # [upsampled dec_conv2b | input padded to 16]
-        self.packed = {name: pack_weight(*self.raw[name], *maps[name]) for name, _, _ in LAYERS}
+        # operands are rounded to TF32 once, here and in the layer epilogues, so the tensor core's truncation is exact (unbiased rounding)
+        self.packed = {name: pack_weight(*self.raw[name], *maps[name], round_weights=True) for name, _, _ in LAYERS}
 
     @staticmethod
     def random(seed: int = 0, device='cuda'):
@@ -123,7 +130,7 @@ class UNet:
         PL, PO, UP = _abi.CONV_PLAIN, _abi.CONV_POOL2, _abi.CONV_UPSAMPLE2
 
         def L(name, src, s_off, cin, dst, d_off, cout, mode=PL, relu=True):
-            conv3x3(B[src], s_off, cin, *P[name], B[dst], d_off, cout, mode, relu)
+            conv3x3(B[src], s_off, cin, *P[name], B[dst], d_off, cout, mode, relu, round_tf32=relu)  # every hidden activation feeds convolutions only
         L("enc_conv0", 'cat1', _DC2B, 16, 'e0', 0, _EC1)
         L("enc_conv1", 'e0', 0, _EC1, 'cat2', _DC3, _EC1, PO)            # pool1 -> skip slice of concat2
         L("enc_conv2", 'cat2', _DC3, _EC1, 'cat3', _DC4, _EC2, PO)       # pool2 -> concat3

@@ -270,6 +270,8 @@ typedef struct drp_conv3x3_params {
     int32_t cin, in_stride, in_offset;
     int32_t cout_pad, cout_store, out_stride, out_offset;
     int32_t mode, relu;
+    int32_t round_tf32; /* != 0: round the stored activations to TF32 (nearest) -- for outputs that only feed further drp_conv3x3 layers,
+                         * so that the tensor core's operand truncation is exact and rounding stays unbiased across the net */
 } drp_conv3x3_params_t;
 int drp_conv3x3(const drp_conv3x3_params_t* params, void* stream);
 

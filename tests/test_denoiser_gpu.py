@@ -69,8 +69,9 @@ def math_sqrt(v):
 
 # ---- whole network ------------------------------------------------------------------------------------------------------------
 def torch_unet(sd, x, trunc=False):
-    """Plain torch restatement of UNet.forward (denoiser.py:117-173), NCHW fp32; ``trunc`` rounds every conv operand to TF32 like the MMA."""
-    q = tf32_trunc if trunc else (lambda v: v)
+    """Plain torch restatement of UNet.forward (denoiser.py:117-173), NCHW fp32; ``trunc`` rounds every conv operand to the nearest TF32,
+    which is what the kernels do (weights at pack time, activations in the producing layer's epilogue)."""
+    q = dn.round_tf32 if trunc else (lambda v: v)
 
     def conv(name, v, relu=True):
         v = F.conv2d(q(v.contiguous()), q(sd[name + ".weight"].contiguous()), sd[name + ".bias"], padding=1)
@@ -92,8 +93,8 @@ def torch_unet(sd, x, trunc=False):
 
 
 # stated tolerance for the whole net: 16 chained TF32 layers, relative to max|output|
-NET_TOL_FP32 = 1.5e-2
-NET_TOL_TF32_EMULATED = 3e-3   # re-truncation after every layer amplifies accumulation-order differences
+NET_TOL_FP32 = 5e-3
+NET_TOL_TF32_EMULATED = 2e-3   # re-rounding after every layer amplifies accumulation-order differences
 
 
 @pytest.mark.parametrize("H,W", [(16, 16), (64, 96), (128, 80)])
@@ -104,7 +105,7 @@ def test_unet_matches_torch(H, W):
     sd = {k: v.cuda() for k, v in sd.items()}
     net = dn.UNet(weights)
     g = torch.Generator(device='cuda').manual_seed(H + W)
-    x = torch.rand(H, W, 9, device='cuda', generator=g)
+    x = dn.round_tf32(torch.rand(H, W, 9, device='cuda', generator=g))     # drp_denoise_pack rounds the network input the same way
     buf, off = net.input_slice(H, W)
     buf[..., off:off + 9] = x
     out = net.forward(H, W)[..., :3]
