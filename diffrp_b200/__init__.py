@@ -10,6 +10,8 @@ from .raycaster import Raycaster, B200Raycaster
 from .path_tracing import PathTracingSession, PathTracingSessionOptions, RayOutputs, hammersley
 from .flatten import VertexArrayObject
 from .generic import SurfaceInput, SurfaceUniform, MaskedSparseInterpolator
-from . import synthetic, tonemap
+from . import synthetic, tonemap, denoiser
+from .tonemap import agx_base_contrast, linear_to_srgb, to_uint8
+from .denoiser import get_denoiser, run_denoiser
 
 __version__ = "0.1.0"

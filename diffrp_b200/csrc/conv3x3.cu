@@ -104,23 +104,13 @@ __device__ __forceinline__ float round_tf32(float v) {  // round-to-nearest on t
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ void store16(float* o, const float v[16], int n_store) {
-    if (n_store == 16) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < n_store) o[i] = v[i];
-    }
-}
-
 // TR = output rows per CTA (8 or 16): the M = 128 accumulator(s) cover 8 rows x 16 columns each.
 // Per k-step (filter column kx, 16-channel chunk) ONE activation box of TR+2 rows is loaded; the three filter rows are the same
 // shared-memory tile read at row offsets 0 / 1 / 2 (a row of 16 pixels = 1024 B, a multiple of the swizzle period), so every
 // activation element crosses L2 -> SM 3 (TR+2)/TR times per layer instead of 9, and the weights once per TR*16 pixels.
 template <int TR>
 __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                              const ConvArgs a) {
+                                                              const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
     constexpr int HALVES = TR / 8;
     constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;     // (TR+2) KB, 1024-aligned
     extern __shared__ uint8_t smem_raw[];
@@ -140,6 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,47 +182,70 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
         }
     } else {
         // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----
+        // TMEM -> registers (bias, ReLU, TF32 rounding, 2x2 max) -> shared memory tile [pixel][16 channels] (64 B rows, SWIZZLE_64B) ->
+        // TMA tensor store.  The store's tensor map does the addressing: channel slice + pixel stride, clipping at the image border
+        // and at cout_store, and for the upsampling layers the 2x replication (four stores of one tile to the (a, b) sub-lattices).
         const int quad = warp & 3;
         const int m = quad * 32 + lane;           // accumulator row = pixel of the 8 x 16 half tile
         const int ty = m >> 4, tx = m & 15;
-        const int x = x0 + tx;
+        const int et = (int)threadIdx.x - 64;     // 0..127 among the epilogue threads
+        constexpr int OUT_BYTES = TR * TILE_W * KC * 4;   // one 16-channel group of the whole tile; two buffers alias the (drained) pipeline stages
         mbar_wait(acc_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int buf = 0;
+        for (int c0 = 0; c0 < a.cout_store; c0 += 16, buf ^= 1) {
+            uint8_t* stage_out = smem_a + buf * OUT_BYTES;
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this buffer has read it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int half = 0; half < HALVES; ++half) {
-            const int y = y0 + half * 8 + ty;
-            const bool inside = y < a.height && x < a.width;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * a.cout_pad);
-            for (int c0 = 0; c0 < a.cout_pad; c0 += 16) {
+            for (int half = 0; half < HALVES; ++half) {
                 float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);   // whole warp, also lanes outside the image
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * a.cout_pad + c0), v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     v[i] += __ldg(a.bias + c0 + i);
                     if (a.relu) v[i] = fmaxf(v[i], 0.0f);
                     if (a.round_tf32) v[i] = round_tf32(v[i]);
                 }
+                int row = half * 128 + m;
+                bool writer = true;
                 if (a.mode == DRP_CONV_POOL2) {       // rows 2q, 2q+1 of the half tile sit in this warp: lanes l, l^1, l^16, l^17
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
                         v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
                     }
+                    writer = (lane & 17) == 0;        // lane 2j of the even row owns the window
+                    row = (half * 4 + (ty >> 1)) * (TILE_W / 2) + (tx >> 1);
                 }
-                if (!inside || c0 >= a.cout_store) continue;
-                const int n_store = min(16, a.cout_store - c0);
-                if (a.mode == DRP_CONV_PLAIN) {
-                    store16(a.out + ((int64_t)y * a.width + x) * a.out_stride + a.out_offset + c0, v, n_store);
-                } else if (a.mode == DRP_CONV_POOL2) {
-                    if ((lane & 17) == 0)             // lane 2j of the even row owns the window
-                        store16(a.out + ((int64_t)(y >> 1) * (a.width >> 1) + (x >> 1)) * a.out_stride + a.out_offset + c0, v, n_store);
-                } else {                              // DRP_CONV_UPSAMPLE2: nearest-neighbour 2x, written straight into the concat buffer
+                if (writer) {
+                    float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
+                    const int sw = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        store16(a.out + ((int64_t)(2 * y + (r >> 1)) * (2 * a.width) + 2 * x + (r & 1)) * a.out_stride + a.out_offset + c0, v, n_store);
+                    for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+                const uint32_t src = smem_u32(stage_out);
+                const uint64_t mo = reinterpret_cast<uint64_t>(&map_out);
+                if (a.mode == DRP_CONV_PLAIN) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0), "r"(y0) : "memory");
+                } else if (a.mode == DRP_CONV_POOL2) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0 >> 1), "r"(y0 >> 1) : "memory");
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                                     ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(x0), "r"(r >> 1), "r"(y0) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA retires its shared memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -266,8 +280,8 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     if (!p.in || !p.weight || !p.bias || !p.out) { drp_set_error("drp_conv3x3: NULL tensor"); return DRP_ERR_INVALID; }
     if (p.cin < 16 || p.cin % 16 || p.in_stride % 16 || p.in_offset % 16 || p.in_offset + p.cin > p.in_stride) {
         drp_set_error("drp_conv3x3: cin / in_stride / in_offset must be multiples of 16 with in_offset + cin <= in_stride"); return DRP_ERR_INVALID; }
-    if (p.cout_pad < 16 || p.cout_pad > 256 || p.cout_pad % 16 || p.cout_store < 1 || p.cout_store > p.cout_pad) {
-        drp_set_error("drp_conv3x3: cout_pad must be a multiple of 16 in [16, 256] and 1 <= cout_store <= cout_pad"); return DRP_ERR_INVALID; }
+    if (p.cout_pad < 16 || p.cout_pad > 256 || p.cout_pad % 16 || p.cout_store < 4 || p.cout_store % 4 || p.cout_store > p.cout_pad) {
+        drp_set_error("drp_conv3x3: cout_pad must be a multiple of 16 in [16, 256], cout_store a multiple of 4 (TMA stores 16-byte units) <= cout_pad"); return DRP_ERR_INVALID; }
     if (p.out_stride % 4 || p.out_offset % 4 || p.out_offset + p.cout_store > p.out_stride) {
         drp_set_error("drp_conv3x3: out_stride / out_offset must be multiples of 4 with out_offset + cout_store <= out_stride"); return DRP_ERR_INVALID; }
     if (p.mode < DRP_CONV_PLAIN || p.mode > DRP_CONV_UPSAMPLE2) { drp_set_error("drp_conv3x3: unknown mode"); return DRP_ERR_INVALID; }
@@ -298,6 +312,28 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
     }
+    CUtensorMap map_out;
+    {   // output: channel slice [out_offset, out_offset + cout_store) of the NHWC buffer; the store clips at the image border and at cout_store
+        float* base = p.out + p.out_offset;
+        const cuuint64_t ps = (cuuint64_t)p.out_stride * 4;   // pixel stride in bytes
+        CUresult r;
+        if (p.mode == DRP_CONV_UPSAMPLE2) {                    // (c, b, x, a, y): output pixel (2y + a, 2x + b)
+            const cuuint64_t dims[5] = {(cuuint64_t)p.cout_store, 2, (cuuint64_t)p.width, 2, (cuuint64_t)p.height};
+            const cuuint64_t strides[4] = {ps, 2 * ps, 2 * (cuuint64_t)p.width * ps, 4 * (cuuint64_t)p.width * ps};
+            const cuuint32_t box[5] = {KC, 1, TILE_W, 1, (cuuint32_t)tr}, estr[5] = {1, 1, 1, 1, 1};
+            r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const int sh = p.mode == DRP_CONV_POOL2 ? 1 : 0;
+            const cuuint64_t ow = (cuuint64_t)(p.width >> sh), oh = (cuuint64_t)(p.height >> sh);
+            const cuuint64_t dims[3] = {(cuuint64_t)p.cout_store, ow, oh};
+            const cuuint64_t strides[2] = {ps, ow * ps};
+            const cuuint32_t box[3] = {KC, (cuuint32_t)(TILE_W >> sh), (cuuint32_t)(tr >> sh)}, estr[3] = {1, 1, 1};
+            r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
+    }
     ConvArgs a;
     a.bias = p.bias; a.out = p.out; a.height = p.height; a.width = p.width;
     a.chunks = p.cin / KC; a.k_steps = 3 * a.chunks; a.cin = p.cin;
@@ -306,7 +342,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     const int acc_cols = (tr / 8) * p.cout_pad;
     a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const size_t stage_bytes = (size_t)(tr + 2) * TILE_W * KC * 4 + 3 * (size_t)p.cout_pad * KC * 4;
-    size_t budget = 72 * 1024;                                    // ~3 CTAs per SM: one tile's epilogue overlaps the others' main loops
+    size_t budget = 48 * 1024;                                    // ~3 CTAs per SM: one tile's epilogue overlaps the others' main loops
     if (const char* e = getenv("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, budget / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.k_steps));
@@ -320,8 +356,8 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     DRP_CUDA_CHECK(attr_err);
     if (smem > 220 * 1024) { drp_set_error("drp_conv3x3: tile does not fit in shared memory"); return DRP_ERR_INVALID; }
     const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + tr - 1) / tr));
-    if (tr == 16) k_conv3x3_tf32<16><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
-    else k_conv3x3_tf32<8><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+    if (tr == 16) k_conv3x3_tf32<16><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
+    else k_conv3x3_tf32<8><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }

@@ -146,7 +146,7 @@ class UNet:
         L("dec_conv2b", 'd2', 0, _DC2A, 'cat1', 0, _DC2B, UP)
         L("dec_conv1a", 'cat1', 0, _DC2B + 16, 'd1a', 0, _DC1A)
         L("dec_conv1b", 'd1a', 0, _DC1A, 'd1b', 0, _DC1B)
-        L("dec_conv0", 'd1b', 0, _DC1B, 'out', 0, _OC, PL, False)
+        L("dec_conv0", 'd1b', 0, _DC1B, 'out', 0, 4, PL, False)          # 3 channels + one zero (stores move 16-byte units)
         return B['out']
 
 

@@ -257,7 +257,7 @@ int drp_tonemap(const float* src, int64_t height, int64_t width, const drp_tonem
  *   out : mode DRP_CONV_PLAIN     (y,x)        -> out[(y*width + x)*out_stride + out_offset + c], c < cout_store
  *         mode DRP_CONV_POOL2     max over 2x2 -> out[((y/2)*(width/2) + x/2)*out_stride + ...]       (height, width even)
  *         mode DRP_CONV_UPSAMPLE2 replicated   -> out[((2y+a)*(2*width) + 2x+b)*out_stride + ...], a,b in {0,1}
- * All strides / offsets in floats, multiples of 4 (16 for the input side).  relu != 0 applies max(.,0) before pooling / replication. */
+ * All strides / offsets / cout_store in floats, multiples of 4 (16 for the input side): the tensor stores move 16-byte units.  relu != 0 applies max(.,0) before pooling / replication. */
 #define DRP_CONV_PLAIN 0
 #define DRP_CONV_POOL2 1
 #define DRP_CONV_UPSAMPLE2 2

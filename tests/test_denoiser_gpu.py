@@ -36,7 +36,7 @@ def reference_layer(x_nhwc, w, b, mode, relu):
     (8, 16, 96, 96, _abi.CONV_UPSAMPLE2, True),
     (6, 10, 80, 96, _abi.CONV_PLAIN, True),       # ragged tiles: neither dimension a multiple of the 8 x 16 tile
     (2, 2, 96, 96, _abi.CONV_UPSAMPLE2, True),    # smaller than one tile
-    (40, 72, 32, 3, _abi.CONV_PLAIN, False),      # output layer: 3 of 16 padded channels stored, no ReLU
+    (40, 72, 32, 3, _abi.CONV_PLAIN, False),      # output layer: 3 (+1 zero: stores move 16-byte units) of 16 padded channels stored, no ReLU
 ])
 def test_single_layer_matches_torch(H, W, cin, cout, mode, relu):
     g = torch.Generator(device='cuda').manual_seed(H * 1000 + W + cin + cout)
@@ -48,7 +48,8 @@ def test_single_layer_matches_torch(H, W, cin, cout, mode, relu):
     oh, ow = {_abi.CONV_PLAIN: (H, W), _abi.CONV_POOL2: (H // 2, W // 2), _abi.CONV_UPSAMPLE2: (2 * H, 2 * W)}[mode]
     out_stride, out_offset = dn._pad16(cout) + 16, 4 if cout == 3 else 16
     out = torch.full((oh, ow, out_stride), -7.0, device='cuda')
-    dn.conv3x3(buf, in_offset, cin, wm, bm, out, out_offset, cout, mode, relu)
+    stored = (cout + 3) // 4 * 4
+    dn.conv3x3(buf, in_offset, cin, wm, bm, out, out_offset, stored, mode, relu)
     torch.cuda.synchronize()
     x = buf[..., in_offset:in_offset + cin].contiguous()
     ref = reference_layer(x, w, b, mode, relu)
@@ -60,7 +61,8 @@ def test_single_layer_matches_torch(H, W, cin, cout, mode, relu):
     print("max|err| vs fp32 %.3e (scale %.3f), vs tf32-truncated operands %.3e" % (err, scale, err_t))
     assert err <= TF32_TOL * scale, (err, scale)
     # nothing outside the slice was touched
-    assert (out[..., :out_offset] == -7.0).all() and (out[..., out_offset + cout:] == -7.0).all()
+    assert (out[..., :out_offset] == -7.0).all() and (out[..., out_offset + stored:] == -7.0).all()
+    assert (out[..., out_offset + cout:out_offset + stored] == 0.0).all()      # padded output channels: zero weights, zero bias
 
 
 def math_sqrt(v):
@@ -148,3 +150,20 @@ def test_denoiser_argument_errors():
         dn.run_denoiser(net, x, x, x, alignment=32)
     with pytest.raises(ValueError):
         net.forward(24, 40)
+
+
+def test_documented_chain_pbr_denoise_tonemap():
+    """docs/source/ptpbr.md:55-58 of the reference, with this package's names: pbr -> run_denoiser(pbr, srgb(albedo), normal) -> agx -> bytes."""
+    import scenes
+    import diffrp_b200 as drp
+    g = dict(np.load(__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), "golden", "tonemap.npz")))
+    scene, cam = scenes.mixed_scene(), drp.PerspectiveCamera(h=72, w=100)
+    pbr, alpha, extras = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=4, ray_depth=3, seed=2)).pbr()
+    denoiser = drp.get_denoiser(seed=5)
+    den = drp.run_denoiser(denoiser, pbr, drp.linear_to_srgb(extras['albedo']), extras['world_normal'])
+    assert den.shape == pbr.shape and torch.isfinite(den).all()
+    img = drp.to_uint8(torch.cat([drp.agx_base_contrast(den, torch.from_numpy(g['lut']).cuda()), alpha], -1))
+    assert img.shape == (72, 100, 4) and img.dtype == torch.uint8
+    # same inputs, same bytes: the whole chain is deterministic
+    den2 = drp.run_denoiser(denoiser, pbr, drp.linear_to_srgb(extras['albedo']), extras['world_normal'])
+    assert torch.equal(den, den2)
