@@ -15,7 +15,13 @@ cam = drp.PerspectiveCamera.from_orbit(h=48, w=64, radius=3.0, azim=25, elev=15,
 for opt in (dict(rng='native'), dict(rng='torch', pbr_ray_last_bounce='skybox'), dict(shard_rank=1, shard_world=2, shard_mode='tile', tile_size=32)):
     s = drp.PathTracingSession(scenes.mixed_scene(), cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=3, **opt))
     acc = s.render_accumulators(); out = s.finalize(acc)
+# colour epilogue + denoiser (tcgen05 / TMA kernels): odd sizes so that clipped tiles and reflection padding are exercised
+lut = torch.rand(8, 8, 8, 3, device='cuda')
+img = s.pbr_image('agx', lut=lut)
+den = drp.get_denoiser(seed=1)
+rad, alpha, extras = drp.PathTracingSession(scenes.mixed_scene(), cam, drp.PathTracingSessionOptions(ray_spp=1, ray_depth=2)).pbr()
+dn = drp.run_denoiser(den, rad[:41, :53].contiguous(), drp.linear_to_srgb(extras['albedo'][:41, :53].contiguous()), extras['world_normal'][:41, :53].contiguous())
 torch.cuda.synchronize()
-print("SANITIZER_RUN_COMPLETE", float(t.mean()), float(out[0].mean()))
+print("SANITIZER_RUN_COMPLETE", float(t.mean()), float(out[0].mean()), float(dn.mean()), int(img.sum()))
 PY
 tail -5 gpurun_out/sanitizer.log
