@@ -408,6 +408,40 @@ def main():
                         "sample": "%d steps of a %dx%d central window x %d spp x %d bounces of the same scene (%d ray-bounces, %.1f s); CPU BVH build %.1f s excluded"
                                   % (args.cpu_baseline_steps, args.ref_window, args.ref_window, args.ref_spp, DEPTH, nn, tt, build_s)}
 
+    # ---- the steps after the path, timed on this frame: informational, not part of `value` ----------------
+    post = None
+    if world == 1:
+        from diffrp_b200 import denoiser as dn, tonemap as tm
+
+        def timed(fn, iters=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        lut = torch.rand(32, 32, 32, 3, device=dev)
+        net = dn.get_denoiser(seed=0)
+        alb = tm.linear_to_srgb(extras['albedo'])
+        den_ms = timed(lambda: dn.run_denoiser(net, radiance, alb, extras['world_normal']))
+        tone_ms = timed(lambda: tm.tonemap(accum.view(RES, RES, 16), 'agx', lut=lut, scale=1.0 / total_spp, alpha_offset=3, flip_rows=True))
+        macs = sum(9 * cin * cout * (RES // r) ** 2 for (_, cin, cout), r in zip(dn.LAYERS, (1, 1, 2, 4, 8, 16, 16, 8, 8, 4, 4, 2, 2, 1, 1, 1)))
+        tf32_peak = None
+        try:
+            tf32_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2.0
+        except Exception:
+            pass
+        tfl = 2 * macs / (den_ms * 1e-3) / 1e12
+        post = {"denoiser": {"ms": den_ms, "what": "run_denoiser: pack + 16 tcgen05 TF32 conv layers + unpack at %dx%d, seeded stand-in weights" % (RES, RES),
+                             "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "peak": tf32_peak,
+                                          "frac": (tfl / tf32_peak) if tf32_peak else None,
+                                          "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 issues at half the bf16 rate)"}},
+                "tonemap": {"ms": tone_ms, "what": "drp_tonemap: accumulator -> /spp, flipud, AgX LUT, sRGB, alpha, RGBA8",
+                            "gbs": RES * RES * (64 + 4) / (tone_ms * 1e-3) / 1e9}}
+
     torch_baseline = None
     if world == 1 and not args.no_torch_baseline:
         try:
@@ -436,6 +470,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "gpu_torch_baseline": torch_baseline,
+        "post_path": post,
         "native_library": loaded_path(),
         "native_build": build_config(),
     }))
