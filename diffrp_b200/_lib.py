@@ -34,6 +34,7 @@ def _declare(L):
     L.drp_set_profiling.argtypes = [u64, C.c_int]
     L.drp_get_profile.argtypes = [u64, C.POINTER(_abi.Profile)]
     L.drp_tonemap.argtypes = [vp, i64, i64, C.POINTER(_abi.TonemapParams), vp, vp, vp]
+    L.drp_surface_attrs.argtypes = [u64, C.POINTER(_abi.Scene), vp, vp, vp, vp, f32, i64, vp, vp]
     L.drp_conv3x3.argtypes = [C.POINTER(_abi.Conv3x3Params), vp]
     L.drp_denoise_pack.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]
     L.drp_denoise_unpack.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]

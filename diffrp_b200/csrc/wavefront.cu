@@ -747,6 +747,64 @@ int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, fl
     return DRP_OK;
 }
 
+// ---- drp_surface_attrs: the material layer for arbitrary ray batches (custom samplers) -------------------------------------
+// layer_material_rays + _super_collector + g-buffer collect (path_tracing.py:158-187, mixin.py:115-155, interpolator.py:32-48) for a
+// batch of (ray, t, primitive id): one thread per ray, attrs (R,12) = [albedo3 | normal3 | metal | smooth | alpha | emission3], zeros on a
+// miss -- the same function (shade.cuh: surface_attrs) the fused k_shade calls.
+__global__ void __launch_bounds__(128) k_surface_attrs(const drp_scene_t sc, const float* __restrict__ ro, const float* __restrict__ rd,
+                                                       const float* __restrict__ t, const int32_t* __restrict__ tri, float t_far, int64_t n,
+                                                       float* __restrict__ attrs) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float4* out = reinterpret_cast<float4*>(attrs + 12 * r);
+    const float tt = __ldg(t + r);
+    const int id = __ldg(tri + r);
+    if (!(tt < t_far) || id < 0 || id >= sc.n_tris) {
+        out[0] = out[1] = out[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    const Vec3 o = v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]), d = v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]);
+    const SurfaceAttrs s = surface_attrs(sc, sc.materials, o + d * tt, id);
+    out[0] = make_float4(s.albedo.x, s.albedo.y, s.albedo.z, s.normal.x);
+    out[1] = make_float4(s.normal.y, s.normal.z, s.metal, s.smooth);
+    out[2] = make_float4(s.alpha, s.emission.x, s.emission.y, s.emission.z);
+}
+
+extern "C" int drp_surface_attrs(uint64_t handle, const drp_scene_t* scene, const float* rays_o, const float* rays_d, const float* t,
+                                 const int32_t* tri, float t_far, int64_t n_rays, float* attrs, void* stream) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_surface_attrs: invalid handle"); return DRP_ERR_INVALID; }
+    if (!scene || n_rays < 0) { drp_set_error("drp_surface_attrs: invalid argument"); return DRP_ERR_INVALID; }
+    if (n_rays == 0) return DRP_OK;
+    if (!rays_o || !rays_d || !t || !tri || !attrs) { drp_set_error("drp_surface_attrs: NULL array"); return DRP_ERR_INVALID; }
+    if (scene->n_materials <= 0 || !scene->materials) { drp_set_error("drp_surface_attrs: scene has no materials"); return DRP_ERR_INVALID; }
+    {
+        auto ok = [](const drp_texture_t& x) { return x.data == nullptr || (x.c == 4 && x.h > 0 && x.w > 0); };
+        bool all = true;
+        for (int k = 0; k < scene->n_materials; ++k) {
+            const drp_material_t& m = scene->materials[k];
+            all = all && ok(m.base_color_tex) && ok(m.mr_tex) && ok(m.normal_tex) && ok(m.emissive_tex);
+        }
+        if (!all) { drp_set_error("drp_surface_attrs: textures must be 4-channel (RGBA-padded) fp32 images"); return DRP_ERR_INVALID; }
+    }
+    DeviceGuard guard(h->device);
+    if (!guard.ok) { drp_set_error("drp_surface_attrs: cannot select device"); return DRP_ERR_CUDA; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_workspace(h, 0, scene->n_materials);  // material table only, no ray queues
+    if (rc != DRP_OK) return rc;
+    RenderWorkspace* ws = h->ws;
+    const size_t mbytes = sizeof(drp_material_t) * scene->n_materials;
+    if (ws->mats_host_copy.size() != mbytes || memcmp(ws->mats_host_copy.data(), scene->materials, mbytes) != 0) {
+        ws->mats_host_copy.assign((const unsigned char*)scene->materials, (const unsigned char*)scene->materials + mbytes);
+        DRP_CUDA_CHECK(cudaMemcpyAsync(ws->d_mats, ws->mats_host_copy.data(), mbytes, cudaMemcpyHostToDevice, s));
+    }
+    drp_scene_t sc = *scene;
+    sc.materials = ws->d_mats;
+    k_surface_attrs<<<(unsigned)((n_rays + 127) / 128), 128, 0, s>>>(sc, rays_o, rays_d, t, tri, t_far, n_rays, attrs);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}
+
 extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
     BvhHandle* h = drp_lookup(handle);
     if (!h || !out) { drp_set_error("drp_render_stats: unknown handle"); return DRP_ERR_HANDLE; }

@@ -448,6 +448,23 @@ class PathTracingSession:
         H, W = self.camera.resolution()
         return tonemap(accum.view(H, W, _abi.ACCUM_CHANNELS), tone, lut=lut, scale=1.0 / self.options.ray_spp, alpha_offset=3, flip_rows=True)[1]
 
+    def surface_attributes(self, rays_o: torch.Tensor, rays_d: torch.Tensor, t: torch.Tensor, i: torch.Tensor) -> torch.Tensor:
+        """
+        For custom samplers (``trace_rays(sampler)``): the whole material layer of the built-in sampler -- ``layer_material_rays`` + collectors
+        (path_tracing.py:158-187) -- as ONE kernel over the ray batch.  Returns (R, 12) ``[albedo3 | normal3 | metallic | smoothness | alpha |
+        emission3]`` (world-space shading normal), zeros for rays with ``t >= far``.  Needs Default / GLTF materials (raises otherwise).
+        """
+        fused = self._fused_scene()
+        if fused is None:
+            raise RuntimeError("scene contains custom Python materials: use layer_material_rays() (generic path)")
+        n = rays_o.shape[0]
+        attrs = torch.empty([n, 12], dtype=torch.float32, device=self.device)
+        f32 = lambda x: x.to(self.device, torch.float32).contiguous()  # noqa: E731
+        o, d, tt, ii = f32(rays_o), f32(rays_d), f32(t), i.to(self.device, torch.int32).contiguous()
+        check(lib().drp_surface_attrs(self.raycaster().handle, C.byref(fused[0]), o.data_ptr(), d.data_ptr(), tt.data_ptr(), ii.data_ptr(),
+                                      self.camera_far(), n, attrs.data_ptr(), _stream_ptr(self.device)), "drp_surface_attrs")
+        return attrs
+
     # ---- generic path (user samplers / Python materials): see diffrp_b200/generic.py -------------------------------
     def layer_material_rays(self, rays_o, rays_d, t, i):
         from . import generic

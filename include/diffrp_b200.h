@@ -21,6 +21,7 @@
  *   drp_flatten         RenderSessionMixin.vertex_array_object  diffrp/rendering/mixin.py:74-113
  *   drp_render          PathTracingSession.trace_rays diffrp/rendering/path_tracing.py:310-347
  *                       (section x bounce loop with the built-in sampler_brdf, :250-279)
+ *   drp_surface_attrs   layer_material_rays + collectors  diffrp/rendering/path_tracing.py:158-187, mixin.py:115-155
  *   drp_finalize        trace_rays epilogue           diffrp/rendering/path_tracing.py:348-352
  *   drp_tonemap         agx_base_contrast             diffrp/utils/tone_mapping.py:21-35
  *                       linear_to_srgb                diffrp/utils/colors.py:33-42
@@ -214,6 +215,14 @@ int drp_flatten(const drp_object_t* objects, int32_t n_objects, float* world_pos
  * scene->world_pos / scene->tris.  workspace may be NULL (internally allocated and cached on the handle). */
 int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_render_params_t* params, float* accum,
                void* stream);
+
+/* The material layer for arbitrary ray batches (custom samplers keep the trace_rays(sampler) protocol,
+ * path_tracing.py:281-309, and get attribute interpolation + material evaluation as one kernel).  Replaces, for Default / GLTF
+ * materials, layer_material_rays + _super_collector + the g-buffer collect (path_tracing.py:158-187, mixin.py:115-155,
+ * interpolator.py:32-48, base_material.py:79-276): attrs (R,12) = [albedo3 | normal3 | metal | smooth | alpha | emission3] at the hit
+ * o + d*t of primitive tri[r]; zeros where t >= t_far.  Same per-hit function as the fused shade kernel. */
+int drp_surface_attrs(uint64_t handle, const drp_scene_t* scene, const float* rays_o, const float* rays_d, const float* t,
+                      const int32_t* tri, float t_far, int64_t n_rays, float* attrs, void* stream);
 
 /* accum (H*W,16) sums -> radiance (H,W,3), alpha (H,W,1) saturated, albedo/emission/world_normal/
  * world_position (H,W,3) each; all divided by spp_total and flipped vertically (row 0 = top). */
