@@ -293,7 +293,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
 
     // rows per CTA: 16 halves the weight traffic and the halo overhead, 8 keeps every SM busy on the small (deep) levels
     const int64_t tiles16 = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + 15) / 16);
-    int tr = tiles16 >= 2 * 148 && p.cout_pad <= 128 ? 16 : 8;
+    int tr = tiles16 >= 2 * 148 && p.cout_pad <= 128 && p.cout_pad > 16 ? 16 : 8;   // per-layer sweep: tools/tune_conv.py
     if (const char* e = getenv("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
     CUtensorMap map_a, map_b;
     {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, tr + 2), zero fill outside = padding 1
@@ -342,7 +342,10 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     const int acc_cols = (tr / 8) * p.cout_pad;
     a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const size_t stage_bytes = (size_t)(tr + 2) * TILE_W * KC * 4 + 3 * (size_t)p.cout_pad * KC * 4;
-    size_t budget = 48 * 1024;                                    // ~3 CTAs per SM: one tile's epilogue overlaps the others' main loops
+    // shared-memory budget per CTA (tools/tune_conv.py): ~48 KB keeps 3-4 CTAs per SM so that one tile's epilogue overlaps the others'
+    // main loops; grids below two waves are latency-bound and want every stage they can get; the 16-channel output layer is store-bound
+    const int64_t n_tiles = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + tr - 1) / tr);
+    size_t budget = n_tiles < 2 * 148 ? 100 * 1024 : p.cout_pad <= 16 ? 24 * 1024 : 48 * 1024;
     if (const char* e = getenv("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, budget / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.k_steps));
