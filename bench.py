@@ -122,6 +122,7 @@ def cpu_oracle_setup(tex):
     import oracle
     from diffrp_b200 import synthetic as syn, ops
     import diffrp_b200 as drp
+    host_threads(oracle)
     scene, camkw = syn.teaser_scene('cpu', tex=tex)
     ops.set_default_device('cpu')
     try:
@@ -195,11 +196,21 @@ def gpu_torch_baseline(scene, camkw, dev, args):
                       % (n, res, res, spp, DEPTH, rays, ms * 1e-3, build_s)}
 
 
+def host_threads(oracle):
+    """All the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 for its workers, which would time the CPU arm on one core."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    oracle.set_num_threads(max(1, n))
+
+
 def run_reference(args, world, rank):
     """--impl reference: the reference's own algorithm for the path (CPU oracle port) on the box's host cores."""
     if rank != 0:
         return
     oracle, bvh, hs, p, keep, build_s, n_tris = cpu_oracle_setup(args.tex)
+    host_threads(oracle)
     cores = oracle.num_threads()
     win, spp = args.ref_window, args.ref_spp
     for w in range(min(args.warmup, 1)):
@@ -259,8 +270,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     S, K, W = args.spp_per_step, args.steps, max(args.warmup, 3)
     HW = RES * RES
@@ -401,6 +411,7 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         oracle, bvh, hs, p, keep, build_s, _ = cpu_oracle_setup(args.tex)
+        host_threads(oracle)
         tt, nn = 0.0, 0
         cpu_oracle_step(oracle, bvh, hs, p, keep, args.ref_window, np.arange(args.ref_spp))
         for k in range(args.cpu_baseline_steps):
