@@ -255,6 +255,179 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
     }
 }
 
+// ---- persistent variant: one CTA per SM loops over tiles; the accumulator is double-buffered in TMEM so that the epilogue of tile i
+// (TMEM -> registers -> smem -> TMA store) overlaps the TMA loads and MMAs of tile i+1; the smem stage ring runs across tile boundaries.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int TR>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                                            const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
+    constexpr int HALVES = TR / 8;
+    constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;
+    constexpr int OUT_BYTES = TR * TILE_W * KC * 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_tap_bytes = a.cout_pad * KC * 4;
+    const int b_stage_bytes = 3 * b_tap_bytes;
+    uint8_t* smem_out = smem;                                   // 2 x OUT_BYTES epilogue staging
+    uint8_t* smem_a = smem + 2 * OUT_BYTES;
+    uint8_t* smem_b = smem_a + a.stages * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + a.stages * b_stage_bytes);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* acc_full = empty + MAX_STAGES;                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (a.width + TILE_W - 1) / TILE_W, tiles_y = (a.height + TR - 1) / TR;
+    const int n_tiles = tiles_x * tiles_y;
+    const uint32_t acc_stride = (uint32_t)(HALVES * a.cout_pad);  // TMEM columns per accumulator buffer
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+        for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer ----
+            const uint32_t stage_bytes = (uint32_t)(A_BYTES + b_stage_bytes);
+            int s = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int by = tile / tiles_x, bx = tile - by * tiles_x;
+                const int x0 = bx * TILE_W, y0 = by * TR;
+                for (int kb = 0; kb < a.k_steps; ++kb) {
+                    mbar_wait(&empty[s], phase ^ 1u);
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    const int kx = kb / a.chunks, chunk = kb - kx * a.chunks;
+                    tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KC, x0 + kx - 1, y0 - 1);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                        tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KC, 0);
+                    if (++s == a.stages) { s = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            const uint32_t idesc = umma_idesc_tf32(a.cout_pad);
+            int s = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(&acc_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)ab * acc_stride;
+                for (int kb = 0; kb < a.k_steps; ++kb) {
+                    mbar_wait(&full[s], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t pa = smem_u32(smem_a + s * A_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
+#pragma unroll
+                    for (int half = 0; half < HALVES; ++half)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int k = 0; k < KC / 8; ++k)
+                                umma_tf32(tacc + (uint32_t)(half * a.cout_pad), umma_desc_sw64(pa + (half * 8 + ky) * (TILE_W * KC * 4) + k * 32),
+                                          umma_desc_sw64(pb + ky * b_tap_bytes + k * 32), idesc, (kb | ky | k) != 0);
+                    umma_commit(&empty[s]);
+                    if (++s == a.stages) { s = 0; phase ^= 1u; }
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..5 ----
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const int ty = m >> 4, tx = m & 15;
+        const int et = (int)threadIdx.x - 64;
+        int buf = 0, it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int by = tile / tiles_x, bx = tile - by * tiles_x;
+            const int x0 = bx * TILE_W, y0 = by * TR;
+            const int ab = it & 1;
+            mbar_wait(&acc_full[ab], ((uint32_t)it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + (uint32_t)ab * acc_stride + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < a.cout_store; c0 += 16, buf ^= 1) {
+                uint8_t* stage_out = smem_out + buf * OUT_BYTES;
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int half = 0; half < HALVES; ++half) {
+                    float v[16];
+                    tmem_ld16(tacc + (uint32_t)(half * a.cout_pad + c0), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] += __ldg(a.bias + c0 + i);
+                        if (a.relu) v[i] = fmaxf(v[i], 0.0f);
+                        if (a.round_tf32) v[i] = round_tf32(v[i]);
+                    }
+                    int row = half * 128 + m;
+                    bool writer = true;
+                    if (a.mode == DRP_CONV_POOL2) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                            v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+                        }
+                        writer = (lane & 17) == 0;
+                        row = (half * 4 + (ty >> 1)) * (TILE_W / 2) + (tx >> 1);
+                    }
+                    if (writer) {
+                        float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
+                        const int sw = (row >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const uint32_t src = smem_u32(stage_out);
+                    const uint64_t mo = reinterpret_cast<uint64_t>(&map_out);
+                    if (a.mode == DRP_CONV_PLAIN) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     ::"l"(mo), "r"(src), "r"(c0), "r"(x0), "r"(y0) : "memory");
+                    } else if (a.mode == DRP_CONV_POOL2) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     ::"l"(mo), "r"(src), "r"(c0), "r"(x0 >> 1), "r"(y0 >> 1) : "memory");
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                                         ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(x0), "r"(r >> 1), "r"(y0) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            // every TMEM read of this tile has completed (tcgen05.wait::ld in tmem_ld16): hand the accumulator buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[ab]);
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -349,6 +522,37 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     if (const char* e = getenv("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, budget / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.k_steps));
+    // persistent variant (one CTA per SM, double-buffered TMEM accumulator).  Per-layer A/B (tools/tune_conv.py, TUNE_PERSISTENT=1): it wins
+    // only for 1-2 waves of tiles (U-Net levels at 1/4 resolution: 51 -> 44 us, 52 -> 42 us); with many tiles per SM a single epilogue warp
+    // group per SM is slower than 3-4 co-resident one-tile CTAs (full-resolution layers: 137 -> 210 us, 62 -> 142 us), so those keep the
+    // one-tile kernel.
+    bool persistent = tr == 16 && n_tiles > 148 && n_tiles <= 320 && 2 * acc_cols <= 512;
+    if (const char* e = getenv("DRP_CONV_PERSISTENT")) persistent = atoi(e) != 0 && 2 * acc_cols <= 512;
+    if (persistent) {
+        const int pacc = 2 * acc_cols;
+        a.tmem_cols = pacc <= 32 ? 32 : pacc <= 64 ? 64 : pacc <= 128 ? 128 : pacc <= 256 ? 256 : 512;
+        size_t pbudget = 190 * 1024 - 2 * (size_t)tr * TILE_W * KC * 4;
+        if (const char* e = getenv("DRP_CONV_SMEM_KB")) pbudget = (size_t)atoi(e) * 1024;
+        a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, pbudget / stage_bytes));
+        const size_t psmem = 1024 + 2 * (size_t)tr * TILE_W * KC * 4 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
+        static std::once_flag pattr_once;
+        static cudaError_t pattr_err = cudaSuccess;
+        static int sm_count = 148;
+        std::call_once(pattr_once, [] {
+            pattr_err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            if (pattr_err == cudaSuccess) pattr_err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            int dev = 0; cudaDeviceProp prop;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sm_count = prop.multiProcessorCount;
+        });
+        DRP_CUDA_CHECK(pattr_err);
+        if (psmem <= 220 * 1024) {
+            const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, sm_count);
+            if (tr == 16) k_conv3x3_tf32_persistent<16><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
+            else k_conv3x3_tf32_persistent<8><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
+            DRP_CUDA_CHECK(cudaGetLastError());
+            return DRP_OK;
+        }
+    }
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;

@@ -20,8 +20,18 @@ for (name, cin, cout), r in zip(dn.LAYERS, res):
     cs = (cout + 3) // 4 * 4
     y = torch.empty(oh, ow, dn._pad16(cout), device='cuda')
     best = {}
-    for rows, kb in itertools.product((8, 16), (24, 32, 48, 72, 100)):
-        os.environ['DRP_CONV_ROWS'], os.environ['DRP_CONV_SMEM_KB'] = str(rows), str(kb)
+    combos = [(0, 0)] + list(itertools.product((8, 16), (24, 32, 48, 72, 100)))
+    if os.environ.get('TUNE_PERSISTENT'):
+        combos = [(0, 0), (1, 0), (1, 8), (1, 16)]            # (persistent?, rows) with the default budgets
+    for rows, kb in combos:
+        for k_ in ('DRP_CONV_ROWS', 'DRP_CONV_SMEM_KB', 'DRP_CONV_PERSISTENT'):
+            os.environ.pop(k_, None)
+        if os.environ.get('TUNE_PERSISTENT'):
+            os.environ['DRP_CONV_PERSISTENT'] = str(rows)
+            if kb:
+                os.environ['DRP_CONV_ROWS'] = str(kb)
+        elif rows:
+            os.environ['DRP_CONV_ROWS'], os.environ['DRP_CONV_SMEM_KB'], os.environ['DRP_CONV_PERSISTENT'] = str(rows), str(kb), '0' 
         for _ in range(3):
             dn.conv3x3(x, 0, cb, wm, bm, y, 0, cs, mode, True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,8 +41,7 @@ for (name, cin, cout), r in zip(dn.LAYERS, res):
         e1.record(); torch.cuda.synchronize()
         best[(rows, kb)] = e0.elapsed_time(e1) / 20 * 1e3
     k = min(best, key=best.get)
-    out[name] = dict(best=k, us=round(best[k], 1), default16_48=round(best[(16, 48)], 1), r8_48=round(best[(8, 48)], 1),
-                     all={"%d/%d" % kk: round(v, 1) for kk, v in best.items()})
-    print(name, out[name]['best'], out[name]['us'], 'default', out[name]['default16_48'], flush=True)
+    out[name] = dict(best=k, us=round(best[k], 1), default=round(best[(0, 0)], 1), all={"%d/%d" % kk: round(v, 1) for kk, v in best.items()})
+    print(name, out[name]['best'], out[name]['us'], 'all', out[name]['all'], flush=True)
 json.dump(out, open('gpurun_out/tune_conv.json', 'w'), indent=1)
-print('sum best', sum(v['us'] for v in out.values()), 'sum default', sum(v['default16_48'] for v in out.values()))
+print('sum best', sum(v['us'] for v in out.values()), 'sum default', sum(v['default'] for v in out.values()))
