@@ -104,6 +104,71 @@ __device__ __forceinline__ float round_tf32(float v) {  // round-to-nearest on t
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
+// Epilogue of one tile for one warp (TMEM lane quadrant `quad` = 2 rows x 16 pixels of every 8-row half): TMEM -> registers (bias, ReLU,
+// TF32 rounding, 2x2 max by shuffles) -> this warp's private 2 KB staging buffer (64 B rows, SWIZZLE_64B) -> one TMA tensor store per
+// 16-channel group.  No CTA-wide barrier: the four epilogue warps run independently; the store's tensor map does the addressing
+// (channel slice + pixel stride, clipping at the image border and at cout_store, and the 2x replication of the upsampling layers).
+template <int TR>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const CUtensorMap* map_out, uint32_t tacc, int quad, int lane, int x0, int y0,
+                                              uint8_t* warp_stage, int& buf) {
+    constexpr int HALVES = TR / 8;
+    constexpr int WARP_OUT_BYTES = 32 * KC * 4;   // 32 pixels x 16 channels
+    const int tx = lane & 15;
+    const uint64_t mo = reinterpret_cast<uint64_t>(map_out);
+    for (int c0 = 0; c0 < a.cout_store; c0 += 16) {
+#pragma unroll
+        for (int half = 0; half < HALVES; ++half, buf ^= 1) {
+            uint8_t* stage_out = warp_stage + buf * WARP_OUT_BYTES;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this buffer has read it
+            __syncwarp();
+            float v[16];
+            tmem_ld16(tacc + (uint32_t)(half * a.cout_pad + c0), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] += __ldg(a.bias + c0 + i);
+                if (a.relu) v[i] = fmaxf(v[i], 0.0f);
+                if (a.round_tf32) v[i] = round_tf32(v[i]);
+            }
+            int row = lane;
+            bool writer = true;
+            if (a.mode == DRP_CONV_POOL2) {       // the warp's two tile rows: lanes l, l^1, l^16, l^17 form a 2x2 window
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+                }
+                writer = (lane & 17) == 0;
+                row = tx >> 1;
+            }
+            if (writer) {
+                float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
+                const int sw = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t src = smem_u32(stage_out);
+                const int yy = y0 + half * 8 + quad * 2;   // first of this warp's two rows
+                if (a.mode == DRP_CONV_PLAIN) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0), "r"(yy) : "memory");
+                } else if (a.mode == DRP_CONV_POOL2) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0 >> 1), "r"(yy >> 1) : "memory");
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                                     ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(x0), "r"(r >> 1), "r"(yy) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+}
+
 // TR = output rows per CTA (8 or 16): the M = 128 accumulator(s) cover 8 rows x 16 columns each.
 // Per k-step (filter column kx, 16-channel chunk) ONE activation box of TR+2 rows is loaded; the three filter rows are the same
 // shared-memory tile read at row offsets 0 / 1 / 2 (a row of 16 pixels = 1024 B, a multiple of the swizzle period), so every
@@ -181,71 +246,13 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
             umma_commit(acc_ready);               // accumulators complete
         }
     } else {
-        // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----
-        // TMEM -> registers (bias, ReLU, TF32 rounding, 2x2 max) -> shared memory tile [pixel][16 channels] (64 B rows, SWIZZLE_64B) ->
-        // TMA tensor store.  The store's tensor map does the addressing: channel slice + pixel stride, clipping at the image border
-        // and at cout_store, and for the upsampling layers the 2x replication (four stores of one tile to the (a, b) sub-lattices).
+        // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4; staging aliases the (drained) pipeline stages ----
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;           // accumulator row = pixel of the 8 x 16 half tile
-        const int ty = m >> 4, tx = m & 15;
-        const int et = (int)threadIdx.x - 64;     // 0..127 among the epilogue threads
-        constexpr int OUT_BYTES = TR * TILE_W * KC * 4;   // one 16-channel group of the whole tile; two buffers alias the (drained) pipeline stages
         mbar_wait(acc_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         int buf = 0;
-        for (int c0 = 0; c0 < a.cout_store; c0 += 16, buf ^= 1) {
-            uint8_t* stage_out = smem_a + buf * OUT_BYTES;
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this buffer has read it
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-            for (int half = 0; half < HALVES; ++half) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * a.cout_pad + c0), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] += __ldg(a.bias + c0 + i);
-                    if (a.relu) v[i] = fmaxf(v[i], 0.0f);
-                    if (a.round_tf32) v[i] = round_tf32(v[i]);
-                }
-                int row = half * 128 + m;
-                bool writer = true;
-                if (a.mode == DRP_CONV_POOL2) {       // rows 2q, 2q+1 of the half tile sit in this warp: lanes l, l^1, l^16, l^17
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
-                    }
-                    writer = (lane & 17) == 0;        // lane 2j of the even row owns the window
-                    row = (half * 4 + (ty >> 1)) * (TILE_W / 2) + (tx >> 1);
-                }
-                if (writer) {
-                    float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
-                    const int sw = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-                const uint32_t src = smem_u32(stage_out);
-                const uint64_t mo = reinterpret_cast<uint64_t>(&map_out);
-                if (a.mode == DRP_CONV_PLAIN) {
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0), "r"(y0) : "memory");
-                } else if (a.mode == DRP_CONV_POOL2) {
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                 ::"l"(mo), "r"(src), "r"(c0), "r"(x0 >> 1), "r"(y0 >> 1) : "memory");
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                                     ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(x0), "r"(r >> 1), "r"(y0) : "memory");
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA retires its shared memory
+        epilogue_tile<TR>(a, &map_out, tmem_base + ((uint32_t)(quad * 32) << 16), quad, lane, x0, y0, smem_a + (warp - 2) * (2 * 32 * KC * 4), buf);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires its shared memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
                                                                             const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
     constexpr int HALVES = TR / 8;
     constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;
-    constexpr int OUT_BYTES = TR * TILE_W * KC * 4;
+    constexpr int OUT_BYTES = 4 * 32 * KC * 4;             // per-warp double-buffered staging: 4 warps x 2 x 2 KB = 2 x OUT_BYTES
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tap_bytes = a.cout_pad * KC * 4;
@@ -352,74 +359,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
     } else {
         // ---- epilogue warps 2..5 ----
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;
-        const int ty = m >> 4, tx = m & 15;
-        const int et = (int)threadIdx.x - 64;
+        uint8_t* warp_stage = smem_out + (warp - 2) * (2 * 32 * KC * 4);
         int buf = 0, it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int by = tile / tiles_x, bx = tile - by * tiles_x;
-            const int x0 = bx * TILE_W, y0 = by * TR;
             const int ab = it & 1;
             mbar_wait(&acc_full[ab], ((uint32_t)it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tacc = tmem_base + (uint32_t)ab * acc_stride + ((uint32_t)(quad * 32) << 16);
-            for (int c0 = 0; c0 < a.cout_store; c0 += 16, buf ^= 1) {
-                uint8_t* stage_out = smem_out + buf * OUT_BYTES;
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                for (int half = 0; half < HALVES; ++half) {
-                    float v[16];
-                    tmem_ld16(tacc + (uint32_t)(half * a.cout_pad + c0), v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] += __ldg(a.bias + c0 + i);
-                        if (a.relu) v[i] = fmaxf(v[i], 0.0f);
-                        if (a.round_tf32) v[i] = round_tf32(v[i]);
-                    }
-                    int row = half * 128 + m;
-                    bool writer = true;
-                    if (a.mode == DRP_CONV_POOL2) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                            v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
-                        }
-                        writer = (lane & 17) == 0;
-                        row = (half * 4 + (ty >> 1)) * (TILE_W / 2) + (tx >> 1);
-                    }
-                    if (writer) {
-                        float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
-                        const int sw = (row >> 1) & 3;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    const uint32_t src = smem_u32(stage_out);
-                    const uint64_t mo = reinterpret_cast<uint64_t>(&map_out);
-                    if (a.mode == DRP_CONV_PLAIN) {
-                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                     ::"l"(mo), "r"(src), "r"(c0), "r"(x0), "r"(y0) : "memory");
-                    } else if (a.mode == DRP_CONV_POOL2) {
-                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                     ::"l"(mo), "r"(src), "r"(c0), "r"(x0 >> 1), "r"(y0 >> 1) : "memory");
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                                         ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(x0), "r"(r >> 1), "r"(y0) : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
+            epilogue_tile<TR>(a, &map_out, tmem_base + (uint32_t)ab * acc_stride + ((uint32_t)(quad * 32) << 16), quad, lane, bx * TILE_W, by * TR, warp_stage, buf);
             // every TMEM read of this tile has completed (tcgen05.wait::ld in tmem_ld16): hand the accumulator buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[ab]);
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {
@@ -493,7 +445,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         if (p.mode == DRP_CONV_UPSAMPLE2) {                    // (c, b, x, a, y): output pixel (2y + a, 2x + b)
             const cuuint64_t dims[5] = {(cuuint64_t)p.cout_store, 2, (cuuint64_t)p.width, 2, (cuuint64_t)p.height};
             const cuuint64_t strides[4] = {ps, 2 * ps, 2 * (cuuint64_t)p.width * ps, 4 * (cuuint64_t)p.width * ps};
-            const cuuint32_t box[5] = {KC, 1, TILE_W, 1, (cuuint32_t)tr}, estr[5] = {1, 1, 1, 1, 1};
+            const cuuint32_t box[5] = {KC, 1, TILE_W, 1, 2}, estr[5] = {1, 1, 1, 1, 1};   // one warp's 2 rows x 16 pixels per store
             r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
@@ -501,7 +453,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
             const cuuint64_t ow = (cuuint64_t)(p.width >> sh), oh = (cuuint64_t)(p.height >> sh);
             const cuuint64_t dims[3] = {(cuuint64_t)p.cout_store, ow, oh};
             const cuuint64_t strides[2] = {ps, ow * ps};
-            const cuuint32_t box[3] = {KC, (cuuint32_t)(TILE_W >> sh), (cuuint32_t)(tr >> sh)}, estr[3] = {1, 1, 1};
+            const cuuint32_t box[3] = {KC, (cuuint32_t)(TILE_W >> sh), (cuuint32_t)(2 >> sh)}, estr[3] = {1, 1, 1};   // one warp's 2 rows x 16 pixels (pooled: 1 x 8)
             r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
@@ -531,10 +483,10 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     if (persistent) {
         const int pacc = 2 * acc_cols;
         a.tmem_cols = pacc <= 32 ? 32 : pacc <= 64 ? 64 : pacc <= 128 ? 128 : pacc <= 256 ? 256 : 512;
-        size_t pbudget = 190 * 1024 - 2 * (size_t)tr * TILE_W * KC * 4;
+        size_t pbudget = 190 * 1024 - 16 * 1024;
         if (const char* e = getenv("DRP_CONV_SMEM_KB")) pbudget = (size_t)atoi(e) * 1024;
         a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, pbudget / stage_bytes));
-        const size_t psmem = 1024 + 2 * (size_t)tr * TILE_W * KC * 4 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
+        const size_t psmem = 1024 + 16 * 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
         static std::once_flag pattr_once;
         static cudaError_t pattr_err = cudaSuccess;
         static int sm_count = 148;
