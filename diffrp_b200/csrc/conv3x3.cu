@@ -396,6 +396,28 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+// per-device one-time setup: opt in to > 48 KB of dynamic shared memory for every kernel variant, remember the SM count
+struct ConvDeviceState { bool ready = false; cudaError_t err = cudaSuccess; int sm_count = 148; };
+static ConvDeviceState* conv_device_state() {
+    static std::mutex mu;
+    static ConvDeviceState states[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    ConvDeviceState& st = states[dev];
+    if (!st.ready) {
+        const int limit = 220 * 1024;
+        st.err = cudaFuncSetAttribute(k_conv3x3_tf32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) st.sm_count = prop.multiProcessorCount;
+        st.ready = true;
+    }
+    return &st;
+}
+
 }  // namespace
 
 extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
@@ -418,7 +440,9 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
 
     // rows per CTA: 16 halves the weight traffic and the halo overhead, 8 keeps every SM busy on the small (deep) levels
     const int64_t tiles16 = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + 15) / 16);
-    int tr = tiles16 >= 2 * 148 && p.cout_pad <= 128 && p.cout_pad > 16 ? 16 : 8;   // per-layer sweep: tools/tune_conv.py
+    const bool wide_ok = p.cout_pad <= 128 && p.cout_pad > 16;
+    const bool persist16 = wide_ok && tiles16 > 148 && tiles16 <= 320;              // 1-2 waves of 16-row tiles: persistent kernel (see below)
+    int tr = wide_ok && (tiles16 >= 2 * 148 || persist16) ? 16 : 8;                  // per-layer sweep: tools/tune_conv.py
     if (const char* e = getenv("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
     CUtensorMap map_a, map_b;
     {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, tr + 2), zero fill outside = padding 1
@@ -459,6 +483,8 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         }
         if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
     }
+    ConvDeviceState* dstate = conv_device_state();
+    DRP_CUDA_CHECK(dstate->err);
     ConvArgs a;
     a.bias = p.bias; a.out = p.out; a.height = p.height; a.width = p.width;
     a.chunks = p.cin / KC; a.k_steps = 3 * a.chunks; a.cin = p.cin;
@@ -487,18 +513,8 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         if (const char* e = getenv("DRP_CONV_SMEM_KB")) pbudget = (size_t)atoi(e) * 1024;
         a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, pbudget / stage_bytes));
         const size_t psmem = 1024 + 16 * 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
-        static std::once_flag pattr_once;
-        static cudaError_t pattr_err = cudaSuccess;
-        static int sm_count = 148;
-        std::call_once(pattr_once, [] {
-            pattr_err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-            if (pattr_err == cudaSuccess) pattr_err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-            int dev = 0; cudaDeviceProp prop;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sm_count = prop.multiProcessorCount;
-        });
-        DRP_CUDA_CHECK(pattr_err);
         if (psmem <= 220 * 1024) {
-            const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, sm_count);
+            const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, dstate->sm_count);
             if (tr == 16) k_conv3x3_tf32_persistent<16><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
             else k_conv3x3_tf32_persistent<8><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
             DRP_CUDA_CHECK(cudaGetLastError());
@@ -506,13 +522,6 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         }
     }
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(k_conv3x3_tf32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_conv3x3_tf32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    });
-    DRP_CUDA_CHECK(attr_err);
     if (smem > 220 * 1024) { drp_set_error("drp_conv3x3: tile does not fit in shared memory"); return DRP_ERR_INVALID; }
     const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + tr - 1) / tr));
     if (tr == 16) k_conv3x3_tf32<16><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
