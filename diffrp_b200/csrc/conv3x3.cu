@@ -23,7 +23,8 @@
 namespace {
 
 constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;  // 128 output pixels per CTA = UMMA M
-constexpr int KC = 16;                                         // fp32 per k-step row = 64 B (SWIZZLE_64B span)
+constexpr int OG = 16;                                         // output channels per epilogue group: 64-byte staging rows (SWIZZLE_64B)
+// input-channel chunk per k-step (template parameter KCH): 16 fp32 = 64 B rows (SWIZZLE_64B) or 32 fp32 = 128 B rows (SWIZZLE_128B)
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;                      // a wedged pipeline traps instead of hanging the GPU
@@ -57,13 +58,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO); version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+// UMMA shared-memory descriptor, K-major, rows of ROW_BYTES = 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B): 8-row groups 8*ROW_BYTES apart (SBO);
+// version 1 (sm_100)
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);   // start address, bits [0,14)
-    d |= (uint64_t)(512u >> 4) << 32;                // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                          // descriptor version
-    d |= (uint64_t)4 << 61;                          // layout type SWIZZLE_64B
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);           // start address, bits [0,14)
+    d |= (uint64_t)((8u * ROW_BYTES) >> 4) << 32;            // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version
+    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;         // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
 // instruction descriptor: D fp32, A/B TF32, both K-major, M = 128, N = n
@@ -112,7 +115,7 @@ template <int TR>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const CUtensorMap* map_out, uint32_t tacc, int quad, int lane, int x0, int y0,
                                               uint8_t* warp_stage, int& buf) {
     constexpr int HALVES = TR / 8;
-    constexpr int WARP_OUT_BYTES = 32 * KC * 4;   // 32 pixels x 16 channels
+    constexpr int WARP_OUT_BYTES = 32 * OG * 4;   // 32 pixels x 16 channels
     const int tx = lane & 15;
     const uint64_t mo = reinterpret_cast<uint64_t>(map_out);
     for (int c0 = 0; c0 < a.cout_store; c0 += 16) {
@@ -141,7 +144,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const CUtensorM
                 row = tx >> 1;
             }
             if (writer) {
-                float4* dst = reinterpret_cast<float4*>(stage_out + row * (KC * 4));
+                float4* dst = reinterpret_cast<float4*>(stage_out + row * (OG * 4));
                 const int sw = (row >> 1) & 3;    // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -173,14 +176,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const CUtensorM
 // Per k-step (filter column kx, 16-channel chunk) ONE activation box of TR+2 rows is loaded; the three filter rows are the same
 // shared-memory tile read at row offsets 0 / 1 / 2 (a row of 16 pixels = 1024 B, a multiple of the swizzle period), so every
 // activation element crosses L2 -> SM 3 (TR+2)/TR times per layer instead of 9, and the weights once per TR*16 pixels.
-template <int TR>
+template <int TR, int KCH>
 __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                               const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
     constexpr int HALVES = TR / 8;
-    constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;     // (TR+2) KB, 1024-aligned
+    constexpr int A_BYTES = (TR + 2) * TILE_W * KCH * 4;    // (TR+2) or 2(TR+2) KB, 1024-aligned
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tap_bytes = a.cout_pad * KC * 4;
+    const int b_tap_bytes = a.cout_pad * KCH * 4;
     const int b_stage_bytes = 3 * b_tap_bytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + a.stages * A_BYTES;
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
                 mbar_wait(&empty[s], phase ^ 1u);
                 mbar_expect_tx(&full[s], stage_bytes);
                 const int kx = kb / a.chunks, chunk = kb - kx * a.chunks;
-                tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KC, x0 + kx - 1, y0 - 1);
+                tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KCH, x0 + kx - 1, y0 - 1);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
-                    tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KC, 0);
+                    tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KCH, 0);
                 if (++s == a.stages) { s = 0; phase ^= 1u; }
             }
         }
@@ -232,14 +235,17 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
                 mbar_wait(&full[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t pa = smem_u32(smem_a + s * A_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
+                // descriptors advance in their 14-bit start-address field (16-byte units): A by whole tile rows (1024 B) and 32 B per UMMA K
+                const uint64_t da0 = umma_desc<KCH * 4>(pa), db0 = umma_desc<KCH * 4>(pb);
+                const uint32_t b_tap16 = (uint32_t)b_tap_bytes >> 4;
 #pragma unroll
                 for (int half = 0; half < HALVES; ++half)
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int k = 0; k < KC / 8; ++k)  // UMMA K = 8 TF32 = 32 B along the row
-                            umma_tf32(tmem_base + (uint32_t)(half * a.cout_pad), umma_desc_sw64(pa + (half * 8 + ky) * (TILE_W * KC * 4) + k * 32),
-                                      umma_desc_sw64(pb + ky * b_tap_bytes + k * 32), idesc, (kb | ky | k) != 0);
+                        for (int k = 0; k < KCH / 8; ++k)  // UMMA K = 8 TF32 = 32 B along the row
+                            umma_tf32(tmem_base + (uint32_t)(half * a.cout_pad), da0 + (uint64_t)((half * 8 + ky) * (TILE_W * KCH * 4 / 16) + k * 2),
+                                      db0 + (uint64_t)(ky * b_tap16 + k * 2), idesc, (kb | ky | k) != 0);
                 umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
                 if (++s == a.stages) { s = 0; phase ^= 1u; }
             }
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32(const __grid_const
         mbar_wait(acc_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         int buf = 0;
-        epilogue_tile<TR>(a, &map_out, tmem_base + ((uint32_t)(quad * 32) << 16), quad, lane, x0, y0, smem_a + (warp - 2) * (2 * 32 * KC * 4), buf);
+        epilogue_tile<TR>(a, &map_out, tmem_base + ((uint32_t)(quad * 32) << 16), quad, lane, x0, y0, smem_a + (warp - 2) * (2 * 32 * OG * 4), buf);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires its shared memory
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -268,15 +274,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int TR>
+template <int TR, int KCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                             const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
     constexpr int HALVES = TR / 8;
-    constexpr int A_BYTES = (TR + 2) * TILE_W * KC * 4;
-    constexpr int OUT_BYTES = 4 * 32 * KC * 4;             // per-warp double-buffered staging: 4 warps x 2 x 2 KB = 2 x OUT_BYTES
+    constexpr int A_BYTES = (TR + 2) * TILE_W * KCH * 4;
+    constexpr int OUT_BYTES = 4 * 32 * OG * 4;             // per-warp double-buffered staging: 4 warps x 2 x 2 KB = 2 x OUT_BYTES
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tap_bytes = a.cout_pad * KC * 4;
+    const int b_tap_bytes = a.cout_pad * KCH * 4;
     const int b_stage_bytes = 3 * b_tap_bytes;
     uint8_t* smem_out = smem;                                   // 2 x OUT_BYTES epilogue staging
     uint8_t* smem_a = smem + 2 * OUT_BYTES;
@@ -320,10 +326,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
                     mbar_wait(&empty[s], phase ^ 1u);
                     mbar_expect_tx(&full[s], stage_bytes);
                     const int kx = kb / a.chunks, chunk = kb - kx * a.chunks;
-                    tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KC, x0 + kx - 1, y0 - 1);
+                    tma_load_3d(&map_a, &full[s], smem_a + s * A_BYTES, chunk * KCH, x0 + kx - 1, y0 - 1);
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                        tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KC, 0);
+                        tma_load_2d(&map_b, &full[s], smem_b + s * b_stage_bytes + ky * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * KCH, 0);
                     if (++s == a.stages) { s = 0; phase ^= 1u; }
                 }
             }
@@ -342,14 +348,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
                     mbar_wait(&full[s], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t pa = smem_u32(smem_a + s * A_BYTES), pb = smem_u32(smem_b + s * b_stage_bytes);
+                    const uint64_t da0 = umma_desc<KCH * 4>(pa), db0 = umma_desc<KCH * 4>(pb);
+                    const uint32_t b_tap16 = (uint32_t)b_tap_bytes >> 4;
 #pragma unroll
                     for (int half = 0; half < HALVES; ++half)
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                            for (int k = 0; k < KC / 8; ++k)
-                                umma_tf32(tacc + (uint32_t)(half * a.cout_pad), umma_desc_sw64(pa + (half * 8 + ky) * (TILE_W * KC * 4) + k * 32),
-                                          umma_desc_sw64(pb + ky * b_tap_bytes + k * 32), idesc, (kb | ky | k) != 0);
+                            for (int k = 0; k < KCH / 8; ++k)
+                                umma_tf32(tacc + (uint32_t)(half * a.cout_pad), da0 + (uint64_t)((half * 8 + ky) * (TILE_W * KCH * 4 / 16) + k * 2),
+                                          db0 + (uint64_t)(ky * b_tap16 + k * 2), idesc, (kb | ky | k) != 0);
                     umma_commit(&empty[s]);
                     if (++s == a.stages) { s = 0; phase ^= 1u; }
                 }
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
     } else {
         // ---- epilogue warps 2..5 ----
         const int quad = warp & 3;
-        uint8_t* warp_stage = smem_out + (warp - 2) * (2 * 32 * KC * 4);
+        uint8_t* warp_stage = smem_out + (warp - 2) * (2 * 32 * OG * 4);
         int buf = 0, it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int by = tile / tiles_x, bx = tile - by * tiles_x;
@@ -407,10 +415,11 @@ static ConvDeviceState* conv_device_state() {
     ConvDeviceState& st = states[dev];
     if (!st.ready) {
         const int limit = 220 * 1024;
-        st.err = cudaFuncSetAttribute(k_conv3x3_tf32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute(k_conv3x3_tf32_persistent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+        const void* kernels[8] = {(const void*)k_conv3x3_tf32<8, 16>, (const void*)k_conv3x3_tf32<16, 16>, (const void*)k_conv3x3_tf32<8, 32>,
+                                  (const void*)k_conv3x3_tf32<16, 32>, (const void*)k_conv3x3_tf32_persistent<8, 16>,
+                                  (const void*)k_conv3x3_tf32_persistent<16, 16>, (const void*)k_conv3x3_tf32_persistent<8, 32>,
+                                  (const void*)k_conv3x3_tf32_persistent<16, 32>};
+        for (int k = 0; k < 8 && st.err == cudaSuccess; ++k) st.err = cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) st.sm_count = prop.multiProcessorCount;
         st.ready = true;
@@ -444,21 +453,28 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     const bool persist16 = wide_ok && tiles16 > 148 && tiles16 <= 320;              // 1-2 waves of 16-row tiles: persistent kernel (see below)
     int tr = wide_ok && (tiles16 >= 2 * 148 || persist16) ? 16 : 8;                  // per-layer sweep: tools/tune_conv.py
     if (const char* e = getenv("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
+    // input channels per k-step: 16 (64-byte rows, SWIZZLE_64B) or 32 (128-byte rows, SWIZZLE_128B: half the k-steps, stages twice as big).
+    // Per-layer A/B (tools/tune_conv.py, TUNE_KC=1): 32 only pays on the latency-bound sub-wave grids of the deep levels (20.8 -> 18.4 us);
+    // on the wide layers the bigger stages cost co-resident CTAs (82 -> 108 us, 90 -> 125 us), so 16 stays the default there.
+    const int64_t tiles8 = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + 7) / 8);
+    int kch = p.cin % 32 == 0 && tiles8 <= 148 ? 32 : 16;
+    if (const char* e = getenv("DRP_CONV_KC")) { const int v = atoi(e); if (v == 16 || (v == 32 && p.cin % 32 == 0)) kch = v; }
+    const CUtensorMapSwizzle in_swizzle = kch == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap map_a, map_b;
-    {   // activations: (C, W, H) fp32 view of the channel slice, box (16, 16, tr + 2), zero fill outside = padding 1
+    {   // activations: (C, W, H) fp32 view of the channel slice, box (kch, 16, tr + 2), zero fill outside = padding 1
         const cuuint64_t dims[3] = {(cuuint64_t)p.cin, (cuuint64_t)p.width, (cuuint64_t)p.height};
         const cuuint64_t strides[2] = {(cuuint64_t)p.in_stride * 4, (cuuint64_t)p.in_stride * 4 * (cuuint64_t)p.width};
-        const cuuint32_t box[3] = {KC, TILE_W, (cuuint32_t)(tr + 2)}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)kch, TILE_W, (cuuint32_t)(tr + 2)}, estr[3] = {1, 1, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.in + p.in_offset), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, in_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
     }
     {   // weights: (K = 9*cin, cout_pad), box (16, cout_pad)
         const cuuint64_t dims[2] = {(cuuint64_t)9 * p.cin, (cuuint64_t)p.cout_pad};
         const cuuint64_t strides[1] = {(cuuint64_t)9 * p.cin * 4};
-        const cuuint32_t box[2] = {KC, (cuuint32_t)p.cout_pad}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)p.cout_pad}, estr[2] = {1, 1};
         CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.weight), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, in_swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
     }
     CUtensorMap map_out;
@@ -469,7 +485,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         if (p.mode == DRP_CONV_UPSAMPLE2) {                    // (c, b, x, a, y): output pixel (2y + a, 2x + b)
             const cuuint64_t dims[5] = {(cuuint64_t)p.cout_store, 2, (cuuint64_t)p.width, 2, (cuuint64_t)p.height};
             const cuuint64_t strides[4] = {ps, 2 * ps, 2 * (cuuint64_t)p.width * ps, 4 * (cuuint64_t)p.width * ps};
-            const cuuint32_t box[5] = {KC, 1, TILE_W, 1, 2}, estr[5] = {1, 1, 1, 1, 1};   // one warp's 2 rows x 16 pixels per store
+            const cuuint32_t box[5] = {OG, 1, TILE_W, 1, 2}, estr[5] = {1, 1, 1, 1, 1};   // one warp's 2 rows x 16 pixels per store
             r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
@@ -477,7 +493,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
             const cuuint64_t ow = (cuuint64_t)(p.width >> sh), oh = (cuuint64_t)(p.height >> sh);
             const cuuint64_t dims[3] = {(cuuint64_t)p.cout_store, ow, oh};
             const cuuint64_t strides[2] = {ps, ow * ps};
-            const cuuint32_t box[3] = {KC, (cuuint32_t)(TILE_W >> sh), (cuuint32_t)(2 >> sh)}, estr[3] = {1, 1, 1};   // one warp's 2 rows x 16 pixels (pooled: 1 x 8)
+            const cuuint32_t box[3] = {OG, (cuuint32_t)(TILE_W >> sh), (cuuint32_t)(2 >> sh)}, estr[3] = {1, 1, 1};   // one warp's 2 rows x 16 pixels (pooled: 1 x 8)
             r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
@@ -487,12 +503,12 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     DRP_CUDA_CHECK(dstate->err);
     ConvArgs a;
     a.bias = p.bias; a.out = p.out; a.height = p.height; a.width = p.width;
-    a.chunks = p.cin / KC; a.k_steps = 3 * a.chunks; a.cin = p.cin;
+    a.chunks = p.cin / kch; a.k_steps = 3 * a.chunks; a.cin = p.cin;
     a.cout_pad = p.cout_pad; a.cout_store = p.cout_store; a.out_stride = p.out_stride; a.out_offset = p.out_offset; a.mode = p.mode; a.relu = p.relu;
     a.round_tf32 = p.round_tf32;
     const int acc_cols = (tr / 8) * p.cout_pad;
     a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
-    const size_t stage_bytes = (size_t)(tr + 2) * TILE_W * KC * 4 + 3 * (size_t)p.cout_pad * KC * 4;
+    const size_t stage_bytes = (size_t)(tr + 2) * TILE_W * kch * 4 + 3 * (size_t)p.cout_pad * kch * 4;
     // shared-memory budget per CTA (tools/tune_conv.py): ~48 KB keeps 3-4 CTAs per SM so that one tile's epilogue overlaps the others'
     // main loops; grids below two waves are latency-bound and want every stage they can get; the 16-channel output layer is store-bound
     const int64_t n_tiles = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + tr - 1) / tr);
@@ -515,8 +531,11 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
         const size_t psmem = 1024 + 16 * 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
         if (psmem <= 220 * 1024) {
             const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, dstate->sm_count);
-            if (tr == 16) k_conv3x3_tf32_persistent<16><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
-            else k_conv3x3_tf32_persistent<8><<<grid, NUM_THREADS, psmem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
+            cudaStream_t st = (cudaStream_t)stream;
+            if (tr == 16 && kch == 32) k_conv3x3_tf32_persistent<16, 32><<<grid, NUM_THREADS, psmem, st>>>(map_a, map_b, map_out, a);
+            else if (tr == 16) k_conv3x3_tf32_persistent<16, 16><<<grid, NUM_THREADS, psmem, st>>>(map_a, map_b, map_out, a);
+            else if (kch == 32) k_conv3x3_tf32_persistent<8, 32><<<grid, NUM_THREADS, psmem, st>>>(map_a, map_b, map_out, a);
+            else k_conv3x3_tf32_persistent<8, 16><<<grid, NUM_THREADS, psmem, st>>>(map_a, map_b, map_out, a);
             DRP_CUDA_CHECK(cudaGetLastError());
             return DRP_OK;
         }
@@ -524,8 +543,11 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
     if (smem > 220 * 1024) { drp_set_error("drp_conv3x3: tile does not fit in shared memory"); return DRP_ERR_INVALID; }
     const dim3 grid((unsigned)((p.width + TILE_W - 1) / TILE_W), (unsigned)((p.height + tr - 1) / tr));
-    if (tr == 16) k_conv3x3_tf32<16><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
-    else k_conv3x3_tf32<8><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tr == 16 && kch == 32) k_conv3x3_tf32<16, 32><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, map_out, a);
+    else if (tr == 16) k_conv3x3_tf32<16, 16><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, map_out, a);
+    else if (kch == 32) k_conv3x3_tf32<8, 32><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, map_out, a);
+    else k_conv3x3_tf32<8, 16><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, map_out, a);
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }

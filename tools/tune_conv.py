@@ -23,10 +23,14 @@ for (name, cin, cout), r in zip(dn.LAYERS, res):
     combos = [(0, 0)] + list(itertools.product((8, 16), (24, 32, 48, 72, 100)))
     if os.environ.get('TUNE_PERSISTENT'):
         combos = [(0, 0), (1, 0), (1, 8), (1, 16)]            # (persistent?, rows) with the default budgets
+    if os.environ.get('TUNE_KC'):
+        combos = [(pp * 100 + kc, rows) for pp in (0, 1) for kc in (16, 32) for rows in (8, 16)]   # persistent x chunk x rows
     for rows, kb in combos:
         for k_ in ('DRP_CONV_ROWS', 'DRP_CONV_SMEM_KB', 'DRP_CONV_PERSISTENT'):
             os.environ.pop(k_, None)
-        if os.environ.get('TUNE_PERSISTENT'):
+        if os.environ.get('TUNE_KC'):
+            os.environ['DRP_CONV_PERSISTENT'], os.environ['DRP_CONV_KC'], os.environ['DRP_CONV_ROWS'] = str(rows // 100), str(rows % 100), str(kb)
+        elif os.environ.get('TUNE_PERSISTENT'):
             os.environ['DRP_CONV_PERSISTENT'] = str(rows)
             if kb:
                 os.environ['DRP_CONV_ROWS'] = str(kb)
@@ -41,7 +45,7 @@ for (name, cin, cout), r in zip(dn.LAYERS, res):
         e1.record(); torch.cuda.synchronize()
         best[(rows, kb)] = e0.elapsed_time(e1) / 20 * 1e3
     k = min(best, key=best.get)
-    out[name] = dict(best=k, us=round(best[k], 1), default=round(best[(0, 0)], 1), all={"%d/%d" % kk: round(v, 1) for kk, v in best.items()})
+    out[name] = dict(best=k, us=round(best[k], 1), default=round(best.get((0, 0), best[k]), 1), all={"%d/%d" % kk: round(v, 1) for kk, v in best.items()})
     print(name, out[name]['best'], out[name]['us'], 'all', out[name]['all'], flush=True)
 json.dump(out, open('gpurun_out/tune_conv.json', 'w'), indent=1)
 print('sum best', sum(v['us'] for v in out.values()), 'sum default', sum(v['default'] for v in out.values()))
