@@ -188,8 +188,21 @@ DRP_HD VertexIn load_vertex(const drp_scene_t& sc, int i) {
     return v;
 }
 
-DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id) {
+// radiance_only: the caller uses nothing but `emission` and `alpha` (last bounce of a path: no next ray is sampled and no g-buffer is
+// written, path_tracing.py:336-338), so everything that cannot influence those two is skipped -- for an opaque material without emission that
+// is the whole evaluation, including the vertex fetches.  The values that are produced are computed by the same code as in the full mode.
+DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id, const bool radiance_only = false) {
     SurfaceAttrs s;
+    if (radiance_only) {
+        const drp_material_t& m0 = mats[ldg(sc.tri_material + tri_id)];
+        const bool need_alpha = m0.kind != DRP_MAT_DEFAULT && (m0.alpha_mode == DRP_ALPHA_MASK || m0.alpha_mode == DRP_ALPHA_BLEND);
+        const bool need_em = m0.kind != DRP_MAT_DEFAULT && m0.has_emissive && m0.emissive_tex.data;
+        if (!need_alpha && !need_em) {
+            s.albedo = s.normal = s.emission = v3(0.0f, 0.0f, 0.0f);
+            s.metal = 0.0f; s.smooth = 0.5f; s.alpha = 1.0f;
+            return s;
+        }
+    }
     const int i0 = ldg(sc.tris + 3 * (int64_t)tri_id), i1 = ldg(sc.tris + 3 * (int64_t)tri_id + 1), i2 = ldg(sc.tris + 3 * (int64_t)tri_id + 2);
     const VertexIn q0 = load_vertex(sc, i0), q1 = load_vertex(sc, i1), q2 = load_vertex(sc, i2);
     float u, v;
@@ -208,7 +221,9 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
     const float2 t0 = q0.uv, t1 = q1.uv, t2 = q2.uv;
     float tu = lerp3(t0.x, t1.x, t2.x, u, v), tv = lerp3(t0.y, t1.y, t2.y, u, v);
     float bc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, mr[4] = {0.0f, 0.0f, 0.0f, 0.0f}, nt[4] = {0.0f, 0.0f, 0.0f, 0.0f}, em[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const bool use_nt = m.has_normal_tex && m.normal_tex.data, use_em = m.has_emissive && m.emissive_tex.data;
+    const bool use_nt = !radiance_only && m.has_normal_tex && m.normal_tex.data, use_em = m.has_emissive && m.emissive_tex.data;
+    const bool use_bc = m.base_color_tex.data && !(radiance_only && m.alpha_mode != DRP_ALPHA_MASK && m.alpha_mode != DRP_ALPHA_BLEND);
+    const bool use_mr = m.mr_tex.data && !radiance_only;
 #ifdef __CUDA_ARCH__
     const bool rgba = true;  // drp_render only accepts RGBA-padded textures (validated on the host side)
 #else
@@ -217,22 +232,22 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
 #endif
     if (rgba) {  // device path: address stage for all textures first, then all loads back to back
         TexTaps ta, tb, tc, td;
-        if (m.base_color_tex.data) ta = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
-        if (m.mr_tex.data) tb = tex_taps(m.mr_tex.h, m.mr_tex.w, m.mr_tex.wrap, m.mr_tex.interp, tu, tv);
+        if (use_bc) ta = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
+        if (use_mr) tb = tex_taps(m.mr_tex.h, m.mr_tex.w, m.mr_tex.wrap, m.mr_tex.interp, tu, tv);
         if (use_nt) tc = tex_taps(m.normal_tex.h, m.normal_tex.w, m.normal_tex.wrap, m.normal_tex.interp, tu, tv);
         if (use_em) td = tex_taps(m.emissive_tex.h, m.emissive_tex.w, m.emissive_tex.wrap, m.emissive_tex.interp, tu, tv);
-        if (m.base_color_tex.data) { float4 r = tex_fetch4(m.base_color_tex.data, ta); bc[0] = r.x; bc[1] = r.y; bc[2] = r.z; bc[3] = r.w; }
-        if (m.mr_tex.data) { float4 r = tex_fetch4(m.mr_tex.data, tb); mr[1] = r.y; mr[2] = r.z; }
+        if (use_bc) { float4 r = tex_fetch4(m.base_color_tex.data, ta); bc[0] = r.x; bc[1] = r.y; bc[2] = r.z; bc[3] = r.w; }
+        if (use_mr) { float4 r = tex_fetch4(m.mr_tex.data, tb); mr[1] = r.y; mr[2] = r.z; }
         if (use_nt) { float4 r = tex_fetch4(m.normal_tex.data, tc); nt[0] = r.x; nt[1] = r.y; nt[2] = r.z; }
         if (use_em) { float4 r = tex_fetch4(m.emissive_tex.data, td); em[0] = r.x; em[1] = r.y; em[2] = r.z; }
     }
 #ifndef __CUDA_ARCH__
     else {
-        if (m.base_color_tex.data) {
+        if (use_bc) {
             tex_fetch(m.base_color_tex, tu, tv, bc);
             if (m.base_color_tex.c < 4) bc[3] = 1.0f;
         }
-        if (m.mr_tex.data) tex_fetch(m.mr_tex, tu, tv, mr);
+        if (use_mr) tex_fetch(m.mr_tex, tu, tv, mr);
         if (use_nt) tex_fetch(m.normal_tex, tu, tv, nt);
         if (use_em) tex_fetch(m.emissive_tex, tu, tv, em);
     }

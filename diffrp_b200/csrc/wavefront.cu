@@ -394,22 +394,30 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                 const bool is_hit = MODE == SHADE_HITS ? true : (MODE == SHADE_MISSES ? false : t < c.p.t_far);
                 SurfaceAttrs s;
                 if (is_hit) {
-                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y));
+                    // last bounce of a path (not the first): only emission and alpha reach the outputs, skip the rest of the material
+                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y), !PRIMARY && last);
                 } else {
                     s.albedo = s.normal = s.emission = v3(0, 0, 0);
                     s.metal = s.smooth = s.alpha = 0.0f;
                 }
                 Vec3 env = (always_sky || !is_hit) ? env_fetch(c.scene.env, d) : v3(0, 0, 0);  // path_tracing.py:267-269
-                float u[6];
+                float u[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
                 const int lpix = ri % c.HW, ly = lpix / c.tw;
                 const int pix = (c.ty0 + ly) * c.p.width + c.tx0 + (lpix - ly * c.tw);  // global pixel: accumulator row and RNG key
-                if (c.p.rng_mode == DRP_RNG_REPLAY) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) u[q] = __ldg(c.p.replay_u + ((int64_t)bounce * 6 + q) * c.R_total + ri);
+                BounceOut r;
+                if (!PRIMARY && last) {  // nothing is sampled after the last bounce: radiance only (shade.cuh: brdf_sample line 1-2)
+                    r.hit_pos = o + d * t;
+                    r.radiance = s.emission + env;
+                    r.next_d = d; r.transfer = v3(0.0f, 0.0f, 0.0f);
                 } else {
-                    philox_uniform6(c.p.seed, (uint32_t)pix, (uint32_t)__ldg(c.p.sample_ids + ri / c.HW), (uint32_t)bounce, u);
+                    if (c.p.rng_mode == DRP_RNG_REPLAY) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) u[q] = __ldg(c.p.replay_u + ((int64_t)bounce * 6 + q) * c.R_total + ri);
+                    } else {
+                        philox_uniform6(c.p.seed, (uint32_t)pix, (uint32_t)__ldg(c.p.sample_ids + ri / c.HW), (uint32_t)bounce, u);
+                    }
+                    r = brdf_sample(s, t, o, d, env, u);
                 }
-                BounceOut r = brdf_sample(s, t, o, d, env, u);
                 float* acc = c.accum + (int64_t)DRP_ACCUM_CHANNELS * pix;
                 accum_add4(acc, T.x * r.radiance.x, T.y * r.radiance.y, T.z * r.radiance.z, s.alpha);  // path_tracing.py:336-337
                 if (PRIMARY) {  // extras on the first hit, path_tracing.py:340-347
