@@ -49,6 +49,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = build_library() if os.environ.get("DIFFRP_B200_NO_BUILD") != "1" else LIB_PATH
+        if os.environ.get("DIFFRP_B200_LIB"):  # A/B experiments: a library built with other -D switches (tools/build_variants.sh)
+            path = os.environ["DIFFRP_B200_LIB"]
         if not os.path.exists(path):
             raise DiffrpB200Error("libdiffrp_b200.so is missing and could not be built; there is no CPU fallback")
         L = C.CDLL(path)

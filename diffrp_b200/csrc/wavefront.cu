@@ -171,6 +171,12 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 #endif
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
+#ifndef CWK_SHARE
+#define CWK_SHARE 0   // warp-shared triangle tests (see the triangle phase of k_extend_cw).  A/B on B200 (config 3, extend ms per step):
+                      // per-lane loop 5.31, shared through shuffles + __fns 7.00, shared through shared memory 5.90 (56 registers, spills) /
+                      // 5.54 vs 5.38 at 64 registers: the triangle phase does run at ~6 of 32 lanes (22 % of the issue slots), but dealing
+                      // the tests out costs as much as it saves
+#endif
 #endif
 
 #define SRC_QUEUE 0    // rays from the float4 queues, result to hit[]
@@ -219,6 +225,12 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
 #endif
     uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
     bool overflow = false;
+#if CWK_SHARE
+    __shared__ uint32_t s_item[WF_BLOCK / 32][32];   // work items of the shared triangle phase: (packed triangle index << 5) | owner lane
+    __shared__ float2 s_res[WF_BLOCK / 32][32];      // (t, id) posted by the helper of each item
+    __shared__ float4 s_ray[WF_BLOCK / 32][32][2];   // origin / direction of every lane's current ray
+    const int wid = threadIdx.x >> 5;
+#endif
 #if CWK_SMEM_STACK == 0
 #define CWK_PUSH(X, Y)                                                 \
     do {                                                               \
@@ -275,6 +287,10 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
                 }
                 r = cw_make_ray(o, d, c.cw_bias);
+#if CWK_SHARE
+                s_ray[wid][lane][0] = make_float4(o.x, o.y, o.z, 0.0f);
+                s_ray[wid][lane][1] = make_float4(d.x, d.y, d.z, 0.0f);
+#endif
                 t_best = c.p.t_far;
                 id_best = 0x7fffffff;
                 sp = 0;
@@ -314,6 +330,55 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
                     ng_x = 0; ng_y = 0;
                 }
+#if CWK_SHARE
+                {   // ---- triangle phase, work-shared across the warp --------------------------------------------------------------
+                    // Only ~1/3 of the traversing lanes hold pending triangles at any time and a lane holds up to several (every triangle of
+                    // each hit leaf child), so a per-lane loop runs its Moller-Trumbore tests at ~10 of 32 lanes for several rounds.  Instead
+                    // the pending (ray, triangle) pairs of all lanes are dealt out as work items through shared memory: up to three per owner
+                    // and round, item i to the i-th traversing lane; a helper reads the owner's ray (staged in shared memory when the ray was
+                    // fetched), tests one triangle and posts (t, id); the owner merges its results with the (t, id) order of leaf_intersect,
+                    // so the outcome does not depend on who tested what.
+                    const unsigned act = __activemask();
+                    const int nact = __popc(act);
+                    const int hr = __popc(act & lt_mask);                            // my rank among the traversing lanes = my item slot
+                    for (;;) {
+                        unsigned have = __ballot_sync(act, tg_y != 0);
+                        if (!have) break;
+                        if ((float)__popc(have) < CWK_POSTPONE * (float)nact) {   // too few lanes have triangles: postpone (lanes with stack room)
+                            if (tg_y != 0 && sp < CW_STACK) { CWK_PUSH(tg_x, tg_y); tg_y = 0; }
+                            have = __ballot_sync(act, tg_y != 0);
+                            if (!have) break;
+                        }
+                        uint32_t m = tg_y;
+                        int t0 = -1, t1 = -1, t2 = -1;
+                        if (m) { t0 = 31 - __clz(m); m &= ~(1u << t0); }
+                        if (m) { t1 = 31 - __clz(m); m &= ~(1u << t1); }
+                        if (m) { t2 = 31 - __clz(m); }
+                        unsigned b1 = __ballot_sync(act, t1 >= 0), b2 = __ballot_sync(act, t2 >= 0);
+                        const int n0 = __popc(have);
+                        int n1 = __popc(b1), n2 = __popc(b2);
+                        if (n0 + n1 + n2 > nact) { b2 = 0; n2 = 0; if (n0 + n1 > nact) { b1 = 0; n1 = 0; } }   // more items than helpers: next round
+                        const bool i0 = t0 >= 0, i1 = (b1 >> lane) & 1u, i2 = (b2 >> lane) & 1u;
+                        const int p0 = __popc(have & lt_mask), p1 = n0 + __popc(b1 & lt_mask), p2 = n0 + n1 + __popc(b2 & lt_mask);
+                        if (i0) s_item[wid][p0] = ((tg_x + (uint32_t)t0) << 5) | (uint32_t)lane;
+                        if (i1) s_item[wid][p1] = ((tg_x + (uint32_t)t1) << 5) | (uint32_t)lane;
+                        if (i2) s_item[wid][p2] = ((tg_x + (uint32_t)t2) << 5) | (uint32_t)lane;
+                        __syncwarp(act);
+                        if (hr < n0 + n1 + n2) {
+                            const uint32_t it = s_item[wid][hr];
+                            const float4 ro = s_ray[wid][it & 31u][0], rd = s_ray[wid][it & 31u][1];
+                            float ht = c.p.t_far;
+                            int hid = 0x7fffffff;
+                            leaf_intersect(c.tris, (int)(it >> 5), 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), c.eps, ht, hid);
+                            s_res[wid][hr] = make_float2(ht, __int_as_float(hid));
+                        }
+                        __syncwarp(act);
+                        if (i0) { const float2 q = s_res[wid][p0]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t0); }
+                        if (i1) { const float2 q = s_res[wid][p1]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t1); }
+                        if (i2) { const float2 q = s_res[wid][p2]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t2); }
+                    }
+                }
+#else
                 const int total_active = __popc(__activemask());
                 while (tg_y != 0) {
                     if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
@@ -324,6 +389,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     tg_y &= ~(1u << ti);
                     leaf_intersect(c.tris, (int)tg_x + ti, 1, r.o, r.d, c.eps, t_best, id_best);
                 }
+#endif
                 if (ng_y <= 0x00ffffffu) {
                     if (sp > 0) {
                         CWK_POP(ng_x, ng_y);
