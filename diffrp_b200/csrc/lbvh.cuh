@@ -143,8 +143,12 @@ DRP_HD float box_area(float4 lo, float4 hi) {
 //   C(n,1) = min(leaf: A P Cprim if P <= max_leaf, internal: A Cnode + D(n,8));  C(n,i) = min(D(n,i), C(n,i-1))
 //   D(n,j) = min over 0<k<j of C(left,k) + C(right,j-k)
 // Returns whether n taken as ONE slot is a leaf.
+#ifndef DRP_DP_CNODE
 #define DRP_DP_CNODE 1.0f
-#define DRP_DP_CPRIM 0.3f
+#endif
+#ifndef DRP_DP_CPRIM
+#define DRP_DP_CPRIM 1.0f   // B200 sweep on config 3 (extend ms per step): 0.15 -> 5.37, 0.3 -> 5.31, 0.6 -> 5.25, 1.0 -> 5.24, 1.5 -> 5.25
+#endif
 DRP_HD bool lbvh_dp_node(const LbvhBuild& b, int p, int lc, int rc, float area, int count) {
     float cl[8], cr[8];
     for (int i = 1; i < 8; ++i) {
