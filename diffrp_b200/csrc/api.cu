@@ -324,12 +324,17 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
             st.pop_back();
             md = depth > md ? depth : md;
             const float4* p = nodes.data() + (size_t)ni * 5;
-            uint32_t imask = f2u(p[0].w) >> 24, m[2] = {f2u(p[1].z), f2u(p[1].w)};
+            uint32_t imask = f2u(p[0].w) >> 24;
             int base = f2i(p[1].x), rank = 0;
             for (int sl = 0; sl < 8; ++sl) {
-                uint32_t meta = (m[sl / 4] >> (8 * (sl % 4))) & 0xffu;
+#if DRP_CW_V2
+                const bool leaf = cw_slot_kind(p, sl) > 0;
+#else
+                const uint32_t m[2] = {f2u(p[1].z), f2u(p[1].w)};
+                const bool leaf = ((m[sl / 4] >> (8 * (sl % 4))) & 0xffu) != 0;
+#endif
                 if (imask & (1u << sl)) st.push_back({base + rank++, depth + 1});
-                else if (meta) ++leaves;
+                else if (leaf) ++leaves;
             }
         }
         out->n_leaves = leaves;

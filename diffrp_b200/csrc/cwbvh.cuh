@@ -26,6 +26,17 @@
 #ifndef DRP_CW_HALFSKIP
 #define DRP_CW_HALFSKIP 0
 #endif
+// Node format 2 (DRP_CW_V2, default): n1 = (child_base, tri_base, V, 0) with V = the valid-triangle mask of the node, bit 3*slot+k set
+// iff leaf slot `slot` holds a k-th triangle.  The per-slot meta bytes are gone: the box test leaves one hit bit per slot
+// (sign bit of cmax - cmin funnel-shifted into a byte: 1 ALU-pipe op per slot instead of 6), and the per-node expansion of
+// that byte -- internal children permuted into traversal priority (slot ^ octant), leaf children spread to 3 bits per
+// slot and masked with V -- is two table lookups (shared memory in k_extend_cw, arithmetic elsewhere).  Triangles of a node
+// are stored compactly in slot order, so triangle bit j is triangle tri_base + popc(V & ((1 << j) - 1)).
+// Why: ncu shows the traversal bound by the ALU pipe (PRMT / FMNMX / SHF / LOP3 at one warp instruction per two cycles) with
+// the FMA pipe half idle; format 1 spends ~52 of its ~170 ALU-pipe instructions per node visit on building the hit mask.
+#ifndef DRP_CW_V2
+#define DRP_CW_V2 1
+#endif
 #define CW_MAX_LEAF 3
 #define CW_STACK 48
 #define CW_SLACK 4.76837158203125e-07f  // 2^-21: relative widening of every slab distance
@@ -158,7 +169,7 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         inv_scale[a] = i2f((127 - ea) << 23);
     }
     uint32_t meta[8], q[6][8];
-    uint32_t imask = 0;
+    uint32_t imask = 0, vmask = 0;
     int n_inner = 0, n_tris = 0;
     for (int s = 0; s < 8; ++s) {
         int j = slot_child[s];
@@ -177,6 +188,7 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         if (cw_is_leaf_child(b, c)) {
             int cnt = cw_leaf_count(b, c);
             meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)n_tris;
+            vmask |= ((1u << cnt) - 1u) << (3 * s);
             n_tris += cnt;
         } else {
             meta[s] = (1u << 5) | (24u + (uint32_t)s);
@@ -213,7 +225,12 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
     float4* o = cw.cw_nodes + 5 * (int64_t)ni;
     uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16) | (imask << 24);
     o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
+#if DRP_CW_V2
+    o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(vmask), u2f(0u));
+#else
+    (void)vmask;
     o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(cw_pack4(meta)), u2f(cw_pack4(meta + 4)));
+#endif
     o[2] = make_float4(u2f(cw_pack4(q[0])), u2f(cw_pack4(q[0] + 4)), u2f(cw_pack4(q[1])), u2f(cw_pack4(q[1] + 4)));
     o[3] = make_float4(u2f(cw_pack4(q[2])), u2f(cw_pack4(q[2] + 4)), u2f(cw_pack4(q[3])), u2f(cw_pack4(q[3] + 4)));
     o[4] = make_float4(u2f(cw_pack4(q[4])), u2f(cw_pack4(q[4] + 4)), u2f(cw_pack4(q[5])), u2f(cw_pack4(q[5] + 4)));
@@ -244,7 +261,11 @@ DRP_HD void cw_emit_tiny(const CwBuild& cw) {
     }
     uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16);
     o[0] = make_float4(lo.x, lo.y, lo.z, u2f(ebits));
+#if DRP_CW_V2
+    o[1] = make_float4(i2f(0), i2f(0), u2f(meta0 ? 1u : 0u), u2f(0u));
+#else
     o[1] = make_float4(i2f(0), i2f(0), u2f(meta0), u2f(0u));
+#endif
     const uint32_t lo_q = 0xffffff00u, hi_q = 0x000000ffu;  // slot 0 spans the grid, slots 1..7 are empty (lo 255 > hi 0)
     o[2] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(lo_q), u2f(0xffffffffu));
     o[3] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(hi_q), u2f(0u));
@@ -300,6 +321,68 @@ DRP_HD CwRay cw_make_ray(Vec3 o, Vec3 d, uint32_t bias = 0x47000000u) {
     return r;
 }
 
+#if DRP_CW_V2
+// slot s of node p: -1 = internal child, 0 = empty, n > 0 = leaf with n triangles (statistics / tests)
+DRP_HD int cw_slot_kind(const float4* p, int s) {
+    if ((f2u(p[0].w) >> 24) & (1u << s)) return -1;
+    return cw_popc((f2u(p[1].z) >> (3 * s)) & 7u);
+}
+// 8 bits (one per slot) -> the same bits at position (slot ^ octinv): internal children in traversal priority
+DRP_HD uint32_t cw_perm8(uint32_t x, uint32_t octinv) {
+    if (octinv & 4u) x = ((x & 0x0fu) << 4) | ((x >> 4) & 0x0fu);
+    if (octinv & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (octinv & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    return x;
+}
+// 8 bits (one per slot) -> bits 3*slot .. 3*slot+2 all set: every triangle position of the hit leaf slots
+DRP_HD uint32_t cw_spread3x7(uint32_t x) {
+    x = (x | (x << 8)) & 0x0000f00fu;
+    x = (x | (x << 4)) & 0x000c30c3u;
+    x = (x | (x << 2)) & 0x00249249u;
+    return x * 7u;
+}
+// index of the triangle behind bit j of a node's triangle mask (triangles are stored compactly in slot order)
+DRP_HD int cw_tri_index(uint32_t tri_base, uint32_t vmask, int j) { return (int)(tri_base + (uint32_t)cw_popc(vmask & ((1u << j) - 1u))); }
+
+// intersect the 8 quantised child boxes of one node; returns one hit bit per slot (bit s = slot s)
+DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n2, float4 n3, float4 n4, float t_cull) {
+    const uint32_t ebits = f2u(n0.w);
+    const int ex = (int)(int8_t)(ebits & 0xffu), ey = (int)(int8_t)((ebits >> 8) & 0xffu), ez = (int)(int8_t)((ebits >> 16) & 0xffu);
+    const float ax = i2f((ex + 127) << 23) * r.idir.x, ay = i2f((ey + 127) << 23) * r.idir.y, az = i2f((ez + 127) << 23) * r.idir.z;
+    const float ox = (n0.x - r.o.x) * r.idir.x, oy = (n0.y - r.o.y) * r.idir.y, oz = (n0.z - r.o.z) * r.idir.z;
+    // conservative widening: the FMA form cancels, its error is relative to |origin term| + |grid term|
+    const float sx = CW_SLACK * fabsf(ox) + CW_GRID_SLACK * fabsf(ax), sy = CW_SLACK * fabsf(oy) + CW_GRID_SLACK * fabsf(ay),
+                sz = CW_SLACK * fabsf(oz) + CW_GRID_SLACK * fabsf(az);
+    // addends with the byte bias folded in: t = (32768 + q) * a + (o -+ slack - 32768 a)
+    const float bx = ox - CW_BIAS * ax, by = oy - CW_BIAS * ay, bz = oz - CW_BIAS * az;
+    const float oxl = bx - sx, oxh = bx + sx, oyl = by - sy, oyh = by + sy, ozl = bz - sz, ozh = bz + sz;
+    uint32_t miss = 0;  // slot 7 is tested first and ends up in bit 7: every test shifts the sign of (cmax - cmin) in from the right
+#pragma unroll
+    for (int half = 1; half >= 0; --half) {
+        const uint32_t qlx = f2u(half ? n2.y : n2.x), qly = f2u(half ? n2.w : n2.z), qlz = f2u(half ? n3.y : n3.x);
+        const uint32_t qhx = f2u(half ? n3.w : n3.z), qhy = f2u(half ? n4.y : n4.x), qhz = f2u(half ? n4.w : n4.z);
+        const uint32_t nx = r.idir.x < 0.0f ? qhx : qlx, fx = r.idir.x < 0.0f ? qlx : qhx;
+        const uint32_t ny = r.idir.y < 0.0f ? qhy : qly, fy = r.idir.y < 0.0f ? qly : qhy;
+        const uint32_t nz = r.idir.z < 0.0f ? qhz : qlz, fz = r.idir.z < 0.0f ? qlz : qhz;
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            float tnx = cw_byte_biased(nx, i, r.bias) * ax + oxl, tny = cw_byte_biased(ny, i, r.bias) * ay + oyl, tnz = cw_byte_biased(nz, i, r.bias) * az + ozl;
+            float tfx = cw_byte_biased(fx, i, r.bias) * ax + oxh, tfy = cw_byte_biased(fy, i, r.bias) * ay + oyh, tfz = cw_byte_biased(fz, i, r.bias) * az + ozh;
+            float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t_cull));
+            // hit iff cmin <= cmax.  cmin >= 0 and cmax <= t_cull are never NaN (FMNMX drops NaN operands), so the sign of the
+            // difference decides; an empty slot (lo 255 > hi 0) always misses.  (-0) - (+0) counts as a miss: the widened box then
+            // ends at the ray origin and cannot hold a hit with t > 0.
+#ifdef __CUDA_ARCH__
+            miss = __funnelshift_l(__float_as_uint(__fsub_rn(cmax, cmin)), miss, 1);   // FADD (FMA pipe) + SHF (ALU pipe)
+#else
+            miss = (miss << 1) | (f2u(cmax - cmin) >> 31);
+#endif
+        }
+    }
+    return ~miss & 0xffu;
+}
+#else
 // intersect the 8 quantised child boxes of one node; returns the hit mask (internal children in bits 24..31 at their
 // traversal priority, triangles of leaf children in bits 0..23)
 DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4, float t_cull) {
@@ -341,6 +424,65 @@ DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, fl
     return hitmask;
 }
 
+#endif
+
+#if DRP_CW_V2
+DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
+                           bool& overflow) {
+    const CwRay r = cw_make_ray(o, d);
+    const uint32_t octinv = r.octinv4 & 0xffu;
+    uint32_t st_x[CW_STACK], st_y[CW_STACK];
+    int sp = 0;
+    float t_best = t_far;
+    int id_best = 0x7fffffff;
+    uint32_t ng_x = 0, ng_y = 0x80000000u;  // node group: (child base, hits in bits 24..31 | imask in bits 0..7); starts at the root
+    uint32_t tg_x = 0, tg_y = 0;            // triangle group: (node index, pending triangle bits 3*slot+k)
+    for (;;) {
+        if (ng_y > 0x00ffffffu) {
+            const uint32_t hits = ng_y;
+            const int child_bit = cw_bfind(hits);
+            const uint32_t base = ng_x;
+            ng_y &= ~(1u << child_bit);
+            if (ng_y > 0x00ffffffu) {
+                if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
+                else overflow = true;
+            }
+            const uint32_t slot = (uint32_t)(child_bit - 24) ^ octinv;
+            const uint32_t rel = (uint32_t)cw_popc(hits & ~(0xffffffffu << slot));
+            const float4* p = nodes + 5 * (int64_t)(base + rel);
+            const float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3), n4 = ldg(p + 4);
+            DRP_COUNT_NODE();
+            const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
+            const uint32_t imask = f2u(n0.w) >> 24;
+            ng_x = f2u(n1.x);
+            ng_y = (cw_perm8(hit8 & imask, octinv) << 24) | imask;
+            tg_x = base + rel;
+            tg_y = cw_spread3x7(hit8 & ~imask) & f2u(n1.z);
+        } else {
+            tg_x = ng_x; tg_y = ng_y;
+            ng_x = 0; ng_y = 0;
+        }
+        if (tg_y != 0) {
+            const float4 n1 = ldg(nodes + 5 * (int64_t)tg_x + 1);
+            while (tg_y != 0) {
+                const int ti = cw_bfind(tg_y);
+                tg_y &= ~(1u << ti);
+                leaf_intersect(tris, cw_tri_index(f2u(n1.y), f2u(n1.z), ti), 1, r.o, r.d, eps, t_best, id_best);
+            }
+        }
+        if (ng_y <= 0x00ffffffu) {
+            if (sp == 0) break;
+            --sp;
+            ng_x = st_x[sp]; ng_y = st_y[sp];
+        }
+    }
+    RayHit h;
+    const bool hit = t_best < t_far;
+    h.t = hit ? t_best : t_far;
+    h.id = hit ? id_best : 0;
+    return h;
+}
+#else
 DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
                            bool& overflow) {
     const CwRay r = cw_make_ray(o, d);
@@ -391,3 +533,4 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
     h.id = hit ? id_best : 0;
     return h;
 }
+#endif

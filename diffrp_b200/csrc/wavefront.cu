@@ -225,6 +225,19 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
 #endif
     uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
     bool overflow = false;
+#if DRP_CW_V2
+#if CWK_SHARE
+#error "CWK_SHARE is implemented for node format 1 only (DRP_CW_V2=0)"
+#endif
+    // node format 2: the two expansions of the per-slot hit byte as tables (cwbvh.cuh: cw_perm8, cw_spread3x7)
+    __shared__ uint8_t s_perm[8 * 256];
+    __shared__ uint32_t s_spread[256];
+    for (int e = threadIdx.x; e < 8 * 256; e += WF_BLOCK) s_perm[e] = (uint8_t)cw_perm8((uint32_t)e & 0xffu, (uint32_t)e >> 8);
+    for (int e = threadIdx.x; e < 256; e += WF_BLOCK) s_spread[e] = cw_spread3x7((uint32_t)e);
+    __syncthreads();
+    uint32_t tri_base = 0, tri_valid = 0;  // of the node the current triangle group belongs to
+    uint32_t oct_row = 0;                  // octinv << 8: this ray's row of s_perm
+#endif
 #if CWK_SHARE
     __shared__ uint32_t s_item[WF_BLOCK / 32][32];   // work items of the shared triangle phase: (packed triangle index << 5) | owner lane
     __shared__ float2 s_res[WF_BLOCK / 32][32];      // (t, id) posted by the helper of each item
@@ -287,6 +300,9 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
                 }
                 r = cw_make_ray(o, d, c.cw_bias);
+#if DRP_CW_V2
+                oct_row = (r.octinv4 & 0xffu) << 8;
+#endif
 #if CWK_SHARE
                 s_ray[wid][lane][0] = make_float4(o.x, o.y, o.z, 0.0f);
                 s_ray[wid][lane][1] = make_float4(d.x, d.y, d.z, 0.0f);
@@ -313,11 +329,22 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
                     const float4* p = c.nodes + 5 * (int64_t)(base + rel);
                     const float4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
+#if DRP_CW_V2
+                    const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
+                    const uint32_t imask = __float_as_uint(n0.w) >> 24;
+                    ng_x = __float_as_uint(n1.x);
+                    ng_y = ((uint32_t)s_perm[oct_row + (hit8 & imask)] << 24) | imask;
+                    tg_x = base + rel;  // a triangle group is (node index, pending bits): tri_base / V are re-read when it comes off the stack
+                    tri_base = __float_as_uint(n1.y);
+                    tri_valid = __float_as_uint(n1.z);
+                    tg_y = s_spread[hit8 & ~imask] & tri_valid;
+#else
                     const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
                     ng_x = __float_as_uint(n1.x);
                     ng_y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
                     tg_x = __float_as_uint(n1.y);
                     tg_y = hitmask & 0x00ffffffu;
+#endif
 #if CWK_PREFETCH
                     if (ng_y > 0x00ffffffu) {  // the child visited next is already known: pull its two cache lines towards L1 while triangles are tested
                         const uint32_t nslot = (uint32_t)(31 - __clz(ng_y) - 24) ^ (r.octinv4 & 0xffu);
@@ -329,6 +356,11 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                 } else {
                     tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
                     ng_x = 0; ng_y = 0;
+#if DRP_CW_V2
+                    const float4 m1 = __ldg(c.nodes + 5 * (int64_t)tg_x + 1);
+                    tri_base = __float_as_uint(m1.y);
+                    tri_valid = __float_as_uint(m1.z);
+#endif
                 }
 #if CWK_SHARE
                 {   // ---- triangle phase, work-shared across the warp --------------------------------------------------------------
@@ -387,7 +419,11 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     }
                     const int ti = 31 - __clz(tg_y);
                     tg_y &= ~(1u << ti);
+#if DRP_CW_V2
+                    leaf_intersect(c.tris, cw_tri_index(tri_base, tri_valid, ti), 1, r.o, r.d, c.eps, t_best, id_best);
+#else
                     leaf_intersect(c.tris, (int)tg_x + ti, 1, r.o, r.d, c.eps, t_best, id_best);
+#endif
                 }
 #endif
                 if (ng_y <= 0x00ffffffu) {
@@ -914,7 +950,8 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
 extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
-           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH);
+           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
+           " DRP_CW_V2=" DRP_STR(DRP_CW_V2);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

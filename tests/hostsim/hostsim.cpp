@@ -136,14 +136,22 @@ extern "C" void hs_stats_wide(const HsBvh* h, int64_t* out) {
     int64_t inner = 0, leaf = 0, tris = 0, maxt = 0;
     for (int ni = 0; ni < h->cw_count; ++ni) {
         const float4* p = h->cw_nodes.data() + 5 * (size_t)ni;
-        uint32_t m[2] = {f2u(p[1].z), f2u(p[1].w)};
         int64_t nt = 0;
+#if DRP_CW_V2
+        for (int s = 0; s < 8; ++s) {
+            const int kind = cw_slot_kind(p, s);
+            if (kind < 0) ++inner;
+            else if (kind > 0) { ++leaf; nt += kind; }
+        }
+#else
+        uint32_t m[2] = {f2u(p[1].z), f2u(p[1].w)};
         for (int s = 0; s < 8; ++s) {
             uint32_t meta = (m[s / 4] >> (8 * (s % 4))) & 0xffu;
             if (meta == 0) continue;
             if ((meta & 0x18u) == 0x18u && (meta >> 5) == 1u) ++inner;
             else { ++leaf; nt += cw_popc(meta >> 5); }
         }
+#endif
         tris += nt;
         maxt = std::max(maxt, nt);
     }
