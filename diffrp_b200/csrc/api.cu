@@ -174,7 +174,7 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     uint64_t* keys_in = nullptr; uint32_t* vals_in = nullptr; void* sort_tmp = nullptr;
     size_t sort_bytes = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * (h->wide ? 5 : 4) * (size_t)h->n_nodes, s));
+    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * (h->wide ? CW_NODE_F4 : 4) * (size_t)h->n_nodes, s));
     DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->packed, sizeof(float4) * 3 * nn, s));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->sah, sizeof(float)));
@@ -310,10 +310,10 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
     DRP_CUDA_CHECK(cudaMemcpy(&out->sah_cost, h->sah, sizeof(float), cudaMemcpyDeviceToHost));
     if (h->wide) {
         const int64_t used = h->n_nodes_used;
-        std::vector<float4> nodes((size_t)used * 5);
+        std::vector<float4> nodes((size_t)used * CW_NODE_F4);
         DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
         out->n_nodes = used;
-        out->node_bytes = used * 80;
+        out->node_bytes = used * 16 * CW_NODE_F4;
         int64_t leaves = 0;
         // depth by walking child links
         std::vector<std::pair<int, int>> st;
@@ -323,7 +323,7 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
             auto [ni, depth] = st.back();
             st.pop_back();
             md = depth > md ? depth : md;
-            const float4* p = nodes.data() + (size_t)ni * 5;
+            const float4* p = nodes.data() + (size_t)ni * CW_NODE_F4;
             uint32_t imask = f2u(p[0].w) >> 24;
             int base = f2i(p[1].x), rank = 0;
             for (int sl = 0; sl < 8; ++sl) {

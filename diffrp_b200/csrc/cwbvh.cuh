@@ -37,6 +37,15 @@
 #ifndef DRP_CW_V2
 #define DRP_CW_V2 1
 #endif
+// DRP_CW_NODE96 (A/B switch, off): nodes padded to 96 bytes (6 x float4, the last one unused) so that a node is three
+// 32-byte-aligned 256-bit loads (ld.global.nc.v8.f32 -> LDG.E.ENL2.256, sm_100+; CWK_LD256 in wavefront.cu) instead of five
+// 128-bit ones.  tools/ld_probe.cu (divergent record fetches, B200): 96 vs 77 G records/s from a 19-23 MB array, but 166 vs 235
+// when the array is L1-resident; in the traversal itself (config 3, extend ms per launch): 80 B + 5 x LDG.128 1.237,
+// 96 B + 5 x LDG.128 1.254, 96 B + 3 x LDG.256 1.264 -- the wider loads do not pay for the 20 % larger node array.
+#ifndef DRP_CW_NODE96
+#define DRP_CW_NODE96 0
+#endif
+#define CW_NODE_F4 (DRP_CW_NODE96 ? 6 : 5)
 #define CW_MAX_LEAF 3
 #define CW_STACK 48
 #define CW_SLACK 4.76837158203125e-07f  // 2^-21: relative widening of every slab distance
@@ -44,7 +53,7 @@
 
 struct CwBuild {
     LbvhBuild b;       // the binary hierarchy (left/right, boxes with area in box_hi.w, collapsed flags, ranges, vals)
-    float4* cw_nodes;  // (capacity, 5)
+    float4* cw_nodes;  // (capacity, CW_NODE_F4)
     float4* cw_tris;   // (n, 3) triangles in node order: A, B, C, original id
     int* work;         // (capacity) binary node collapsed into each wide node
     int* counters;     // [0] wide nodes allocated, [1] triangles placed, [8 + L] first node of level L
@@ -222,7 +231,8 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
             toff += cnt;
         }
     }
-    float4* o = cw.cw_nodes + 5 * (int64_t)ni;
+    float4* o = cw.cw_nodes + CW_NODE_F4 * (int64_t)ni;
+    if (CW_NODE_F4 > 5) o[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16) | (imask << 24);
     o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
 #if DRP_CW_V2
@@ -270,6 +280,7 @@ DRP_HD void cw_emit_tiny(const CwBuild& cw) {
     o[2] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(lo_q), u2f(0xffffffffu));
     o[3] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(hi_q), u2f(0u));
     o[4] = make_float4(u2f(hi_q), u2f(0u), u2f(hi_q), u2f(0u));
+    if (CW_NODE_F4 > 5) o[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---- traversal ----------------------------------------------------------------------------------------------------
@@ -449,7 +460,7 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
             }
             const uint32_t slot = (uint32_t)(child_bit - 24) ^ octinv;
             const uint32_t rel = (uint32_t)cw_popc(hits & ~(0xffffffffu << slot));
-            const float4* p = nodes + 5 * (int64_t)(base + rel);
+            const float4* p = nodes + CW_NODE_F4 * (int64_t)(base + rel);
             const float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3), n4 = ldg(p + 4);
             DRP_COUNT_NODE();
             const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
@@ -463,7 +474,7 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
             ng_x = 0; ng_y = 0;
         }
         if (tg_y != 0) {
-            const float4 n1 = ldg(nodes + 5 * (int64_t)tg_x + 1);
+            const float4 n1 = ldg(nodes + CW_NODE_F4 * (int64_t)tg_x + 1);
             while (tg_y != 0) {
                 const int ti = cw_bfind(tg_y);
                 tg_y &= ~(1u << ti);
@@ -504,7 +515,7 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
             }
             const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
             const uint32_t rel = (uint32_t)cw_popc(hits & ~(0xffffffffu << slot));
-            const float4* p = nodes + 5 * (int64_t)(base + rel);
+            const float4* p = nodes + CW_NODE_F4 * (int64_t)(base + rel);
             const float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3), n4 = ldg(p + 4);
             DRP_COUNT_NODE();
             const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);

@@ -169,6 +169,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 #ifndef CWK_NW
 #define CWK_NW 8
 #endif
+#ifndef CWK_LD256
+#define CWK_LD256 1   // node fetch by 256-bit loads (needs the 96-byte node stride, DRP_CW_NODE96)
+#endif
+__device__ __forceinline__ void cw_ld256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
 #ifndef CWK_SHARE
@@ -327,8 +334,21 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     if (ng_y > 0x00ffffffu) CWK_PUSH(ng_x, ng_y);
                     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
                     const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
-                    const float4* p = c.nodes + 5 * (int64_t)(base + rel);
+                    const float4* p = c.nodes + CW_NODE_F4 * (int64_t)(base + rel);
+#if DRP_CW_NODE96 && CWK_LD256
+                    float4 n0, n1, n2, n3, n4;
+                    if (CWK_LD256 == 1 || SRC != SRC_PRIMARY) {  // CWK_LD256 == 2: incoherent rays only
+                        // three 256-bit loads (LDG.E.ENL2.256): 3 instead of 5 requests per lane through the L1 data pipe
+                        float4 pad;
+                        cw_ld256(p, n0, n1);
+                        cw_ld256(p + 2, n2, n3);
+                        cw_ld256(p + 4, n4, pad);
+                    } else {
+                        n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+                    }
+#else
                     const float4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
+#endif
 #if DRP_CW_V2
                     const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
                     const uint32_t imask = __float_as_uint(n0.w) >> 24;
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
 #if CWK_PREFETCH
                     if (ng_y > 0x00ffffffu) {  // the child visited next is already known: pull its two cache lines towards L1 while triangles are tested
                         const uint32_t nslot = (uint32_t)(31 - __clz(ng_y) - 24) ^ (r.octinv4 & 0xffu);
-                        const float4* np = c.nodes + 5 * (int64_t)(ng_x + __popc(ng_y & ~(0xffffffffu << nslot)));
+                        const float4* np = c.nodes + CW_NODE_F4 * (int64_t)(ng_x + __popc(ng_y & ~(0xffffffffu << nslot)));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 4));
                     }
@@ -357,7 +377,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
                     ng_x = 0; ng_y = 0;
 #if DRP_CW_V2
-                    const float4 m1 = __ldg(c.nodes + 5 * (int64_t)tg_x + 1);
+                    const float4 m1 = __ldg(c.nodes + CW_NODE_F4 * (int64_t)tg_x + 1);
                     tri_base = __float_as_uint(m1.y);
                     tri_valid = __float_as_uint(m1.z);
 #endif
@@ -951,7 +971,7 @@ extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
            " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
-           " DRP_CW_V2=" DRP_STR(DRP_CW_V2);
+           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

@@ -96,7 +96,7 @@ static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_t
         CwBuild cw;
         cw.b = b;
         cw.capacity = n > 1 ? n - 1 : 1;
-        h->cw_nodes.resize(5 * (size_t)cw.capacity);
+        h->cw_nodes.resize(CW_NODE_F4 * (size_t)cw.capacity);
         h->cw_tris.resize(3 * nn);
         std::vector<int> work(cw.capacity, 0), counters(128, 0);
         cw.cw_nodes = h->cw_nodes.data(); cw.cw_tris = h->cw_tris.data(); cw.work = work.data(); cw.counters = counters.data();
@@ -135,7 +135,7 @@ extern "C" int64_t hs_trace_wide(const HsBvh* h, const float* ro, const float* r
 extern "C" void hs_stats_wide(const HsBvh* h, int64_t* out) {
     int64_t inner = 0, leaf = 0, tris = 0, maxt = 0;
     for (int ni = 0; ni < h->cw_count; ++ni) {
-        const float4* p = h->cw_nodes.data() + 5 * (size_t)ni;
+        const float4* p = h->cw_nodes.data() + CW_NODE_F4 * (size_t)ni;
         int64_t nt = 0;
 #if DRP_CW_V2
         for (int s = 0; s < 8; ++s) {
