@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -35,6 +35,7 @@ class Material(C.Structure):
         ("emissive_factor", C.c_float * 4),
         ("metallic_factor", C.c_float), ("roughness_factor", C.c_float), ("alpha_cutoff", C.c_float), ("_pad", C.c_float),
         ("base_color_tex", Texture), ("mr_tex", Texture), ("normal_tex", Texture), ("emissive_tex", Texture),
+        ("texel_records", C.c_void_p),
     ]
 
 
@@ -161,6 +162,11 @@ def pack_material(desc, ptr_of, keep) -> Material:
     m.normal_tex = pack_texture(desc.get('normal_tex'), ptr_of, keep)
     m.has_normal_tex = int(desc.get('normal_tex') is not None)
     m.emissive_tex = pack_texture(desc.get('emissive_tex'), ptr_of, keep)
+    rec = desc.get('texel_records')
+    if rec is not None:  # (H,W,12) interleaved copy of the four textures (flatten.texel_records)
+        assert tuple(rec.shape) == (m.base_color_tex.h, m.base_color_tex.w, 12)
+        keep.append(rec)
+        m.texel_records = ptr_of(rec)
     return m
 
 

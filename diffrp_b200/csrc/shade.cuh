@@ -114,14 +114,24 @@ DRP_HD void tex_fetch(const drp_texture_t& t, float u, float v, float out[4]) {
         }
     }
 }
-// RGBA-only fetch from precomputed taps: four independent 128-bit loads
-DRP_HD float4 tex_fetch4(const float* __restrict__ data, const TexTaps& tp) {
-    const float4* p = reinterpret_cast<const float4*>(data);
-    float4 a = ldg(p + tp.off[0]), b = ldg(p + tp.off[1]), c = ldg(p + tp.off[2]), d = ldg(p + tp.off[3]);
+// weighted sum of the four taps (the order of tex_fetch: tap 0..3)
+DRP_HD float4 tex_combine(float4 a, float4 b, float4 c, float4 d, const TexTaps& tp) {
     return make_float4(a.x * tp.wt[0] + b.x * tp.wt[1] + c.x * tp.wt[2] + d.x * tp.wt[3],
                        a.y * tp.wt[0] + b.y * tp.wt[1] + c.y * tp.wt[2] + d.y * tp.wt[3],
                        a.z * tp.wt[0] + b.z * tp.wt[1] + c.z * tp.wt[2] + d.z * tp.wt[3],
                        a.w * tp.wt[0] + b.w * tp.wt[1] + c.w * tp.wt[2] + d.w * tp.wt[3]);
+}
+// part `part` (0..2) of the 48-byte interleaved texels (drp_material_t.texel_records)
+DRP_HD float4 tex_fetch_record(const float* __restrict__ records, const TexTaps& tp, int part) {
+    const float4* p = reinterpret_cast<const float4*>(records) + part;
+    float4 a = ldg(p + 3 * (int64_t)tp.off[0]), b = ldg(p + 3 * (int64_t)tp.off[1]), c = ldg(p + 3 * (int64_t)tp.off[2]), d = ldg(p + 3 * (int64_t)tp.off[3]);
+    return tex_combine(a, b, c, d, tp);
+}
+// RGBA-only fetch from precomputed taps: four independent 128-bit loads
+DRP_HD float4 tex_fetch4(const float* __restrict__ data, const TexTaps& tp) {
+    const float4* p = reinterpret_cast<const float4*>(data);
+    float4 a = ldg(p + tp.off[0]), b = ldg(p + tp.off[1]), c = ldg(p + tp.off[2]), d = ldg(p + tp.off[3]);
+    return tex_combine(a, b, c, d, tp);
 }
 
 DRP_HD Vec3 env_fetch(const drp_texture_t& env, Vec3 d) {
@@ -230,7 +240,17 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
     const bool rgba = (!m.base_color_tex.data || m.base_color_tex.c == 4) && (!m.mr_tex.data || m.mr_tex.c == 4) &&
                       (!use_nt || m.normal_tex.c == 4) && (!use_em || m.emissive_tex.c == 4);
 #endif
-    if (rgba) {  // device path: address stage for all textures first, then all loads back to back
+    if (m.texel_records) {  // interleaved texels: one address stage, the taps of all four textures in the same sectors
+        const TexTaps tp = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
+        float4 r0 = make_float4(1.0f, 1.0f, 1.0f, 1.0f), r1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r2 = r1;
+        if (use_bc) r0 = tex_fetch_record(m.texel_records, tp, 0);
+        if (use_mr || use_nt) r1 = tex_fetch_record(m.texel_records, tp, 1);
+        if (use_nt || use_em) r2 = tex_fetch_record(m.texel_records, tp, 2);
+        if (use_bc) { bc[0] = r0.x; bc[1] = r0.y; bc[2] = r0.z; bc[3] = r0.w; }
+        if (use_mr) { mr[1] = r1.x; mr[2] = r1.y; }
+        if (use_nt) { nt[0] = r1.z; nt[1] = r1.w; nt[2] = r2.x; }
+        if (use_em) { em[0] = r2.y; em[1] = r2.z; em[2] = r2.w; }
+    } else if (rgba) {  // device path: address stage for all textures first, then all loads back to back
         TexTaps ta, tb, tc, td;
         if (use_bc) ta = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
         if (use_mr) tb = tex_taps(m.mr_tex.h, m.mr_tex.w, m.mr_tex.wrap, m.mr_tex.interp, tu, tv);

@@ -6,6 +6,7 @@ world-space normals / tangents that ``SurfaceInput.interpolate_ex`` would comput
 
 Device-agnostic torch code (runs once per session; not the hot path).
 """
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -150,6 +151,23 @@ def pad_rgba(img: torch.Tensor) -> torch.Tensor:
     return torch.cat([img, torch.ones_like(img[..., :1])], -1).contiguous()
 
 
+def texel_records(d: dict) -> Optional[torch.Tensor]:
+    """(H,W,12) interleaved copy of a GLTF material's four RGBA-padded textures, [base rgba | mr.g mr.b n.x n.y | n.z e.r e.g e.b]
+    (drp_material_t.texel_records), or None when a texture is missing or their sizes / wrap / filter modes differ."""
+    tex = [d.get(k) for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex')]
+    if d.get('kind') != 'gltf' or any(t is None for t in tex) or d.get('emissive_factor') is None:
+        return None
+    first = tex[0]
+    for t in tex[1:]:
+        if tuple(t['image'].shape[:2]) != tuple(first['image'].shape[:2]) or t.get('wrap', 'repeat') != first.get('wrap', 'repeat') \
+                or t.get('interp', 'linear') != first.get('interp', 'linear'):
+            return None
+    b, m, n, e = (t['image'] for t in tex)
+    if any(x.shape[-1] != 4 for x in (b, m, n, e)):
+        return None
+    return torch.cat([b, m[..., 1:3], n[..., :3], e[..., :3]], -1).contiguous()
+
+
 def material_descriptions(objs: List, dev, rgba: bool = False) -> Optional[List[dict]]:
     """Per-object drp_material_t descriptions (textures moved to ``dev``, RGBA-padded for the CUDA path when ``rgba``),
     or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
@@ -168,6 +186,12 @@ def material_descriptions(objs: List, dev, rgba: bool = False) -> Optional[List[
                     img = src.to(dev, torch.float32, non_blocking=True)
                     uploaded[key] = pad_rgba(img) if rgba else img.contiguous()
                 d[k] = dict(d[k], image=uploaded[key])
+        if rgba and os.environ.get('DIFFRP_B200_TEXEL_RECORDS', '1') != '0':  # CUDA path: interleaved texels, shared between the objects that share the material
+            key = ('records',) + tuple(d[k]['image'].data_ptr() if d.get(k) is not None else 0 for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
+            if key not in uploaded:
+                uploaded[key] = texel_records(d)
+            if uploaded[key] is not None:
+                d['texel_records'] = uploaded[key]
         descs.append(d)
     if not descs:
         descs = [dict(kind='default', tint=None)]

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 4
+#define DRP_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -89,6 +89,12 @@ typedef struct drp_material {
     drp_texture_t mr_tex;
     drp_texture_t normal_tex;
     drp_texture_t emissive_tex;
+    /* Optional (H,W,12) fp32 interleaved copy of the four textures above, 48 B per texel:
+     * [base r g b a | mr.g mr.b normal.x normal.y | normal.z emissive.r emissive.g emissive.b].
+     * Only valid when all four textures are present with the same h, w, wrap and interp (those are read from
+     * base_color_tex).  drp_render / drp_surface_attrs prefer it: one address computation and 12 instead of 16
+     * 128-bit loads per hit, and the taps of the four textures share their 32-byte sectors.  NULL = not provided. */
+    const float* texel_records;
 } drp_material_t;
 
 /* The scene flattened the way RenderSessionMixin.vertex_array_object does

@@ -154,3 +154,20 @@ def test_native_rng_high_spp_matches_reference_image_by_psnr():
     sess = run_session(scenes.mixed_scene(), drp.PerspectiveCamera.from_orbit(**HI_ORBIT), ray_spp=256, ray_depth=3, rng='native', seed=11,
                        pbr_ray_last_bounce='skybox')
     check_statistical_parity(as_numpy(*sess.pbr()), g)
+
+
+def test_texel_records_equal_separate_textures(monkeypatch):
+    """drp_material_t.texel_records (the four textures of a material interleaved, 48 B per texel) is a layout change only:
+    same taps, same weights, same summation order as the four RGBA textures."""
+    from diffrp_b200.flatten import material_descriptions
+    cam_kw = dict(h=96, w=128)
+    imgs = []
+    for flag in ('1', '0'):
+        monkeypatch.setenv('DIFFRP_B200_TEXEL_RECORDS', flag)
+        scene = scenes.to_device(scenes.mixed_scene(), 'cuda')
+        descs = material_descriptions(scene.objects, torch.device('cuda'), rgba=True)
+        assert any('texel_records' in d for d in descs) == (flag == '1')
+        sess = run_session(scene, drp.PerspectiveCamera(**cam_kw), ray_spp=8, ray_depth=3, rng='native', seed=21, reproducible=True)
+        imgs.append(as_numpy(*sess.pbr()))
+    for k in imgs[0]:
+        assert np.array_equal(imgs[0][k], imgs[1][k]), k
