@@ -201,10 +201,22 @@ DRP_HD VertexIn load_vertex(const drp_scene_t& sc, int i) {
 // radiance_only: the caller uses nothing but `emission` and `alpha` (last bounce of a path: no next ray is sampled and no g-buffer is
 // written, path_tracing.py:336-338), so everything that cannot influence those two is skipped -- for an opaque material without emission that
 // is the whole evaluation, including the vertex fetches.  The values that are produced are computed by the same code as in the full mode.
-DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id, const bool radiance_only = false) {
+// vertex indices + material id of a triangle; k_shade loads them one iteration ahead of their use
+struct TriIdx {
+    int i0, i1, i2, mat;
+};
+DRP_HD TriIdx load_tri_idx(const drp_scene_t& sc, int tri_id) {
+    TriIdx x;
+    x.i0 = ldg(sc.tris + 3 * (int64_t)tri_id); x.i1 = ldg(sc.tris + 3 * (int64_t)tri_id + 1); x.i2 = ldg(sc.tris + 3 * (int64_t)tri_id + 2);
+    x.mat = ldg(sc.tri_material + tri_id);
+    return x;
+}
+DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* __restrict__ mats, Vec3 hit_pos, int tri_id, const bool radiance_only = false,
+                                  const TriIdx* pre = nullptr) {
     SurfaceAttrs s;
+    const int mat_id = pre ? pre->mat : ldg(sc.tri_material + tri_id);
     if (radiance_only) {
-        const drp_material_t& m0 = mats[ldg(sc.tri_material + tri_id)];
+        const drp_material_t& m0 = mats[mat_id];
         const bool need_alpha = m0.kind != DRP_MAT_DEFAULT && (m0.alpha_mode == DRP_ALPHA_MASK || m0.alpha_mode == DRP_ALPHA_BLEND);
         const bool need_em = m0.kind != DRP_MAT_DEFAULT && m0.has_emissive && m0.emissive_tex.data;
         if (!need_alpha && !need_em) {
@@ -213,11 +225,12 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
             return s;
         }
     }
-    const int i0 = ldg(sc.tris + 3 * (int64_t)tri_id), i1 = ldg(sc.tris + 3 * (int64_t)tri_id + 1), i2 = ldg(sc.tris + 3 * (int64_t)tri_id + 2);
+    const int i0 = pre ? pre->i0 : ldg(sc.tris + 3 * (int64_t)tri_id), i1 = pre ? pre->i1 : ldg(sc.tris + 3 * (int64_t)tri_id + 1),
+              i2 = pre ? pre->i2 : ldg(sc.tris + 3 * (int64_t)tri_id + 2);
     const VertexIn q0 = load_vertex(sc, i0), q1 = load_vertex(sc, i1), q2 = load_vertex(sc, i2);
     float u, v;
     hit_barycentric(q0.pos, q1.pos, q2.pos, hit_pos, u, v);
-    const drp_material_t& m = mats[ldg(sc.tri_material + tri_id)];
+    const drp_material_t& m = mats[mat_id];
     Vec3 nu = lerp3v(q0.nrm, q1.nrm, q2.nrm, u, v);  // world_normal_unnormalized
     const float4 c0 = q0.color, c1 = q1.color, c2 = q2.color;
     float col[4] = {lerp3(c0.x, c1.x, c2.x, u, v), lerp3(c0.y, c1.y, c2.y, u, v), lerp3(c0.z, c1.z, c2.z, u, v), lerp3(c0.w, c1.w, c2.w, u, v)};

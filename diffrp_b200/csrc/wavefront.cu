@@ -25,7 +25,9 @@
 #include "shade.cuh"
 
 #define WF_BLOCK 128
+#ifndef WF_FETCH
 #define WF_FETCH 128  // rays fetched per warp per atomic
+#endif
 
 struct RenderWorkspace {
     int64_t capacity = 0;  // rays
@@ -176,6 +178,9 @@ __device__ __forceinline__ void cw_ld256(const float4* p, float4& a, float4& b) 
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
+#ifndef CWK_LUT
+#define CWK_LUT 1     // node format 2: hit-byte expansion by shared-memory tables (1), arithmetic (0), tables for primary rays only (2)
+#endif
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
 #ifndef CWK_SHARE
@@ -206,8 +211,11 @@ struct Partition {
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
 #endif
+#ifndef DRP_SHADE_PIPELINE
+#define DRP_SHADE_PIPELINE 0   // software-pipelined hit / index loads: B200 A/B shade 2.07 -> 2.22 ms per step (slower: the kernel is bound by DRAM throughput on random sectors, not by the per-ray latency chain)
+#endif
 #ifndef DRP_SHADE_MINBLOCKS
-#define DRP_SHADE_MINBLOCKS 5
+#define DRP_SHADE_MINBLOCKS 6   // B200 A/B with the interleaved texels (shade ms per step): 4 -> 2.30, 5 -> 2.12, 6 -> 2.04 (80 registers)
 #endif
 template <int SRC, bool PART>
 __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
@@ -353,11 +361,12 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
                     const uint32_t imask = __float_as_uint(n0.w) >> 24;
                     ng_x = __float_as_uint(n1.x);
-                    ng_y = ((uint32_t)s_perm[oct_row + (hit8 & imask)] << 24) | imask;
+                    const bool use_lut = CWK_LUT == 1 || (CWK_LUT == 2 && SRC == SRC_PRIMARY);
+                    ng_y = ((use_lut ? (uint32_t)s_perm[oct_row + (hit8 & imask)] : cw_perm8(hit8 & imask, oct_row >> 8)) << 24) | imask;
                     tg_x = base + rel;  // a triangle group is (node index, pending bits): tri_base / V are re-read when it comes off the stack
                     tri_base = __float_as_uint(n1.y);
                     tri_valid = __float_as_uint(n1.z);
-                    tg_y = s_spread[hit8 & ~imask] & tri_valid;
+                    tg_y = (use_lut ? s_spread[hit8 & ~imask] : cw_spread3x7(hit8 & ~imask)) & tri_valid;
 #else
                     const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
                     ng_x = __float_as_uint(n1.x);
@@ -506,24 +515,57 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
         if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
+#if DRP_SHADE_PIPELINE
+        // Software pipeline over the chunk (SHADE_ALL): the kernel is bound by the dependent DRAM round trips of one ray
+        // (ray + hit record -> vertex indices / material id -> vertex records -> texels; ncu: long scoreboard ~10 warps per issue at
+        // 0.3 IPC).  The hit record is loaded two iterations and the index quadruple one iteration before use, and the next ray's
+        // queue entries are pulled towards L2, so that an iteration starts at the vertex fetch.
+        const float2 h_miss = make_float2(c.p.t_far, 0.0f);
+        float2 h_cur = h_miss, h_nxt = h_miss;
+        TriIdx idx_cur = {0, 0, 0, 0};
+        if (MODE == SHADE_ALL) {
+            if (base + lane < count) h_cur = __ldg(hit + base + lane);
+            if (base + 32 + lane < count) h_nxt = __ldg(hit + base + 32 + lane);
+            if (h_cur.x < c.p.t_far) idx_cur = load_tri_idx(c.scene, __float_as_int(h_cur.y));
+        }
+#endif
 #pragma unroll 1
         for (int j = 0; j < WF_FETCH; j += 32) {
             const int slot = base + j + lane;
             bool alive = false;
             Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
             int ri = 0;
+#if DRP_SHADE_PIPELINE
+            float2 h_n2 = h_miss;
+            TriIdx idx_nxt = {0, 0, 0, 0};
+            if (MODE == SHADE_ALL) {
+                if (j + 64 < WF_FETCH && slot + 64 < count) h_n2 = __ldg(hit + slot + 64);
+                if (j + 32 < WF_FETCH && h_nxt.x < c.p.t_far) idx_nxt = load_tri_idx(c.scene, __float_as_int(h_nxt.y));
+                if (!PRIMARY && j + 32 < WF_FETCH && slot + 32 < count) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qa + slot + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qb + slot + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qt + slot + 32));
+                }
+            }
+#endif
             if (slot < count) {
                 const int k = MODE == SHADE_ALL ? slot : __ldg(index_list + slot);  // queue slot of the ray
                 Vec3 o, d;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
                 if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
+#if DRP_SHADE_PIPELINE
+                float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : (MODE == SHADE_ALL ? h_cur : __ldg(hit + k));
+                const TriIdx* pre = MODE == SHADE_ALL ? &idx_cur : nullptr;
+#else
                 float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : __ldg(hit + k);
+                const TriIdx* pre = nullptr;
+#endif
                 const float t = h.x;
                 const bool is_hit = MODE == SHADE_HITS ? true : (MODE == SHADE_MISSES ? false : t < c.p.t_far);
                 SurfaceAttrs s;
                 if (is_hit) {
                     // last bounce of a path (not the first): only emission and alpha reach the outputs, skip the rest of the material
-                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y), !PRIMARY && last);
+                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y), !PRIMARY && last, pre);
                 } else {
                     s.albedo = s.normal = s.emission = v3(0, 0, 0);
                     s.metal = s.smooth = s.alpha = 0.0f;
@@ -561,6 +603,9 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                     if (c.p.compaction && !is_hit) alive = ray_may_reach_box(no, nd, c.box_lo, c.box_hi);
                 }
             }
+#if DRP_SHADE_PIPELINE
+            h_cur = h_nxt; h_nxt = h_n2; idx_cur = idx_nxt;
+#endif
             // warp-aggregated append to the output queue
             unsigned m = __ballot_sync(0xffffffffu, alive);
             if (m) {
@@ -971,7 +1016,7 @@ extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
            " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
-           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256);
+           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

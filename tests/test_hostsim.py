@@ -101,6 +101,37 @@ def test_shading_logic_matches_oracle(hs, scene_name, last, records):
     np.testing.assert_allclose(acc2, acc, rtol=2e-5, atol=2e-5)
 
 
+def test_texel_records_match_separate_textures_on_the_host(hs):
+    """drp_material_t.texel_records (interleaved 48-byte texels) through the same shade.cuh code the kernels compile:
+    identical accumulators to the four separate textures."""
+    import torch
+    from diffrp_b200.flatten import material_descriptions, pad_rgba, texel_records
+    scene = scenes.mixed_scene()
+    cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
+    vao, hscene, p, keep = scenes.oracle_inputs(scene, cam, 2, 3, seed=7)
+    wp, tr = hscene.arrays['world_pos'], hscene.arrays['tris']
+    h = hs.hs_build(wp.ctypes.data, tr.ctypes.data, len(wp), len(tr))
+    acc_a = np.zeros((40 * 56, 16), np.float32)
+    hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc_a.ctypes.data)
+    recs, n_rec = [], 0
+    for k, d in enumerate(material_descriptions(scene.objects, 'cpu')):
+        d = dict(d)
+        for name in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
+            if d.get(name) is not None:
+                d[name] = dict(d[name], image=pad_rgba(d[name]['image']))
+        rec = texel_records(d)
+        if rec is not None:
+            recs.append(rec)
+            hscene.struct.materials[k].texel_records = rec.data_ptr()
+            n_rec += 1
+    assert n_rec >= 1  # the OPAQUE / repeat / linear sphere has all four textures
+    acc_b = np.zeros_like(acc_a)
+    hs.hs_render(h, C.byref(hscene.struct), C.byref(p), 1e-8, acc_b.ctypes.data)
+    hs.hs_free(h)
+    assert np.abs(acc_a).sum() > 0
+    assert np.array_equal(acc_a, acc_b)
+
+
 def test_tile_render_matches_oracle_tile(hs):
     scene = scenes.mixed_scene()
     cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
