@@ -128,6 +128,35 @@ DRP_HD float x_dot3(Vec3 a, Vec3 b) { return x_add(x_add(x_mul(a.x, b.x), x_mul(
 // Moller-Trumbore exactly as the reference's _ray_tri_intersect (diffrp/utils/raycaster.py:58-79), which unbinds the
 // triangle's vertices (0,1,2) as (v1, v2, v0).  Returns true and t on a hit.  `eps` is the |det| threshold
 // (PathTracingSessionOptions.raycaster_epsilon; 0 disables it).
+// Edge form: e1 = A - C and e2 = B - C are rounded exactly as below, so the traversal layouts store (e1, e2, C) per triangle
+// (DRP_TRI_EDGES) and skip the six subtractions per test without changing a bit of the result.
+DRP_HD bool tri_test_edges(Vec3 o, Vec3 d, Vec3 e1, Vec3 e2, Vec3 C, float eps, float& t_out) {
+    Vec3 cr = x_cross3(d, e2);
+    float det = x_dot3(e1, cr);
+    float inv_det = x_rcp(det);
+    Vec3 s = x_sub3(o, C);
+    float u = x_mul(inv_det, x_dot3(s, cr));
+    Vec3 sc = x_cross3(s, e1);
+    float v = x_mul(inv_det, x_dot3(d, sc));
+    float t = x_mul(inv_det, x_dot3(e2, sc));
+    t_out = t;
+    return (fabsf(det) > eps) & (u >= 0.0f) & (v >= 0.0f) & (x_add(u, v) <= 1.0f) & (t > 0.0f);
+}
+#ifndef DRP_TRI_EDGES
+#define DRP_TRI_EDGES 1
+#endif
+// 48-byte triangle record of the traversal layouts: (e1, e2, C, primitive id) -- or (A, B, C, id) with DRP_TRI_EDGES=0
+DRP_HD void pack_triangle(float4* o, Vec3 A, Vec3 B, Vec3 C, int prim) {
+#if DRP_TRI_EDGES
+    const Vec3 e1 = x_sub3(A, C), e2 = x_sub3(B, C);
+    o[0] = make_float4(e1.x, e1.y, e1.z, e2.x);
+    o[1] = make_float4(e2.y, e2.z, C.x, C.y);
+#else
+    o[0] = make_float4(A.x, A.y, A.z, B.x);
+    o[1] = make_float4(B.y, B.z, C.x, C.y);
+#endif
+    o[2] = make_float4(C.z, i2f(prim), 0.0f, 0.0f);
+}
 DRP_HD bool tri_test_mt(Vec3 o, Vec3 d, Vec3 A, Vec3 B, Vec3 C, float eps, float& t_out) {
     Vec3 e1 = x_sub3(A, C);
     Vec3 e2 = x_sub3(B, C);

@@ -75,6 +75,22 @@ DRP_HD int cw_leaf_gather(const LbvhBuild& b, int c, int* out) {
     return k;
 }
 
+// Per-axis grid exponents (|e| <= 100) are stored as IEEE-biased bytes (e + 127) in n0.w bits 0..23, so that the scale 2^e of an
+// axis is one shift and one mask away (DRP_CW_BIASED_EXP=0: two's-complement bytes, 3-4 instructions per axis to decode).
+#ifndef DRP_CW_BIASED_EXP
+#define DRP_CW_BIASED_EXP 1
+#endif
+DRP_HD uint32_t cw_pack_exponents(int ex, int ey, int ez) {
+    const int bias = DRP_CW_BIASED_EXP ? 127 : 0;
+    return ((uint32_t)(ex + bias) & 0xffu) | (((uint32_t)(ey + bias) & 0xffu) << 8) | (((uint32_t)(ez + bias) & 0xffu) << 16);
+}
+DRP_HD float cw_axis_scale(uint32_t ebits, int axis) {  // 2^e of axis 0..2
+#if DRP_CW_BIASED_EXP
+    return u2f(axis == 0 ? (ebits << 23) & 0x7f800000u : (axis == 1 ? (ebits << 15) & 0x7f800000u : (ebits << 7) & 0x7f800000u));
+#else
+    return i2f(((int)(int8_t)((ebits >> (8 * axis)) & 0xffu) + 127) << 23);
+#endif
+}
 DRP_HD uint32_t cw_pack4(const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
 
 // Collapse the binary subtree rooted at work[ni] into wide node ni.  `atomic_add(ptr, v)` returns the old value.
@@ -223,17 +239,14 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
                 Vec3 A = load_vert(b.verts, b.tris[3 * (int64_t)prim]);
                 Vec3 B = load_vert(b.verts, b.tris[3 * (int64_t)prim + 1]);
                 Vec3 C = load_vert(b.verts, b.tris[3 * (int64_t)prim + 2]);
-                float4* o = cw.cw_tris + 3 * (int64_t)(tri_base + toff + t);
-                o[0] = make_float4(A.x, A.y, A.z, B.x);
-                o[1] = make_float4(B.y, B.z, C.x, C.y);
-                o[2] = make_float4(C.z, i2f(prim), 0.0f, 0.0f);
+                pack_triangle(cw.cw_tris + 3 * (int64_t)(tri_base + toff + t), A, B, C, prim);
             }
             toff += cnt;
         }
     }
     float4* o = cw.cw_nodes + CW_NODE_F4 * (int64_t)ni;
     if (CW_NODE_F4 > 5) o[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16) | (imask << 24);
+    uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]) | (imask << 24);
     o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
 #if DRP_CW_V2
     o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(vmask), u2f(0u));
@@ -257,9 +270,7 @@ DRP_HD void cw_emit_tiny(const CwBuild& cw) {
         pad_box(lo, hi, lbvh_abs_pad(b));
         meta0 = 1u << 5;
         Vec3 A = load_vert(b.verts, b.tris[0]), B = load_vert(b.verts, b.tris[1]), C = load_vert(b.verts, b.tris[2]);
-        cw.cw_tris[0] = make_float4(A.x, A.y, A.z, B.x);
-        cw.cw_tris[1] = make_float4(B.y, B.z, C.x, C.y);
-        cw.cw_tris[2] = make_float4(C.z, i2f(0), 0.0f, 0.0f);
+        pack_triangle(cw.cw_tris, A, B, C, 0);
     }
     int e[3];
     for (int a = 0; a < 3; ++a) {
@@ -269,7 +280,7 @@ DRP_HD void cw_emit_tiny(const CwBuild& cw) {
         while (ext > 255.0f * i2f((ea + 127) << 23) && ea < 100) ++ea;
         e[a] = ea;
     }
-    uint32_t ebits = ((uint32_t)e[0] & 0xffu) | (((uint32_t)e[1] & 0xffu) << 8) | (((uint32_t)e[2] & 0xffu) << 16);
+    uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]);
     o[0] = make_float4(lo.x, lo.y, lo.z, u2f(ebits));
 #if DRP_CW_V2
     o[1] = make_float4(i2f(0), i2f(0), u2f(meta0 ? 1u : 0u), u2f(0u));
@@ -358,8 +369,7 @@ DRP_HD int cw_tri_index(uint32_t tri_base, uint32_t vmask, int j) { return (int)
 // intersect the 8 quantised child boxes of one node; returns one hit bit per slot (bit s = slot s)
 DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n2, float4 n3, float4 n4, float t_cull) {
     const uint32_t ebits = f2u(n0.w);
-    const int ex = (int)(int8_t)(ebits & 0xffu), ey = (int)(int8_t)((ebits >> 8) & 0xffu), ez = (int)(int8_t)((ebits >> 16) & 0xffu);
-    const float ax = i2f((ex + 127) << 23) * r.idir.x, ay = i2f((ey + 127) << 23) * r.idir.y, az = i2f((ez + 127) << 23) * r.idir.z;
+    const float ax = cw_axis_scale(ebits, 0) * r.idir.x, ay = cw_axis_scale(ebits, 1) * r.idir.y, az = cw_axis_scale(ebits, 2) * r.idir.z;
     const float ox = (n0.x - r.o.x) * r.idir.x, oy = (n0.y - r.o.y) * r.idir.y, oz = (n0.z - r.o.z) * r.idir.z;
     // conservative widening: the FMA form cancels, its error is relative to |origin term| + |grid term|
     const float sx = CW_SLACK * fabsf(ox) + CW_GRID_SLACK * fabsf(ax), sy = CW_SLACK * fabsf(oy) + CW_GRID_SLACK * fabsf(ay),
@@ -398,8 +408,7 @@ DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n2, float4 n3, fl
 // traversal priority, triangles of leaf children in bits 0..23)
 DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4, float t_cull) {
     const uint32_t ebits = f2u(n0.w);
-    const int ex = (int)(int8_t)(ebits & 0xffu), ey = (int)(int8_t)((ebits >> 8) & 0xffu), ez = (int)(int8_t)((ebits >> 16) & 0xffu);
-    const float ax = i2f((ex + 127) << 23) * r.idir.x, ay = i2f((ey + 127) << 23) * r.idir.y, az = i2f((ez + 127) << 23) * r.idir.z;
+    const float ax = cw_axis_scale(ebits, 0) * r.idir.x, ay = cw_axis_scale(ebits, 1) * r.idir.y, az = cw_axis_scale(ebits, 2) * r.idir.z;
     const float ox = (n0.x - r.o.x) * r.idir.x, oy = (n0.y - r.o.y) * r.idir.y, oz = (n0.z - r.o.z) * r.idir.z;
     // conservative widening: the FMA form cancels, its error is relative to |origin term| + |grid term|
     const float sx = CW_SLACK * fabsf(ox) + CW_GRID_SLACK * fabsf(ax), sy = CW_SLACK * fabsf(oy) + CW_GRID_SLACK * fabsf(ay),

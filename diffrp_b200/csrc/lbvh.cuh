@@ -284,8 +284,5 @@ DRP_HD void lbvh_pack_tri(const LbvhBuild& b, int j) {
     Vec3 A = load_vert(b.verts, b.tris[3 * (int64_t)prim]);
     Vec3 B = load_vert(b.verts, b.tris[3 * (int64_t)prim + 1]);
     Vec3 C = load_vert(b.verts, b.tris[3 * (int64_t)prim + 2]);
-    float4* o = b.packed + 3 * (int64_t)j;
-    o[0] = make_float4(A.x, A.y, A.z, B.x);
-    o[1] = make_float4(B.y, B.z, C.x, C.y);
-    o[2] = make_float4(C.z, i2f(prim), 0.0f, 0.0f);
+    pack_triangle(b.packed + 3 * (int64_t)j, A, B, C, prim);
 }

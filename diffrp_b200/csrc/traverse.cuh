@@ -49,7 +49,12 @@ DRP_HD void leaf_intersect(const float4* __restrict__ tris, int first, int count
         float4 a = ldg(p), b = ldg(p + 1), c = ldg(p + 2);
         DRP_COUNT_TRI();
         float t;
-        if (tri_test_mt(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t)) {
+#if DRP_TRI_EDGES
+        const bool is_hit = tri_test_edges(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
+#else
+        const bool is_hit = tri_test_mt(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
+#endif
+        if (is_hit) {
             int id = f2i(c.y);
             if (t < t_best || (t == t_best && id < id_best)) { t_best = t; id_best = id; }
         }
