@@ -51,7 +51,15 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def wait_ready(self, timeout=5.0):
+        """Block until the sampler delivers rows (nvidia-smi start-up -- fork, NVML init -- can stall driver calls of this process
+        for ~100 ms, so it must be over before the timed region starts), then count only rows from here on."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -76,7 +84,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
@@ -297,6 +305,9 @@ def main():
     my_ids = torch.arange(total_spp, dtype=torch.int32, device=dev)[rank::world]  # global Hammersley indices of this rank
     step_ids = [my_ids[j * S:(j + 1) * S] for j in range(K)]
     scratch = sess.new_accumulators()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # started before the warm-up: its start-up cost stays out of the timed region
     for j in range(W):
         sess.render_samples(step_ids[j % K], scratch)
     if world > 1:
@@ -306,9 +317,8 @@ def main():
     sess.set_profiling(True)
     launches0 = 0
     accum = sess.new_accumulators()
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.wait_ready()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
