@@ -312,6 +312,7 @@ def main():
         sess.render_samples(step_ids[j % K], scratch)
     if world > 1:
         dist.all_reduce(scratch)
+    sess.finalize(scratch)  # the warm-up runs everything the timed region runs (first use of a kernel / first allocation of the outputs)
     torch.cuda.synchronize()
     sess.get_profile()
     sess.set_profiling(True)
@@ -319,17 +320,23 @@ def main():
     accum = sess.new_accumulators()
     if rank == 0:
         clocks.wait_ready()
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pause between the launches of the timed region (re-enabled right after it)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
+    t_host0 = time.perf_counter()
     for j in range(K):
         sess.render_samples(step_ids[j], accum)
     if world > 1:
         dist.all_reduce(accum)  # the path's one exchange step: fp32 accumulators over NVLink
     radiance, alpha, extras = sess.finalize(accum)
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3  # host time to issue the region's launches (diagnostic; with per-kernel event spans the launch queue fills up, so this is mostly back-pressure from the GPU, not host work: tools/host_overhead.py measures 0.09 ms of host time per step without spans)
     e1.record()
     torch.cuda.synchronize()
+    gc.enable()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -481,7 +488,7 @@ def main():
         "spp_per_second": world * K * S / (ms_max * 1e-3),
         "live_ray_fraction": prof["extend_rays"] / max(1, K * S * HW * DEPTH),
         "bvh_build_ms": build_ms,
-        "clocks": clk,
+        "clocks": clk, "host_issue_ms": host_issue_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "steps": K,
                 "ms_per_step": e2e_job_ms / K, "ms_total": e2e_job_ms, "h2d_bytes_total": h2d, "d2h_bytes_total": d2h,
                 "what": "ONE public-API call for the whole job: PathTracingSession(host-pinned scene, camera, options(ray_spp=%d, spp-sharded x%d)).pbr() "

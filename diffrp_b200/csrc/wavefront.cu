@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
         if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
-#if DRP_SHADE_PIPELINE
+#if DRP_SHADE_PIPELINE == 1
         // Software pipeline over the chunk (SHADE_ALL): the kernel is bound by the dependent DRAM round trips of one ray
         // (ray + hit record -> vertex indices / material id -> vertex records -> texels; ncu: long scoreboard ~10 warps per issue at
         // 0.3 IPC).  The hit record is loaded two iterations and the index quadruple one iteration before use, and the next ray's
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
             bool alive = false;
             Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
             int ri = 0;
-#if DRP_SHADE_PIPELINE
+#if DRP_SHADE_PIPELINE == 1
             float2 h_n2 = h_miss;
             TriIdx idx_nxt = {0, 0, 0, 0};
             if (MODE == SHADE_ALL) {
@@ -548,12 +548,28 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                 }
             }
 #endif
+#if DRP_SHADE_PIPELINE == 2
+            // prefetch-only variant: no carried registers, the next ray's index lines and queue entries are pulled towards L2
+            if (MODE == SHADE_ALL && j + 32 < WF_FETCH && slot + 32 < count) {
+                const float2 hn = __ldg(hit + slot + 32);
+                if (hn.x < c.p.t_far) {
+                    const int idn = __float_as_int(hn.y);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.scene.tris + 3 * (int64_t)idn));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.scene.tri_material + idn));
+                }
+                if (!PRIMARY) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qa + slot + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qb + slot + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qt + slot + 32));
+                }
+            }
+#endif
             if (slot < count) {
                 const int k = MODE == SHADE_ALL ? slot : __ldg(index_list + slot);  // queue slot of the ray
                 Vec3 o, d;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
                 if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
-#if DRP_SHADE_PIPELINE
+#if DRP_SHADE_PIPELINE == 1
                 float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : (MODE == SHADE_ALL ? h_cur : __ldg(hit + k));
                 const TriIdx* pre = MODE == SHADE_ALL ? &idx_cur : nullptr;
 #else
@@ -603,7 +619,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                     if (c.p.compaction && !is_hit) alive = ray_may_reach_box(no, nd, c.box_lo, c.box_hi);
                 }
             }
-#if DRP_SHADE_PIPELINE
+#if DRP_SHADE_PIPELINE == 1
             h_cur = h_nxt; h_nxt = h_n2; idx_cur = idx_nxt;
 #endif
             // warp-aggregated append to the output queue
@@ -756,6 +772,25 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_render: cannot select device"); return DRP_ERR_CUDA; }
     cudaStream_t s = (cudaStream_t)stream;
+    // Experiment (DRP_L2_PERSIST_MB=<n>): pin the wide-node array in L2 (persisting access-policy window on the render stream) so that the
+    // texel / queue streams of k_shade do not evict the hierarchy between two extend launches.
+    static const int persist_mb = getenv("DRP_L2_PERSIST_MB") ? atoi(getenv("DRP_L2_PERSIST_MB")) : 0;
+    if (persist_mb > 0 && h->wide) {
+        static bool limit_set = false;
+        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20); limit_set = true; }
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        const size_t node_bytes = (size_t)h->n_nodes_used * 16 * CW_NODE_F4;
+        av.accessPolicyWindow.base_ptr = (void*)h->nodes;
+        av.accessPolicyWindow.num_bytes = node_bytes;
+        av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)((size_t)persist_mb << 20) / (double)std::max<size_t>(node_bytes, 1)));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaError_t e = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+        static bool reported = false;
+        if (!reported) { fprintf(stderr, "[diffrp_b200] L2 persisting window: %zu bytes of nodes, %d MB set aside: %s\n", node_bytes, persist_mb, cudaGetErrorString(e)); reported = true; }
+        (void)cudaGetLastError();
+    }
     const int spb = p.reproducible ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
     int rc = ensure_workspace(h, (((int64_t)spb * HW + 1) / 2) * 2 + 64, scene->n_materials);
     if (rc != DRP_OK) return rc;
