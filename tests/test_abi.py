@@ -59,3 +59,30 @@ def test_product_has_no_cpu_fallback():
         for f in files:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/", ""), f
+
+
+def test_texel_records_layout_and_eligibility():
+    """Host side of drp_material_t.texel_records: channel order of the 48-byte texel, and the cases that must fall back to four textures."""
+    import torch
+    import scenes
+    from diffrp_b200.flatten import material_descriptions, pad_rgba, texel_records
+    objs = scenes.mixed_scene().objects
+    descs = material_descriptions(objs, 'cpu', rgba=True)
+    with_rec = [d for d in descs if 'texel_records' in d]
+    assert len(with_rec) == 1  # only the OPAQUE sphere has all four textures (BLEND: no emission, MASK: no normal map)
+    d = with_rec[0]
+    rec = d['texel_records']
+    b, m, n, e = (d[k]['image'] for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
+    assert rec.shape == (b.shape[0], b.shape[1], 12) and rec.dtype == torch.float32 and rec.is_contiguous()
+    assert torch.equal(rec[..., 0:4], b) and torch.equal(rec[..., 4:6], m[..., 1:3])
+    assert torch.equal(rec[..., 6:9], n[..., :3]) and torch.equal(rec[..., 9:12], e[..., :3])
+    # packing into the C struct keeps the pointer and checks the shape
+    keep = []
+    mat = _abi.pack_material(d, lambda t: t.data_ptr(), keep)
+    assert mat.texel_records == rec.data_ptr() and any(k is rec for k in keep)
+    # fall-backs: a texture of another size, another wrap mode, a missing texture
+    other = dict(d, mr_tex=dict(d['mr_tex'], image=pad_rgba(torch.rand(8, 8, 3))))
+    assert texel_records(other) is None
+    assert texel_records(dict(d, normal_tex=dict(d['normal_tex'], wrap='clamp'))) is None
+    assert texel_records(dict(d, emissive_tex=None)) is None
+    assert texel_records(dict(kind='default', tint=None)) is None
