@@ -131,6 +131,16 @@ extern "C" int64_t hs_trace_wide(const HsBvh* h, const float* ro, const float* r
     return overflow;
 }
 
+#if DRP_CW_V2
+// node format 2 helpers exactly as the kernels build their shared-memory tables: perm[octinv * 256 + byte], spread[byte], and the
+// triangle index behind bit j of a node's triangle mask
+extern "C" void hs_cw_tables(uint8_t* perm, uint32_t* spread) {
+    for (int e = 0; e < 8 * 256; ++e) perm[e] = (uint8_t)cw_perm8((uint32_t)e & 0xffu, (uint32_t)e >> 8);
+    for (int e = 0; e < 256; ++e) spread[e] = cw_spread3x7((uint32_t)e);
+}
+extern "C" int hs_cw_tri_index(uint32_t tri_base, uint32_t vmask, int j) { return cw_tri_index(tri_base, vmask, j); }
+#endif
+
 // wide-layout statistics: [nodes, levels, inner children, leaf children, triangles referenced, max tris per node]
 extern "C" void hs_stats_wide(const HsBvh* h, int64_t* out) {
     int64_t inner = 0, leaf = 0, tris = 0, maxt = 0;

@@ -212,3 +212,42 @@ def test_tonemap_pixel_function_equals_oracle(hs):
             fo, bo = oracle.tonemap(rgba, name, lut=lut, scale=0.5, alpha_offset=alpha_offset)
             assert np.array_equal(f.view(np.uint32), fo.view(np.uint32)), (name, alpha_offset, np.abs(f - fo).max())
             assert np.array_equal(b, bo)
+
+
+def test_node_format2_tables_and_triangle_index(hs):
+    """The two table expansions of the per-slot hit byte (cwbvh.cuh, node format 2) against their definitions: internal children move to
+    bit (slot ^ octinv) -- so that the highest set bit is the child to visit first --, leaf slots spread to 3 triangle bits each; triangle bit
+    j of a node is the popc(V below j)-th triangle after tri_base."""
+    if not hasattr(hs, 'hs_cw_tables'):
+        pytest.skip("host simulator built for node format 1")
+    perm = np.zeros(8 * 256, np.uint8)
+    spread = np.zeros(256, np.uint32)
+    hs.hs_cw_tables.argtypes = [C.c_void_p, C.c_void_p]
+    hs.hs_cw_tables(perm.ctypes.data, spread.ctypes.data)
+    for octinv in range(8):
+        for byte in range(256):
+            want = 0
+            for slot in range(8):
+                if byte >> slot & 1:
+                    want |= 1 << (slot ^ octinv)
+            assert perm[octinv * 256 + byte] == want
+    for byte in range(256):
+        want = 0
+        for slot in range(8):
+            if byte >> slot & 1:
+                want |= 7 << (3 * slot)
+        assert spread[byte] == want
+    hs.hs_cw_tri_index.restype = C.c_int
+    hs.hs_cw_tri_index.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        counts = rng.integers(0, 4, 8)                      # triangles per slot (0 = empty or internal)
+        vmask = 0
+        for slot, c in enumerate(counts):
+            vmask |= ((1 << int(c)) - 1) << (3 * slot)
+        base = int(rng.integers(0, 1 << 20))
+        k = 0
+        for slot, c in enumerate(counts):                   # compact storage in slot order
+            for t in range(int(c)):
+                assert hs.hs_cw_tri_index(base, vmask, 3 * slot + t) == base + k
+                k += 1
