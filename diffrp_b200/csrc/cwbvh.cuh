@@ -7,13 +7,18 @@
 // (node group + triangle group bitmasks) postpones triangle tests so that lanes of a warp stay in the same phase.
 //
 // Node = 5 x float4 (80 B):
-//   n0 = (p.x, p.y, p.z, bits{ex, ey, ez, imask})          origin of the local grid, per-axis exponent, internal mask
-//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])     first child node / first triangle, per-slot meta byte
+//   n0 = (p.x, p.y, p.z, bits{ex, ey, ez, imask})          origin of the local grid, per-axis exponent bytes (IEEE-biased, see
+//                                                           cw_pack_exponents), mask of the slots that hold internal children
+//   n1 = (child_base, tri_base, V, 0)                       first child node / first triangle; V = valid-triangle mask, bit 3*slot+k set
+//                                                           iff leaf slot `slot` holds a k-th triangle (node format 2, the default)
+//      = (child_base, tri_base, meta[0..3], meta[4..7])     node format 1 (DRP_CW_V2=0): per-slot meta byte, 0 = empty; internal child:
+//                                                           0b001'11sss (low 5 bits = 24 + slot); leaf child: unary triangle count (1..3)
+//                                                           in the top 3 bits, offset of its first triangle from tri_base in the low 5
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
 //   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
 //   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
-// meta byte: 0 = empty; internal child: 0b001'11sss (low 5 bits = 24 + slot); leaf child: unary triangle count (1..3) in
-// the top 3 bits, offset of its first triangle relative to tri_base in the low 5 bits.  Child boxes are
+// Internal children of a node are consecutive nodes from child_base in slot order; the triangles of its leaf slots are consecutive
+// 48-byte records from tri_base in slot order (common.cuh: pack_triangle).  Child boxes are
 // lo = p + qlo * 2^e, hi = p + qhi * 2^e (rounded outwards), and contain the padded boxes of lbvh.cuh, so the traversal is
 // conservative and the closest hit equals the exhaustive one (traverse.cuh contract).
 #pragma once
