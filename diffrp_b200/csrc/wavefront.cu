@@ -211,6 +211,9 @@ struct Partition {
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
 #endif
+#ifndef DRP_SHADE_CHUNK_PARTITION
+#define DRP_SHADE_CHUNK_PARTITION 0   // not measured yet (written after the GPU budget of the round was spent): see k_shade
+#endif
 #ifndef DRP_SHADE_PIPELINE
 #define DRP_SHADE_PIPELINE 0   // software-pipelined hit / index loads: B200 A/B shade 2.07 -> 2.22 ms per step (slower: the kernel is bound by DRAM throughput on random sectors, not by the per-ray latency chain)
 #endif
@@ -529,9 +532,55 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
             if (h_cur.x < c.p.t_far) idx_cur = load_tri_idx(c.scene, __float_as_int(h_cur.y));
         }
 #endif
+#if DRP_SHADE_CHUNK_PARTITION
+#if DRP_SHADE_PIPELINE
+#error "DRP_SHADE_CHUNK_PARTITION reorders the rays of a chunk and cannot be combined with DRP_SHADE_PIPELINE"
+#endif
+        // Experiment for the next measurement round (ncu, profiles/README.md section 3: the secondary-bounce shade kernel executes at 13 of 32
+        // lanes because hits -- vertex / texel fetches + BRDF -- and misses -- environment lookup -- share warps).  The chunk of WF_FETCH rays a
+        // warp owns is classified with one ballot per 32 rays and then walked class by class: lane l of iteration i takes the (32 i + l)-th
+        // hit, later the (32 i' + l)-th miss, so that a warp runs one of the two code paths with (nearly) all lanes.  Rays stay inside their
+        // chunk (no global lists, no indirection through memory: the extend-side partition of DRP_PARTITION lost to its finish-ordered reads).
+        constexpr int NQ = WF_FETCH / 32;
+        const bool part_chunk = !PRIMARY && MODE == SHADE_ALL;
+        unsigned cls_hit[NQ], cls_miss[NQ];
+        int n_hit = 0, n_miss = 0;
+        if (part_chunk) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int sl = base + 32 * q + lane;
+                const bool valid = sl < count;
+                const bool ish = valid && __ldg(hit + sl).x < c.p.t_far;
+                cls_hit[q] = __ballot_sync(0xffffffffu, ish);
+                cls_miss[q] = __ballot_sync(0xffffffffu, valid && !ish);
+                n_hit += __popc(cls_hit[q]);
+                n_miss += __popc(cls_miss[q]);
+            }
+        }
+        const int it_hit = (n_hit + 31) >> 5, it_all = part_chunk ? it_hit + ((n_miss + 31) >> 5) : NQ;
+#pragma unroll 1
+        for (int it = 0; it < it_all; ++it) {
+            const int j = 32 * it;
+            int slot = base + j + lane;
+            if (part_chunk) {
+                const bool hit_phase = it < it_hit;
+                int rank = (hit_phase ? it : it - it_hit) * 32 + lane;
+                slot = count;  // no ray for this lane
+                if (rank < (hit_phase ? n_hit : n_miss)) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const unsigned m = hit_phase ? cls_hit[q] : cls_miss[q];
+                        const int cq = __popc(m);
+                        if (rank >= 0 && rank < cq) { slot = base + 32 * q + (int)__fns(m, 0, rank + 1); rank = -1; }
+                        else if (rank >= 0) rank -= cq;
+                    }
+                }
+            }
+#else
 #pragma unroll 1
         for (int j = 0; j < WF_FETCH; j += 32) {
             const int slot = base + j + lane;
+#endif
             bool alive = false;
             Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
             int ri = 0;
@@ -1051,7 +1100,7 @@ extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
            " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
-           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE);
+           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE) " DRP_SHADE_CHUNK_PARTITION=" DRP_STR(DRP_SHADE_CHUNK_PARTITION);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {
