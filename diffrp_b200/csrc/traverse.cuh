@@ -42,22 +42,26 @@ DRP_HD bool slab_test(float lox, float loy, float loz, float hix, float hiy, flo
     return tn * DRP_T_SHRINK <= tf * DRP_T_GROW;
 }
 
+// one packed triangle record against the ray; updates the closest hit with the (t, id) order of the contract
+DRP_HD void leaf_update(float4 a, float4 b, float4 c, Vec3 o, Vec3 d, float eps, float& t_best, int& id_best) {
+    DRP_COUNT_TRI();
+    float t;
+#if DRP_TRI_EDGES
+    const bool is_hit = tri_test_edges(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
+#else
+    const bool is_hit = tri_test_mt(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
+#endif
+    if (is_hit) {
+        int id = f2i(c.y);
+        if (t < t_best || (t == t_best && id < id_best)) { t_best = t; id_best = id; }
+    }
+}
 DRP_HD void leaf_intersect(const float4* __restrict__ tris, int first, int count, Vec3 o, Vec3 d, float eps, float& t_best,
                            int& id_best) {
     for (int k = 0; k < count; ++k) {
         const float4* p = tris + 3 * (int64_t)(first + k);
         float4 a = ldg(p), b = ldg(p + 1), c = ldg(p + 2);
-        DRP_COUNT_TRI();
-        float t;
-#if DRP_TRI_EDGES
-        const bool is_hit = tri_test_edges(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
-#else
-        const bool is_hit = tri_test_mt(o, d, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), eps, t);
-#endif
-        if (is_hit) {
-            int id = f2i(c.y);
-            if (t < t_best || (t == t_best && id < id_best)) { t_best = t; id_best = id; }
-        }
+        leaf_update(a, b, c, o, d, eps, t_best, id_best);
     }
 }
 

@@ -178,6 +178,9 @@ __device__ __forceinline__ void cw_ld256(const float4* p, float4& a, float4& b) 
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
+#ifndef CWK_TRI_PIPE
+#define CWK_TRI_PIPE 0   // triangle records requested one test ahead: written after the round's GPU budget was spent, not measured yet
+#endif
 #ifndef CWK_LUT
 #define CWK_LUT 1     // node format 2: hit-byte expansion by shared-memory tables (1), arithmetic (0), tables for primary rays only (2)
 #endif
@@ -440,6 +443,41 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                         if (i0) { const float2 q = s_res[wid][p0]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t0); }
                         if (i1) { const float2 q = s_res[wid][p1]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t1); }
                         if (i2) { const float2 q = s_res[wid][p2]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t2); }
+                    }
+                }
+#elif CWK_TRI_PIPE && DRP_CW_V2
+                // Experiment for the next measurement round (profiles/README.md section 2, per-instruction view: 8.8 % of the stall samples of the
+                // secondary-bounce kernel wait for the triangle record): the record of the next pending triangle is requested before the
+                // current one is tested.  Same tests, same (t, id) order, same postponing rule.
+                {
+                    const int total_active = __popc(__activemask());
+                    if (tg_y != 0) {
+                        if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
+                            CWK_PUSH(tg_x, tg_y);  // postpone: too few lanes have triangles
+                        } else {
+                            int ti = 31 - __clz(tg_y);
+                            tg_y &= ~(1u << ti);
+                            const float4* tp = c.tris + 3 * (int64_t)cw_tri_index(tri_base, tri_valid, ti);
+                            float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+                            for (;;) {
+                                bool more = tg_y != 0;
+                                float4 na = ta, nb = tb, nc = tc;
+                                if (more) {
+                                    if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
+                                        CWK_PUSH(tg_x, tg_y);
+                                        more = false;
+                                    } else {
+                                        ti = 31 - __clz(tg_y);
+                                        tg_y &= ~(1u << ti);
+                                        tp = c.tris + 3 * (int64_t)cw_tri_index(tri_base, tri_valid, ti);
+                                        na = __ldg(tp); nb = __ldg(tp + 1); nc = __ldg(tp + 2);
+                                    }
+                                }
+                                leaf_update(ta, tb, tc, r.o, r.d, c.eps, t_best, id_best);
+                                if (!more) break;
+                                ta = na; tb = nb; tc = nc;
+                            }
+                        }
                     }
                 }
 #else
@@ -1100,7 +1138,7 @@ extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
            " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
            " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
-           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE) " DRP_SHADE_CHUNK_PARTITION=" DRP_STR(DRP_SHADE_CHUNK_PARTITION);
+           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE) " DRP_SHADE_CHUNK_PARTITION=" DRP_STR(DRP_SHADE_CHUNK_PARTITION) " CWK_TRI_PIPE=" DRP_STR(CWK_TRI_PIPE);
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {
