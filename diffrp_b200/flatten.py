@@ -153,9 +153,10 @@ def pad_rgba(img: torch.Tensor) -> torch.Tensor:
 
 def texel_records(d: dict) -> Optional[torch.Tensor]:
     """(H,W,12) interleaved copy of a GLTF material's four RGBA-padded textures, [base rgba | mr.g mr.b n.x n.y | n.z e.r e.g e.b]
-    (drp_material_t.texel_records), or None when a texture is missing or their sizes / wrap / filter modes differ."""
+    (drp_material_t.texel_records), or None when a texture is missing or their sizes / wrap / filter modes differ.  A material without
+    an emissive factor still qualifies (its emissive texture is interleaved but never read: has_emissive = 0)."""
     tex = [d.get(k) for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex')]
-    if d.get('kind') != 'gltf' or any(t is None for t in tex) or d.get('emissive_factor') is None:
+    if d.get('kind') != 'gltf' or any(t is None for t in tex):
         return None
     first = tex[0]
     for t in tex[1:]:

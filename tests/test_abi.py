@@ -69,7 +69,8 @@ def test_texel_records_layout_and_eligibility():
     objs = scenes.mixed_scene().objects
     descs = material_descriptions(objs, 'cpu', rgba=True)
     with_rec = [d for d in descs if 'texel_records' in d]
-    assert len(with_rec) == 1  # only the OPAQUE sphere has all four textures (BLEND: no emission, MASK: no normal map)
+    assert len(with_rec) == 2  # the OPAQUE and the BLEND sphere (no emissive factor, but all four textures); MASK has no normal map
+    assert [d.get('emissive_factor') is None for d in with_rec] == [False, True]
     d = with_rec[0]
     rec = d['texel_records']
     b, m, n, e = (d[k]['image'] for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
