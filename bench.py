@@ -214,28 +214,34 @@ def host_threads(oracle):
 
 
 def run_reference(args, world, rank):
-    """--impl reference: the reference's own algorithm for the path (CPU oracle port) on the box's host cores."""
+    """--impl reference: the reference's own implementation of the path on the box's host cores -- unmodified diffrp from baseline/_ref
+    (kind "reference"); the CPU oracle port only when no reference install travelled with the repo (kind "port")."""
     if rank != 0:
         return
-    oracle, bvh, hs, p, keep, build_s, n_tris = cpu_oracle_setup(args.tex)
-    host_threads(oracle)
-    cores = oracle.num_threads()
-    win, spp = args.ref_window, args.ref_spp
-    for w in range(min(args.warmup, 1)):
-        cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(spp))
-    tot_t, tot_n = 0.0, 0
-    for k in range(args.steps):
-        dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(k * spp, (k + 1) * spp) % 1024)
-        tot_t += dt
-        tot_n += n
-    val = tot_n / tot_t / 1e6
-    sample = "%dx%d central window of the %dx%d frame, %d spp, %d bounces per step (%d ray-bounces), 2,097,152-tri scene, CPU BVH build %.1f s excluded" % (
-        win, win, RES, RES, spp, DEPTH, win * win * spp * DEPTH, build_s)
+    from baseline import ref_bench
+    if ref_bench.reference_available() and not args.ref_port:
+        r = ref_bench.run('cpu', args.tex, args.ref_window, args.ref_spp, args.steps, min(args.warmup, args.ref_max_warmup))
+        val, cores, kind, sample, ms_step, n_tris = r["value"], r["cores"], r["kind"], r["sample"], r["ms_per_step"], r["n_tris"]
+    else:
+        oracle, bvh, hs, p, keep, build_s, n_tris = cpu_oracle_setup(args.tex)
+        host_threads(oracle)
+        cores, kind = oracle.num_threads(), "port"
+        win, spp = args.ref_window, args.ref_spp
+        for w in range(min(args.warmup, 1)):
+            cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(spp))
+        tot_t, tot_n = 0.0, 0
+        for k in range(args.steps):
+            dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, win, np.arange(k * spp, (k + 1) * spp) % 1024)
+            tot_t += dt
+            tot_n += n
+        val, ms_step = tot_n / tot_t / 1e6, tot_t / max(1, args.steps) * 1e3
+        sample = "CPU oracle port (no baseline/_ref): %dx%d central window of the %dx%d frame, %d spp, %d bounces per step (%d ray-bounces), 2,097,152-tri scene, CPU BVH build %.1f s excluded" % (
+            win, win, RES, RES, spp, DEPTH, win * win * spp * DEPTH, build_s)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": tot_t / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(n_tris, args),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -258,13 +264,18 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=8)
     ap.add_argument("--tex", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=6)
-    ap.add_argument("--ref-window", type=int, default=128)
-    ap.add_argument("--ref-spp", type=int, default=8)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=8)
+    ap.add_argument("--ref-window", type=int, default=256, help="--impl reference: window edge of one step (the reference's CPU throughput grows with the batch: "
+                    "0.035 / 0.096 / 0.17 Mrays/s at 128^2 / 256^2 / 512^2 x 4 spp on 8 cores; 256 keeps a 20-step run within minutes)")
+    ap.add_argument("--cpu-baseline-window", type=int, default=512)
+    ap.add_argument("--ref-spp", type=int, default=4)
+    ap.add_argument("--ref-port", action="store_true", help="reference legs: time the CPU oracle port instead of the installed reference")
+    ap.add_argument("--ref-max-warmup", type=int, default=2, help="--impl reference: cap on the untimed warm-up steps (each is seconds of CPU work)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-baseline-res", type=int, default=256)
-    ap.add_argument("--torch-baseline-spp", type=int, default=4)
-    ap.add_argument("--torch-baseline-steps", type=int, default=2)
+    ap.add_argument("--torch-baseline-res", type=int, default=1024, help="window edge of the reference's GPU leg: 1024 x 8 spp = one real section of the "
+                    "reference (ray_split_size = 8M rays, path_tracing.py:74,318) = exactly one bench step")
+    ap.add_argument("--torch-baseline-spp", type=int, default=8)
+    ap.add_argument("--torch-baseline-steps", type=int, default=1)
     ap.add_argument("--no-torch-baseline", action="store_true")
     args = ap.parse_args()
     world, rank, local = dist_setup(args.gpus)
@@ -430,18 +441,49 @@ def main():
                         "traffic is ~10x lower because the upper BVH levels stay in L1/L2 -- the kernel is issue-bound (ncu: math-pipe throttle, "
                         "~0.7 inst/cycle/SMSP, 19-21 of 32 lanes active), see profiles/README.md")
 
+    # ---- the reference timed in the same run (rank 0, N = 1): its torch GPU path on this B200, then its CPU path on the host cores --------
+    # Both legs run UNMODIFIED diffrp from baseline/_ref (baseline/ref_bench.py); the restatements (oracle port / torch port) only stand in
+    # when no reference install travelled with the repo.
+    from baseline import ref_bench, ref_loader
+    have_ref = ref_bench.reference_available() and not args.ref_port
+    torch_baseline = None
+    if world == 1 and not args.no_torch_baseline:
+        try:
+            if have_ref:
+                try:
+                    r = ref_bench.run('cuda', args.tex, args.torch_baseline_res, args.torch_baseline_spp, args.torch_baseline_steps, 1)
+                except torch.cuda.OutOfMemoryError:  # the reference holds >= 12 full-R temporaries per bounce: retry with a quarter of the rays
+                    ref_loader.unload_reference()
+                    torch.cuda.empty_cache()
+                    r = ref_bench.run('cuda', args.tex, args.torch_baseline_res // 2, args.torch_baseline_spp, args.torch_baseline_steps, 1)
+                torch_baseline = {"value": r["value"], "unit": UNIT, "kind": "reference", "device": "same B200, same run", "ms_per_step": r["ms_per_step"],
+                                  "what": "the reference's own torch GPU path (NaivePBBVH, splitaxis) + its torch shading", "sample": r["sample"]}
+                ref_loader.unload_reference()
+                torch.cuda.empty_cache()
+            else:
+                torch_baseline = gpu_torch_baseline(scene, camkw, dev, args)
+        except Exception as exc:  # a baseline must never take the product's line down
+            torch_baseline = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        oracle, bvh, hs, p, keep, build_s, _ = cpu_oracle_setup(args.tex)
-        host_threads(oracle)
-        tt, nn = 0.0, 0
-        cpu_oracle_step(oracle, bvh, hs, p, keep, args.ref_window, np.arange(args.ref_spp))
-        for k in range(args.cpu_baseline_steps):
-            dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, args.ref_window, np.arange(k * args.ref_spp, (k + 1) * args.ref_spp))
-            tt += dt; nn += n
-        cpu_baseline = {"value": nn / tt / 1e6, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                        "sample": "%d steps of a %dx%d central window x %d spp x %d bounces of the same scene (%d ray-bounces, %.1f s); CPU BVH build %.1f s excluded"
-                                  % (args.cpu_baseline_steps, args.ref_window, args.ref_window, args.ref_spp, DEPTH, nn, tt, build_s)}
+        if have_ref:
+            try:
+                r = ref_bench.run('cpu', args.tex, args.cpu_baseline_window, args.ref_spp, args.cpu_baseline_steps, 0)
+                cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                                "sample": "%d steps (%.1f s): %s" % (args.cpu_baseline_steps, r["seconds"], r["sample"])}
+            except Exception as exc:
+                cpu_baseline = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        if cpu_baseline is None or "unavailable" in cpu_baseline:
+            oracle, bvh, hs, p, keep, build_s, _ = cpu_oracle_setup(args.tex)
+            host_threads(oracle)
+            tt, nn = 0.0, 0
+            cpu_oracle_step(oracle, bvh, hs, p, keep, 128, np.arange(8))
+            for k in range(8):
+                dt, n = cpu_oracle_step(oracle, bvh, hs, p, keep, 128, np.arange(k * 8, (k + 1) * 8))
+                tt += dt; nn += n
+            cpu_baseline = {"value": nn / tt / 1e6, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                            "sample": "%d steps of a %dx%d central window x %d spp x %d bounces of the same scene (%d ray-bounces, %.1f s); CPU BVH build %.1f s excluded"
+                                      % (8, 128, 128, 8, DEPTH, nn, tt, build_s)}
 
     # ---- the steps after the path, timed on this frame: informational, not part of `value` ----------------
     post = None
@@ -476,13 +518,6 @@ def main():
                                           "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 issues at half the bf16 rate)"}},
                 "tonemap": {"ms": tone_ms, "what": "drp_tonemap: accumulator -> /spp, flipud, AgX LUT, sRGB, alpha, RGBA8",
                             "gbs": RES * RES * (64 + 4) / (tone_ms * 1e-3) / 1e9}}
-
-    torch_baseline = None
-    if world == 1 and not args.no_torch_baseline:
-        try:
-            torch_baseline = gpu_torch_baseline(scene, camkw, dev, args)
-        except Exception as exc:  # a baseline must never take the product's line down
-            torch_baseline = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,

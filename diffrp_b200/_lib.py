@@ -30,6 +30,8 @@ def _declare(L):
     L.drp_render.argtypes = [u64, C.POINTER(_abi.Scene), C.POINTER(_abi.RenderParams), vp, vp]
     L.drp_finalize.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.drp_render_stats.argtypes = [u64, C.POINTER(_abi.RenderStats)]
+    L.drp_status.argtypes = [u64]
+    L.drp_debug_set_stack_limit.argtypes = [u64, i32]
     L.drp_flatten.argtypes = [C.POINTER(_abi.Object), i32] + [vp] * 13
     L.drp_set_profiling.argtypes = [u64, C.c_int]
     L.drp_get_profile.argtypes = [u64, C.POINTER(_abi.Profile)]

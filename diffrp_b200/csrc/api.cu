@@ -10,7 +10,6 @@
 #include "lbvh.cuh"
 #include "traverse.cuh"
 #include "cwbvh.cuh"
-#include "trace_kernels.cuh"
 #include <cstdlib>
 #include <chrono>
 
@@ -92,20 +91,6 @@ __global__ void __launch_bounds__(256) k_refit(LbvhBuild b) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < b.n) lbvh_refit(b, j, [](int* p) { return atomicAdd(p, 1); }, []() { __threadfence(); });
 }
-__global__ void __launch_bounds__(256) k_emit(LbvhBuild b, float* sah) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b.n < 2) {
-        if (i == 0) { lbvh_emit_tiny(b); *sah = 1.0f; }
-        return;
-    }
-    if (i < b.n - 1) lbvh_emit(b, i);
-    if (i == 0) *sah = b.box_lo[0].w / fmaxf(b.box_hi[0].w, 1e-30f);
-}
-__global__ void __launch_bounds__(256) k_pack(LbvhBuild b) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < b.n) lbvh_pack_tri(b, j);
-}
-
 __global__ void k_cw_init(CwBuild cw) {
     cw.counters[0] = 1;  // root allocated
     cw.counters[1] = 0;
@@ -158,28 +143,28 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
             pool_ready[device] = true;
         }
     }
-    static const bool timing = getenv("DRP_BUILD_TIMING") != nullptr;
+    const bool timing = g_drp_log_level >= 4;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     BvhHandle* h = new BvhHandle();
     h->device = device;
     h->n_tris = n_tris;
     h->n_nodes = n > 1 ? n - 1 : 1;
-    const char* layout_env = getenv("DRP_LAYOUT");  // "bvh2" selects the binary layout (kept for A/B profiling)
-    h->wide = !(layout_env && strcmp(layout_env, "bvh2") == 0);
+    h->stack_cap = CW_STACK;
 
     LbvhBuild b;
     memset(&b, 0, sizeof(b));
-    b.verts = verts; b.tris = tris; b.n = n; b.max_leaf = h->wide ? CW_MAX_LEAF : DRP_MAX_LEAF;
+    b.verts = verts; b.tris = tris; b.n = n; b.max_leaf = CW_MAX_LEAF;
     uint64_t* keys_in = nullptr; uint32_t* vals_in = nullptr; void* sort_tmp = nullptr;
     size_t sort_bytes = 0;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * (h->wide ? CW_NODE_F4 : 4) * (size_t)h->n_nodes, s));
+    DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * CW_NODE_F4 * (size_t)h->n_nodes, s));
     DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->packed, sizeof(float4) * 3 * nn, s));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
     DRP_CUDA_CHECK(cudaMalloc((void**)&h->sah, sizeof(float)));
-    DRP_CUDA_CHECK(cudaMalloc((void**)&h->dev_flags, sizeof(int) * 4));
-    DRP_CUDA_CHECK(cudaMemsetAsync(h->dev_flags, 0, sizeof(int) * 4, s));
+    DRP_CUDA_CHECK(cudaHostAlloc((void**)&h->sticky_host, sizeof(int), cudaHostAllocMapped));
+    *h->sticky_host = 0;
+    DRP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->sticky_dev, h->sticky_host, 0));
     b.bounds = h->bounds; b.nodes = h->nodes; b.packed = h->packed;
     DRP_CUDA_CHECK(alloc_async(&b.prim_lo, nn, s));
     DRP_CUDA_CHECK(alloc_async(&b.prim_hi, nn, s));
@@ -197,11 +182,9 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     DRP_CUDA_CHECK(alloc_async(&b.arrive, nn, s));
     DRP_CUDA_CHECK(alloc_async(&b.collapsed, nn, s));
     DRP_CUDA_CHECK(alloc_async(&b.count, 2 * nn, s));
-    static const bool greedy = getenv("DRP_COLLAPSE") && strcmp(getenv("DRP_COLLAPSE"), "greedy") == 0;  // A/B switch; default = optimal (DP)
-    if (h->wide && !greedy) {
-        DRP_CUDA_CHECK(alloc_async(&b.dp_cost, 16 * nn, s));
-        DRP_CUDA_CHECK(alloc_async(&b.dp_dec, 16 * nn, s));
-    }
+    // optimal (DP) collapse tables; the greedy collapse measured 2 % slower traversal and 40 % more nodes (profiles/README.md)
+    DRP_CUDA_CHECK(alloc_async(&b.dp_cost, 16 * nn, s));
+    DRP_CUDA_CHECK(alloc_async(&b.dp_dec, 16 * nn, s));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.arrive, 0, sizeof(int) * nn, s));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.collapsed, 0, nn, s));
 
@@ -222,12 +205,9 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
             k_karras<<<G, T, 0, s>>>(b);
             k_refit<<<G, T, 0, s>>>(b);
         }
-        if (!h->wide) k_pack<<<G, T, 0, s>>>(b);
     }
     int* cw_work = nullptr; int* cw_counters = nullptr;
-    if (!h->wide) {
-        k_emit<<<G, T, 0, s>>>(b, h->sah);
-    } else {
+    {
         CwBuild cw;
         cw.b = b;
         cw.cw_nodes = h->nodes; cw.cw_tris = h->packed; cw.capacity = (int)h->n_nodes;
@@ -282,7 +262,7 @@ extern "C" int drp_release(uint64_t handle) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     drp_free_workspace(h);
-    cudaFreeAsync(h->nodes, 0); cudaFreeAsync(h->packed, 0); cudaFree(h->bounds); cudaFree(h->sah); cudaFree(h->dev_flags);
+    cudaFreeAsync(h->nodes, 0); cudaFreeAsync(h->packed, 0); cudaFree(h->bounds); cudaFree(h->sah); cudaFreeHost(h->sticky_host);
     delete h;
     return DRP_OK;
 }
@@ -308,7 +288,7 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
     DRP_CUDA_CHECK(cudaMemcpy(ob, h->bounds, sizeof(ob), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 6; ++k) out->bounds[k] = ord2f(ob[k]);
     DRP_CUDA_CHECK(cudaMemcpy(&out->sah_cost, h->sah, sizeof(float), cudaMemcpyDeviceToHost));
-    if (h->wide) {
+    {
         const int64_t used = h->n_nodes_used;
         std::vector<float4> nodes((size_t)used * CW_NODE_F4);
         DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
@@ -327,40 +307,14 @@ extern "C" int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out) {
             uint32_t imask = f2u(p[0].w) >> 24;
             int base = f2i(p[1].x), rank = 0;
             for (int sl = 0; sl < 8; ++sl) {
-#if DRP_CW_V2
                 const bool leaf = cw_slot_kind(p, sl) > 0;
-#else
-                const uint32_t m[2] = {f2u(p[1].z), f2u(p[1].w)};
-                const bool leaf = ((m[sl / 4] >> (8 * (sl % 4))) & 0xffu) != 0;
-#endif
                 if (imask & (1u << sl)) st.push_back({base + rank++, depth + 1});
                 else if (leaf) ++leaves;
             }
         }
         out->n_leaves = leaves;
         out->max_depth = md;
-        return DRP_OK;
     }
-    // walk the emitted nodes on the host for leaf count / depth (debug-only path)
-    std::vector<float4> nodes((size_t)h->n_nodes * 4);
-    DRP_CUDA_CHECK(cudaMemcpy(nodes.data(), h->nodes, sizeof(float4) * nodes.size(), cudaMemcpyDeviceToHost));
-    std::vector<std::pair<int, int>> stack;
-    stack.push_back({0, 1});
-    int64_t leaves = 0, live_nodes = 0;
-    int max_depth = 0;
-    while (!stack.empty()) {
-        auto [node, depth] = stack.back();
-        stack.pop_back();
-        if (depth > max_depth) max_depth = depth;
-        if (node < 0) { ++leaves; continue; }
-        ++live_nodes;
-        float4 n3 = nodes[(size_t)node * 4 + 3];
-        stack.push_back({f2i(n3.x), depth + 1});
-        stack.push_back({f2i(n3.y), depth + 1});
-    }
-    out->n_leaves = leaves;
-    out->n_nodes = live_nodes;
-    out->max_depth = max_depth;
     return DRP_OK;
 }
 
@@ -376,10 +330,8 @@ extern "C" int drp_trace(uint64_t handle, const float* rays_o, const float* rays
     if (n_rays == 0) return DRP_OK;
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_trace: cannot select device"); return DRP_ERR_CUDA; }
-    static const bool simple = getenv("DRP_EXTEND") && strcmp(getenv("DRP_EXTEND"), "simple") == 0;  // A/B profiling switch
-    if (h->wide && !simple) return drp_trace_wide_persistent(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream);
-    DRP_CUDA_CHECK(launch_trace_aos(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream));
-    return DRP_OK;
+    if (int rc = drp_check_sticky(h, "drp_trace")) return rc;
+    return drp_trace_wide_persistent(h, rays_o, rays_d, out_t, out_i, t_far, n_rays, (cudaStream_t)stream);
 }
 
 __global__ void __launch_bounds__(128) k_bruteforce(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t n_tris,

@@ -429,6 +429,17 @@ static ConvDeviceState* conv_device_state() {
 
 }  // namespace
 
+// Tile / stage overrides for tools/tune_conv.py: compiled in only with -DDRP_EXPERIMENTAL (DRP_NVCC_EXTRA); the shipped library reads no
+// environment variable.
+static inline const char* tune_env(const char* name) {
+#ifdef DRP_EXPERIMENTAL
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
 extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     if (!pp) { drp_set_error("drp_conv3x3: params is NULL"); return DRP_ERR_INVALID; }
     const drp_conv3x3_params_t p = *pp;
@@ -452,13 +463,13 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     const bool wide_ok = p.cout_pad <= 128 && p.cout_pad > 16;
     const bool persist16 = wide_ok && tiles16 > 148 && tiles16 <= 320;              // 1-2 waves of 16-row tiles: persistent kernel (see below)
     int tr = wide_ok && (tiles16 >= 2 * 148 || persist16) ? 16 : 8;                  // per-layer sweep: tools/tune_conv.py
-    if (const char* e = getenv("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
+    if (const char* e = tune_env("DRP_CONV_ROWS")) { const int v = atoi(e); if (v == 8 || (v == 16 && p.cout_pad <= 128)) tr = v; }
     // input channels per k-step: 16 (64-byte rows, SWIZZLE_64B) or 32 (128-byte rows, SWIZZLE_128B: half the k-steps, stages twice as big).
     // Per-layer A/B (tools/tune_conv.py, TUNE_KC=1): 32 only pays on the latency-bound sub-wave grids of the deep levels (20.8 -> 18.4 us);
     // on the wide layers the bigger stages cost co-resident CTAs (82 -> 108 us, 90 -> 125 us), so 16 stays the default there.
     const int64_t tiles8 = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + 7) / 8);
     int kch = p.cin % 32 == 0 && tiles8 <= 148 ? 32 : 16;
-    if (const char* e = getenv("DRP_CONV_KC")) { const int v = atoi(e); if (v == 16 || (v == 32 && p.cin % 32 == 0)) kch = v; }
+    if (const char* e = tune_env("DRP_CONV_KC")) { const int v = atoi(e); if (v == 16 || (v == 32 && p.cin % 32 == 0)) kch = v; }
     const CUtensorMapSwizzle in_swizzle = kch == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap map_a, map_b;
     {   // activations: (C, W, H) fp32 view of the channel slice, box (kch, 16, tr + 2), zero fill outside = padding 1
@@ -513,7 +524,7 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     // main loops; grids below two waves are latency-bound and want every stage they can get; the 16-channel output layer is store-bound
     const int64_t n_tiles = (int64_t)((p.width + TILE_W - 1) / TILE_W) * ((p.height + tr - 1) / tr);
     size_t budget = n_tiles < 2 * 148 ? 100 * 1024 : p.cout_pad <= 16 ? 24 * 1024 : 48 * 1024;
-    if (const char* e = getenv("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+    if (const char* e = tune_env("DRP_CONV_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, budget / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.k_steps));
     // persistent variant (one CTA per SM, double-buffered TMEM accumulator).  Per-layer A/B (tools/tune_conv.py, TUNE_PERSISTENT=1): it wins
@@ -521,12 +532,12 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
     // group per SM is slower than 3-4 co-resident one-tile CTAs (full-resolution layers: 137 -> 210 us, 62 -> 142 us), so those keep the
     // one-tile kernel.
     bool persistent = tr == 16 && n_tiles > 148 && n_tiles <= 320 && 2 * acc_cols <= 512;
-    if (const char* e = getenv("DRP_CONV_PERSISTENT")) persistent = atoi(e) != 0 && 2 * acc_cols <= 512;
+    if (const char* e = tune_env("DRP_CONV_PERSISTENT")) persistent = atoi(e) != 0 && 2 * acc_cols <= 512;
     if (persistent) {
         const int pacc = 2 * acc_cols;
         a.tmem_cols = pacc <= 32 ? 32 : pacc <= 64 ? 64 : pacc <= 128 ? 128 : pacc <= 256 ? 256 : 512;
         size_t pbudget = 190 * 1024 - 16 * 1024;
-        if (const char* e = getenv("DRP_CONV_SMEM_KB")) pbudget = (size_t)atoi(e) * 1024;
+        if (const char* e = tune_env("DRP_CONV_SMEM_KB")) pbudget = (size_t)atoi(e) * 1024;
         a.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(2, pbudget / stage_bytes));
         const size_t psmem = 1024 + 16 * 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 4) * sizeof(uint64_t) + 16;
         if (psmem <= 220 * 1024) {

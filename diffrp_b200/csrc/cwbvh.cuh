@@ -10,10 +10,7 @@
 //   n0 = (p.x, p.y, p.z, bits{ex, ey, ez, imask})          origin of the local grid, per-axis exponent bytes (IEEE-biased, see
 //                                                           cw_pack_exponents), mask of the slots that hold internal children
 //   n1 = (child_base, tri_base, V, 0)                       first child node / first triangle; V = valid-triangle mask, bit 3*slot+k set
-//                                                           iff leaf slot `slot` holds a k-th triangle (node format 2, the default)
-//      = (child_base, tri_base, meta[0..3], meta[4..7])     node format 1 (DRP_CW_V2=0): per-slot meta byte, 0 = empty; internal child:
-//                                                           0b001'11sss (low 5 bits = 24 + slot); leaf child: unary triangle count (1..3)
-//                                                           in the top 3 bits, offset of its first triangle from tri_base in the low 5
+//                                                           iff leaf slot `slot` holds a k-th triangle
 //   n2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
 //   n3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
 //   n4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
@@ -26,33 +23,17 @@
 #include "lbvh.cuh"
 #include "traverse.cuh"
 
-// A/B-measured on B200 (profiles/README.md): packing <= 4 children into slots 0..3 and skipping the empty half LOSES ~1-3 %
-// (worse front-to-back order, extra divergent branch), so it is off.
-#ifndef DRP_CW_HALFSKIP
-#define DRP_CW_HALFSKIP 0
-#endif
-// Node format 2 (DRP_CW_V2, default): n1 = (child_base, tri_base, V, 0) with V = the valid-triangle mask of the node, bit 3*slot+k set
-// iff leaf slot `slot` holds a k-th triangle.  The per-slot meta bytes are gone: the box test leaves one hit bit per slot
-// (sign bit of cmax - cmin funnel-shifted into a byte: 1 ALU-pipe op per slot instead of 6), and the per-node expansion of
-// that byte -- internal children permuted into traversal priority (slot ^ octant), leaf children spread to 3 bits per
-// slot and masked with V -- is two table lookups (shared memory in k_extend_cw, arithmetic elsewhere).  Triangles of a node
-// are stored compactly in slot order, so triangle bit j is triangle tri_base + popc(V & ((1 << j) - 1)).
-// Why: ncu shows the traversal bound by the ALU pipe (PRMT / FMNMX / SHF / LOP3 at one warp instruction per two cycles) with
-// the FMA pipe half idle; format 1 spends ~52 of its ~170 ALU-pipe instructions per node visit on building the hit mask.
-#ifndef DRP_CW_V2
-#define DRP_CW_V2 1
-#endif
-// DRP_CW_NODE96 (A/B switch, off): nodes padded to 96 bytes (6 x float4, the last one unused) so that a node is three
-// 32-byte-aligned 256-bit loads (ld.global.nc.v8.f32 -> LDG.E.ENL2.256, sm_100+; CWK_LD256 in wavefront.cu) instead of five
-// 128-bit ones.  tools/ld_probe.cu (divergent record fetches, B200): 96 vs 77 G records/s from a 19-23 MB array, but 166 vs 235
-// when the array is L1-resident; in the traversal itself (config 3, extend ms per launch): 80 B + 5 x LDG.128 1.237,
-// 96 B + 5 x LDG.128 1.254, 96 B + 3 x LDG.256 1.264 -- the wider loads do not pay for the 20 % larger node array.
-#ifndef DRP_CW_NODE96
-#define DRP_CW_NODE96 0
-#endif
-#define CW_NODE_F4 (DRP_CW_NODE96 ? 6 : 5)
+// Node format ("format 2" in profiles/README.md; the per-slot meta-byte format 1, the 96-byte / 256-bit-load variant and the half-skip
+// packing all lost their A/Bs on B200 and were removed): n1 = (child_base, tri_base, V, 0) with V = the valid-triangle mask of the
+// node.  The box test leaves one hit bit per slot (sign bit of cmax - cmin funnel-shifted into a byte: 1 ALU-pipe op per slot), and the
+// per-node expansion of that byte -- internal children permuted into traversal priority (slot ^ octant), leaf children spread to 3 bits
+// per slot and masked with V -- is two table lookups (shared memory in k_extend_cw, arithmetic elsewhere).  Triangles of a node are
+// stored compactly in slot order, so triangle bit j is triangle tri_base + popc(V & ((1 << j) - 1)).
+#define DRP_CW_V2 1   // (tests/hostsim keys on it)
+#define CW_NODE_F4 5
 #define CW_MAX_LEAF 3
-#define CW_STACK 48
+#define CW_STACK 48       // per-thread entries of the fast path; deeper rays are re-traced by k_extend_fixup with CW_DEEP_STACK entries
+#define CW_DEEP_STACK 256
 #define CW_SLACK 4.76837158203125e-07f  // 2^-21: relative widening of every slab distance
 #define CW_GRID_SLACK 0.0079f           // + this many grid steps: 256 * 2^-21 (FMA cancellation) + 2^-8 (bias folding, x2 margin)
 
@@ -81,20 +62,12 @@ DRP_HD int cw_leaf_gather(const LbvhBuild& b, int c, int* out) {
 }
 
 // Per-axis grid exponents (|e| <= 100) are stored as IEEE-biased bytes (e + 127) in n0.w bits 0..23, so that the scale 2^e of an
-// axis is one shift and one mask away (DRP_CW_BIASED_EXP=0: two's-complement bytes, 3-4 instructions per axis to decode).
-#ifndef DRP_CW_BIASED_EXP
-#define DRP_CW_BIASED_EXP 1
-#endif
+// axis is one shift and one mask away.
 DRP_HD uint32_t cw_pack_exponents(int ex, int ey, int ez) {
-    const int bias = DRP_CW_BIASED_EXP ? 127 : 0;
-    return ((uint32_t)(ex + bias) & 0xffu) | (((uint32_t)(ey + bias) & 0xffu) << 8) | (((uint32_t)(ez + bias) & 0xffu) << 16);
+    return ((uint32_t)(ex + 127) & 0xffu) | (((uint32_t)(ey + 127) & 0xffu) << 8) | (((uint32_t)(ez + 127) & 0xffu) << 16);
 }
 DRP_HD float cw_axis_scale(uint32_t ebits, int axis) {  // 2^e of axis 0..2
-#if DRP_CW_BIASED_EXP
     return u2f(axis == 0 ? (ebits << 23) & 0x7f800000u : (axis == 1 ? (ebits << 15) & 0x7f800000u : (ebits << 7) & 0x7f800000u));
-#else
-    return i2f(((int)(int8_t)((ebits >> (8 * axis)) & 0xffu) + 127) << 23);
-#endif
 }
 DRP_HD uint32_t cw_pack4(const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
 
@@ -160,19 +133,7 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         float cz = 0.5f * (lo[j][2] + hi[j][2]) - 0.5f * (nlo[2] + nhi[2]);
         for (int s = 0; s < 8; ++s) cost[j][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
     }
-    // Nodes with <= 4 children use slots 0..3 only (ordered by the y/z octant bits), so the traversal can skip the empty
-    // half -- unless x is the axis along which the children are spread most, where losing the x ordering would cost more.
-    int n_slots = 8;
-    if (DRP_CW_HALFSKIP && k <= 4) {
-        float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
-        for (int j = 0; j < k; ++j)
-            for (int a = 0; a < 3; ++a) {
-                float cc = lo[j][a] + hi[j][a];
-                mn[a] = fminf(mn[a], cc); mx[a] = fmaxf(mx[a], cc);
-            }
-        float sx = mx[0] - mn[0], sy = mx[1] - mn[1], sz = mx[2] - mn[2];
-        if (!(sx > sy && sx > sz)) n_slots = 4;
-    }
+    const int n_slots = 8;
     int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     bool child_done[8] = {false, false, false, false, false, false, false, false};
     for (int it = 0; it < k; ++it) {
@@ -198,13 +159,12 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         scale[a] = i2f((ea + 127) << 23);
         inv_scale[a] = i2f((127 - ea) << 23);
     }
-    uint32_t meta[8], q[6][8];
+    uint32_t q[6][8];
     uint32_t imask = 0, vmask = 0;
     int n_inner = 0, n_tris = 0;
     for (int s = 0; s < 8; ++s) {
         int j = slot_child[s];
         if (j < 0) {
-            meta[s] = 0;
             for (int a = 0; a < 3; ++a) { q[a][s] = 255; q[3 + a][s] = 0; }
             continue;
         }
@@ -217,11 +177,9 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         int c = child[j];
         if (cw_is_leaf_child(b, c)) {
             int cnt = cw_leaf_count(b, c);
-            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)n_tris;
             vmask |= ((1u << cnt) - 1u) << (3 * s);
             n_tris += cnt;
         } else {
-            meta[s] = (1u << 5) | (24u + (uint32_t)s);
             imask |= 1u << s;
             ++n_inner;
         }
@@ -250,15 +208,9 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         }
     }
     float4* o = cw.cw_nodes + CW_NODE_F4 * (int64_t)ni;
-    if (CW_NODE_F4 > 5) o[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]) | (imask << 24);
     o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
-#if DRP_CW_V2
     o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(vmask), u2f(0u));
-#else
-    (void)vmask;
-    o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(cw_pack4(meta)), u2f(cw_pack4(meta + 4)));
-#endif
     o[2] = make_float4(u2f(cw_pack4(q[0])), u2f(cw_pack4(q[0] + 4)), u2f(cw_pack4(q[1])), u2f(cw_pack4(q[1] + 4)));
     o[3] = make_float4(u2f(cw_pack4(q[2])), u2f(cw_pack4(q[2] + 4)), u2f(cw_pack4(q[3])), u2f(cw_pack4(q[3] + 4)));
     o[4] = make_float4(u2f(cw_pack4(q[4])), u2f(cw_pack4(q[4] + 4)), u2f(cw_pack4(q[5])), u2f(cw_pack4(q[5] + 4)));
@@ -287,28 +239,14 @@ DRP_HD void cw_emit_tiny(const CwBuild& cw) {
     }
     uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]);
     o[0] = make_float4(lo.x, lo.y, lo.z, u2f(ebits));
-#if DRP_CW_V2
     o[1] = make_float4(i2f(0), i2f(0), u2f(meta0 ? 1u : 0u), u2f(0u));
-#else
-    o[1] = make_float4(i2f(0), i2f(0), u2f(meta0), u2f(0u));
-#endif
     const uint32_t lo_q = 0xffffff00u, hi_q = 0x000000ffu;  // slot 0 spans the grid, slots 1..7 are empty (lo 255 > hi 0)
     o[2] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(lo_q), u2f(0xffffffffu));
     o[3] = make_float4(u2f(lo_q), u2f(0xffffffffu), u2f(hi_q), u2f(0u));
     o[4] = make_float4(u2f(hi_q), u2f(0u), u2f(hi_q), u2f(0u));
-    if (CW_NODE_F4 > 5) o[5] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---- traversal ----------------------------------------------------------------------------------------------------
-DRP_HD uint32_t cw_sign_extend_s8x4(uint32_t x) {
-#ifdef __CUDA_ARCH__
-    uint32_t r;  // prmt with selector bit 3 set replicates the sign bit of the selected byte (__byte_perm masks that bit off)
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0x0000ba98u));
-    return r;
-#else
-    return ((x & 0x80u) ? 0xffu : 0u) | ((x & 0x8000u) ? 0xff00u : 0u) | ((x & 0x800000u) ? 0xff0000u : 0u) | ((x & 0x80000000u) ? 0xff000000u : 0u);
-#endif
-}
 // Byte i of x as the float 32768 + byte, without an I2F (quarter-rate XU pipe; 48 per node otherwise): one PRMT drops the
 // byte into mantissa bits 8..15 of 2^15.  The 32768 is folded into the FMA's addend (cw_node_hits), whose rounding then
 // costs at most 2^-9 of a grid step -- covered by the conservative slack.
@@ -348,7 +286,6 @@ DRP_HD CwRay cw_make_ray(Vec3 o, Vec3 d, uint32_t bias = 0x47000000u) {
     return r;
 }
 
-#if DRP_CW_V2
 // slot s of node p: -1 = internal child, 0 = empty, n > 0 = leaf with n triangles (statistics / tests)
 DRP_HD int cw_slot_kind(const float4* p, int s) {
     if ((f2u(p[0].w) >> 24) & (1u << s)) return -1;
@@ -408,55 +345,24 @@ DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n2, float4 n3, fl
     }
     return ~miss & 0xffu;
 }
-#else
-// intersect the 8 quantised child boxes of one node; returns the hit mask (internal children in bits 24..31 at their
-// traversal priority, triangles of leaf children in bits 0..23)
-DRP_HD uint32_t cw_node_hits(const CwRay& r, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4, float t_cull) {
-    const uint32_t ebits = f2u(n0.w);
-    const float ax = cw_axis_scale(ebits, 0) * r.idir.x, ay = cw_axis_scale(ebits, 1) * r.idir.y, az = cw_axis_scale(ebits, 2) * r.idir.z;
-    const float ox = (n0.x - r.o.x) * r.idir.x, oy = (n0.y - r.o.y) * r.idir.y, oz = (n0.z - r.o.z) * r.idir.z;
-    // conservative widening: the FMA form cancels, its error is relative to |origin term| + |grid term|
-    const float sx = CW_SLACK * fabsf(ox) + CW_GRID_SLACK * fabsf(ax), sy = CW_SLACK * fabsf(oy) + CW_GRID_SLACK * fabsf(ay),
-                sz = CW_SLACK * fabsf(oz) + CW_GRID_SLACK * fabsf(az);
-    // addends with the byte bias folded in: t = (32768 + q) * a + (o -+ slack - 32768 a)
-    const float bx = ox - CW_BIAS * ax, by = oy - CW_BIAS * ay, bz = oz - CW_BIAS * az;
-    const float oxl = bx - sx, oxh = bx + sx, oyl = by - sy, oyh = by + sy, ozl = bz - sz, ozh = bz + sz;
-    uint32_t hitmask = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t meta4 = f2u(half ? n1.w : n1.z);
-#if DRP_CW_HALFSKIP
-        if (half && meta4 == 0u) break;  // slots 4..7 empty: the builder packs nodes with <= 4 children into slots 0..3
-#endif
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = cw_sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlx = f2u(half ? n2.y : n2.x), qly = f2u(half ? n2.w : n2.z), qlz = f2u(half ? n3.y : n3.x);
-        const uint32_t qhx = f2u(half ? n3.w : n3.z), qhy = f2u(half ? n4.y : n4.x), qhz = f2u(half ? n4.w : n4.z);
-        const uint32_t nx = r.idir.x < 0.0f ? qhx : qlx, fx = r.idir.x < 0.0f ? qlx : qhx;
-        const uint32_t ny = r.idir.y < 0.0f ? qhy : qly, fy = r.idir.y < 0.0f ? qly : qhy;
-        const uint32_t nz = r.idir.z < 0.0f ? qhz : qlz, fz = r.idir.z < 0.0f ? qlz : qhz;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float tnx = cw_byte_biased(nx, i, r.bias) * ax + oxl, tny = cw_byte_biased(ny, i, r.bias) * ay + oyl, tnz = cw_byte_biased(nz, i, r.bias) * az + ozl;
-            float tfx = cw_byte_biased(fx, i, r.bias) * ax + oxh, tfy = cw_byte_biased(fy, i, r.bias) * ay + oyh, tfz = cw_byte_biased(fz, i, r.bias) * az + ozh;
-            float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-            float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t_cull));
-            if (cmin <= cmax) hitmask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
-        }
-    }
-    return hitmask;
-}
-
-#endif
-
-#if DRP_CW_V2
-DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
-                           bool& overflow) {
+// One ray over the wide layout with a caller-supplied stack of `cap` (node group | postponed triangle group) entries.  The closest hit
+// does not depend on the visiting order; `overflow` is set when an entry had to be dropped (the result is then not trustworthy).
+struct CwPairStack {     // two private arrays (registers / local memory)
+    uint32_t *x, *y;
+    DRP_HD void put(int i, uint32_t a, uint32_t b) const { x[i] = a; y[i] = b; }
+    DRP_HD void get(int i, uint32_t& a, uint32_t& b) const { a = x[i]; b = y[i]; }
+};
+struct CwStridedStack {  // entry i of this thread at base[i * stride]: [entry][thread] in global memory, coalesced across a warp
+    uint2* base;
+    int64_t stride;
+    DRP_HD void put(int i, uint32_t a, uint32_t b) const { uint2 v; v.x = a; v.y = b; base[i * stride] = v; }
+    DRP_HD void get(int i, uint32_t& a, uint32_t& b) const { const uint2 v = base[i * stride]; a = v.x; b = v.y; }
+};
+template <typename Stack>
+DRP_HD RayHit cw_trace_one_stack(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
+                                 const Stack st, int cap, bool& overflow) {
     const CwRay r = cw_make_ray(o, d);
     const uint32_t octinv = r.octinv4 & 0xffu;
-    uint32_t st_x[CW_STACK], st_y[CW_STACK];
     int sp = 0;
     float t_best = t_far;
     int id_best = 0x7fffffff;
@@ -469,7 +375,7 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
             const uint32_t base = ng_x;
             ng_y &= ~(1u << child_bit);
             if (ng_y > 0x00ffffffu) {
-                if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
+                if (sp < cap) { st.put(sp, ng_x, ng_y); ++sp; }
                 else overflow = true;
             }
             const uint32_t slot = (uint32_t)(child_bit - 24) ^ octinv;
@@ -498,7 +404,7 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
         if (ng_y <= 0x00ffffffu) {
             if (sp == 0) break;
             --sp;
-            ng_x = st_x[sp]; ng_y = st_y[sp];
+            st.get(sp, ng_x, ng_y);
         }
     }
     RayHit h;
@@ -507,55 +413,8 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
     h.id = hit ? id_best : 0;
     return h;
 }
-#else
 DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __restrict__ tris, Vec3 o, Vec3 d, float t_far, float eps,
                            bool& overflow) {
-    const CwRay r = cw_make_ray(o, d);
     uint32_t st_x[CW_STACK], st_y[CW_STACK];
-    int sp = 0;
-    float t_best = t_far;
-    int id_best = 0x7fffffff;
-    uint32_t ng_x = 0, ng_y = 0x80000000u;  // node group: (child base, hits in bits 24..31 | imask in bits 0..7); starts at the root
-    uint32_t tg_x = 0, tg_y = 0;            // triangle group: (triangle base, pending triangle bits)
-    for (;;) {
-        if (ng_y > 0x00ffffffu) {
-            const uint32_t hits = ng_y;
-            const int child_bit = cw_bfind(hits);
-            const uint32_t base = ng_x;
-            ng_y &= ~(1u << child_bit);
-            if (ng_y > 0x00ffffffu) {
-                if (sp < CW_STACK) { st_x[sp] = ng_x; st_y[sp] = ng_y; ++sp; }
-                else overflow = true;
-            }
-            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
-            const uint32_t rel = (uint32_t)cw_popc(hits & ~(0xffffffffu << slot));
-            const float4* p = nodes + CW_NODE_F4 * (int64_t)(base + rel);
-            const float4 n0 = ldg(p), n1 = ldg(p + 1), n2 = ldg(p + 2), n3 = ldg(p + 3), n4 = ldg(p + 4);
-            DRP_COUNT_NODE();
-            const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
-            ng_x = f2u(n1.x);
-            ng_y = (hitmask & 0xff000000u) | (f2u(n0.w) >> 24);
-            tg_x = f2u(n1.y);
-            tg_y = hitmask & 0x00ffffffu;
-        } else {
-            tg_x = ng_x; tg_y = ng_y;
-            ng_x = 0; ng_y = 0;
-        }
-        while (tg_y != 0) {
-            const int ti = cw_bfind(tg_y);
-            tg_y &= ~(1u << ti);
-            leaf_intersect(tris, (int)tg_x + ti, 1, r.o, r.d, eps, t_best, id_best);
-        }
-        if (ng_y <= 0x00ffffffu) {
-            if (sp == 0) break;
-            --sp;
-            ng_x = st_x[sp]; ng_y = st_y[sp];
-        }
-    }
-    RayHit h;
-    const bool hit = t_best < t_far;
-    h.t = hit ? t_best : t_far;
-    h.id = hit ? id_best : 0;
-    return h;
+    return cw_trace_one_stack(nodes, tris, o, d, t_far, eps, CwPairStack{st_x, st_y}, CW_STACK, overflow);
 }
-#endif

@@ -13,12 +13,13 @@ struct BvhHandle {
     int64_t n_nodes = 0;       // allocated
     int64_t n_nodes_used = 0;  // wide layout: nodes actually emitted
     float eps = 1e-8f;          // |det| threshold of the triangle test (raycaster_epsilon)
-    int wide = 1;               // 1: compressed 8-wide layout (cwbvh.cuh, 5 float4 / node); 0: binary layout (lbvh.cuh, 4 float4 / node)
-    float4* nodes = nullptr;    // (n_nodes, wide ? 5 : 4)
+    float4* nodes = nullptr;    // (n_nodes, 5): compressed 8-wide layout (cwbvh.cuh)
     float4* packed = nullptr;   // (n_tris, 3) triangles in leaf order
     uint32_t* bounds = nullptr; // (12) ordered-uint scene bounds (device)
     float* sah = nullptr;       // device: root cost / root area
-    int* dev_flags = nullptr;   // device: [0] traversal stack overflow count
+    int* sticky_host = nullptr; // host-mapped failure flag (see drp_check_sticky): rays that outgrew even the deep traversal stack
+    int* sticky_dev = nullptr;  // device alias of sticky_host
+    int stack_cap = 0;          // per-thread stack entries of the fast traversal path (CW_STACK; lowered only by drp_debug_set_stack_limit)
     RenderWorkspace* ws = nullptr;
     drp_render_stats_t last_render = {0, 0, 0};
 };
@@ -26,6 +27,7 @@ struct BvhHandle {
 void drp_set_error(const std::string& msg);
 BvhHandle* drp_lookup(uint64_t handle);
 void drp_free_workspace(BvhHandle* h);
+int drp_check_sticky(BvhHandle* h, const char* who);
 int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, float* out_t, int32_t* out_i, float t_far, int64_t n, cudaStream_t s);
 extern int g_drp_log_level;
 

@@ -4,13 +4,13 @@
 // (diffrp/rendering/path_tracing.py:250-279, 310-352).  Per batch of samples and per bounce, two persistent kernels:
 //   k_extend_cw : closest hit for every live ray over the compressed 8-wide BVH (cwbvh.cuh): one ray per lane, dynamic ray
 //                 fetch by warp ballot, triangle postponing; bounce 0 generates the primary ray from the ray index instead
-//                 of reading it; writes (t, id).  (k_extend: the simple one-warp-batch kernel, kept for the binary layout.)
+//                 of reading it; writes (t, id).  k_extend_fixup re-traces the (rare) rays that outgrew the per-thread stack.
 //   k_shade     : surface attributes + env lookup + BRDF sample + fp32 accumulation (RED.ADD.F32x4) + next ray, appended to
 //                 the output queue through a warp-aggregated atomic (stream compaction fused into the shade kernel)
 // Ray state lives in HBM as float4 SoA queues (coalesced 128-bit accesses):
 //   q_a[k] = (o.x, o.y, o.z, d.x)   q_b[k] = (d.y, d.z, bits(ray index), 0)   q_t[k] = (T.r, T.g, T.b, 0)   hit[k] = (t, bits(id))
-// Compile-time / environment switches exist for every design alternative that was measured (see profiles/README.md and
-// drp_build_config()); the defaults are the fastest measured configuration.
+// No environment variable changes what these kernels do; the design alternatives that were measured and lost are recorded in
+// profiles/README.md and no longer exist in the source.  Scheduling constants (CWK_*) can be overridden at compile time only.
 #include <vector>
 #include <algorithm>
 #include <string>
@@ -23,6 +23,7 @@
 #include "traverse.cuh"
 #include "cwbvh.cuh"
 #include "shade.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 #define WF_BLOCK 128
 #ifndef WF_FETCH
@@ -33,20 +34,18 @@ struct RenderWorkspace {
     int64_t capacity = 0;  // rays
     float4 *qa[2] = {nullptr, nullptr}, *qb[2] = {nullptr, nullptr}, *qt[2] = {nullptr, nullptr};
     float2* hit = nullptr;
-    int* hit_list = nullptr;   // queue slots of the rays that hit / missed in the last extend (partitioned shading)
-    int* miss_list = nullptr;
-    int* counters = nullptr;  // [0..D] live counts per bounce, [64..64+2D) fetch cursors
+    int* ovf_list = nullptr;   // queue slots of the rays whose traversal outgrew the per-thread stack (k_extend_fixup)
+    uint2* deep_stack = nullptr;
+    int* counters = nullptr;  // [0..D] live counts per bounce, [64..64+2D) fetch cursors, [192..192+D) flagged-ray counts
     int n_counters = 0;
     drp_material_t* d_mats = nullptr;
     int mats_capacity = 0;
     std::vector<unsigned char> mats_host_copy;
     unsigned long long* d_traced = nullptr;  // device: live rays traced by the last call (sum over batches and bounces)
     int sm_count = 0;
-    int grid_extend[2] = {0, 0}, grid_shade[2] = {0, 0};
+    int grid_extend[2] = {0, 0}, grid_shade[2] = {0, 0};  // [1]: bounce 0 (primary) kernels
     bool have_box = false;
     float box_lo[3], box_hi[3];
-    cudaStream_t streams[2] = {nullptr, nullptr};  // DRP_OVERLAP: one internal stream per ray group
-    cudaEvent_t sync_events[4] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing (drp_set_profiling)
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int kind; int bounce; unsigned long long* traced_slot; };
@@ -76,13 +75,11 @@ struct WfConst {
     float eps;
     int HW;             // pixels rendered per sample (the tile's pixel count when tile sharding)
     int tx0, ty0, tw;   // tile origin and width (tw == frame width, origin 0 for a full frame)
-    int tiled8x4;       // primary rays enumerated in 8x4 pixel blocks (rectangle width % 8 == 0 and height % 4 == 0)
     int sample_minor;   // > 0: primary rays enumerated pixel-major / sample-minor with this many samples per batch (see load_ray)
     int64_t R;          // rays in this batch
     int64_t R_total;    // rays of the whole call (replay indexing)
     int64_t ray_base;   // index (within the call) of this launch group's first ray: s_local * HW + pixel of queue slot 0 at bounce 0
     float* accum;
-    int* flags;
     uint32_t cw_bias;   // 0x47000000 (cwbvh.cuh: cw_byte_biased), passed through the constant bank
 };
 
@@ -90,22 +87,14 @@ template <bool PRIMARY>
 __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restrict__ qa, const float4* __restrict__ qb, int k, Vec3& o,
                                          Vec3& d, int& ray_index) {
     if (PRIMARY) {
-        // Queue slot -> (sample, pixel).  Scanline order by default; DRP_PRIMARY_ORDER=tiled enumerates 8x4-pixel blocks so that a
-        // warp starts on a compact screen tile instead of a 32x1 strip (measured: no gain, see drp_render).
+        // Queue slot -> (sample, pixel): sample-major, or pixel-major / sample-minor within the batch (sample_minor > 0).
         // The ray index (RNG key, replay index, accumulator row) is the reference's s * HW + y * W + x either way.
         const int kk = k + (int)c.ray_base;
         int s = kk / c.HW;
         int pix = kk - s * c.HW;
         if (c.sample_minor > 0) {  // the samples of one pixel sit next to each other in the queue: they hit the same triangles / texels
-            const int j = kk - (int)c.ray_base;               // ray_base is a multiple of HW in this mode
-            pix = j / c.sample_minor;
-            s = (int)(c.ray_base / c.HW) + (j - pix * c.sample_minor);
-        }
-        if (c.tiled8x4) {
-            const int blocks_x = c.tw >> 3;
-            const int blk = pix >> 5, in = pix & 31;
-            const int by = blk / blocks_x, bx = blk - by * blocks_x;
-            pix = ((by << 2) + (in >> 3)) * c.tw + (bx << 3) + (in & 7);
+            pix = k / c.sample_minor;                          // ray_base is a multiple of HW in this mode
+            s = (int)(c.ray_base / c.HW) + (k - pix * c.sample_minor);
         }
         ray_index = s * c.HW + pix;
         int y = pix / c.tw, x = pix - y * c.tw;
@@ -121,32 +110,6 @@ __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restr
     }
 }
 
-template <bool PRIMARY, bool WIDE>
-__global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
-                                                     float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor) {
-    const int count = PRIMARY ? (int)c.R : *count_ptr;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-#pragma unroll 1
-        for (int j = 0; j < WF_FETCH; j += 32) {
-            int k = base + j + lane;
-            if (k < count) {
-                Vec3 o, d;
-                int ri;
-                load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
-                bool overflow = false;
-                RayHit h = WIDE ? cw_trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow) : trace_one(c.nodes, c.tris, o, d, c.p.t_far, c.eps, overflow);
-                hit[k] = make_float2(h.t, __int_as_float(h.id));
-                if (overflow) atomicAdd(&c.flags[0], 1);
-            }
-        }
-    }
-}
-
 // ---- persistent-thread extend over the wide layout -----------------------------------------------------------------
 // Every lane owns one ray and walks the 8-wide hierarchy with the (node group, triangle group) state of cwbvh.cuh.
 //  * dynamic ray fetch (Aila & Laine 2009 / Ylitie et al. 2017): a lane whose ray terminated does not wait for the slowest
@@ -156,12 +119,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 //  * triangle postponing: a triangle group is pushed back on the stack when fewer than CWK_POSTPONE of the warp's active
 //    lanes have triangles to test, so that the warp stays in the node phase.
 // Scheduling only: the closest hit found is the exhaustive one whatever the order (min t, then min id).
-#ifndef CWK_SMEM_STACK
-#define CWK_SMEM_STACK 0
-#endif
-#ifndef CWK_PREFETCH
-#define CWK_PREFETCH 0
-#endif
+// Every alternative that was measured and lost (shared-memory stack, L1 prefetch of the next child, warp-shared triangle tests, triangle
+// lookahead, 96-byte nodes / 256-bit loads, extend-side hit/miss partition, two-stream overlap) is recorded in profiles/README.md and
+// was removed from the source.
 #ifndef CWK_CHUNK
 #define CWK_CHUNK 64   // B200 sweep (profiles/README.md): 32-128 within 1 %, 256 -4 %, 1024 -35 %
 #endif
@@ -171,27 +131,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_extend(const __grid_constant__ WfC
 #ifndef CWK_NW
 #define CWK_NW 8
 #endif
-#ifndef CWK_LD256
-#define CWK_LD256 1   // node fetch by 256-bit loads (needs the 96-byte node stride, DRP_CW_NODE96)
-#endif
-__device__ __forceinline__ void cw_ld256(const float4* p, float4& a, float4& b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-}
-#ifndef CWK_TRI_PIPE
-#define CWK_TRI_PIPE 0   // triangle records requested one test ahead: written after the round's GPU budget was spent, not measured yet
-#endif
-#ifndef CWK_LUT
-#define CWK_LUT 1     // node format 2: hit-byte expansion by shared-memory tables (1), arithmetic (0), tables for primary rays only (2)
-#endif
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
-#ifndef CWK_SHARE
-#define CWK_SHARE 0   // warp-shared triangle tests (see the triangle phase of k_extend_cw).  A/B on B200 (config 3, extend ms per step):
-                      // per-lane loop 5.31, shared through shuffles + __fns 7.00, shared through shared memory 5.90 (56 registers, spills) /
-                      // 5.54 vs 5.38 at 64 registers: the triangle phase does run at ~6 of 32 lanes (22 % of the issue slots), but dealing
-                      // the tests out costs as much as it saves
-#endif
 #endif
 
 #define SRC_QUEUE 0    // rays from the float4 queues, result to hit[]
@@ -203,30 +144,49 @@ struct AosRays {
     float* out_t;
     int32_t* out_i;
 };
-// optional hit / miss partition of the finished rays (queue slots), consumed by k_shade<., SHADE_HITS / SHADE_MISSES>
-struct Partition {
-    int* hit_list;
-    int* miss_list;
-    int* hit_count;
-    int* miss_count;
+// Rays whose traversal needed more than `stack_cap` stack entries (deep, degenerate hierarchies): their queue slots are appended to `list`
+// (at most WF_OVF_CAP of them; *count keeps counting) and their result is written with the sentinel id WF_OVF_ID; k_extend_fixup, launched
+// right behind every extend, re-traces exactly those rays with CW_DEEP_STACK entries each and overwrites the result.
+#define WF_OVF_CAP (1 << 20)
+#define WF_OVF_ID (-2)
+struct Overflow {
+    int* count;
+    int* list;
+    int stack_cap;   // <= CW_STACK; smaller values only through drp_debug_set_stack_limit (tests)
 };
 
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
 #endif
-#ifndef DRP_SHADE_CHUNK_PARTITION
-#define DRP_SHADE_CHUNK_PARTITION 0   // not measured yet (written after the GPU budget of the round was spent): see k_shade
-#endif
-#ifndef DRP_SHADE_PIPELINE
-#define DRP_SHADE_PIPELINE 0   // software-pipelined hit / index loads: B200 A/B shade 2.07 -> 2.22 ms per step (slower: the kernel is bound by DRAM throughput on random sectors, not by the per-ray latency chain)
-#endif
 #ifndef DRP_SHADE_MINBLOCKS
 #define DRP_SHADE_MINBLOCKS 6   // B200 A/B with the interleaved texels (shade ms per step): 4 -> 2.30, 5 -> 2.12, 6 -> 2.04 (80 registers)
 #endif
-template <int SRC, bool PART>
+
+template <int SRC>
+__device__ __forceinline__ void fetch_ray(const WfConst& c, const float4* __restrict__ qa, const float4* __restrict__ qb, const AosRays& aos, int k,
+                                          Vec3& o, Vec3& d) {
+    if (SRC == SRC_AOS) {
+        o = v3(__ldg(aos.ro + 3 * (int64_t)k), __ldg(aos.ro + 3 * (int64_t)k + 1), __ldg(aos.ro + 3 * (int64_t)k + 2));
+        d = v3(__ldg(aos.rd + 3 * (int64_t)k), __ldg(aos.rd + 3 * (int64_t)k + 1), __ldg(aos.rd + 3 * (int64_t)k + 2));
+    } else {
+        int ri;
+        load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
+    }
+}
+template <int SRC>
+__device__ __forceinline__ void store_hit(float2* __restrict__ hit, const AosRays& aos, int k, float t, int id) {
+    if (SRC == SRC_AOS) {
+        aos.out_t[k] = t;
+        aos.out_i[k] = id;
+    } else {
+        hit[k] = make_float2(t, __int_as_float(id));
+    }
+}
+
+template <int SRC>
 __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
                                                         float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos,
-                                                        Partition part) {
+                                                        Overflow ovf) {
     const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -237,20 +197,10 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     float t_best = 0.0f;
     int id_best = 0, sp = 0;
     uint32_t ng_x = 0, ng_y = 0, tg_x = 0, tg_y = 0;
-    // Traversal stack.  CWK_SMEM_STACK > 0 keeps the first entries of every thread in shared memory ([entry][thread],
-    // conflict-free 64-bit accesses) and spills deeper ones to local memory.  A/B on B200 (profiles/README.md): the
-    // all-local stack (L1-resident, no extra branch per push/pop) is ~5 % FASTER than 8 shared entries, so the default is 0.
-#if CWK_SMEM_STACK > 0
-    __shared__ uint2 s_stack[CWK_SMEM_STACK][WF_BLOCK];
-    const int tid = threadIdx.x;
-#endif
-    uint32_t st_x[CW_STACK - CWK_SMEM_STACK], st_y[CW_STACK - CWK_SMEM_STACK];
-    bool overflow = false;
-#if DRP_CW_V2
-#if CWK_SHARE
-#error "CWK_SHARE is implemented for node format 1 only (DRP_CW_V2=0)"
-#endif
-    // node format 2: the two expansions of the per-slot hit byte as tables (cwbvh.cuh: cw_perm8, cw_spread3x7)
+    // Traversal stack: all in local memory (L1-resident; 8 entries per thread in shared memory were 5 % slower, profiles/README.md)
+    uint32_t st_x[CW_STACK], st_y[CW_STACK];
+    bool overflow = false;              // this lane's current ray dropped a stack entry
+    // the two expansions of the per-slot hit byte as tables (cwbvh.cuh: cw_perm8, cw_spread3x7); arithmetic instead: +4 %
     __shared__ uint8_t s_perm[8 * 256];
     __shared__ uint32_t s_spread[256];
     for (int e = threadIdx.x; e < 8 * 256; e += WF_BLOCK) s_perm[e] = (uint8_t)cw_perm8((uint32_t)e & 0xffu, (uint32_t)e >> 8);
@@ -258,35 +208,12 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     __syncthreads();
     uint32_t tri_base = 0, tri_valid = 0;  // of the node the current triangle group belongs to
     uint32_t oct_row = 0;                  // octinv << 8: this ray's row of s_perm
-#endif
-#if CWK_SHARE
-    __shared__ uint32_t s_item[WF_BLOCK / 32][32];   // work items of the shared triangle phase: (packed triangle index << 5) | owner lane
-    __shared__ float2 s_res[WF_BLOCK / 32][32];      // (t, id) posted by the helper of each item
-    __shared__ float4 s_ray[WF_BLOCK / 32][32][2];   // origin / direction of every lane's current ray
-    const int wid = threadIdx.x >> 5;
-#endif
-#if CWK_SMEM_STACK == 0
-#define CWK_PUSH(X, Y)                                                 \
-    do {                                                               \
-        if (sp < CW_STACK) { st_x[sp] = (X); st_y[sp] = (Y); ++sp; }   \
-        else overflow = true;                                          \
+#define CWK_PUSH(X, Y)                                                     \
+    do {                                                                   \
+        if (sp < ovf.stack_cap) { st_x[sp] = (X); st_y[sp] = (Y); ++sp; }  \
+        else overflow = true;                                              \
     } while (0)
 #define CWK_POP(X, Y) do { --sp; (X) = st_x[sp]; (Y) = st_y[sp]; } while (0)
-#else
-#define CWK_PUSH(X, Y)                                                                   \
-    do {                                                                                 \
-        if (sp < CWK_SMEM_STACK) s_stack[sp][tid] = make_uint2((X), (Y));                \
-        else if (sp < CW_STACK) { st_x[sp - CWK_SMEM_STACK] = (X); st_y[sp - CWK_SMEM_STACK] = (Y); } \
-        else overflow = true;                                                            \
-        if (sp < CW_STACK) ++sp;                                                         \
-    } while (0)
-#define CWK_POP(X, Y)                                                                    \
-    do {                                                                                 \
-        --sp;                                                                            \
-        if (sp < CWK_SMEM_STACK) { uint2 _v = s_stack[sp][tid]; (X) = _v.x; (Y) = _v.y; } \
-        else { (X) = st_x[sp - CWK_SMEM_STACK]; (Y) = st_y[sp - CWK_SMEM_STACK]; }       \
-    } while (0)
-#endif
     for (;;) {
         // ---- refill idle lanes --------------------------------------------------------------------------------
         const unsigned need = __ballot_sync(0xffffffffu, k < 0);
@@ -313,21 +240,9 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
             }
             if (k >= 0 && (need >> lane & 1u)) {  // freshly assigned: load / generate the ray, reset the traversal state
                 Vec3 o, d;
-                int ri;
-                if (SRC == SRC_AOS) {
-                    o = v3(__ldg(aos.ro + 3 * (int64_t)k), __ldg(aos.ro + 3 * (int64_t)k + 1), __ldg(aos.ro + 3 * (int64_t)k + 2));
-                    d = v3(__ldg(aos.rd + 3 * (int64_t)k), __ldg(aos.rd + 3 * (int64_t)k + 1), __ldg(aos.rd + 3 * (int64_t)k + 2));
-                } else {
-                    load_ray<SRC == SRC_PRIMARY>(c, qa, qb, k, o, d, ri);
-                }
+                fetch_ray<SRC>(c, qa, qb, aos, k, o, d);
                 r = cw_make_ray(o, d, c.cw_bias);
-#if DRP_CW_V2
                 oct_row = (r.octinv4 & 0xffu) << 8;
-#endif
-#if CWK_SHARE
-                s_ray[wid][lane][0] = make_float4(o.x, o.y, o.z, 0.0f);
-                s_ray[wid][lane][1] = make_float4(d.x, d.y, d.z, 0.0f);
-#endif
                 t_best = c.p.t_far;
                 id_best = 0x7fffffff;
                 sp = 0;
@@ -349,173 +264,44 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
                     const uint32_t slot = (uint32_t)(child_bit - 24) ^ (r.octinv4 & 0xffu);
                     const uint32_t rel = __popc(hits & ~(0xffffffffu << slot));
                     const float4* p = c.nodes + CW_NODE_F4 * (int64_t)(base + rel);
-#if DRP_CW_NODE96 && CWK_LD256
-                    float4 n0, n1, n2, n3, n4;
-                    if (CWK_LD256 == 1 || SRC != SRC_PRIMARY) {  // CWK_LD256 == 2: incoherent rays only
-                        // three 256-bit loads (LDG.E.ENL2.256): 3 instead of 5 requests per lane through the L1 data pipe
-                        float4 pad;
-                        cw_ld256(p, n0, n1);
-                        cw_ld256(p + 2, n2, n3);
-                        cw_ld256(p + 4, n4, pad);
-                    } else {
-                        n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
-                    }
-#else
                     const float4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
-#endif
-#if DRP_CW_V2
                     const uint32_t hit8 = cw_node_hits(r, n0, n2, n3, n4, t_best * DRP_T_GROW);
                     const uint32_t imask = __float_as_uint(n0.w) >> 24;
                     ng_x = __float_as_uint(n1.x);
-                    const bool use_lut = CWK_LUT == 1 || (CWK_LUT == 2 && SRC == SRC_PRIMARY);
-                    ng_y = ((use_lut ? (uint32_t)s_perm[oct_row + (hit8 & imask)] : cw_perm8(hit8 & imask, oct_row >> 8)) << 24) | imask;
+                    ng_y = ((uint32_t)s_perm[oct_row + (hit8 & imask)] << 24) | imask;
                     tg_x = base + rel;  // a triangle group is (node index, pending bits): tri_base / V are re-read when it comes off the stack
                     tri_base = __float_as_uint(n1.y);
                     tri_valid = __float_as_uint(n1.z);
-                    tg_y = (use_lut ? s_spread[hit8 & ~imask] : cw_spread3x7(hit8 & ~imask)) & tri_valid;
-#else
-                    const uint32_t hitmask = cw_node_hits(r, n0, n1, n2, n3, n4, t_best * DRP_T_GROW);
-                    ng_x = __float_as_uint(n1.x);
-                    ng_y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
-                    tg_x = __float_as_uint(n1.y);
-                    tg_y = hitmask & 0x00ffffffu;
-#endif
-#if CWK_PREFETCH
-                    if (ng_y > 0x00ffffffu) {  // the child visited next is already known: pull its two cache lines towards L1 while triangles are tested
-                        const uint32_t nslot = (uint32_t)(31 - __clz(ng_y) - 24) ^ (r.octinv4 & 0xffu);
-                        const float4* np = c.nodes + CW_NODE_F4 * (int64_t)(ng_x + __popc(ng_y & ~(0xffffffffu << nslot)));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 4));
-                    }
-#endif
+                    tg_y = s_spread[hit8 & ~imask] & tri_valid;
                 } else {
                     tg_x = ng_x; tg_y = ng_y;  // a postponed triangle group came off the stack
                     ng_x = 0; ng_y = 0;
-#if DRP_CW_V2
                     const float4 m1 = __ldg(c.nodes + CW_NODE_F4 * (int64_t)tg_x + 1);
                     tri_base = __float_as_uint(m1.y);
                     tri_valid = __float_as_uint(m1.z);
-#endif
                 }
-#if CWK_SHARE
-                {   // ---- triangle phase, work-shared across the warp --------------------------------------------------------------
-                    // Only ~1/3 of the traversing lanes hold pending triangles at any time and a lane holds up to several (every triangle of
-                    // each hit leaf child), so a per-lane loop runs its Moller-Trumbore tests at ~10 of 32 lanes for several rounds.  Instead
-                    // the pending (ray, triangle) pairs of all lanes are dealt out as work items through shared memory: up to three per owner
-                    // and round, item i to the i-th traversing lane; a helper reads the owner's ray (staged in shared memory when the ray was
-                    // fetched), tests one triangle and posts (t, id); the owner merges its results with the (t, id) order of leaf_intersect,
-                    // so the outcome does not depend on who tested what.
-                    const unsigned act = __activemask();
-                    const int nact = __popc(act);
-                    const int hr = __popc(act & lt_mask);                            // my rank among the traversing lanes = my item slot
-                    for (;;) {
-                        unsigned have = __ballot_sync(act, tg_y != 0);
-                        if (!have) break;
-                        if ((float)__popc(have) < CWK_POSTPONE * (float)nact) {   // too few lanes have triangles: postpone (lanes with stack room)
-                            if (tg_y != 0 && sp < CW_STACK) { CWK_PUSH(tg_x, tg_y); tg_y = 0; }
-                            have = __ballot_sync(act, tg_y != 0);
-                            if (!have) break;
-                        }
-                        uint32_t m = tg_y;
-                        int t0 = -1, t1 = -1, t2 = -1;
-                        if (m) { t0 = 31 - __clz(m); m &= ~(1u << t0); }
-                        if (m) { t1 = 31 - __clz(m); m &= ~(1u << t1); }
-                        if (m) { t2 = 31 - __clz(m); }
-                        unsigned b1 = __ballot_sync(act, t1 >= 0), b2 = __ballot_sync(act, t2 >= 0);
-                        const int n0 = __popc(have);
-                        int n1 = __popc(b1), n2 = __popc(b2);
-                        if (n0 + n1 + n2 > nact) { b2 = 0; n2 = 0; if (n0 + n1 > nact) { b1 = 0; n1 = 0; } }   // more items than helpers: next round
-                        const bool i0 = t0 >= 0, i1 = (b1 >> lane) & 1u, i2 = (b2 >> lane) & 1u;
-                        const int p0 = __popc(have & lt_mask), p1 = n0 + __popc(b1 & lt_mask), p2 = n0 + n1 + __popc(b2 & lt_mask);
-                        if (i0) s_item[wid][p0] = ((tg_x + (uint32_t)t0) << 5) | (uint32_t)lane;
-                        if (i1) s_item[wid][p1] = ((tg_x + (uint32_t)t1) << 5) | (uint32_t)lane;
-                        if (i2) s_item[wid][p2] = ((tg_x + (uint32_t)t2) << 5) | (uint32_t)lane;
-                        __syncwarp(act);
-                        if (hr < n0 + n1 + n2) {
-                            const uint32_t it = s_item[wid][hr];
-                            const float4 ro = s_ray[wid][it & 31u][0], rd = s_ray[wid][it & 31u][1];
-                            float ht = c.p.t_far;
-                            int hid = 0x7fffffff;
-                            leaf_intersect(c.tris, (int)(it >> 5), 1, v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), c.eps, ht, hid);
-                            s_res[wid][hr] = make_float2(ht, __int_as_float(hid));
-                        }
-                        __syncwarp(act);
-                        if (i0) { const float2 q = s_res[wid][p0]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t0); }
-                        if (i1) { const float2 q = s_res[wid][p1]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t1); }
-                        if (i2) { const float2 q = s_res[wid][p2]; const int qi = __float_as_int(q.y); if (q.x < t_best || (q.x == t_best && qi < id_best)) { t_best = q.x; id_best = qi; } tg_y &= ~(1u << t2); }
-                    }
-                }
-#elif CWK_TRI_PIPE && DRP_CW_V2
-                // Experiment for the next measurement round (profiles/README.md section 2, per-instruction view: 8.8 % of the stall samples of the
-                // secondary-bounce kernel wait for the triangle record): the record of the next pending triangle is requested before the
-                // current one is tested.  Same tests, same (t, id) order, same postponing rule.
-                {
-                    const int total_active = __popc(__activemask());
-                    if (tg_y != 0) {
-                        if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
-                            CWK_PUSH(tg_x, tg_y);  // postpone: too few lanes have triangles
-                        } else {
-                            int ti = 31 - __clz(tg_y);
-                            tg_y &= ~(1u << ti);
-                            const float4* tp = c.tris + 3 * (int64_t)cw_tri_index(tri_base, tri_valid, ti);
-                            float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-                            for (;;) {
-                                bool more = tg_y != 0;
-                                float4 na = ta, nb = tb, nc = tc;
-                                if (more) {
-                                    if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
-                                        CWK_PUSH(tg_x, tg_y);
-                                        more = false;
-                                    } else {
-                                        ti = 31 - __clz(tg_y);
-                                        tg_y &= ~(1u << ti);
-                                        tp = c.tris + 3 * (int64_t)cw_tri_index(tri_base, tri_valid, ti);
-                                        na = __ldg(tp); nb = __ldg(tp + 1); nc = __ldg(tp + 2);
-                                    }
-                                }
-                                leaf_update(ta, tb, tc, r.o, r.d, c.eps, t_best, id_best);
-                                if (!more) break;
-                                ta = na; tb = nb; tc = nc;
-                            }
-                        }
-                    }
-                }
-#else
                 const int total_active = __popc(__activemask());
                 while (tg_y != 0) {
-                    if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < CW_STACK) {
+                    if ((float)__popc(__activemask()) < CWK_POSTPONE * (float)total_active && sp < ovf.stack_cap) {
                         CWK_PUSH(tg_x, tg_y);  // postpone: too few lanes have triangles
                         break;
                     }
                     const int ti = 31 - __clz(tg_y);
                     tg_y &= ~(1u << ti);
-#if DRP_CW_V2
                     leaf_intersect(c.tris, cw_tri_index(tri_base, tri_valid, ti), 1, r.o, r.d, c.eps, t_best, id_best);
-#else
-                    leaf_intersect(c.tris, (int)tg_x + ti, 1, r.o, r.d, c.eps, t_best, id_best);
-#endif
                 }
-#endif
                 if (ng_y <= 0x00ffffffu) {
                     if (sp > 0) {
                         CWK_POP(ng_x, ng_y);
                     } else {  // ray finished
                         const bool is_hit = t_best < c.p.t_far;
-                        if (SRC == SRC_AOS) {
-                            aos.out_t[k] = is_hit ? t_best : c.p.t_far;
-                            aos.out_i[k] = is_hit ? id_best : 0;
+                        if (overflow) {  // (rare) an entry was dropped: hand the ray to k_extend_fixup
+                            const int pos = atomicAdd(ovf.count, 1);
+                            if (pos < WF_OVF_CAP) ovf.list[pos] = k;
+                            store_hit<SRC>(hit, aos, k, c.p.t_far, WF_OVF_ID);
+                            overflow = false;
                         } else {
-                            hit[k] = make_float2(is_hit ? t_best : c.p.t_far, __int_as_float(is_hit ? id_best : 0));
-                            if (PART) {  // warp-aggregated append of this iteration's finished rays to the hit / miss lists
-                                const unsigned fin = __activemask();
-                                const unsigned hm = __ballot_sync(fin, is_hit), mm = fin & ~hm;
-                                const unsigned mine = is_hit ? hm : mm;
-                                const int leader = __ffs(mine) - 1;
-                                int pos = 0;
-                                if (lane == leader) pos = atomicAdd(is_hit ? part.hit_count : part.miss_count, __popc(mine));
-                                pos = __shfl_sync(mine, pos, leader);
-                                (is_hit ? part.hit_list : part.miss_list)[pos + __popc(mine & lt_mask)] = k;
-                            }
+                            store_hit<SRC>(hit, aos, k, is_hit ? t_best : c.p.t_far, is_hit ? id_best : 0);
                         }
                         k = -1;
                         break;
@@ -528,26 +314,57 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
             }
         }
     }
-    if (overflow) atomicAdd(&c.flags[0], 1);
+#undef CWK_PUSH
+#undef CWK_POP
+}
+
+// Re-trace of the rays k_extend_cw flagged (see Overflow): one ray per thread, stack of CW_DEEP_STACK entries per thread in global memory
+// ([entry][thread], coalesced).  The wide hierarchy is at most as deep as the binary one (<= 63 Morton + 27 index bits), a ray stacks at most one
+// node group per level, and nothing is postponed here, so CW_DEEP_STACK = 256 entries cannot run out; should it happen regardless, the handle's
+// sticky error flag is raised (host-mapped: every later call on the handle fails loudly).
+// When more than WF_OVF_CAP rays were flagged, the list is incomplete and the kernel scans all results for the sentinel instead.
+#define WF_FIXUP_BLOCKS 148
+template <int SRC>
+__global__ void __launch_bounds__(WF_BLOCK) k_extend_fixup(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
+                                                           float2* __restrict__ hit, const int* __restrict__ count_ptr, AosRays aos, Overflow ovf,
+                                                           uint2* __restrict__ deep_stack, int* __restrict__ sticky) {
+    const int n_ovf = *ovf.count;
+    if (n_ovf == 0) return;
+    const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
+    const bool scan = n_ovf > WF_OVF_CAP;
+    const int n_items = scan ? count : n_ovf;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    uint2* st = deep_stack + tid;
+    for (int item = tid; item < n_items; item += nthreads) {
+        int k = item;
+        if (scan) {
+            const int id = SRC == SRC_AOS ? aos.out_i[k] : __float_as_int(hit[k].y);
+            if (id != WF_OVF_ID) continue;
+        } else {
+            k = ovf.list[item];
+        }
+        Vec3 o, d;
+        fetch_ray<SRC>(c, qa, qb, aos, k, o, d);
+        bool overflow = false;
+        const RayHit h = cw_trace_one_stack(c.nodes, c.tris, o, d, c.p.t_far, c.eps, CwStridedStack{st, (int64_t)nthreads}, CW_DEEP_STACK, overflow);
+        store_hit<SRC>(hit, aos, k, h.t, h.id);
+        if (overflow) atomicAdd(sticky, 1);
+    }
 }
 
 __device__ __forceinline__ void accum_add4(float* p, float a, float b, float c, float d) {
     atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));  // RED.E.ADD.F32x4 (sm_90+)
 }
 
-// MODE: SHADE_ALL walks the queue itself (hits and misses mixed in one warp); SHADE_HITS / SHADE_MISSES walk the index lists the
-// extend kernel partitions finished rays into, so a warp runs either the surface + BRDF path or the environment path, not both
-// serialised (ncu: 14-16 of 32 lanes active on bounces >= 1 with the mixed kernel).
-#define SHADE_ALL 0
-#define SHADE_HITS 1
-#define SHADE_MISSES 2
-template <bool PRIMARY, int MODE>
+// One kernel per bounce walks the ray queue: hits (surface + BRDF) and misses (environment) share warps.  Measured alternatives that lost
+// and were removed (profiles/README.md section 3, profiles/r2/ab_tripipe_chunkpart_r2a.json): separate hit / miss kernels over index lists written
+// by the extend kernel (-5 %), hit-first / miss-second walk inside a warp's chunk (+-0), software-pipelined or prefetched loads (-3 ... -7 %).
+template <bool PRIMARY>
 __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WfConst c, int bounce, const float4* __restrict__ qa,
                                                     const float4* __restrict__ qb, const float4* __restrict__ qt, const float2* __restrict__ hit,
                                                     float4* __restrict__ oa, float4* __restrict__ ob, float4* __restrict__ ot,
-                                                    const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor,
-                                                    const int* __restrict__ index_list) {
-    const int count = (PRIMARY && MODE == SHADE_ALL) ? (int)c.R : *count_ptr;
+                                                    const int* __restrict__ count_ptr, int* __restrict__ out_count, int* __restrict__ cursor) {
+    const int count = PRIMARY ? (int)c.R : *count_ptr;
     const int lane = threadIdx.x & 31;
     const bool last = bounce == c.p.ray_depth - 1;
     const bool always_sky = last && c.p.last_bounce_skybox;  // path_tracing.py:260
@@ -556,119 +373,23 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
         if (lane == 0) base = atomicAdd(cursor, WF_FETCH);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
-#if DRP_SHADE_PIPELINE == 1
-        // Software pipeline over the chunk (SHADE_ALL): the kernel is bound by the dependent DRAM round trips of one ray
-        // (ray + hit record -> vertex indices / material id -> vertex records -> texels; ncu: long scoreboard ~10 warps per issue at
-        // 0.3 IPC).  The hit record is loaded two iterations and the index quadruple one iteration before use, and the next ray's
-        // queue entries are pulled towards L2, so that an iteration starts at the vertex fetch.
-        const float2 h_miss = make_float2(c.p.t_far, 0.0f);
-        float2 h_cur = h_miss, h_nxt = h_miss;
-        TriIdx idx_cur = {0, 0, 0, 0};
-        if (MODE == SHADE_ALL) {
-            if (base + lane < count) h_cur = __ldg(hit + base + lane);
-            if (base + 32 + lane < count) h_nxt = __ldg(hit + base + 32 + lane);
-            if (h_cur.x < c.p.t_far) idx_cur = load_tri_idx(c.scene, __float_as_int(h_cur.y));
-        }
-#endif
-#if DRP_SHADE_CHUNK_PARTITION
-#if DRP_SHADE_PIPELINE
-#error "DRP_SHADE_CHUNK_PARTITION reorders the rays of a chunk and cannot be combined with DRP_SHADE_PIPELINE"
-#endif
-        // Experiment for the next measurement round (ncu, profiles/README.md section 3: the secondary-bounce shade kernel executes at 13 of 32
-        // lanes because hits -- vertex / texel fetches + BRDF -- and misses -- environment lookup -- share warps).  The chunk of WF_FETCH rays a
-        // warp owns is classified with one ballot per 32 rays and then walked class by class: lane l of iteration i takes the (32 i + l)-th
-        // hit, later the (32 i' + l)-th miss, so that a warp runs one of the two code paths with (nearly) all lanes.  Rays stay inside their
-        // chunk (no global lists, no indirection through memory: the extend-side partition of DRP_PARTITION lost to its finish-ordered reads).
-        constexpr int NQ = WF_FETCH / 32;
-        const bool part_chunk = !PRIMARY && MODE == SHADE_ALL;
-        unsigned cls_hit[NQ], cls_miss[NQ];
-        int n_hit = 0, n_miss = 0;
-        if (part_chunk) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const int sl = base + 32 * q + lane;
-                const bool valid = sl < count;
-                const bool ish = valid && __ldg(hit + sl).x < c.p.t_far;
-                cls_hit[q] = __ballot_sync(0xffffffffu, ish);
-                cls_miss[q] = __ballot_sync(0xffffffffu, valid && !ish);
-                n_hit += __popc(cls_hit[q]);
-                n_miss += __popc(cls_miss[q]);
-            }
-        }
-        const int it_hit = (n_hit + 31) >> 5, it_all = part_chunk ? it_hit + ((n_miss + 31) >> 5) : NQ;
-#pragma unroll 1
-        for (int it = 0; it < it_all; ++it) {
-            const int j = 32 * it;
-            int slot = base + j + lane;
-            if (part_chunk) {
-                const bool hit_phase = it < it_hit;
-                int rank = (hit_phase ? it : it - it_hit) * 32 + lane;
-                slot = count;  // no ray for this lane
-                if (rank < (hit_phase ? n_hit : n_miss)) {
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const unsigned m = hit_phase ? cls_hit[q] : cls_miss[q];
-                        const int cq = __popc(m);
-                        if (rank >= 0 && rank < cq) { slot = base + 32 * q + (int)__fns(m, 0, rank + 1); rank = -1; }
-                        else if (rank >= 0) rank -= cq;
-                    }
-                }
-            }
-#else
 #pragma unroll 1
         for (int j = 0; j < WF_FETCH; j += 32) {
-            const int slot = base + j + lane;
-#endif
+            const int k = base + j + lane;  // queue slot of the ray
             bool alive = false;
             Vec3 no = v3(0, 0, 0), nd = v3(0, 0, 0), T = v3(1, 1, 1);
             int ri = 0;
-#if DRP_SHADE_PIPELINE == 1
-            float2 h_n2 = h_miss;
-            TriIdx idx_nxt = {0, 0, 0, 0};
-            if (MODE == SHADE_ALL) {
-                if (j + 64 < WF_FETCH && slot + 64 < count) h_n2 = __ldg(hit + slot + 64);
-                if (j + 32 < WF_FETCH && h_nxt.x < c.p.t_far) idx_nxt = load_tri_idx(c.scene, __float_as_int(h_nxt.y));
-                if (!PRIMARY && j + 32 < WF_FETCH && slot + 32 < count) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qa + slot + 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qb + slot + 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qt + slot + 32));
-                }
-            }
-#endif
-#if DRP_SHADE_PIPELINE == 2
-            // prefetch-only variant: no carried registers, the next ray's index lines and queue entries are pulled towards L2
-            if (MODE == SHADE_ALL && j + 32 < WF_FETCH && slot + 32 < count) {
-                const float2 hn = __ldg(hit + slot + 32);
-                if (hn.x < c.p.t_far) {
-                    const int idn = __float_as_int(hn.y);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.scene.tris + 3 * (int64_t)idn));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.scene.tri_material + idn));
-                }
-                if (!PRIMARY) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qa + slot + 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qb + slot + 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qt + slot + 32));
-                }
-            }
-#endif
-            if (slot < count) {
-                const int k = MODE == SHADE_ALL ? slot : __ldg(index_list + slot);  // queue slot of the ray
+            if (k < count) {
                 Vec3 o, d;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
                 if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
-#if DRP_SHADE_PIPELINE == 1
-                float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : (MODE == SHADE_ALL ? h_cur : __ldg(hit + k));
-                const TriIdx* pre = MODE == SHADE_ALL ? &idx_cur : nullptr;
-#else
-                float2 h = MODE == SHADE_MISSES ? make_float2(c.p.t_far, 0.0f) : __ldg(hit + k);
-                const TriIdx* pre = nullptr;
-#endif
+                const float2 h = __ldg(hit + k);
                 const float t = h.x;
-                const bool is_hit = MODE == SHADE_HITS ? true : (MODE == SHADE_MISSES ? false : t < c.p.t_far);
+                const bool is_hit = t < c.p.t_far;
                 SurfaceAttrs s;
                 if (is_hit) {
                     // last bounce of a path (not the first): only emission and alpha reach the outputs, skip the rest of the material
-                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y), !PRIMARY && last, pre);
+                    s = surface_attrs(c.scene, c.scene.materials, o + d * t, __float_as_int(h.y), !PRIMARY && last, nullptr);
                 } else {
                     s.albedo = s.normal = s.emission = v3(0, 0, 0);
                     s.metal = s.smooth = s.alpha = 0.0f;
@@ -706,9 +427,6 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                     if (c.p.compaction && !is_hit) alive = ray_may_reach_box(no, nd, c.box_lo, c.box_hi);
                 }
             }
-#if DRP_SHADE_PIPELINE == 1
-            h_cur = h_nxt; h_nxt = h_n2; idx_cur = idx_nxt;
-#endif
             // warp-aggregated append to the output queue
             unsigned m = __ballot_sync(0xffffffffu, alive);
             if (m) {
@@ -785,23 +503,26 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
         cudaDeviceProp prop;
         DRP_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
         h->ws->sm_count = prop.multiProcessorCount;
-        h->ws->n_counters = 1024;  // two launch groups x (64 live counts, 128 fetch cursors, 4 x 64 partition counters / cursors)
+        h->ws->n_counters = 1024;  // [0,64) live counts per bounce, [64,192) fetch cursors, [192,256) flagged-ray counts per bounce, [1020] / [1021] drp_trace
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->counters, sizeof(int) * 1024));
         DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->d_traced, sizeof(unsigned long long)));
         int nb = 0;
-        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY, false>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_PRIMARY>, WF_BLOCK, 0));
         h->ws->grid_extend[1] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(h->wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_QUEUE, false>, WF_BLOCK, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_cw<SRC_QUEUE>, WF_BLOCK, 0));
         h->ws->grid_extend[0] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true, SHADE_ALL>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true>, WF_BLOCK, 0));
         h->ws->grid_shade[1] = std::max(1, nb) * h->ws->sm_count;
-        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<false, SHADE_ALL>, WF_BLOCK, 0));
+        DRP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<false>, WF_BLOCK, 0));
         h->ws->grid_shade[0] = std::max(1, nb) * h->ws->sm_count;
+        // deep-traversal fix-up (k_extend_fixup): list of flagged rays + one CW_DEEP_STACK-entry stack per fix-up thread (39 MB)
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->ovf_list, sizeof(int) * WF_OVF_CAP));
+        DRP_CUDA_CHECK(cudaMalloc((void**)&h->ws->deep_stack, sizeof(uint2) * (size_t)CW_DEEP_STACK * WF_FIXUP_BLOCKS * WF_BLOCK));
     }
     RenderWorkspace* ws = h->ws;
     if (rays > 0 && rays > ws->capacity) {
         for (int k = 0; k < 2; ++k) { cudaFree(ws->qa[k]); cudaFree(ws->qb[k]); cudaFree(ws->qt[k]); }
-        cudaFree(ws->hit); cudaFree(ws->hit_list); cudaFree(ws->miss_list);
+        cudaFree(ws->hit);
         ws->capacity = 0;
         for (int k = 0; k < 2; ++k) {
             DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qa[k], sizeof(float4) * rays));
@@ -809,8 +530,6 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
             DRP_CUDA_CHECK(cudaMalloc((void**)&ws->qt[k], sizeof(float4) * rays));
         }
         DRP_CUDA_CHECK(cudaMalloc((void**)&ws->hit, sizeof(float2) * rays));
-        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->hit_list, sizeof(int) * rays));
-        DRP_CUDA_CHECK(cudaMalloc((void**)&ws->miss_list, sizeof(int) * rays));
         ws->capacity = rays;
     }
     if (n_mats > ws->mats_capacity) {
@@ -825,10 +544,27 @@ static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
 #define WF_MAX_BATCH_RAYS (int64_t(1) << 24)  // 16M rays per internal batch (~1.9 GB of queues)
 #define WF_MAX_DEPTH 60
 
+// Sticky failure flag of a handle (host-mapped, written by k_extend_fixup when even the deep stack ran out): checked, without a
+// synchronisation, at the start of every call on the handle and by drp_status().
+int drp_check_sticky(BvhHandle* h, const char* who) {
+    if (h->sticky_host && *(volatile int*)h->sticky_host != 0) {
+        drp_set_error(std::string(who) + ": an earlier traversal on this handle ran out of its " + std::to_string(CW_DEEP_STACK) +
+                      "-entry deep stack (" + std::to_string(*(volatile int*)h->sticky_host) + " rays): results of that call are invalid");
+        return DRP_ERR_INVALID;
+    }
+    return DRP_OK;
+}
+
+struct NvtxRange {   // host-side ranges for nsys / ncu --nvtx: drp_render > batch > bounce (free when no tool is attached)
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_render_params_t* params, float* accum, void* stream) {
     BvhHandle* h = drp_lookup(handle);
     if (!h) { drp_set_error("drp_render: unknown handle"); return DRP_ERR_HANDLE; }
     if (!scene || !params || !accum) { drp_set_error("drp_render: null argument"); return DRP_ERR_INVALID; }
+    if (int rc = drp_check_sticky(h, "drp_render")) return rc;
     const drp_render_params_t& p = *params;
     if (p.height <= 0 || p.width <= 0 || p.ray_depth <= 0 || p.ray_depth > WF_MAX_DEPTH || p.n_samples < 0) {
         drp_set_error("drp_render: bad resolution / depth / sample count");
@@ -855,31 +591,29 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     const int64_t HW = tiled ? (int64_t)p.tile_w * p.tile_h : (int64_t)p.height * p.width;
     if (HW > WF_MAX_BATCH_RAYS) { drp_set_error("drp_render: more than 2^24 pixels per frame not supported"); return DRP_ERR_INVALID; }
     if (p.n_samples == 0) return DRP_OK;
-    if (HW * p.n_samples >= (int64_t(1) << 31)) { drp_set_error("drp_render: more than 2^31 rays per call; render the samples in several calls"); return DRP_ERR_INVALID; }
+    if (HW * p.n_samples >= (int64_t(1) << 31)) {
+        // ray indices are 32-bit: render the samples in several passes (the native RNG is keyed by pixel and GLOBAL sample id, the jitter
+        // tables are per sample, so the split changes nothing but the accumulation order); the reference sections the same way
+        // (path_tracing.py:318-325)
+        if (p.rng_mode == DRP_RNG_REPLAY) { drp_set_error("drp_render: more than 2^31 rays per call in replay mode; render the samples in several calls"); return DRP_ERR_INVALID; }
+        const int per_pass = (int)std::max<int64_t>(1, ((int64_t(1) << 31) - 1) / HW);
+        int64_t launches = 0, nominal = 0;
+        for (int s0 = 0; s0 < p.n_samples; s0 += per_pass) {
+            drp_render_params_t q = p;
+            q.n_samples = std::min(per_pass, p.n_samples - s0);
+            q.jitter_x = p.jitter_x + s0; q.jitter_y = p.jitter_y + s0; q.sample_ids = p.sample_ids + s0;
+            if (int rc = drp_render(handle, scene, &q, accum, stream)) return rc;
+            launches += h->last_render.kernel_launches; nominal += h->last_render.rays_nominal;
+        }
+        h->last_render.kernel_launches = launches; h->last_render.rays_nominal = nominal;  // (rays_traced: last pass only)
+        return DRP_OK;
+    }
     DeviceGuard guard(h->device);
     if (!guard.ok) { drp_set_error("drp_render: cannot select device"); return DRP_ERR_CUDA; }
     cudaStream_t s = (cudaStream_t)stream;
-    // Experiment (DRP_L2_PERSIST_MB=<n>): pin the wide-node array in L2 (persisting access-policy window on the render stream) so that the
-    // texel / queue streams of k_shade do not evict the hierarchy between two extend launches.
-    static const int persist_mb = getenv("DRP_L2_PERSIST_MB") ? atoi(getenv("DRP_L2_PERSIST_MB")) : 0;
-    if (persist_mb > 0 && h->wide) {
-        static bool limit_set = false;
-        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20); limit_set = true; }
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        const size_t node_bytes = (size_t)h->n_nodes_used * 16 * CW_NODE_F4;
-        av.accessPolicyWindow.base_ptr = (void*)h->nodes;
-        av.accessPolicyWindow.num_bytes = node_bytes;
-        av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)((size_t)persist_mb << 20) / (double)std::max<size_t>(node_bytes, 1)));
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaError_t e = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-        static bool reported = false;
-        if (!reported) { fprintf(stderr, "[diffrp_b200] L2 persisting window: %zu bytes of nodes, %d MB set aside: %s\n", node_bytes, persist_mb, cudaGetErrorString(e)); reported = true; }
-        (void)cudaGetLastError();
-    }
+    NvtxRange range_call("drp_render");
     const int spb = p.reproducible ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(p.n_samples, WF_MAX_BATCH_RAYS / HW));  // samples per batch
-    int rc = ensure_workspace(h, (((int64_t)spb * HW + 1) / 2) * 2 + 64, scene->n_materials);
+    int rc = ensure_workspace(h, (int64_t)spb * HW + 64, scene->n_materials);
     if (rc != DRP_OK) return rc;
     RenderWorkspace* ws = h->ws;
     // material table -> device (skipped when unchanged since the previous call)
@@ -898,15 +632,8 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     c.eps = h->eps;
     c.HW = (int)HW;
     c.tx0 = tiled ? p.tile_x0 : 0; c.ty0 = tiled ? p.tile_y0 : 0; c.tw = tiled ? p.tile_w : p.width;
-    {
-        const int rect_h = tiled ? p.tile_h : p.height;
-        // A/B on B200: 8x4 blocks leave extend unchanged and make shade 5 % slower (accumulator RED rows less contiguous) -> off by default
-        static const bool blocks = getenv("DRP_PRIMARY_ORDER") && (strcmp(getenv("DRP_PRIMARY_ORDER"), "tiled") == 0 || strcmp(getenv("DRP_PRIMARY_ORDER"), "sample_tiled") == 0);
-        c.tiled8x4 = (blocks && c.tw % 8 == 0 && rect_h % 4 == 0) ? 1 : 0;
-    }
     c.R_total = HW * p.n_samples;
     c.accum = accum;
-    c.flags = h->dev_flags;
     c.cw_bias = 0x47000000u;
     if (!ws->have_box) {  // padded scene box for the exact compaction rule: one host read per handle, then cached
         uint32_t ob[12];
@@ -922,114 +649,61 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
     }
     for (int a = 0; a < 3; ++a) { c.box_lo[a] = ws->box_lo[a]; c.box_hi[a] = ws->box_hi[a]; }
     const int D = p.ray_depth;
-    static const bool simple_extend = getenv("DRP_EXTEND") && strcmp(getenv("DRP_EXTEND"), "simple") == 0;  // A/B profiling switch
     int64_t launches = 0;
     h->last_render.rays_nominal = HW * p.n_samples * D;
     DRP_CUDA_CHECK(cudaMemsetAsync(ws->d_traced, 0, sizeof(unsigned long long), s));
-    // Overlap (DRP_OVERLAP=1, experimental): every batch is split into two ray groups that run as independent kernel chains on two
-    // internal streams, the second one bounce-phase behind the first, with grids sized so that an (ALU-bound) extend kernel
-    // of one group and a (DRAM-latency-bound) shade kernel of the other are co-resident on every SM.
-    static const bool overlap_env = getenv("DRP_OVERLAP") && atoi(getenv("DRP_OVERLAP")) != 0;
-    static const int ovl_e = getenv("DRP_OVL_E") ? atoi(getenv("DRP_OVL_E")) : 5, ovl_s = getenv("DRP_OVL_S") ? atoi(getenv("DRP_OVL_S")) : 2;
-    const bool overlap = overlap_env && h->wide && !simple_extend;
-    // A/B on B200: partitioned shading is 5 % SLOWER on config 3 (shade 3.36 vs 3.04 ms / step: the indirect, finish-ordered ray reads cost
-    // more than the hit/miss divergence they remove) -> off unless DRP_PARTITION=1
-    static const bool partition_env = getenv("DRP_PARTITION") && atoi(getenv("DRP_PARTITION")) != 0;
-    const bool partition = partition_env && h->wide && !simple_extend;
-    if (overlap && !ws->streams[0]) {
-        for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamCreateWithFlags(&ws->streams[g], cudaStreamNonBlocking));
-        for (int g = 0; g < 4; ++g) DRP_CUDA_CHECK(cudaEventCreateWithFlags(&ws->sync_events[g], cudaEventDisableTiming));
-    }
     for (int s0 = 0; s0 < p.n_samples; s0 += spb) {
         const int ns = std::min(spb, p.n_samples - s0);
-        const int64_t R_batch = (int64_t)ns * HW;
-        const int G = (overlap && R_batch >= (1 << 18)) ? 2 : 1;
+        NvtxRange range_batch("batch");
         DRP_CUDA_CHECK(cudaMemsetAsync(ws->counters, 0, sizeof(int) * ws->n_counters, s));  // (a memset node, not counted as a kernel launch)
-        if (G == 2) {  // fork: both internal streams start after everything already queued on the caller's stream
-            DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[0], s));
-            for (int g = 0; g < 2; ++g) DRP_CUDA_CHECK(cudaStreamWaitEvent(ws->streams[g], ws->sync_events[0], 0));
-        }
+        c.R = (int64_t)ns * HW;
+        c.ray_base = (int64_t)s0 * HW;
+        // primary queue pixel-major / sample-minor: the samples of a pixel sit in adjacent lanes (A/B on config 3: 8.41 -> 7.57 ms per step;
+        // 8x4-pixel blocks on top of it: extend unchanged, shade 5 % slower -- removed)
+        c.sample_minor = ns > 1 ? ns : 0;
+        int* counts = ws->counters;         // [0..D]
+        int* cursors = ws->counters + 64;   // [0..2D)
+        float2* hit = ws->hit;
         for (int b = 0; b < D; ++b) {
-            for (int g = 0; g < G; ++g) {
-                cudaStream_t sg = G == 2 ? ws->streams[g] : s;
-                const int64_t r0 = R_batch * g / G, r1 = R_batch * (g + 1) / G;
-                const int64_t qoff = (int64_t)g * (ws->capacity / 2);  // each group owns one half of every queue
-                c.R = r1 - r0;
-                c.ray_base = (int64_t)s0 * HW + r0;
-                // default: pixel-major / sample-minor (A/B on config 3: 8.41 -> 7.57 ms per step); DRP_PRIMARY_ORDER=scan restores sample-major
-                static const bool sample_order = !getenv("DRP_PRIMARY_ORDER") || strcmp(getenv("DRP_PRIMARY_ORDER"), "sample") == 0 ||
-                                                 strcmp(getenv("DRP_PRIMARY_ORDER"), "sample_tiled") == 0;
-                c.sample_minor = (sample_order && G == 1 && ns > 1) ? ns : 0;
-                int* counts = ws->counters + 512 * g;        // [0..D]
-                int* cursors = ws->counters + 512 * g + 64;  // [0..2D)
-                int* pc = ws->counters + 512 * g + 192;      // partition: hit counts [0..63], miss counts [64..127], hit cursors [128..191], miss cursors [192..255]
-                Partition part = {nullptr, nullptr, nullptr, nullptr};
-                if (partition) part = Partition{ws->hit_list + qoff, ws->miss_list + qoff, pc + b, pc + 64 + b};
-                float2* hit = ws->hit + qoff;
-                const int in = b & 1, out = in ^ 1;
-                float4 *qa_in = ws->qa[in] + qoff, *qb_in = ws->qb[in] + qoff, *qt_in = ws->qt[in] + qoff;
-                float4 *qa_out = ws->qa[out] + qoff, *qb_out = ws->qb[out] + qoff, *qt_out = ws->qt[out] + qoff;
-                const int ge = G == 2 ? ws->sm_count * ovl_e : ws->grid_extend[b == 0], gs = G == 2 ? ws->sm_count * ovl_s : ws->grid_shade[b == 0];
-                if (G == 2 && g == 1 && b == 0) DRP_CUDA_CHECK(cudaStreamWaitEvent(sg, ws->sync_events[1], 0));  // phase offset: after group 0's first extend
-                auto span_begin = [&](int kind, const int* count_ptr) -> int {
-                    if (!ws->profiling || ws->live_used >= ws->live_capacity) return -1;
-                    RenderWorkspace::Span sp;
-                    sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
-                    sp.traced_slot = ws->d_live + ws->live_used++;
-                    k_record_live<<<1, 1, 0, sg>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
-                    ++launches;
-                    cudaEventRecord(sp.a, sg);
-                    ws->spans.push_back(sp);
-                    return (int)ws->spans.size() - 1;
-                };
-                auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, sg); };
-                if (b == 0) {
-                    int sp = span_begin(0, nullptr);
-                    if (h->wide && !simple_extend) { if (partition) k_extend_cw<SRC_PRIMARY, true><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), part);
-                      else k_extend_cw<SRC_PRIMARY, false><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), part); }
-                    else if (h->wide) k_extend<true, true><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
-                    else k_extend<true, false><<<ge, WF_BLOCK, 0, sg>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0);
-                    span_end(sp);
-                    if (G == 2 && g == 0) DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[1], sg));
-                    sp = span_begin(1, nullptr);
-                    if (partition) {
-                        k_shade<true, SHADE_HITS><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, pc + b, counts + 1, pc + 128 + b, part.hit_list);
-                        k_shade<true, SHADE_MISSES><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, pc + 64 + b, counts + 1, pc + 192 + b, part.miss_list);
-                        ++launches;
-                    } else {
-                        k_shade<true, SHADE_ALL><<<gs, WF_BLOCK, 0, sg>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1, nullptr);
-                    }
-                    span_end(sp);
-                } else {
-                    int sp = span_begin(0, counts + b);
-                    if (h->wide && !simple_extend) { if (partition) k_extend_cw<SRC_QUEUE, true><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays(), part);
-                      else k_extend_cw<SRC_QUEUE, false><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays(), part); }
-                    else if (h->wide) k_extend<false, true><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
-                    else k_extend<false, false><<<ge, WF_BLOCK, 0, sg>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b);
-                    span_end(sp);
-                    sp = span_begin(1, counts + b);
-                    if (partition) {
-                        k_shade<false, SHADE_HITS><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, pc + b, counts + b + 1, pc + 128 + b, part.hit_list);
-                        k_shade<false, SHADE_MISSES><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, pc + 64 + b, counts + b + 1, pc + 192 + b, part.miss_list);
-                        ++launches;
-                    } else {
-                        k_shade<false, SHADE_ALL><<<gs, WF_BLOCK, 0, sg>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, counts + b, counts + b + 1, cursors + 2 * b + 1, nullptr);
-                    }
-                    span_end(sp);
-                }
-                launches += 2;
-                if (b == D - 1) {
-                    k_count_traced<<<1, 1, 0, sg>>>(counts, D, (unsigned long long)c.R, ws->d_traced);  // read lazily by drp_render_stats
-                    ++launches;
-                }
+            NvtxRange range_bounce(b == 0 ? "bounce 0" : (b == 1 ? "bounce 1" : (b == 2 ? "bounce 2" : "bounce 3+")));
+            const Overflow ovf = {ws->counters + 192 + b, ws->ovf_list, h->stack_cap};
+            const int in = b & 1, out = in ^ 1;
+            float4 *qa_in = ws->qa[in], *qb_in = ws->qb[in], *qt_in = ws->qt[in];
+            float4 *qa_out = ws->qa[out], *qb_out = ws->qb[out], *qt_out = ws->qt[out];
+            const int ge = ws->grid_extend[b == 0], gs = ws->grid_shade[b == 0];
+            auto span_begin = [&](int kind, const int* count_ptr) -> int {
+                if (!ws->profiling || ws->live_used >= ws->live_capacity) return -1;
+                RenderWorkspace::Span sp;
+                sp.a = wf_event(ws); sp.b = wf_event(ws); sp.kind = kind; sp.bounce = b;
+                sp.traced_slot = ws->d_live + ws->live_used++;
+                k_record_live<<<1, 1, 0, s>>>(count_ptr, (unsigned long long)c.R, sp.traced_slot);
+                ++launches;
+                cudaEventRecord(sp.a, s);
+                ws->spans.push_back(sp);
+                return (int)ws->spans.size() - 1;
+            };
+            auto span_end = [&](int idx) { if (idx >= 0) cudaEventRecord(ws->spans[idx].b, s); };
+            if (b == 0) {
+                int sp = span_begin(0, nullptr);
+                k_extend_cw<SRC_PRIMARY><<<ge, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), ovf);
+                k_extend_fixup<SRC_PRIMARY><<<WF_FIXUP_BLOCKS, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, hit, nullptr, AosRays(), ovf, ws->deep_stack, h->sticky_dev);
+                span_end(sp);
+                sp = span_begin(1, nullptr);
+                k_shade<true><<<gs, WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1);
+                span_end(sp);
+            } else {
+                int sp = span_begin(0, counts + b);
+                k_extend_cw<SRC_QUEUE><<<ge, WF_BLOCK, 0, s>>>(c, qa_in, qb_in, hit, counts + b, cursors + 2 * b, AosRays(), ovf);
+                k_extend_fixup<SRC_QUEUE><<<WF_FIXUP_BLOCKS, WF_BLOCK, 0, s>>>(c, qa_in, qb_in, hit, counts + b, AosRays(), ovf, ws->deep_stack, h->sticky_dev);
+                span_end(sp);
+                sp = span_begin(1, counts + b);
+                k_shade<false><<<gs, WF_BLOCK, 0, s>>>(c, b, qa_in, qb_in, qt_in, hit, qa_out, qb_out, qt_out, counts + b, counts + b + 1, cursors + 2 * b + 1);
+                span_end(sp);
             }
+            launches += 3;
         }
-        if (G == 2) {  // join: the caller's stream continues after both chains
-            for (int g = 0; g < 2; ++g) {
-                DRP_CUDA_CHECK(cudaEventRecord(ws->sync_events[2 + g], ws->streams[g]));
-                DRP_CUDA_CHECK(cudaStreamWaitEvent(s, ws->sync_events[2 + g], 0));
-            }
-        }
+        k_count_traced<<<1, 1, 0, s>>>(counts, D, (unsigned long long)c.R, ws->d_traced);  // read lazily by drp_render_stats
+        ++launches;
     }
     DRP_CUDA_CHECK(cudaGetLastError());
     h->last_render.kernel_launches = launches;
@@ -1044,12 +718,13 @@ int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, fl
     if (n > 0x7fffff00) { drp_set_error("drp_trace: more than 2^31 rays per call"); return DRP_ERR_INVALID; }
     WfConst c;
     memset(&c, 0, sizeof(c));
-    c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.flags = h->dev_flags; c.cw_bias = 0x47000000u;
+    c.nodes = h->nodes; c.tris = h->packed; c.eps = h->eps; c.R = n; c.p.t_far = t_far; c.cw_bias = 0x47000000u;
     int* cursor = ws->counters + 1020;
-    DRP_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int), s));
-    AosRays aos = {ro, rd, out_t, out_i};
-    int grid = ws->grid_extend[1];
-    k_extend_cw<SRC_AOS, false><<<grid, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, cursor, aos, Partition{nullptr, nullptr, nullptr, nullptr});
+    DRP_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(int), s));
+    const AosRays aos = {ro, rd, out_t, out_i};
+    const Overflow ovf = {ws->counters + 1021, ws->ovf_list, h->stack_cap};
+    k_extend_cw<SRC_AOS><<<ws->grid_extend[1], WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, cursor, aos, ovf);
+    k_extend_fixup<SRC_AOS><<<WF_FIXUP_BLOCKS, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, nullptr, nullptr, aos, ovf, ws->deep_stack, h->sticky_dev);
     DRP_CUDA_CHECK(cudaGetLastError());
     return DRP_OK;
 }
@@ -1081,6 +756,7 @@ extern "C" int drp_surface_attrs(uint64_t handle, const drp_scene_t* scene, cons
                                  const int32_t* tri, float t_far, int64_t n_rays, float* attrs, void* stream) {
     BvhHandle* h = drp_lookup(handle);
     if (!h) { drp_set_error("drp_surface_attrs: invalid handle"); return DRP_ERR_INVALID; }
+    if (int rc = drp_check_sticky(h, "drp_surface_attrs")) return rc;
     if (!scene || n_rays < 0) { drp_set_error("drp_surface_attrs: invalid argument"); return DRP_ERR_INVALID; }
     if (n_rays == 0) return DRP_OK;
     if (!rays_o || !rays_d || !t || !tri || !attrs) { drp_set_error("drp_surface_attrs: NULL array"); return DRP_ERR_INVALID; }
@@ -1123,22 +799,30 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
         DRP_CUDA_CHECK(cudaMemcpy(&traced, h->ws->d_traced, sizeof(traced), cudaMemcpyDeviceToHost));
         out->rays_traced = (int64_t)traced;
     }
-    int flags[4] = {0, 0, 0, 0};
-    DRP_CUDA_CHECK(cudaMemcpy(flags, h->dev_flags, sizeof(flags), cudaMemcpyDeviceToHost));
-    if (flags[0] != 0) {
-        drp_set_error("traversal stack overflow on " + std::to_string(flags[0]) + " rays: results are invalid");
-        return DRP_ERR_INVALID;
-    }
+    if (int rc = drp_check_sticky(h, "drp_render_stats")) return rc;
     return DRP_OK;
 }
 
 #define DRP_STR2(x) #x
 #define DRP_STR(x) DRP_STR2(x)
 extern "C" const char* drp_build_config(void) {
-    return "compiled " __DATE__ " " __TIME__ "; DRP_CW_HALFSKIP=" DRP_STR(DRP_CW_HALFSKIP) " DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS)
-           " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS) " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW)
-           " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE) " CWK_SMEM_STACK=" DRP_STR(CWK_SMEM_STACK) " CWK_PREFETCH=" DRP_STR(CWK_PREFETCH)
-           " DRP_CW_V2=" DRP_STR(DRP_CW_V2) " DRP_CW_NODE96=" DRP_STR(DRP_CW_NODE96) " CWK_LD256=" DRP_STR(CWK_LD256) " CWK_LUT=" DRP_STR(CWK_LUT) " DRP_SHADE_PIPELINE=" DRP_STR(DRP_SHADE_PIPELINE) " DRP_SHADE_CHUNK_PARTITION=" DRP_STR(DRP_SHADE_CHUNK_PARTITION) " CWK_TRI_PIPE=" DRP_STR(CWK_TRI_PIPE);
+    return "compiled " __DATE__ " " __TIME__ "; DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS) " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS)
+           " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW) " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE)
+           " CW_STACK=" DRP_STR(CW_STACK) " CW_DEEP_STACK=" DRP_STR(CW_DEEP_STACK);
+}
+
+extern "C" int drp_status(uint64_t handle) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_status: unknown handle"); return DRP_ERR_HANDLE; }
+    return drp_check_sticky(h, "drp_status");
+}
+
+extern "C" int drp_debug_set_stack_limit(uint64_t handle, int entries) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_debug_set_stack_limit: unknown handle"); return DRP_ERR_HANDLE; }
+    if (entries < 0 || entries > CW_STACK) { drp_set_error("drp_debug_set_stack_limit: entries must be in [0, " DRP_STR(CW_STACK) "]"); return DRP_ERR_INVALID; }
+    h->stack_cap = entries;
+    return DRP_OK;
 }
 
 extern "C" int drp_set_profiling(uint64_t handle, int enable) {

@@ -39,11 +39,11 @@ class SurfaceUniform:
 class MaskedSparseInterpolator:
     """Barycentric attribute interpolation for the rays selected by ``mask`` (interpolator.py:87-97)."""
 
-    def __init__(self, vi_data: torch.Tensor, tri_ids: torch.Tensor, tris: torch.Tensor, mask: torch.Tensor):
+    def __init__(self, vi_data: torch.Tensor, tris: torch.Tensor, mask: torch.Tensor):
         self.tris = tris
         self.indices = mask.nonzero(as_tuple=True)
         self.vi_data = vi_data[self.indices]  # (u, v, t, 1-based triangle id as float)
-        self.tri_idx = tris[tri_ids[self.indices].long() - 1].long()
+        self.tri_idx = tris[(float_to_triidx(self.vi_data[..., -1]) - 1).long()].long()
 
     def interpolate(self, vertex_buffer: torch.Tensor) -> torch.Tensor:
         corners = vertex_buffer[self.tri_idx]  # (n, 3, C)
@@ -171,7 +171,7 @@ def layer_material_rays(sess, rays_o, rays_d, t, i) -> List[Tuple[SurfaceInput, 
     mats = []
     for k, obj in enumerate(sess.scene.objects):
         su = SurfaceUniform(obj.M.to(vi_data.device), V, P)
-        si = SurfaceInput(su, vao, MaskedSparseInterpolator(vi_data, ids, vao.tris, stencil == k + 1))
+        si = SurfaceInput(su, vao, MaskedSparseInterpolator(vi_data, vao.tris, stencil == k + 1))
         if len(si.interpolator.indices[0]) == 0:
             mats.append((si, SurfaceOutputStandard()))
         else:
@@ -327,7 +327,7 @@ def trace_rays(sess, sampler: Callable, radiance_channels: int = 3):
         rays_o, rays_d = primary_rays(sess, grid)
         throughput = ones_like_vec(rays_o, radiance_channels)
         for d in range(opt.ray_depth):
-            t, i = rc.query(rays_o, rays_d, far)
+            t, i = rc.query(rays_o.detach(), rays_d.detach(), far)
             out = sampler(rays_o, rays_d, t, i, d)
             radiance = radiance + (throughput * out.radiance).view(n, -1, radiance_channels).sum(0)
             alpha = alpha + out.alpha.reshape(n, -1, 1).sum(0)

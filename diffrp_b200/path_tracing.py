@@ -44,7 +44,9 @@ class PathTracingSessionOptions:
             in HBM; ``'torch'`` -- draw the six ``torch.rand((R,1))`` tensors per bounce exactly like the reference's
             sampler (path_tracing.py:205-223) and replay them in the kernel: with the same ``torch.manual_seed`` the image
             reproduces the reference's within fp32 tolerance.
-        seed (int): key of the native RNG.
+        seed (int): key of the native RNG.  NOTE (difference from the reference, which advances torch's global generator): two ``pbr()``
+            calls with the same seed return the same noise; pass ``seed=None`` to draw a fresh key from torch's generator per session
+            (``torch.manual_seed`` then makes a sequence of renders reproducible as a whole, and averaging renders reduces variance).
         reproducible (bool): the accumulators are updated with fp32 atomic adds, so the low bits of an image depend on the order in
             which rays of the same pixel retire.  With ``reproducible=True`` every launch batch holds one sample per pixel, which fixes the
             order (bounce by bounce, sample by sample) at the price of smaller launches.
@@ -69,7 +71,7 @@ class PathTracingSessionOptions:
     raycaster_builder: str = 'splitaxis'
     optix_log_level: int = 3
     rng: str = 'native'
-    seed: int = 0
+    seed: Optional[int] = 0
     compaction: bool = True
     shard_rank: int = 0
     shard_world: int = 1
@@ -141,8 +143,12 @@ def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
     """The path's one exchange step: sum the packed fp32 accumulators over all ranks (NCCL on GPUs, gloo in CPU tests)."""
     if world > 1:
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("shard_world=%d but torch.distributed is not initialised: the image would hold 1/%d of the samples. "
+                               "Initialise a process group, or combine render_accumulators() of the shards yourself." % (world, world))
+        if dist.get_world_size() != world:
+            raise RuntimeError("shard_world=%d does not match the process group's world size %d" % (world, dist.get_world_size()))
+        dist.all_reduce(accum, op=dist.ReduceOp.SUM)
     return accum
 
 
@@ -239,13 +245,14 @@ class PathTracingSession:
         """Per-scene cache shared between sessions (options.reuse_scene), else private to this session."""
         if '_store' not in self.__dict__:
             self._store = (_shared_scene_cache(self.scene, self.device, self.options.raycaster_epsilon)
-                           if self.options.reuse_scene else {})
+                           if self.options.reuse_scene and not self._wants_grad() else {})
         return self._store
 
     def vertex_array_object(self) -> VertexArrayObject:
         st = self._scene_store()
         if 'vao' not in st:
-            st['vao'] = flatten_scene_cuda(self.scene.objects, self.device)  # one drp_flatten pass (flatten_scene = torch twin for CPU tests)
+            # one drp_flatten pass; its torch twin (differentiable) when some scene tensor requires grad
+            st['vao'] = (flatten_scene if self._wants_grad() else flatten_scene_cuda)(self.scene.objects, self.device)
         return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
@@ -259,7 +266,7 @@ class PathTracingSession:
             vao = self.vertex_array_object()
             cfg = {'epsilon': self.options.raycaster_epsilon, 'builder': self.options.raycaster_builder,
                    'optix_log_level': self.options.optix_log_level}
-            rc = st['raycaster'] = B200Raycaster(vao.world_pos, vao.tris, cfg)
+            rc = st['raycaster'] = B200Raycaster(vao.world_pos.detach(), vao.tris, cfg)
         return rc
 
     def _single_env_light(self):
@@ -322,7 +329,12 @@ class PathTracingSession:
         p.step_epsilon, p.t_far, p.t_near = opt.pbr_ray_step_epsilon, tab['t_far'], tab['t_near']
         p.cam_pos[:3] = tab['cam_pos']
         p.inv_vp[:] = tab['inv_vp']
-        p.seed = opt.seed
+        if opt.seed is None:  # fresh key per session, drawn from torch's (seedable) CPU generator
+            if '_drawn_seed' not in self.__dict__:
+                self._drawn_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            p.seed = self._drawn_seed
+        else:
+            p.seed = opt.seed
         p.ndc_x, p.ndc_y = tab['ndc_x'].data_ptr(), tab['ndc_y'].data_ptr()
         return fused[0], tab, p, fused[1]
 
@@ -410,7 +422,7 @@ class PathTracingSession:
 
     def render_stats(self) -> dict:
         st = _abi.RenderStats()
-        check(lib().drp_render_stats(self.raycaster().handle, C.byref(st)), "drp_render_stats")
+        check(lib().drp_render_stats(self.raycaster().handle, C.byref(st)), "drp_render_stats")  # also fails on the handle's sticky device-error flag
         return dict(rays_traced=st.rays_traced, rays_nominal=st.rays_nominal, kernel_launches=st.kernel_launches)
 
     def set_profiling(self, enable: bool = True):
@@ -421,16 +433,40 @@ class PathTracingSession:
         check(lib().drp_get_profile(self.raycaster().handle, C.byref(pr)), "drp_get_profile")
         return {k: getattr(pr, k) for k, _ in _abi.Profile._fields_}
 
-    @torch.no_grad()
+    def _wants_grad(self) -> bool:
+        """True when autograd is on and some scene tensor (geometry, vertex attribute, material factor / texture, light) requires grad."""
+        if not torch.is_grad_enabled():
+            return False
+
+        def g(x):
+            return isinstance(x, torch.Tensor) and x.requires_grad
+        for o in self.scene.objects:
+            if any(g(x) for x in (o.verts, o.normals, o.M, o.color, o.uv, o.tangents)) or any(g(v) for v in (o.custom_attrs or {}).values()):
+                return True
+            m = o.material
+            if any(g(v) for v in vars(m).values()) or any(g(getattr(v, 'image', None)) for v in vars(m).values()):
+                return True
+        return any(g(getattr(l, 'image', None)) or g(l.color) or g(l.intensity) for l in self.scene.lights)
+
     def pbr(self):
         """
         Path-traced PBR rendering; returns ``(radiance (H,W,3), alpha (H,W,1), extras)`` with extras ``albedo``,
         ``emission``, ``world_normal`` and ``world_position`` (H,W,3) -- same contract as path_tracing.py:354-367.
+
+        Differentiability: the fused kernels have no backward pass.  Like the reference -- whose ``trace_rays`` is differentiable through the
+        material / sampler torch code and detached only through ``raycaster.query`` -- a scene with tensors that require grad is rendered on
+        the generic path (CUDA intersection + the per-bounce torch algebra of ``generic.py``), so gradients flow to materials, vertex
+        attributes and lights; everything else takes the fused path.
         """
-        if self._fused_scene() is None:
+        if self._fused_scene() is None or self._wants_grad():
+            if self.options.shard_world > 1:
+                raise ValueError("sharded rendering needs the fused path (built-in materials, no tensors that require grad)")
             return self.trace_rays(self.sampler_brdf)
-        accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
-        return self.finalize(accum)
+        with torch.no_grad():
+            accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
+            out = self.finalize(accum)
+        self.raycaster().check_status()
+        return out
 
     @torch.no_grad()
     def pbr_image(self, tone='agx', lut: torch.Tensor = None):
@@ -474,7 +510,20 @@ class PathTracingSession:
         from . import generic
         return generic.sampler_brdf(self, rays_o, rays_d, t, i, d)
 
-    @torch.no_grad()
     def trace_rays(self, sampler: Callable, radiance_channels: int = 3):
+        """Differentiable through the sampler / material torch code; only ``raycaster.query`` is detached (as in the reference)."""
         from . import generic
         return generic.trace_rays(self, sampler, radiance_channels)
+
+    # the helper names the reference's docstring points sampler authors to (path_tracing.py:296, mixin.py:115-155)
+    def _gbuffer_collect_layer_impl_stencil_masked(self, mats, operator, initial):
+        from . import generic
+        return generic.collect_gbuffer(mats, operator, initial)
+
+    def _super_collector(self, si, so):
+        from . import generic
+        return generic.surface_row(si, so)
+
+    def _collector_world_normal(self, si, so):
+        from . import generic
+        return generic.world_normal_of(si, so)

@@ -102,6 +102,10 @@ class B200Raycaster(Raycaster):
                                              _stream_ptr(rays_o.device)), "drp_trace_bruteforce")
         return out_t, out_i
 
+    def check_status(self) -> None:
+        """Raise if an earlier traversal on this structure failed on the device (drp_status: non-blocking read of the handle's sticky flag)."""
+        check(self._lib.drp_status(self.handle), "drp_status")
+
     def stats(self) -> dict:
         st = _abi.BVHStats()
         check(self._lib.drp_bvh_stats(self.handle, C.byref(st)), "drp_bvh_stats")

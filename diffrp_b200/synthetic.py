@@ -172,3 +172,59 @@ def teaser_scene(device='cpu', n_spheres=48, sphere_res=(160, 128), ground=256, 
     scene.add_light(ImageEnvironmentLight(intensity=1.0, color=put(torch.ones(3)), image=put(env.contiguous())))
     cam = dict(radius=4.6, azim=32.0, elev=24.0, origin=[0.0, -0.35, 0.0], fov=40.0, near=0.1, far=20.0)
     return scene, cam
+
+
+def rigid_matrix(rng, scale=1.0, translate=(0.0, 0.0, 0.0)):
+    """Seeded rigid transform (random rotation x uniform scale + translation) as a (4, 4) fp32 numpy array."""
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = q * scale
+    m[:3, 3] = translate
+    return m
+
+
+def datagen_scene(device='cpu', n_theta=500, n_phi=500, env_res=(256, 512)):
+    """
+    Config 4 (multi-view datagen): one displaced UV sphere of 2 * n_theta * n_phi triangles (500,000 by default) with a
+    ``DefaultMaterial`` and seeded vertex colours, env-lit.  Returns (Scene, camera factory: (k, n_views, res) -> orbit kwargs).
+    """
+    import torch
+    from .scene import Scene, MeshObject, ImageEnvironmentLight
+    from .materials import DefaultMaterial
+    Tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    v, f, n, uv, tg = uv_sphere(n_theta, n_phi, radius=0.8, bump=0.05, noise=0.01, seed=0, with_attrs=True)
+    col = (torch.rand(len(v), 4, generator=torch.Generator().manual_seed(3)) * 0.6 + 0.4).to(device)
+    scene = Scene().add_mesh_object(MeshObject(DefaultMaterial(), Tn(v), Tn(f), normals=Tn(n), color=col, uv=Tn(uv)))
+    env = (torch_noise_texture(env_res[0], env_res[1], 3, 7, 0.0, 1.0) ** 3 * 5.0 + 0.1).to(device)
+    scene.add_light(ImageEnvironmentLight(1.0, torch.ones(3, device=device), env))
+
+    def orbit(k, n_views, res=512):
+        return dict(h=res, w=res, radius=3.0, azim=360.0 * k / n_views, elev=20.0 * math.sin(2 * math.pi * k / n_views), origin=[0, 0, 0])
+    return scene, orbit
+
+
+def instanced_scene(device='cpu', n_instances=1000, mesh_res=(100, 50), env_res=(256, 512), seed=0, spread=(1.6, 0.9, 1.0)):
+    """
+    Config 5 (instanced scene): ``n_instances`` MeshObjects that SHARE one displaced-sphere mesh (2 * mesh_res[0] * mesh_res[1]
+    triangles: 10,000 by default -> 10 M triangles flattened) with seeded rigid transforms and one ``DefaultMaterial`` each of 8
+    tints, env-lit.  Returns (Scene, orbit-camera kwargs without the resolution).
+    """
+    import torch
+    from .scene import Scene, MeshObject, ImageEnvironmentLight
+    from .materials import DefaultMaterial
+    Tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    v, f, n, uv, tg = uv_sphere(mesh_res[0], mesh_res[1], radius=0.045, bump=0.004, noise=0.001, seed=1, with_attrs=True)
+    Vt, Ft, Nt = Tn(v), Tn(f), Tn(n)
+    tints = ([1, .3, .3], [.3, 1, .3], [.3, .3, 1], [1, 1, .3], [1, .3, 1], [.3, 1, 1], [.9, .9, .9], [.5, .5, .5])
+    mats = [DefaultMaterial(torch.tensor(c, dtype=torch.float32, device=device)) for c in tints]
+    rng = np.random.default_rng(seed)
+    scene = Scene()
+    lo, hi = [-spread[0], -spread[1], -spread[2]], list(spread)
+    for k in range(n_instances):
+        pos = rng.uniform(lo, hi)
+        scene.add_mesh_object(MeshObject(mats[k % 8], Vt, Ft, normals=Nt, M=Tn(rigid_matrix(rng, 0.6 + rng.random(), pos))))
+    env = (torch_noise_texture(env_res[0], env_res[1], 3, 7, 0.0, 1.0) ** 3 * 5.0 + 0.1).to(device)
+    scene.add_light(ImageEnvironmentLight(1.0, torch.ones(3, device=device), env))
+    return scene, dict(radius=4.0, azim=20.0, elev=10.0, origin=[0, 0, 0], fov=35)

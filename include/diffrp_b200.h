@@ -308,6 +308,15 @@ typedef struct drp_render_stats {
 } drp_render_stats_t;
 int drp_render_stats(uint64_t handle, drp_render_stats_t* out);
 
+/* Health of a handle, without synchronising.  A ray whose traversal outgrows the per-thread stack of the fast kernel is re-traced by a fix-up
+ * kernel with a 256-entry stack (deeper than any hierarchy the builder can emit: <= 63 Morton + 27 index levels), so results stay exact on
+ * degenerate scenes.  Should even that stack run out, the kernel raises a sticky host-mapped flag: drp_status and EVERY later call on the handle
+ * (drp_trace, drp_render, drp_surface_attrs, drp_render_stats) return DRP_ERR_INVALID -- never a silent wrong hit.  (The reference's
+ * NaivePBBVH.query is stackless, utils/raycaster.py:226-260; torchoptix's trace has no failure mode to mirror.) */
+int drp_status(uint64_t handle);
+/* Test hook: lower the per-thread stack depth of the fast traversal path (0..48 entries) so that ordinary scenes exercise the fix-up path. */
+int drp_debug_set_stack_limit(uint64_t handle, int32_t entries);
+
 /* Optional per-kernel timing (measurement aid, no reference equivalent): when enabled, drp_render brackets every
  * extend / shade launch with CUDA events on the launch stream; drp_get_profile synchronises, sums the elapsed times
  * since the last call, and resets.  rays_* are the live rays those launches processed. */

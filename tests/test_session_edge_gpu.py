@@ -172,3 +172,57 @@ def test_cuda_flatten_matches_torch_flatten(where):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     rec = torch.cat([b.world_pos, b.world_nrm, b.uv, b.color, b.world_tan], 1)
     torch.testing.assert_close(a.records, rec, rtol=1e-6, atol=1e-6)
+
+
+def test_pbr_is_differentiable_like_the_reference():
+    """The reference's trace_rays is differentiable through material / sampler code (only raycaster.query is no_grad).  A scene whose
+    tensors require grad is routed to the generic path: gradients reach vertex colours; without grad the fused path returns plain tensors."""
+    scene = scenes.icosphere_scene()
+    obj = scene.objects[0]
+    obj.color = obj.color.clone().cuda().requires_grad_(True)
+    cam = drp.PerspectiveCamera(h=24, w=24)
+    torch.manual_seed(0)
+    rad, alpha, extras = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=4, ray_depth=2)).pbr()
+    assert rad.requires_grad and extras['albedo'].requires_grad
+    (rad.sum() + extras['albedo'].sum()).backward()
+    g = obj.color.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0.0
+    with torch.no_grad():
+        rad2, _, _ = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=4, ray_depth=2)).pbr()
+    assert not rad2.requires_grad
+    # same estimator on both paths: albedo AOV is noise-free up to the jittered sub-pixel positions (identical Hammersley set)
+    obj.color = obj.color.detach()
+    _, _, ex3 = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=4, ray_depth=2)).pbr()
+    np.testing.assert_allclose(ex3['albedo'].cpu().numpy(), extras['albedo'].detach().cpu().numpy(), atol=2e-5)
+
+
+def test_fixup_path_renders_the_same_image():
+    """Whole renders with the fast traversal stack lowered to 1 entry (every deep ray goes through k_extend_fixup) are bit-identical to the
+    normal ones in reproducible mode."""
+    from diffrp_b200._lib import lib, check
+    scene = scenes.mixed_scene()
+    cam = drp.PerspectiveCamera(h=48, w=64)
+    opt = dict(ray_spp=4, ray_depth=3, seed=11, reproducible=True, reuse_scene=False)
+    s1 = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**opt))
+    a = s1.pbr()
+    s2 = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(**opt))
+    check(lib().drp_debug_set_stack_limit(s2.raycaster().handle, 1), "drp_debug_set_stack_limit")
+    b = s2.pbr()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[2]:
+        assert torch.equal(a[2][k], b[2][k]), k
+
+
+def test_more_than_2_pow_31_rays_in_one_pbr_call():
+    """1024 x 1024 at 2049 spp is > 2^31 primary rays; drp_render sections the samples internally (like the reference's
+    ray_split_size sections) instead of refusing.  Depth 1 over an empty scene keeps it cheap: every pixel must see exactly spp samples."""
+    scene = drp.Scene().add_light(drp.ImageEnvironmentLight(1.0, torch.ones(3), torch.ones(4, 8, 3)))
+    rad, alpha, _ = drp.PathTracingSession(scene, drp.PerspectiveCamera(h=1024, w=1024), drp.PathTracingSessionOptions(ray_spp=2049, ray_depth=1)).pbr()
+    np.testing.assert_allclose(rad.cpu().numpy(), 1.0, rtol=1e-4)
+    assert float(alpha.max()) == 0.0
+
+
+def test_unsharded_process_cannot_silently_lose_samples():
+    scene = scenes.icosphere_scene()
+    with pytest.raises(RuntimeError):
+        drp.PathTracingSession(scene, drp.PerspectiveCamera(h=8, w=8), drp.PathTracingSessionOptions(ray_spp=4, shard_world=2)).pbr()
