@@ -277,6 +277,8 @@ def main():
     ap.add_argument("--torch-baseline-spp", type=int, default=8)
     ap.add_argument("--torch-baseline-steps", type=int, default=1)
     ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 1024-spp frame split over the ranks)")
+    ap.add_argument("--strong-spp", type=int, default=1024)
     args = ap.parse_args()
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
@@ -373,19 +375,23 @@ def main():
     # env) from pinned host memory, flatten, LBVH build, all K sections, the accumulator all-reduce, finalize, D2H.
     # Also timed (reported as `single_section_session`): the same call for ONE section (ray_spp = S), i.e. the scene upload
     # and build are paid again for every 8 spp -- the worst case for a single-use session API.
-    out_host = torch.empty([RES, RES, 16], dtype=torch.float32).pin_memory()
+    # one CONTIGUOUS pinned buffer per output: each read is a single DMA.  (Round 1 copied into channel slices of one (H, W, 16) pinned array;
+    # torch stages such strided device->host copies through a CPU-side strided memcpy on all host threads -- 7 ms at N = 1, 49 ms per rank at
+    # N = 2 when the ranks' thread pools oversubscribe the cores: tools/e2e_phases.py, profiles/r2/e2e_phases_*.json.)
+    out_keys = ("radiance", "alpha", "albedo", "emission", "world_normal", "world_position")
+    out_host = {k: torch.empty([RES, RES, 1 if k == "alpha" else 3], dtype=torch.float32).pin_memory() for k in out_keys}
     h2d = scene_bytes(scene_host)
-    d2h = out_host.numel() * 4
+    d2h = sum(v.numel() for v in out_host.values()) * 4
 
     def e2e_call(spp_total, seed, sharded):
         o = drp.PathTracingSessionOptions(ray_spp=spp_total, ray_depth=DEPTH, rng='native', seed=seed, reuse_scene=False,  # nothing cached between calls
                                           shard_rank=rank if sharded else 0, shard_world=world if sharded else 1)
         s = drp.PathTracingSession(scene_host, cam, o)          # pinned host tensors: H2D of the whole scene happens inside
         r, a, x = s.pbr()                                       # flatten + LBVH build + wavefront (+ all-reduce) + finalize
-        out_host[..., 0:3].copy_(r, non_blocking=True)          # D2H of every output
-        out_host[..., 3:4].copy_(a, non_blocking=True)
-        for q, k in enumerate(("albedo", "emission", "world_normal", "world_position")):
-            out_host[..., 4 + 3 * q:7 + 3 * q].copy_(x[k], non_blocking=True)
+        out_host["radiance"].copy_(r, non_blocking=True)        # D2H of every output
+        out_host["alpha"].copy_(a, non_blocking=True)
+        for k in ("albedo", "emission", "world_normal", "world_position"):
+            out_host[k].copy_(x[k], non_blocking=True)
         torch.cuda.synchronize()
         s.raycaster().release()
 
@@ -409,6 +415,41 @@ def main():
     e2e_value = world * K * S * HW * DEPTH / (e2e_job_ms * 1e-3) / 1e6
     e2e_sec_ms = timed_calls(E, S, False)                         # one section per session, every rank its own frame
     e2e_sec_value = world * S * HW * DEPTH / (e2e_sec_ms * 1e-3) / 1e6
+
+    # ---- strong scaling of the north-star job: ONE 1024-spp frame (fixed total work) split over the N ranks ----------------------
+    # device-resident: this rank's 1024 / N samples in sections of S, all-reduce, finalize; e2e: the same public-API call as above with
+    # ray_spp = 1024.  Reported at every N (N = 1 included) so that the ratio between two lines of a scaling run is the strong-scaling speed-up.
+    strong = None
+    if not args.no_strong:
+        FRAME_SPP = args.strong_spp
+        s_opts = drp.PathTracingSessionOptions(ray_spp=FRAME_SPP, ray_depth=DEPTH, rng='native', seed=1, shard_rank=rank, shard_world=world)
+        s_sess = drp.PathTracingSession(scene, cam, s_opts)
+        s_ids = torch.arange(FRAME_SPP, dtype=torch.int32, device=dev)[rank::world]
+        s_steps = [s_ids[j:j + S] for j in range(0, len(s_ids), S)]
+        s_acc = s_sess.new_accumulators()
+        s_sess.render_samples(s_steps[0], s_acc)   # warm-up of this session's tables
+        s_acc.zero_()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for ids_j in s_steps:
+            s_sess.render_samples(ids_j, s_acc)
+        if world > 1:
+            dist.all_reduce(s_acc)
+        s_out = s_sess.finalize(s_acc)
+        e1.record()
+        torch.cuda.synchronize()
+        t_s = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        s_dev_ms = float(t_s.item())
+        s_e2e_ms = timed_calls(1, FRAME_SPP, True)
+        rays = FRAME_SPP * HW * DEPTH
+        strong = {"job": "one %dx%d frame, %d spp, %d bounces (fixed total work), spp-sharded x%d" % (RES, RES, FRAME_SPP, DEPTH, world),
+                  "device_ms": s_dev_ms, "e2e_ms": s_e2e_ms, "value": rays / (s_dev_ms * 1e-3) / 1e6, "e2e_value": rays / (s_e2e_ms * 1e-3) / 1e6,
+                  "unit": UNIT, "scaling": "strong"}
+        del s_out, s_acc
 
     if rank != 0:
         if world > 1:
@@ -527,7 +568,9 @@ def main():
         "live_ray_fraction": prof["extend_rays"] / max(1, K * S * HW * DEPTH),
         "bvh_build_ms": build_ms,
         "clocks": clk, "host_issue_ms": host_issue_ms,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "steps": K,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": world * d2h / K, "steps": K,
+                "bytes_note": "job totals over all ranks: the scene crosses PCIe once in total (each rank uploads 1/N of every tensor, NVLink all-gather "
+                              "completes it: options.scene_upload), every rank reads the full result back",
                 "ms_per_step": e2e_job_ms / K, "ms_total": e2e_job_ms, "h2d_bytes_total": h2d, "d2h_bytes_total": d2h,
                 "what": "ONE public-API call for the whole job: PathTracingSession(host-pinned scene, camera, options(ray_spp=%d, spp-sharded x%d)).pbr() "
                         "+ D2H of all outputs; timed region = H2D scene upload, flatten, LBVH build, %d sections, all-reduce, finalize, D2H"
@@ -535,6 +578,7 @@ def main():
                 "single_section_session": {"value": e2e_sec_value, "unit": UNIT, "ms_per_call": e2e_sec_ms, "calls": E,
                                            "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
                                            "what": "same call with ray_spp=%d: scene upload + build paid per section" % S}},
+        "strong_scaling": strong,
         "gpu_launches": int(launches_per_step * K + 1),  # kernels of libdiffrp_b200.so in the timed region: per step 4 x (k_extend_cw + k_shade)
                                                           # + k_count_traced + 8 x k_record_live (profiling spans); + 1 k_finalize
         "roofline": roofline,

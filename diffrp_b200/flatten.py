@@ -74,7 +74,33 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
         cat(wn, [0, 3]), cat(wt, [0, 4]), cat(tm, [0], torch.int32))
 
 
-def flatten_scene_cuda(objs: List, dev) -> VertexArrayObject:
+#: host tensors smaller than this are uploaded whole by every rank even when sharded upload is on (latency-bound anyway)
+SHARD_MIN_BYTES = 1 << 20
+
+
+def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
+    """
+    Host -> device move of one scene tensor.  ``shard=(rank, world)`` (scene replicated over the ranks of an initialised NCCL group, the
+    precondition of spp / tile sharding): every rank DMA-copies only its 1/world slice of the (identical) host tensor over its own PCIe link and
+    an in-place all-gather over NVLink completes it on every GPU -- world x less host-memory and PCIe traffic than ``world`` full uploads
+    from one host, at NVLink instead of PCIe speed.  Collective: every rank must upload the same tensors in the same order.
+    """
+    if (shard is not None and shard[1] > 1 and not t.is_cuda and t.dtype == dtype and t.is_contiguous()
+            and t.numel() * t.element_size() >= SHARD_MIN_BYTES):
+        import torch.distributed as dist
+        rank, world = shard
+        n = t.numel()
+        per = -(-n // world)
+        out = torch.empty([world * per], dtype=dtype, device=dev)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        if hi > lo:
+            out[lo:hi].copy_(t.view(-1)[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
+        return out[:n].view(t.shape)
+    return t.to(dev, dtype, non_blocking=True)
+
+
+def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     """
     ``flatten_scene`` in one CUDA pass (``drp_flatten``): sources that already live on ``dev`` are read in place, host tensors are
     first moved with one asynchronous DMA copy each (measured on B200: letting the kernel read pinned host memory directly works --
@@ -90,7 +116,7 @@ def flatten_scene_cuda(objs: List, dev) -> VertexArrayObject:
     def src(t, dtype):
         ok = t.dtype == dtype and t.is_contiguous() and t.is_cuda and t.device == dev
         if not ok:
-            t = t.to(dev, dtype, non_blocking=True).contiguous()
+            t = upload(t, dev, dtype, shard).contiguous()
         keep.append(t)
         return t
 
@@ -169,7 +195,11 @@ def texel_records(d: dict) -> Optional[torch.Tensor]:
     return torch.cat([b, m[..., 1:3], n[..., :3], e[..., :3]], -1).contiguous()
 
 
-def material_descriptions(objs: List, dev, rgba: bool = False) -> Optional[List[dict]]:
+#: interleave the four textures of a material into 48-byte texel records (layout only; tests flip it to prove bit-equality with separate textures)
+INTERLEAVE_TEXELS = True
+
+
+def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Optional[List[dict]]:
     """Per-object drp_material_t descriptions (textures moved to ``dev``, RGBA-padded for the CUDA path when ``rgba``),
     or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
     descs = []
@@ -184,10 +214,10 @@ def material_descriptions(objs: List, dev, rgba: bool = False) -> Optional[List[
                 src = d[k]['image']
                 key = (src.data_ptr(), tuple(src.shape))
                 if key not in uploaded:
-                    img = src.to(dev, torch.float32, non_blocking=True)
+                    img = upload(src, dev, torch.float32, shard)
                     uploaded[key] = pad_rgba(img) if rgba else img.contiguous()
                 d[k] = dict(d[k], image=uploaded[key])
-        if rgba and os.environ.get('DIFFRP_B200_TEXEL_RECORDS', '1') != '0':  # CUDA path: interleaved texels, shared between the objects that share the material
+        if rgba and INTERLEAVE_TEXELS:  # CUDA path: interleaved texels, shared between the objects that share the material
             key = ('records',) + tuple(d[k]['image'].data_ptr() if d.get(k) is not None else 0 for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
             if key not in uploaded:
                 uploaded[key] = texel_records(d)

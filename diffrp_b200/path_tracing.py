@@ -55,10 +55,14 @@ class PathTracingSessionOptions:
             and adopted by the next session over the same unmodified scene -- multi-view rendering builds once, not per view.
         compaction (bool): drop rays that provably contribute nothing to any output (exact; the reference keeps
             tracing them with zero throughput).
+        scene_upload: with ``shard_world > 1`` the scene is replicated; when it still lives in (pinned) host memory, ``'sharded'`` (what ``'auto'``
+            picks under an NCCL group) makes each rank upload 1/world of every large tensor and all-gather the rest over NVLink instead of
+            ``world`` full PCIe uploads from the same host.  Requires identical scenes on all ranks (already the contract of sharding).
         shard_rank / shard_world: this process renders its share of the frame (scene replicated) and the fp32 accumulators
             are summed with ``torch.distributed.all_reduce`` when a process group exists.  ``shard_mode='spp'``: global
             sample indices ``rank::world`` of every pixel; ``shard_mode='tile'``: every sample of the ``tile_size``^2 tiles
-            ``rank::world`` (row-major tile order), the rest of the accumulator stays zero.
+            ``rank::world`` (row-major tile order), the rest of the accumulator stays zero; the exchange is then an all-gather of the owned
+            tiles (``tile_collective``), not a sum of whole frames.
     """
     ray_depth: int = 3
     ray_spp: int = 16
@@ -77,6 +81,8 @@ class PathTracingSessionOptions:
     shard_world: int = 1
     shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
+    tile_collective: str = 'gather'   # 'gather': all-gather of the owned tiles' rows; 'allreduce': sum whole frames
+    scene_upload: str = 'auto'        # host scenes under sharding: 'sharded' = 1/world of every tensor per rank over PCIe + all-gather over NVLink
     reuse_scene: bool = True  # share the flattened scene + BVH between sessions over the same, unmodified Scene
     reproducible: bool = False  # bit-identical images run to run: one sample per launch batch, fixed fp32 accumulation order
 
@@ -150,6 +156,59 @@ def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
             raise RuntimeError("shard_world=%d does not match the process group's world size %d" % (world, dist.get_world_size()))
         dist.all_reduce(accum, op=dist.ReduceOp.SUM)
     return accum
+
+
+def frame_tiles(H: int, W: int, tile: int):
+    """Row-major list of (x0, y0, w, h) tiles of an H x W frame (y counted from the bottom row, like the accumulator)."""
+    T = max(1, int(tile))
+    return [(x, y, min(T, W - x), min(T, H - y)) for y in range(0, H, T) for x in range(0, W, T)]
+
+
+def tile_rows(tiles, W: int, device=None) -> torch.Tensor:
+    """Accumulator row indices (y * W + x) of the pixels of the given tiles, tile after tile, row-major inside a tile."""
+    parts = [(torch.arange(y0, y0 + h, device=device).view(h, 1) * W + torch.arange(x0, x0 + w, device=device).view(1, w)).reshape(-1)
+             for (x0, y0, w, h) in tiles]
+    return torch.cat(parts) if parts else torch.zeros([0], dtype=torch.int64, device=device)
+
+
+def gather_tile_accumulators(accum: torch.Tensor, H: int, W: int, tile: int, rank: int, world: int) -> torch.Tensor:
+    """
+    Exchange step of tile sharding: rank r owns tiles r::world (row-major) and every other accumulator row of its frame is zero, so the sum
+    over ranks is a GATHER of disjoint supports.  Each rank packs the rows of its own tiles, one ``all_gather`` moves them, and every rank
+    scatters the others' rows into its frame: (world-1)/world x frame bytes received per rank and no arithmetic, instead of an all-reduce
+    of the whole frame (2 x (world-1)/world x frame bytes through every link plus the adds; 531 MB per frame at 4K).
+    The result equals ``all_reduce(SUM)`` of the same buffers bit for bit (x + 0 = x).
+    """
+    if world <= 1:
+        return accum
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("shard_world=%d but torch.distributed is not initialised" % world)
+    if dist.get_world_size() != world:
+        raise RuntimeError("shard_world=%d does not match the process group's world size %d" % (world, dist.get_world_size()))
+    tiles = frame_tiles(H, W, tile)
+    rows = [tile_rows(tiles[r::world], W, accum.device) for r in range(world)]
+    n_max = max(len(r) for r in rows)
+    C = accum.shape[-1]
+    recv = accum.new_empty([world, n_max, C])
+    send = recv[rank]                                   # in place: NCCL's all-gather accepts its input inside the output
+    send[:len(rows[rank])] = accum[rows[rank]]
+    if len(rows[rank]) < n_max:
+        send[len(rows[rank]):] = 0
+    dist.all_gather_into_tensor(recv.view(-1), send.reshape(-1)) if dist.get_backend() == 'nccl' else \
+        _all_gather_generic(recv, send.clone(), world)
+    for r in range(world):
+        if r != rank and len(rows[r]):
+            accum[rows[r]] = recv[r, :len(rows[r])]
+    return accum
+
+
+def _all_gather_generic(recv: torch.Tensor, send: torch.Tensor, world: int):
+    import torch.distributed as dist
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send)
+    for r in range(world):
+        recv[r] = parts[r]
 
 
 def _scene_signature(scene: Scene, device) -> tuple:
@@ -248,11 +307,29 @@ class PathTracingSession:
                            if self.options.reuse_scene and not self._wants_grad() else {})
         return self._store
 
+    def _upload_shard(self):
+        """(rank, world) when host scene tensors are uploaded 1/world per rank + all-gather (flatten.upload), else None."""
+        opt = self.options
+        if opt.shard_world <= 1 or opt.scene_upload == 'direct':
+            return None
+        if opt.scene_upload not in ('auto', 'sharded'):
+            raise ValueError("scene_upload must be 'auto', 'direct' or 'sharded'")
+        import torch.distributed as dist
+        ok = dist.is_available() and dist.is_initialized() and dist.get_backend() == 'nccl' and dist.get_world_size() == opt.shard_world
+        if not ok:
+            if opt.scene_upload == 'sharded':
+                raise RuntimeError("scene_upload='sharded' needs an initialised NCCL process group of shard_world ranks")
+            return None
+        return (opt.shard_rank, opt.shard_world)
+
     def vertex_array_object(self) -> VertexArrayObject:
         st = self._scene_store()
         if 'vao' not in st:
             # one drp_flatten pass; its torch twin (differentiable) when some scene tensor requires grad
-            st['vao'] = (flatten_scene if self._wants_grad() else flatten_scene_cuda)(self.scene.objects, self.device)
+            if self._wants_grad():
+                st['vao'] = flatten_scene(self.scene.objects, self.device)
+            else:
+                st['vao'] = flatten_scene_cuda(self.scene.objects, self.device, self._upload_shard())
         return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
@@ -281,7 +358,8 @@ class PathTracingSession:
             if isinstance(light, ImageEnvironmentLight):
                 if env is not None:
                     raise ValueError("Only one environment light is supported in path tracing now.")
-                env = light.image_rh().to(self.device, torch.float32).contiguous()
+                from .flatten import upload
+                env = upload(light.image_rh().contiguous(), self.device, torch.float32, self._upload_shard()).contiguous()
         return env  # None == the reference's 16x16 black texture
 
     # ---- fused path ------------------------------------------------------------------------------------------------
@@ -293,7 +371,7 @@ class PathTracingSession:
 
     def _build_fused_scene(self):
         """drp_scene_t for the fused kernels, or None when some material only exists as Python code."""
-        descs = material_descriptions(self.scene.objects, self.device, rgba=True)
+        descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard())
         if descs is None:
             return None
         vao = self.vertex_array_object()
@@ -345,8 +423,7 @@ class PathTracingSession:
     def tiles(self):
         """Row-major list of (x0, y0, w, h) tiles of the frame (y counted from the bottom row, like the accumulator)."""
         H, W = self.camera.resolution()
-        T = max(1, int(self.options.tile_size))
-        return [(x, y, min(T, W - x), min(T, H - y)) for y in range(0, H, T) for x in range(0, W, T)]
+        return frame_tiles(H, W, self.options.tile_size)
 
     def render_samples(self, sample_ids: torch.Tensor, accum: Optional[torch.Tensor] = None, tile=None) -> torch.Tensor:
         """
@@ -407,6 +484,15 @@ class PathTracingSession:
             raise ValueError("shard_mode must be 'spp' or 'tile'")
         return self.render_samples(shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device))
 
+    def exchange_accumulators(self, accum: torch.Tensor) -> torch.Tensor:
+        """The path's one exchange step between ranks: spp shards are summed (all-reduce); tile shards have disjoint supports and are gathered
+        (``options.tile_collective='gather'``, the default; ``'allreduce'`` sums whole frames like spp sharding -- kept for the A/B)."""
+        opt = self.options
+        if opt.shard_world > 1 and opt.shard_mode == 'tile' and opt.tile_collective == 'gather':
+            H, W = self.camera.resolution()
+            return gather_tile_accumulators(accum, H, W, opt.tile_size, opt.shard_rank, opt.shard_world)
+        return reduce_accumulators(accum, opt.shard_world)
+
     def finalize(self, accum: torch.Tensor):
         """Epilogue of trace_rays (path_tracing.py:348-352): /spp, saturate(alpha), flipud -- one kernel."""
         H, W = self.camera.resolution()
@@ -463,7 +549,7 @@ class PathTracingSession:
                 raise ValueError("sharded rendering needs the fused path (built-in materials, no tensors that require grad)")
             return self.trace_rays(self.sampler_brdf)
         with torch.no_grad():
-            accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
+            accum = self.exchange_accumulators(self.render_accumulators())
             out = self.finalize(accum)
         self.raycaster().check_status()
         return out
@@ -480,7 +566,7 @@ class PathTracingSession:
         if self._fused_scene() is None:
             radiance, alpha, _ = self.trace_rays(self.sampler_brdf)
             return tonemap(torch.cat([radiance, alpha], -1), tone, lut=lut, alpha_offset=3)[1]
-        accum = reduce_accumulators(self.render_accumulators(), self.options.shard_world)
+        accum = self.exchange_accumulators(self.render_accumulators())
         H, W = self.camera.resolution()
         return tonemap(accum.view(H, W, _abi.ACCUM_CHANNELS), tone, lut=lut, scale=1.0 / self.options.ray_spp, alpha_offset=3, flip_rows=True)[1]
 

@@ -68,4 +68,4 @@ def test_degenerate_deep_scene_is_exact():
     assert float((t < 10.0).float().mean()) > 0.2
     from diffrp_b200._lib import lib, check
     check(lib().drp_status(rc.handle), "drp_status")
-    assert rc.stats()['max_depth'] >= 8
+    assert rc.stats()["max_depth"] >= 4

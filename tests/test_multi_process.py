@@ -57,3 +57,29 @@ def test_two_rank_sample_sharding_and_accumulator_reduce(tmp_path):
     a, b = oracle.finalize(summed, H, W, SPP), oracle.finalize(whole, H, W, SPP)
     for k in a:
         np.testing.assert_allclose(a[k], b[k], rtol=1e-5, atol=1e-5)
+
+
+def _tile_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffrp_b200.path_tracing import gather_tile_accumulators, reduce_accumulators, frame_tiles, tile_rows
+    Ht, Wt, tile = 37, 53, 16                      # ragged: partial tiles on both edges, 12 tiles over 2 ranks
+    g = torch.Generator().manual_seed(7)
+    whole = torch.rand(Ht * Wt, 16, generator=g)
+    mine = torch.zeros_like(whole)
+    rows = tile_rows(frame_tiles(Ht, Wt, tile)[rank::world], Wt)
+    mine[rows] = whole[rows]
+    a = gather_tile_accumulators(mine.clone(), Ht, Wt, tile, rank, world)
+    b = reduce_accumulators(mine.clone(), world)
+    assert torch.equal(a, whole) and torch.equal(b, whole), rank     # gather of disjoint supports == sum, bit for bit
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_gather_equals_allreduce(tmp_path):
+    world, port = 2, 31000 + (os.getpid() % 2000)
+    mp.spawn(_tile_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / "ok.npy")[0] == 1

@@ -162,8 +162,9 @@ def test_texel_records_equal_separate_textures(monkeypatch):
     from diffrp_b200.flatten import material_descriptions
     cam_kw = dict(h=96, w=128)
     imgs = []
+    import diffrp_b200.flatten as flatten_mod
     for flag in ('1', '0'):
-        monkeypatch.setenv('DIFFRP_B200_TEXEL_RECORDS', flag)
+        monkeypatch.setattr(flatten_mod, 'INTERLEAVE_TEXELS', flag == '1')
         scene = scenes.to_device(scenes.mixed_scene(), 'cuda')
         descs = material_descriptions(scene.objects, torch.device('cuda'), rgba=True)
         assert any('texel_records' in d for d in descs) == (flag == '1')

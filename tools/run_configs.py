@@ -1,17 +1,21 @@
 """
-BASELINE.json configs[3] and configs[4] at full size (parity-test / capability cases, not bench lines):
+BASELINE.json configs[3] and configs[4] at full size (parity-test / capability cases, not bench lines; reduced-size parity against the oracle:
+tests/test_configs_gpu.py):
 
   --config 4   multi-view datagen: 64 orbit cameras around a 500,000-triangle displaced sphere, 512x512, 64 spp, 3 bounces,
-               radiance + albedo + world_normal AOVs; VIEWS sharded across ranks (no reduction, results gathered).
+               radiance + albedo + world_normal AOVs; VIEWS sharded across ranks (no reduction, results stay on the rank that rendered them).
   --config 5   3840x2160, 256 spp, 3 bounces, env-lit, 10,000,000 triangles = 1000 MeshObjects sharing one 10k-triangle mesh
-               with seeded rigid transforms and 8 tints; TILE-sharded across ranks with an NCCL all-reduce of the accumulator.
+               with seeded rigid transforms and 8 tints; TILE-sharded across ranks; exchange = all-gather of the owned tiles
+               (--tile-collective allreduce: sum of whole frames, for the A/B).
 
     python tools/run_configs.py --config 5            # one GPU
-    torchrun --nproc-per-node 8 tools/run_configs.py --config 5
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_configs.py --config 5 --out gpurun_out/c5_n8.json
+
+Scenes are the seeded generators of diffrp_b200/synthetic.py (datagen_scene, instanced_scene), built on the host and moved to the GPU before the
+timed region (device-resident, like bench.py's `value`).  Roofline: SURVEY 8(d) per-bounce bytes B_bounce = B_query(T) + S_default.
 """
-import argparse, json, os, sys, time
+import argparse, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import torch.distributed as dist
 import diffrp_b200 as drp
@@ -21,76 +25,128 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, required=True, choices=[4, 5])
 ap.add_argument("--scale", type=float, default=1.0, help="scale spp (and views for config 4) for quick runs")
 ap.add_argument("--no-reuse", action="store_true", help="config 4: rebuild the BVH for every view (the reference's behaviour)")
+ap.add_argument("--tile-collective", default="gather", choices=["gather", "allreduce"])
+ap.add_argument("--out", default=None)
+ap.add_argument("--profile", action="store_true", help="config 4: cProfile of the view loop on rank 0 (host overhead per session)")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
-T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-env = syn.torch_noise_texture(256, 512, 3, 7, 0.0, 1.0).to(dev) ** 3 * 5.0 + 0.1
 
 
-def rigid(rng, scale, t):
-    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
-    if np.linalg.det(q) < 0:
-        q[:, 0] = -q[:, 0]
-    m = np.eye(4, dtype=np.float32); m[:3, :3] = q * scale; m[:3, 3] = t
-    return T(m)
+def b_query(n_tris):   # ideal-descent bytes per traced ray (500 k: 980 B, 10 M: 1220 B)
+    return 32 + 48 * math.ceil(math.log2(max(2, n_tris))) + 36
 
 
-ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def peak_gbs():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        j = json.load(open(p))
+        for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_gbs_sustained", "hbm_bw_gbs"):
+            if k in j:
+                return float(j[k]), "MEASURED_PEAKS.json:" + k
+        for k, v in j.items():
+            if "hbm" in k.lower() and isinstance(v, (int, float)):
+                return float(v), "MEASURED_PEAKS.json:" + k
+    except Exception:
+        pass
+    return 7700.0, "fallback (B200_PROFILING.md nominal)"
+
+
+def max_over_ranks(x):
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+S_DEFAULT = 224   # shading bytes per ray-bounce, DefaultMaterial (B_bounce: config 4 = 1204 B, config 5 = 1444 B)
 if args.config == 4:
-    v, f, n, uv, tg = syn.uv_sphere(500, 500, radius=0.8, bump=0.05, noise=0.01, seed=0, with_attrs=True)
-    col = torch.rand(len(v), 4, generator=torch.Generator().manual_seed(3)).to(dev) * 0.6 + 0.4
-    scene = drp.Scene().add_mesh_object(drp.MeshObject(drp.DefaultMaterial(), T(v), T(f), normals=T(n), color=col, uv=T(uv)))
-    scene.add_light(drp.ImageEnvironmentLight(1.0, torch.ones(3, device=dev), env))
-    n_views, spp, depth = max(world, int(64 * args.scale)), max(1, int(64 * args.scale)), 3
+    scene_host, orbit = syn.datagen_scene('cpu')
+    scene = scene_host.to(dev)
+    n_views, spp, depth, res = max(world, int(64 * args.scale)), max(1, int(64 * args.scale)), 3, 512
     views = list(range(n_views))[rank::world]
-    torch.cuda.synchronize(); ev0.record()
+    sess0 = drp.PathTracingSession(scene, drp.PerspectiveCamera.from_orbit(**orbit(0, n_views, res)), drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth))
+    sess0.raycaster(); sess0._fused_scene()   # scene upload + flatten + build once, outside the timed region (options.reuse_scene)
+    n_tris = int(sess0.vertex_array_object().tris.shape[0])
+    if world > 1:
+        dist.barrier()
+    prof = None
+    if args.profile and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
+    torch.cuda.synchronize(); ev[0].record()
     outs, traced = [], 0
     for k in views:
-        cam = drp.PerspectiveCamera.from_orbit(h=512, w=512, radius=3.0, azim=360.0 * k / n_views, elev=20.0 * np.sin(2 * np.pi * k / n_views), origin=[0, 0, 0])
+        cam = drp.PerspectiveCamera.from_orbit(**orbit(k, n_views, res))
         sess = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=k, reuse_scene=not args.no_reuse))
         rad, alpha, extras = sess.pbr()  # a session per view (single-use, like the reference); the scene cache keeps flatten + BVH
-        outs.append(torch.cat([rad, extras['albedo'], extras['world_normal']], -1))
-    ev1.record(); torch.cuda.synchronize()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        outs.append(torch.cat([rad, alpha, extras['albedo'], extras['world_normal']], -1))
+    ev[1].record(); torch.cuda.synchronize()
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
+    ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
     imgs = torch.stack(outs)
-    assert torch.isfinite(imgs).all() and imgs[..., 3:6].max() <= 1.0 + 1e-5
-    nominal = n_views * 512 * 512 * spp * depth
-    res = dict(config=4, n_gpus=world, views=n_views, triangles=int(len(f)), spp=spp, seconds=ms.item() / 1e3, mrays_s=nominal / ms.item() / 1e3,
-               views_per_s=n_views / (ms.item() / 1e3), mean_radiance=float(imgs[..., :3].mean()))
+    assert torch.isfinite(imgs).all() and imgs[..., 4:7].max() <= 1.0 + 1e-5
+    stats = sess.render_stats()
+    live = stats['rays_traced'] / max(1, stats['rays_nominal'])
+    nominal = n_views * res * res * spp * depth
+    peak, peak_src = peak_gbs()
+    bb = b_query(n_tris) + S_DEFAULT
+    res_d = dict(config=4, n_gpus=world, sharding="views rank::world, no exchange", views=n_views, triangles=n_tris, resolution=[res, res], spp=spp, ray_depth=depth,
+                 seconds=ms / 1e3, mrays_s=nominal / ms / 1e3, views_per_s=n_views / (ms / 1e3), live_ray_fraction_last_view=live,
+                 aovs=["radiance", "alpha", "albedo", "world_normal"], mean_radiance=float(imgs[..., :3].mean()), coverage=float((imgs[..., 3] > 0).float().mean()),
+                 roofline=dict(bound="hbm", B_bounce=bb, achieved=nominal * live * bb / (ms * 1e-3) / 1e9 / world, peak=peak, unit="GB/s per GPU",
+                               frac=nominal * live * bb / (ms * 1e-3) / 1e9 / world / peak, peak_source=peak_src,
+                               note="algorithmic bytes = live ray-bounces x B_bounce (SURVEY 8d), per GPU"))
 else:
-    v, f, n, uv, tg = syn.uv_sphere(100, 50, radius=0.045, bump=0.004, noise=0.001, seed=1, with_attrs=True)
-    Vt, Ft, Nt = T(v), T(f), T(n)
-    tints = [torch.tensor(c, device=dev) for c in ([1, .3, .3], [.3, 1, .3], [.3, .3, 1], [1, 1, .3], [1, .3, 1], [.3, 1, 1], [.9, .9, .9], [.5, .5, .5])]
-    mats = [drp.DefaultMaterial(t) for t in tints]
-    rng = np.random.default_rng(0)
-    scene = drp.Scene()
-    for k in range(1000):
-        pos = rng.uniform([-1.6, -0.9, -1.0], [1.6, 0.9, 1.0])
-        scene.add_mesh_object(drp.MeshObject(mats[k % 8], Vt, Ft, normals=Nt, M=rigid(rng, 0.6 + rng.random(), pos)))
-    scene.add_light(drp.ImageEnvironmentLight(1.0, torch.ones(3, device=dev), env))
+    scene_host, camkw = syn.instanced_scene('cpu')
+    scene = scene_host.to(dev)
     H, W, spp, depth = 2160, 3840, max(1, int(256 * args.scale)), 3
-    cam = drp.PerspectiveCamera.from_orbit(h=H, w=W, radius=4.0, azim=20.0, elev=10.0, origin=[0, 0, 0], fov=35)
-    sess = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=2, shard_rank=rank, shard_world=world,
-                                                                          shard_mode='tile', tile_size=256))
-    t0 = time.perf_counter(); sess.raycaster(); torch.cuda.synchronize(); build_s = time.perf_counter() - t0
-    torch.cuda.synchronize(); ev0.record()
-    rad, alpha, extras = sess.pbr()
-    ev1.record(); torch.cuda.synchronize()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    cam = drp.PerspectiveCamera.from_orbit(h=H, w=W, **camkw)
+    opt = drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=2, shard_rank=rank, shard_world=world, shard_mode='tile', tile_size=256,
+                                        tile_collective=args.tile_collective)
+    sess = drp.PathTracingSession(scene, cam, opt)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); sess.raycaster(); sess._fused_scene(); torch.cuda.synchronize(); build_s = time.perf_counter() - t0
+    n_tris = int(sess.vertex_array_object().tris.shape[0])
+    warm = sess.new_accumulators()
+    sess.render_samples(torch.arange(1, dtype=torch.int32, device=dev), warm, tile=sess.tiles()[rank])   # workspace at its full size, kernels loaded
+    sess.exchange_accumulators(warm)
+    del warm
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    torch.cuda.synchronize(); ev[0].record()
+    acc = sess.render_accumulators()
+    ev[1].record()
+    acc = sess.exchange_accumulators(acc)
+    ev[2].record()
+    rad, alpha, extras = sess.finalize(acc)
+    ev[3].record(); torch.cuda.synchronize()
+    ms = max_over_ranks(ev[0].elapsed_time(ev[3]))
+    ms_render, ms_exchange = max_over_ranks(ev[0].elapsed_time(ev[1])), max_over_ranks(ev[1].elapsed_time(ev[2]))
     assert torch.isfinite(rad).all()
     nominal = H * W * spp * depth
-    res = dict(config=5, n_gpus=world, triangles=int(sess.vertex_array_object().tris.shape[0]), resolution=[W, H], spp=spp, flatten_and_build_s=build_s,
-               seconds=ms.item() / 1e3, mrays_s=nominal / ms.item() / 1e3, coverage=float((alpha > 0).float().mean()), mean_radiance=float(rad.mean()),
-               bvh=sess.raycaster().stats())
+    peak, peak_src = peak_gbs()
+    bb = b_query(n_tris) + S_DEFAULT
+    res_d = dict(config=5, n_gpus=world, sharding="256-pixel tiles rank::world, exchange = %s" % args.tile_collective, triangles=n_tris, objects=len(scene.objects),
+                 resolution=[W, H], spp=spp, ray_depth=depth, upload_flatten_build_s=build_s, seconds=ms / 1e3, render_ms=ms_render, exchange_ms=ms_exchange,
+                 exchange_bytes_per_rank=(H * W * 64 * (world - 1) // world) * (1 if args.tile_collective == 'gather' else 2), mrays_s=nominal / ms / 1e3,
+                 coverage=float((alpha > 0).float().mean()), mean_radiance=float(rad.mean()), bvh=sess.raycaster().stats(),
+                 roofline=dict(bound="hbm", B_bounce=bb, peak=peak, unit="GB/s per GPU", peak_source=peak_src,
+                               note="nominal ray-bounces x B_bounce / time / GPUs (live fraction not tracked across tile calls: upper bound of the achieved figure)",
+                               achieved_nominal=nominal * bb / (ms * 1e-3) / 1e9 / world, frac_nominal=nominal * bb / (ms * 1e-3) / 1e9 / world / peak))
 if rank == 0:
-    print(json.dumps(res))
+    txt = json.dumps(res_d)
+    print(txt)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        open(args.out, "w").write(txt + "\n")
 if world > 1:
     dist.destroy_process_group()
