@@ -31,6 +31,8 @@ def _declare(L):
     L.drp_finalize.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.drp_render_stats.argtypes = [u64, C.POINTER(_abi.RenderStats)]
     L.drp_status.argtypes = [u64]
+    L.drp_refit.argtypes = [u64, vp, vp, i64, i64, vp]
+    L.drp_build_instanced.argtypes = [vp, vp, i64, i64, vp, vp, i64, C.c_int, vp, C.POINTER(C.c_uint64)]
     L.drp_debug_set_stack_limit.argtypes = [u64, i32]
     L.drp_flatten.argtypes = [C.POINTER(_abi.Object), i32] + [vp] * 13
     L.drp_set_profiling.argtypes = [u64, C.c_int]

@@ -41,7 +41,15 @@ class Camera:
 
     def V(self) -> torch.Tensor:
         """GL view matrix = inverse of the camera pose ``self.t`` (X right, Y up, -Z forward)."""
-        return gpu_f32(numpy.linalg.inv(self.t).astype(numpy.float32))
+        return gpu_f32(self.V_host())
+
+    def V_host(self) -> numpy.ndarray:
+        """``V()`` as a host fp32 array: the session's set-up reads the matrices on the host, so that no device round trip stalls the
+        stream between two single-use sessions (multi-view rendering)."""
+        return numpy.linalg.inv(self.t).astype(numpy.float32)
+
+    def P_host(self) -> numpy.ndarray:
+        return self.P().detach().cpu().numpy().astype(numpy.float32)
 
     def P(self) -> torch.Tensor:
         raise NotImplementedError
@@ -62,6 +70,9 @@ class RawCamera(Camera):
     def P(self):
         return self.p
 
+    def V_host(self):
+        return self.v.detach().cpu().numpy().astype(numpy.float32)
+
     def resolution(self):
         return self.h, self.w
 
@@ -74,8 +85,11 @@ class PerspectiveCamera(Camera):
         self.fov, self.h, self.w, self.near, self.far = fov, h, w, near, far
 
     def P(self):
+        return gpu_f32(self.P_host())
+
+    def P_host(self) -> numpy.ndarray:
         focal = self.h / (2.0 * math.tan(math.radians(self.fov) / 2.0))  # vertical fov -> focal length in pixels
-        return gpu_f32(gl_perspective(self.w, self.h, self.w / 2, self.h / 2, focal, focal, self.near, self.far).astype(numpy.float32))
+        return gl_perspective(self.w, self.h, self.w / 2, self.h / 2, focal, focal, self.near, self.far).astype(numpy.float32)
 
     def resolution(self):
         return self.h, self.w

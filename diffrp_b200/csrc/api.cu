@@ -4,12 +4,14 @@
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+#include <algorithm>
 #include <cstdio>
 #include "internal.h"
 #include "common.cuh"
 #include "lbvh.cuh"
 #include "traverse.cuh"
 #include "cwbvh.cuh"
+#include "instance_level.h"
 #include <cstdlib>
 #include <chrono>
 
@@ -115,19 +117,9 @@ static cudaError_t alloc_async(T** p, size_t count, cudaStream_t s) {
     return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s);
 }
 
-extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, int device, void* stream,
-                         uint64_t* out_handle) {
-    if (!out_handle || n_tris < 0 || n_verts < 0 || (n_tris > 0 && (!verts || !tris))) {
-        drp_set_error("drp_build: invalid argument");
-        return DRP_ERR_INVALID;
-    }
-    if (n_tris >= (int64_t(1) << 27)) {
-        drp_set_error("drp_build: more than 2^27 triangles are not supported by the leaf encoding");
-        return DRP_ERR_INVALID;
-    }
-    DeviceGuard guard(device);
-    if (!guard.ok) { drp_set_error("drp_build: cannot select device"); return DRP_ERR_CUDA; }
-    cudaStream_t s = (cudaStream_t)stream;
+// Build the wide hierarchy over (verts, tris[0 .. n_tris)) into *h (not registered): device, eps and stack_cap are set by the caller.
+int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, int64_t n_tris, cudaStream_t s) {
+    const int device = h->device;
     const int n = (int)n_tris;
     {   // build scratch comes from the device's default stream-ordered pool; keep freed blocks cached across builds instead of
         // returning them to the driver at every synchronisation (sessions are single-use: one build per frame)
@@ -146,12 +138,8 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
     const bool timing = g_drp_log_level >= 4;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
-    BvhHandle* h = new BvhHandle();
-    h->device = device;
     h->n_tris = n_tris;
     h->n_nodes = n > 1 ? n - 1 : 1;
-    h->stack_cap = CW_STACK;
-
     LbvhBuild b;
     memset(&b, 0, sizeof(b));
     b.verts = verts; b.tris = tris; b.n = n; b.max_leaf = CW_MAX_LEAF;
@@ -230,7 +218,16 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
             DRP_CUDA_CHECK(cudaMemcpyAsync(hc, cw_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
             DRP_CUDA_CHECK(cudaStreamSynchronize(s));
             h->n_nodes_used = n < 2 ? 1 : hc[0];
-            if (n < 2 || levels_done >= 128 || hc[8 + levels_done] >= hc[9 + levels_done]) break;
+            if (n < 2 || levels_done >= 128 || hc[8 + levels_done] >= hc[9 + levels_done]) {
+                // level L occupies nodes [hc[8 + L], hc[9 + L]) (breadth-first allocation): kept for the bottom-up refit
+                h->level_begin.clear();
+                if (n < 2) { h->level_begin = {0, 1}; }
+                else {
+                    for (int L = 0; L < 150 && hc[8 + L] < hc[9 + L]; ++L) h->level_begin.push_back(hc[8 + L]);
+                    h->level_begin.push_back(hc[0]);
+                }
+                break;
+            }
         }
     }
     DRP_CUDA_CHECK(cudaGetLastError());
@@ -239,13 +236,47 @@ extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_vert
                      b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters, b.count, b.dp_cost, b.dp_dec};
     for (void* p : temps)
         if (p) DRP_CUDA_CHECK(cudaFreeAsync(p, s));
-    {
-        std::lock_guard<std::mutex> lk(g_mutex);
-        *out_handle = g_next_handle++;
-        g_handles[*out_handle] = h;
-    }
-    if (timing) fprintf(stderr, "[diffrp_b200] drp_build n=%d: alloc %.2f ms, launch+collapse-sync %.2f ms, free+register %.2f ms\n", n, t_alloc - t_begin,
+    if (timing) fprintf(stderr, "[diffrp_b200] build n=%d: alloc %.2f ms, launch+collapse-sync %.2f ms, free %.2f ms\n", n, t_alloc - t_begin,
                         t_launch - t_alloc, now() - t_launch);
+    return DRP_OK;
+}
+
+void drp_register_handle(BvhHandle* h, uint64_t* out_handle) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    *out_handle = g_next_handle++;
+    g_handles[*out_handle] = h;
+}
+
+BvhHandle* drp_new_handle(int device) {
+    BvhHandle* h = new BvhHandle();
+    h->device = device;
+    h->stack_cap = CW_STACK;
+    return h;
+}
+
+void drp_destroy_handle(BvhHandle* h) {   // device selected by the caller
+    drp_free_workspace(h);
+    cudaFreeAsync(h->nodes, 0); cudaFreeAsync(h->packed, 0); cudaFreeAsync(h->node_box, 0);
+    cudaFree(h->bounds); cudaFree(h->sah); cudaFreeHost(h->sticky_host);
+    delete h;
+}
+
+extern "C" int drp_build(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, int device, void* stream,
+                         uint64_t* out_handle) {
+    if (!out_handle || n_tris < 0 || n_verts < 0 || (n_tris > 0 && (!verts || !tris))) {
+        drp_set_error("drp_build: invalid argument");
+        return DRP_ERR_INVALID;
+    }
+    if (n_tris >= (int64_t(1) << 27)) {
+        drp_set_error("drp_build: more than 2^27 triangles are not supported by the leaf encoding");
+        return DRP_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { drp_set_error("drp_build: cannot select device"); return DRP_ERR_CUDA; }
+    BvhHandle* h = drp_new_handle(device);
+    const int rc = drp_build_structure(h, verts, tris, n_tris, (cudaStream_t)stream);
+    if (rc != DRP_OK) { drp_destroy_handle(h); return rc; }
+    drp_register_handle(h, out_handle);
     if (g_drp_log_level >= 4) fprintf(stderr, "[diffrp_b200] built LBVH over %lld triangles (handle %llu)\n", (long long)n_tris, (unsigned long long)*out_handle);
     return DRP_OK;
 }
@@ -261,9 +292,7 @@ extern "C" int drp_release(uint64_t handle) {
     }
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    drp_free_workspace(h);
-    cudaFreeAsync(h->nodes, 0); cudaFreeAsync(h->packed, 0); cudaFree(h->bounds); cudaFree(h->sah); cudaFreeHost(h->sticky_host);
-    delete h;
+    drp_destroy_handle(h);
     return DRP_OK;
 }
 
@@ -349,5 +378,228 @@ extern "C" int drp_trace_bruteforce(const float* verts, const int32_t* tris, int
     if (n_rays <= 0) return DRP_OK;
     k_bruteforce<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(verts, tris, n_tris, rays_o, rays_d, out_t, out_i, t_far, epsilon, n_rays);
     DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}
+
+// ---- refit and instanced assembly --------------------------------------------------------------------------------------
+// The collapse allocates wide nodes breadth-first, so a bottom-up pass is one launch per level, deepest first (BvhHandle::level_begin).
+struct RefitJob {
+    const float4* src_nodes;   // template hierarchy (== dst for an in-place refit)
+    const float4* src_tris;
+    float4* dst_nodes;
+    float4* dst_tris;
+    float4* node_box;
+    const float* verts;
+    const int32_t* tris;
+    const uint32_t* bounds;    // scene bounds (abs_pad)
+    // instances sharing this template: instance q uses block offsets inst_node_off[q] / inst_tri_off[q] / inst_prim_off[q]; null = one in-place job
+    const int* inst_node_off;
+    const int* inst_tri_off;
+    const int* inst_prim_off;
+    int n_inst;
+};
+__global__ void __launch_bounds__(128) k_cw_refit_level(RefitJob j, int begin, int end) {
+    const int per = end - begin;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)per * j.n_inst) return;
+    const int q = (int)(t / per), ni = begin + (int)(t - (int64_t)q * per);
+    LbvhBuild b;
+    b.bounds = const_cast<uint32_t*>(j.bounds);
+    const float abs_pad = lbvh_abs_pad(b);
+    const int node_off = j.inst_node_off ? j.inst_node_off[q] : 0, tri_off = j.inst_tri_off ? j.inst_tri_off[q] : 0,
+              prim_off = j.inst_prim_off ? j.inst_prim_off[q] : 0;
+    cw_refit_node(j.src_nodes + CW_NODE_F4 * (int64_t)ni, j.src_tris, j.dst_nodes, j.dst_tris, j.node_box, ni + node_off, node_off, tri_off, prim_off,
+                  j.verts, j.tris, abs_pad);
+}
+
+static int scene_bounds(BvhHandle* h, const float* verts, const int32_t* tris, int64_t n_tris, cudaStream_t s) {
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.verts = verts; b.tris = tris; b.n = (int)n_tris; b.bounds = h->bounds;   // prim_lo == null: bounds only
+    k_init_bounds<<<1, 32, 0, s>>>(h->bounds);
+    if (n_tris > 0) k_prim_bounds<<<(int)std::min<int64_t>((n_tris + 255) / 256, 148 * 8), 256, 0, s>>>(b);
+    DRP_CUDA_CHECK(cudaGetLastError());
+    return DRP_OK;
+}
+
+static int ensure_node_box(BvhHandle* h, cudaStream_t s) {
+    if (!h->node_box) DRP_CUDA_CHECK(cudaMallocAsync((void**)&h->node_box, sizeof(float4) * 2 * (size_t)std::max<int64_t>(h->n_nodes_used, 1), s));
+    return DRP_OK;
+}
+
+extern "C" int drp_refit(uint64_t handle, const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, void* stream) {
+    BvhHandle* h = drp_lookup(handle);
+    if (!h) { drp_set_error("drp_refit: unknown handle"); return DRP_ERR_HANDLE; }
+    if (n_tris != h->n_tris || n_verts < 0 || (n_tris > 0 && (!verts || !tris))) {
+        drp_set_error("drp_refit: the triangle count must match the built structure (refit keeps the topology: same index array, new vertex positions)");
+        return DRP_ERR_INVALID;
+    }
+    if (int rc = drp_check_sticky(h, "drp_refit")) return rc;
+    if (n_tris < 2 || h->level_begin.size() < 2) { drp_set_error("drp_refit: structures over fewer than 2 triangles are rebuilt, not refitted"); return DRP_ERR_INVALID; }
+    DeviceGuard guard(h->device);
+    if (!guard.ok) { drp_set_error("drp_refit: cannot select device"); return DRP_ERR_CUDA; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = ensure_node_box(h, s)) return rc;
+    if (int rc = scene_bounds(h, verts, tris, n_tris, s)) return rc;
+    RefitJob j;
+    memset(&j, 0, sizeof(j));
+    j.src_nodes = h->nodes; j.src_tris = h->packed; j.dst_nodes = h->nodes; j.dst_tris = h->packed; j.node_box = h->node_box;
+    j.verts = verts; j.tris = tris; j.bounds = h->bounds; j.n_inst = 1;
+    for (int L = (int)h->level_begin.size() - 2; L >= 0; --L) {
+        const int begin = h->level_begin[L], end = h->level_begin[L + 1];
+        if (end > begin) k_cw_refit_level<<<(end - begin + 127) / 128, 128, 0, s>>>(j, begin, end);
+    }
+    DRP_CUDA_CHECK(cudaGetLastError());
+    if (h->ws) drp_invalidate_scene_box(h);
+    return DRP_OK;
+}
+
+__global__ void k_copy_roots(float4* nodes, const int2* copies, const int* inst_node_off, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * CW_NODE_F4) return;
+    const int c = t / CW_NODE_F4, f = t - c * CW_NODE_F4;
+    nodes[CW_NODE_F4 * (int64_t)copies[c].y + f] = nodes[CW_NODE_F4 * (int64_t)inst_node_off[copies[c].x] + f];
+}
+__global__ void k_gather_root_boxes(const float4* node_box, const int* inst_node_off, int n, float4* out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    out[2 * q] = node_box[2 * (int64_t)inst_node_off[q]];
+    out[2 * q + 1] = node_box[2 * (int64_t)inst_node_off[q] + 1];
+}
+
+extern "C" int drp_build_instanced(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, const int64_t* inst_first_tri,
+                                   const int32_t* inst_mesh, int64_t n_inst, int device, void* stream, uint64_t* out_handle) {
+    if (!out_handle || !verts || !tris || !inst_first_tri || !inst_mesh || n_inst < 1 || n_tris < 2 || n_verts < 0) {
+        drp_set_error("drp_build_instanced: invalid argument");
+        return DRP_ERR_INVALID;
+    }
+    if (n_tris >= (int64_t(1) << 27)) { drp_set_error("drp_build_instanced: more than 2^27 triangles are not supported"); return DRP_ERR_INVALID; }
+    if (inst_first_tri[0] != 0 || inst_first_tri[n_inst] != n_tris) { drp_set_error("drp_build_instanced: instance ranges must tile [0, n_tris)"); return DRP_ERR_INVALID; }
+    // representative (first) instance of every mesh; all instances of a mesh must have its triangle count
+    std::unordered_map<int, int> rep;
+    for (int64_t q = 0; q < n_inst; ++q) {
+        const int64_t cnt = inst_first_tri[q + 1] - inst_first_tri[q];
+        if (cnt < 2) { drp_set_error("drp_build_instanced: every instance needs at least 2 triangles"); return DRP_ERR_INVALID; }
+        auto it = rep.find(inst_mesh[q]);
+        if (it == rep.end()) rep[inst_mesh[q]] = (int)q;
+        else if (inst_first_tri[it->second + 1] - inst_first_tri[it->second] != cnt) {
+            drp_set_error("drp_build_instanced: instances of one mesh must have the same triangle count (and connectivity)");
+            return DRP_ERR_INVALID;
+        }
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { drp_set_error("drp_build_instanced: cannot select device"); return DRP_ERR_CUDA; }
+    cudaStream_t s = (cudaStream_t)stream;
+    // 1. one template hierarchy per mesh, built over its representative instance's world-space triangles (local primitive ids)
+    std::unordered_map<int, BvhHandle*> blas;
+    auto cleanup = [&]() { for (auto& kv : blas) drp_destroy_handle(kv.second); };
+    for (auto& kv : rep) {
+        BvhHandle* t = drp_new_handle(device);
+        const int64_t first = inst_first_tri[kv.second], cnt = inst_first_tri[kv.second + 1] - first;
+        const int rc = drp_build_structure(t, verts, tris + 3 * first, cnt, s);
+        blas[kv.first] = t;
+        if (rc != DRP_OK) { cleanup(); return rc; }
+    }
+    // 2. layout: [instance level (<= 2 n_inst nodes)] [block of instance 0] [block of instance 1] ...; triangles in instance order
+    BvhHandle* h = drp_new_handle(device);
+    std::vector<int> node_off(n_inst), tri_off(n_inst), prim_off(n_inst);
+    const int64_t tlas_cap = 2 * n_inst + 8;
+    int64_t nodes_total = tlas_cap;
+    for (int64_t q = 0; q < n_inst; ++q) {
+        node_off[q] = (int)nodes_total; tri_off[q] = (int)inst_first_tri[q]; prim_off[q] = (int)inst_first_tri[q];
+        nodes_total += blas[inst_mesh[q]]->n_nodes_used;
+    }
+    h->n_tris = n_tris; h->n_nodes = nodes_total; h->n_nodes_used = nodes_total;
+    int *d_node_off = nullptr, *d_tri_off = nullptr, *d_prim_off = nullptr;
+    float4* d_root_boxes = nullptr;
+    int2* d_copies = nullptr;
+    auto fail = [&](int rc) { cleanup(); drp_destroy_handle(h); cudaFreeAsync(d_node_off, s); cudaFreeAsync(d_tri_off, s); cudaFreeAsync(d_prim_off, s);
+                              cudaFreeAsync(d_root_boxes, s); cudaFreeAsync(d_copies, s); return rc; };
+#define DRP_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { drp_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(DRP_ERR_CUDA); } } while (0)
+    DRP_TRY(cudaMallocAsync((void**)&h->nodes, sizeof(float4) * CW_NODE_F4 * (size_t)nodes_total, s));
+    DRP_TRY(cudaMallocAsync((void**)&h->packed, sizeof(float4) * 3 * (size_t)n_tris, s));
+    DRP_TRY(cudaMallocAsync((void**)&h->node_box, sizeof(float4) * 2 * (size_t)nodes_total, s));
+    DRP_TRY(cudaMalloc((void**)&h->bounds, sizeof(uint32_t) * 12));
+    DRP_TRY(cudaMalloc((void**)&h->sah, sizeof(float)));
+    DRP_TRY(cudaMemsetAsync(h->sah, 0, sizeof(float), s));
+    DRP_TRY(cudaHostAlloc((void**)&h->sticky_host, sizeof(int), cudaHostAllocMapped));
+    *h->sticky_host = 0;
+    DRP_TRY(cudaHostGetDevicePointer((void**)&h->sticky_dev, h->sticky_host, 0));
+    DRP_TRY(cudaMemsetAsync(h->nodes, 0, sizeof(float4) * CW_NODE_F4 * (size_t)tlas_cap, s));
+    if (scene_bounds(h, verts, tris, n_tris, s) != DRP_OK) return fail(DRP_ERR_CUDA);
+    DRP_TRY(cudaMallocAsync((void**)&d_node_off, sizeof(int) * n_inst, s));
+    DRP_TRY(cudaMallocAsync((void**)&d_tri_off, sizeof(int) * n_inst, s));
+    DRP_TRY(cudaMallocAsync((void**)&d_prim_off, sizeof(int) * n_inst, s));
+    DRP_TRY(cudaMallocAsync((void**)&d_root_boxes, sizeof(float4) * 2 * n_inst, s));
+    // 3. replicate + refit, mesh by mesh, deepest level first: one thread per (instance, node).  Instances of a mesh are processed together,
+    //    so the offset tables are uploaded grouped by mesh.
+    std::vector<int> order;   // instances grouped by mesh
+    std::vector<std::pair<int, std::pair<int, int>>> groups;   // (mesh, [first, count) in `order`)
+    for (auto& kv : rep) {
+        const int first = (int)order.size();
+        for (int64_t q = 0; q < n_inst; ++q) if (inst_mesh[q] == kv.first) order.push_back((int)q);
+        groups.push_back({kv.first, {first, (int)order.size() - first}});
+    }
+    std::vector<int> g_node(n_inst), g_tri(n_inst), g_prim(n_inst);
+    for (int64_t k = 0; k < n_inst; ++k) {
+        // block offsets are relative to the template's own indices: template node j -> node_off + j
+        g_node[k] = node_off[order[k]]; g_tri[k] = tri_off[order[k]]; g_prim[k] = prim_off[order[k]];
+    }
+    DRP_TRY(cudaMemcpyAsync(d_node_off, g_node.data(), sizeof(int) * n_inst, cudaMemcpyHostToDevice, s));
+    DRP_TRY(cudaMemcpyAsync(d_tri_off, g_tri.data(), sizeof(int) * n_inst, cudaMemcpyHostToDevice, s));
+    DRP_TRY(cudaMemcpyAsync(d_prim_off, g_prim.data(), sizeof(int) * n_inst, cudaMemcpyHostToDevice, s));
+    for (auto& grp : groups) {
+        BvhHandle* t = blas[grp.first];
+        RefitJob j;
+        memset(&j, 0, sizeof(j));
+        j.src_nodes = t->nodes; j.src_tris = t->packed; j.dst_nodes = h->nodes; j.dst_tris = h->packed; j.node_box = h->node_box;
+        j.verts = verts; j.tris = tris; j.bounds = h->bounds;
+        j.inst_node_off = d_node_off + grp.second.first; j.inst_tri_off = d_tri_off + grp.second.first; j.inst_prim_off = d_prim_off + grp.second.first;
+        j.n_inst = grp.second.second;
+        for (int L = (int)t->level_begin.size() - 2; L >= 0; --L) {
+            const int begin = t->level_begin[L], end = t->level_begin[L + 1];
+            const int64_t threads = (int64_t)(end - begin) * j.n_inst;
+            if (threads > 0) k_cw_refit_level<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(j, begin, end);
+        }
+    }
+    // 4. instance level on the host over the refitted root boxes (grouped order -> instance order)
+    k_gather_root_boxes<<<(unsigned)((n_inst + 127) / 128), 128, 0, s>>>(h->node_box, d_node_off, (int)n_inst, d_root_boxes);
+    std::vector<float4> hb(2 * (size_t)n_inst);
+    DRP_TRY(cudaMemcpyAsync(hb.data(), d_root_boxes, sizeof(float4) * 2 * n_inst, cudaMemcpyDeviceToHost, s));
+    DRP_TRY(cudaStreamSynchronize(s));
+    std::vector<float> lo(3 * (size_t)n_inst), hi(3 * (size_t)n_inst);
+    for (int64_t k = 0; k < n_inst; ++k) {
+        const int q = order[k];
+        lo[3 * (size_t)q] = hb[2 * k].x; lo[3 * (size_t)q + 1] = hb[2 * k].y; lo[3 * (size_t)q + 2] = hb[2 * k].z;
+        hi[3 * (size_t)q] = hb[2 * k + 1].x; hi[3 * (size_t)q + 1] = hb[2 * k + 1].y; hi[3 * (size_t)q + 2] = hb[2 * k + 1].z;
+    }
+    TlasBuilder tb(lo, hi);
+    tb.nodes.resize(CW_NODE_F4, make_float4(0, 0, 0, 0));
+    std::vector<int> ids(n_inst);
+    for (int64_t q = 0; q < n_inst; ++q) ids[q] = (int)q;
+    if (n_inst == 1) {   // the root of the instance level has the single instance as its only child
+        tlas_single(tb, lo.data(), hi.data());
+    } else {
+        tb.build(0, ids.data(), (int)n_inst);
+    }
+    if (tb.allocated > tlas_cap) { drp_set_error("drp_build_instanced: instance level larger than its reservation"); return fail(DRP_ERR_INVALID); }
+    tb.nodes.resize((size_t)tb.allocated * CW_NODE_F4, make_float4(0, 0, 0, 0));
+    DRP_TRY(cudaMemcpyAsync(h->nodes, tb.nodes.data(), sizeof(float4) * tb.nodes.size(), cudaMemcpyHostToDevice, s));
+    std::vector<int2> copies(tb.copies.size());
+    for (size_t k = 0; k < copies.size(); ++k) copies[k] = make_int2(tb.copies[k].first, tb.copies[k].second);
+    DRP_TRY(cudaMallocAsync((void**)&d_copies, sizeof(int2) * copies.size(), s));
+    DRP_TRY(cudaMemcpyAsync(d_copies, copies.data(), sizeof(int2) * copies.size(), cudaMemcpyHostToDevice, s));
+    // the copy kernel indexes the offset table by instance id: upload it in instance order
+    DRP_TRY(cudaMemcpyAsync(d_node_off, node_off.data(), sizeof(int) * n_inst, cudaMemcpyHostToDevice, s));
+    k_copy_roots<<<(unsigned)((tb.copies.size() * CW_NODE_F4 + 127) / 128), 128, 0, s>>>(h->nodes, d_copies, d_node_off, (int)tb.copies.size());
+    DRP_TRY(cudaGetLastError());
+    DRP_TRY(cudaStreamSynchronize(s));   // host vectors above are pageable sources of the async copies
+#undef DRP_TRY
+    cudaFreeAsync(d_node_off, s); cudaFreeAsync(d_tri_off, s); cudaFreeAsync(d_prim_off, s); cudaFreeAsync(d_root_boxes, s); cudaFreeAsync(d_copies, s);
+    cleanup();
+    h->level_begin.clear();   // a mixed structure: refit goes through a rebuild
+    drp_register_handle(h, out_handle);
+    if (g_drp_log_level >= 4) fprintf(stderr, "[diffrp_b200] instanced build: %lld instances of %zu meshes, %lld triangles, %lld nodes (instance level %d)\n",
+                                      (long long)n_inst, rep.size(), (long long)n_tris, (long long)nodes_total, tb.allocated);
     return DRP_OK;
 }

@@ -71,6 +71,77 @@ DRP_HD float cw_axis_scale(uint32_t ebits, int axis) {  // 2^e of axis 0..2
 }
 DRP_HD uint32_t cw_pack4(const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
 
+// Encode one wide node from the (padded, conservative) boxes of its occupied slots: node box = their union, per-axis power-of-two grid
+// over it, child boxes quantised outwards to 8 bits.  Slot s is occupied iff it is internal (imask bit s) or holds triangles (vmask bits
+// 3s..3s+2).  Used by the collapse, by the refit of an existing topology (cw_refit_node) and by the host-built instance level.
+DRP_HD void cw_encode_node(float4* o, const float slo[8][3], const float shi[8][3], uint32_t imask, uint32_t vmask, int child_base, int tri_base,
+                           float nlo[3], float nhi[3]) {
+    for (int a = 0; a < 3; ++a) { nlo[a] = 3e38f; nhi[a] = -3e38f; }
+    uint32_t used = imask;
+    for (int s = 0; s < 8; ++s) {
+        if ((vmask >> (3 * s)) & 7u) used |= 1u << s;
+        if (used & (1u << s))
+            for (int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], slo[s][a]); nhi[a] = fmaxf(nhi[a], shi[s][a]); }
+    }
+    if (used == 0) for (int a = 0; a < 3; ++a) { nlo[a] = 0.0f; nhi[a] = 0.0f; }
+    // per-axis exponent of the 8-bit grid
+    int e[3];
+    float inv_scale[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext = nhi[a] - nlo[a];
+        int ea = (int)ceilf(log2f(fmaxf(ext, 1e-30f) / 255.0f));
+        ea = ea < -100 ? -100 : (ea > 100 ? 100 : ea);
+        while (ext > 255.0f * i2f((ea + 127) << 23) && ea < 100) ++ea;
+        e[a] = ea;
+        inv_scale[a] = i2f((127 - ea) << 23);
+    }
+    uint32_t q[6][8];
+    for (int s = 0; s < 8; ++s) {
+        if (!(used & (1u << s))) {
+            for (int a = 0; a < 3; ++a) { q[a][s] = 255; q[3 + a][s] = 0; }   // empty slot: lo 255 > hi 0 never hits
+            continue;
+        }
+        for (int a = 0; a < 3; ++a) {
+            float ql = floorf((slo[s][a] - nlo[a]) * inv_scale[a]);
+            float qh = ceilf((shi[s][a] - nlo[a]) * inv_scale[a]);
+            q[a][s] = (uint32_t)fminf(fmaxf(ql, 0.0f), 255.0f);
+            q[3 + a][s] = (uint32_t)fminf(fmaxf(qh, 0.0f), 255.0f);
+        }
+    }
+    uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]) | (imask << 24);
+    o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
+    o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(vmask), u2f(0u));
+    o[2] = make_float4(u2f(cw_pack4(q[0])), u2f(cw_pack4(q[0] + 4)), u2f(cw_pack4(q[1])), u2f(cw_pack4(q[1] + 4)));
+    o[3] = make_float4(u2f(cw_pack4(q[2])), u2f(cw_pack4(q[2] + 4)), u2f(cw_pack4(q[3])), u2f(cw_pack4(q[3] + 4)));
+    o[4] = make_float4(u2f(cw_pack4(q[4])), u2f(cw_pack4(q[4] + 4)), u2f(cw_pack4(q[5])), u2f(cw_pack4(q[5] + 4)));
+}
+
+// Slot s stands for the octant direction ((s&4)?+:-, (s&2)?+:-, (s&1)?+:-); greedily give each slot the child that lies furthest in
+// that direction (centre relative to the centre of the node box), so that (slot ^ octant) orders children front to back for any ray.
+// lo / hi: k <= 8 child boxes; nlo / nhi: their union.  slot_child[s] = child index or -1.
+DRP_HD void cw_assign_slots(const float lo[8][3], const float hi[8][3], int k, const float nlo[3], const float nhi[3], int slot_child[8]) {
+    float cost[8][8];
+    for (int j = 0; j < k; ++j) {
+        float cx = 0.5f * (lo[j][0] + hi[j][0]) - 0.5f * (nlo[0] + nhi[0]);
+        float cy = 0.5f * (lo[j][1] + hi[j][1]) - 0.5f * (nlo[1] + nhi[1]);
+        float cz = 0.5f * (lo[j][2] + hi[j][2]) - 0.5f * (nlo[2] + nhi[2]);
+        for (int s = 0; s < 8; ++s) cost[j][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
+    }
+    bool child_done[8] = {false, false, false, false, false, false, false, false};
+    for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    for (int it = 0; it < k; ++it) {
+        float bc = -3e38f;
+        int bj = -1, bs = -1;
+        for (int j = 0; j < k; ++j) {
+            if (child_done[j]) continue;
+            for (int s = 0; s < 8; ++s)
+                if (slot_child[s] < 0 && cost[j][s] > bc) { bc = cost[j][s]; bj = j; bs = s; }
+        }
+        slot_child[bs] = bj;
+        child_done[bj] = true;
+    }
+}
+
 // Collapse the binary subtree rooted at work[ni] into wide node ni.  `atomic_add(ptr, v)` returns the old value.
 template <typename AtomicAdd>
 DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
@@ -124,56 +195,16 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
         hi[j][0] = h.x; hi[j][1] = h.y; hi[j][2] = h.z;
         for (int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], lo[j][a]); nhi[a] = fmaxf(nhi[a], hi[j][a]); }
     }
-    // slot assignment: slot s stands for the octant direction ((s&4)?+:-, (s&2)?+:-, (s&1)?+:-); greedily give each slot the
-    // child that lies furthest in that direction, so that (slot ^ octant) orders children front to back for any ray.
-    float cost[8][8];
-    for (int j = 0; j < k; ++j) {
-        float cx = 0.5f * (lo[j][0] + hi[j][0]) - 0.5f * (nlo[0] + nhi[0]);
-        float cy = 0.5f * (lo[j][1] + hi[j][1]) - 0.5f * (nlo[1] + nhi[1]);
-        float cz = 0.5f * (lo[j][2] + hi[j][2]) - 0.5f * (nlo[2] + nhi[2]);
-        for (int s = 0; s < 8; ++s) cost[j][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
-    }
-    const int n_slots = 8;
-    int slot_child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-    bool child_done[8] = {false, false, false, false, false, false, false, false};
-    for (int it = 0; it < k; ++it) {
-        float bc = -3e38f;
-        int bj = -1, bs = -1;
-        for (int j = 0; j < k; ++j) {
-            if (child_done[j]) continue;
-            for (int s = 0; s < n_slots; ++s)
-                if (slot_child[s] < 0 && cost[j][s] > bc) { bc = cost[j][s]; bj = j; bs = s; }
-        }
-        slot_child[bs] = bj;
-        child_done[bj] = true;
-    }
-    // per-axis exponent of the 8-bit grid
-    int e[3];
-    float scale[3], inv_scale[3];
-    for (int a = 0; a < 3; ++a) {
-        float ext = nhi[a] - nlo[a];
-        int ea = (int)ceilf(log2f(fmaxf(ext, 1e-30f) / 255.0f));
-        ea = ea < -100 ? -100 : (ea > 100 ? 100 : ea);
-        while (ext > 255.0f * i2f((ea + 127) << 23) && ea < 100) ++ea;
-        e[a] = ea;
-        scale[a] = i2f((ea + 127) << 23);
-        inv_scale[a] = i2f((127 - ea) << 23);
-    }
-    uint32_t q[6][8];
+    int slot_child[8];
+    cw_assign_slots(lo, hi, k, nlo, nhi, slot_child);
+    // which slots hold internal children / how many triangles the leaf slots hold
     uint32_t imask = 0, vmask = 0;
     int n_inner = 0, n_tris = 0;
+    float slo[8][3], shi[8][3];
     for (int s = 0; s < 8; ++s) {
         int j = slot_child[s];
-        if (j < 0) {
-            for (int a = 0; a < 3; ++a) { q[a][s] = 255; q[3 + a][s] = 0; }
-            continue;
-        }
-        for (int a = 0; a < 3; ++a) {
-            float ql = floorf((lo[j][a] - nlo[a]) * inv_scale[a]);
-            float qh = ceilf((hi[j][a] - nlo[a]) * inv_scale[a]);
-            q[a][s] = (uint32_t)fminf(fmaxf(ql, 0.0f), 255.0f);
-            q[3 + a][s] = (uint32_t)fminf(fmaxf(qh, 0.0f), 255.0f);
-        }
+        if (j < 0) continue;
+        for (int a = 0; a < 3; ++a) { slo[s][a] = lo[j][a]; shi[s][a] = hi[j][a]; }
         int c = child[j];
         if (cw_is_leaf_child(b, c)) {
             int cnt = cw_leaf_count(b, c);
@@ -207,13 +238,8 @@ DRP_HD void cw_collapse_node(const CwBuild& cw, int ni, AtomicAdd atomic_add) {
             toff += cnt;
         }
     }
-    float4* o = cw.cw_nodes + CW_NODE_F4 * (int64_t)ni;
-    uint32_t ebits = cw_pack_exponents(e[0], e[1], e[2]) | (imask << 24);
-    o[0] = make_float4(nlo[0], nlo[1], nlo[2], u2f(ebits));
-    o[1] = make_float4(i2f(child_base), i2f(tri_base), u2f(vmask), u2f(0u));
-    o[2] = make_float4(u2f(cw_pack4(q[0])), u2f(cw_pack4(q[0] + 4)), u2f(cw_pack4(q[1])), u2f(cw_pack4(q[1] + 4)));
-    o[3] = make_float4(u2f(cw_pack4(q[2])), u2f(cw_pack4(q[2] + 4)), u2f(cw_pack4(q[3])), u2f(cw_pack4(q[3] + 4)));
-    o[4] = make_float4(u2f(cw_pack4(q[4])), u2f(cw_pack4(q[4] + 4)), u2f(cw_pack4(q[5])), u2f(cw_pack4(q[5] + 4)));
+    float box_lo[3], box_hi[3];
+    cw_encode_node(cw.cw_nodes + CW_NODE_F4 * (int64_t)ni, slo, shi, imask, vmask, child_base, tri_base, box_lo, box_hi);
 }
 
 // n < 2: one node whose slot 0 is a leaf with n triangles
@@ -417,4 +443,49 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
                            bool& overflow) {
     uint32_t st_x[CW_STACK], st_y[CW_STACK];
     return cw_trace_one_stack(nodes, tris, o, d, t_far, eps, CwPairStack{st_x, st_y}, CW_STACK, overflow);
+}
+
+// ---- refit: new boxes and triangle records for an existing topology ------------------------------------------------
+// Re-derive wide node `src` (5 float4 of a template hierarchy) for new vertex positions and write it as node `dst_ni` of the output
+// hierarchy.  The topology is kept: slot occupancy (imask / V), child order, triangle order; child / triangle bases are shifted by
+// `node_off` / `tri_off` and primitive ids by `prim_off` (0 for an in-place refit; block offsets when the template is replicated for one
+// instance of a shared mesh).  Internal children must already have been refitted (deeper levels first): their exact boxes are read
+// from node_box.  Triangles of leaf slots are re-packed from (verts, tris) -- rounded exactly like the builder's -- and their padded
+// boxes enter the node, so the slab tests stay conservative and closest hits stay the exhaustive ones, whatever the hierarchy.
+DRP_HD void cw_refit_node(const float4* src, const float4* src_tris, float4* out_nodes, float4* out_tris,   // (may alias: in-place refit)
+                          float4* node_box, int dst_ni, int node_off, int tri_off, int prim_off, const float* __restrict__ verts,
+                          const int32_t* __restrict__ tris, float abs_pad) {
+    const uint32_t imask = f2u(src[0].w) >> 24, vmask = f2u(src[1].z);
+    const int cb = f2i(src[1].x), tb = f2i(src[1].y);
+    float slo[8][3], shi[8][3];
+    int rank = 0;
+    for (int s = 0; s < 8; ++s) {
+        if (imask & (1u << s)) {
+            const int child = cb + node_off + rank++;
+            const float4 l = node_box[2 * (int64_t)child], h = node_box[2 * (int64_t)child + 1];
+            slo[s][0] = l.x; slo[s][1] = l.y; slo[s][2] = l.z;
+            shi[s][0] = h.x; shi[s][1] = h.y; shi[s][2] = h.z;
+            continue;
+        }
+        const uint32_t bits = (vmask >> (3 * s)) & 7u;
+        if (!bits) continue;
+        float4 l = make_float4(3e38f, 3e38f, 3e38f, 0.0f), h = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
+        for (int k = 0; k < 3; ++k) {
+            if (!(bits & (1u << k))) continue;
+            const int j = cw_tri_index((uint32_t)tb, vmask, 3 * s + k);
+            const int prim = f2i(src_tris[3 * (int64_t)j + 2].y) + prim_off;
+            const Vec3 A = load_vert(verts, tris[3 * (int64_t)prim]), B = load_vert(verts, tris[3 * (int64_t)prim + 1]),
+                       C = load_vert(verts, tris[3 * (int64_t)prim + 2]);
+            pack_triangle(out_tris + 3 * (int64_t)(j + tri_off), A, B, C, prim);
+            l.x = fminf(l.x, fminf(fminf(A.x, B.x), C.x)); l.y = fminf(l.y, fminf(fminf(A.y, B.y), C.y)); l.z = fminf(l.z, fminf(fminf(A.z, B.z), C.z));
+            h.x = fmaxf(h.x, fmaxf(fmaxf(A.x, B.x), C.x)); h.y = fmaxf(h.y, fmaxf(fmaxf(A.y, B.y), C.y)); h.z = fmaxf(h.z, fmaxf(fmaxf(A.z, B.z), C.z));
+        }
+        pad_box(l, h, abs_pad);
+        slo[s][0] = l.x; slo[s][1] = l.y; slo[s][2] = l.z;
+        shi[s][0] = h.x; shi[s][1] = h.y; shi[s][2] = h.z;
+    }
+    float nlo[3], nhi[3];
+    cw_encode_node(out_nodes + CW_NODE_F4 * (int64_t)dst_ni, slo, shi, imask, vmask, cb + node_off, tb + tri_off, nlo, nhi);
+    node_box[2 * (int64_t)dst_ni] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+    node_box[2 * (int64_t)dst_ni + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
 }

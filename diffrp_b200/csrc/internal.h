@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "../../include/diffrp_b200.h"
 
 struct RenderWorkspace;
@@ -14,6 +15,8 @@ struct BvhHandle {
     int64_t n_nodes_used = 0;  // wide layout: nodes actually emitted
     float eps = 1e-8f;          // |det| threshold of the triangle test (raycaster_epsilon)
     float4* nodes = nullptr;    // (n_nodes, 5): compressed 8-wide layout (cwbvh.cuh)
+    float4* node_box = nullptr; // (n_nodes, 2) exact (lo, hi) box of every node: scratch of the refit / instanced assembly, allocated on first use
+    std::vector<int> level_begin;  // nodes of level L: [level_begin[L], level_begin[L + 1]) -- breadth-first allocation order of the collapse
     float4* packed = nullptr;   // (n_tris, 3) triangles in leaf order
     uint32_t* bounds = nullptr; // (12) ordered-uint scene bounds (device)
     float* sah = nullptr;       // device: root cost / root area
@@ -27,7 +30,12 @@ struct BvhHandle {
 void drp_set_error(const std::string& msg);
 BvhHandle* drp_lookup(uint64_t handle);
 void drp_free_workspace(BvhHandle* h);
+void drp_invalidate_scene_box(BvhHandle* h);   // after a refit: the cached compaction box of the workspace is stale
 int drp_check_sticky(BvhHandle* h, const char* who);
+int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, int64_t n_tris, cudaStream_t s);
+BvhHandle* drp_new_handle(int device);
+void drp_register_handle(BvhHandle* h, uint64_t* out_handle);
+void drp_destroy_handle(BvhHandle* h);
 int drp_trace_wide_persistent(BvhHandle* h, const float* ro, const float* rd, float* out_t, int32_t* out_i, float t_far, int64_t n, cudaStream_t s);
 extern int g_drp_log_level;
 

@@ -66,8 +66,10 @@ DRP_HD void lbvh_prim_bounds(const LbvhBuild& b, int i, Vec3& lo, Vec3& hi) {
     Vec3 C = load_vert(b.verts, b.tris[3 * (int64_t)i + 2]);
     lo = v3(fminf(fminf(A.x, B.x), C.x), fminf(fminf(A.y, B.y), C.y), fminf(fminf(A.z, B.z), C.z));
     hi = v3(fmaxf(fmaxf(A.x, B.x), C.x), fmaxf(fmaxf(A.y, B.y), C.y), fmaxf(fmaxf(A.z, B.z), C.z));
-    b.prim_lo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
-    b.prim_hi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    if (b.prim_lo) {   // (null: scene bounds only -- refit / instanced assembly)
+        b.prim_lo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        b.prim_hi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
 }
 
 // ---- phase 2 --------------------------------------------------------------------------------------------------

@@ -488,6 +488,8 @@ void drp_free_workspace(BvhHandle* h) {
     h->ws = nullptr;
 }
 
+void drp_invalidate_scene_box(BvhHandle* h) { if (h->ws) h->ws->have_box = false; }
+
 static int ensure_workspace(BvhHandle* h, int64_t rays, int n_mats) {
     if (!h->ws) {
         std::lock_guard<std::mutex> lk(g_ws_mutex);

@@ -15,6 +15,8 @@ There is no CPU fallback: without the CUDA library / a CUDA device the session r
 """
 import math
 import ctypes as C
+
+import numpy
 from dataclasses import dataclass
 from typing import Callable, Dict, Optional
 
@@ -53,6 +55,11 @@ class PathTracingSessionOptions:
         reuse_scene (bool): sessions are single-use like the reference's, but the flattened buffers, uploaded textures and the BVH
             of a ``Scene`` are kept (one entry per scene, keyed by the identity, shape and in-place version counter of every tensor)
             and adopted by the next session over the same unmodified scene -- multi-view rendering builds once, not per view.
+        refit_scene (bool): when a later session renders the same ``Scene`` object and only positions / transforms / attributes changed (every
+            object's index tensor is the same, unmodified tensor), the structure of the previous session is refitted -- boxes and triangle
+            records recomputed bottom-up over the old topology (``drp_refit``) -- instead of rebuilt.  Hits are exact either way.
+        instancing (bool): objects that share their vertex and index tensors are built as instances of one mesh (``drp_build_instanced``): the
+            result is still one world-space hierarchy with the flattened primitive ids, the sort / collapse cost is paid once per mesh.
         compaction (bool): drop rays that provably contribute nothing to any output (exact; the reference keeps
             tracing them with zero throughput).
         scene_upload: with ``shard_world > 1`` the scene is replicated; when it still lives in (pinned) host memory, ``'sharded'`` (what ``'auto'``
@@ -82,6 +89,8 @@ class PathTracingSessionOptions:
     shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
     tile_collective: str = 'gather'   # 'gather': all-gather of the owned tiles' rows; 'allreduce': sum whole frames
+    refit_scene: bool = True          # a later session over the same Scene with unchanged connectivity refits the structure instead of rebuilding
+    instancing: bool = True           # objects sharing vertex + index tensors: one hierarchy per mesh, replicated and refitted per instance
     scene_upload: str = 'auto'        # host scenes under sharding: 'sharded' = 1/world of every tensor per rank over PCIe + all-gather over NVLink
     reuse_scene: bool = True  # share the flattened scene + BVH between sessions over the same, unmodified Scene
     reproducible: bool = False  # bit-identical images run to run: one sample per launch batch, fixed fp32 accumulation order
@@ -122,6 +131,8 @@ def raygen_tables(V: torch.Tensor, P: torch.Tensor, H: int, W: int, spp: int, de
     Everything the primary-ray generator needs, computed with the same torch / numpy calls as the reference so the
     values are identical: camera position and inv(VP) (mixin.py:31-39, host numpy inverse), far / near (mixin.py:38,44),
     pixel-centre NDC ramps (coordinates.py:6-10) and the per-sample Hammersley offsets (path_tracing.py:317,329).
+    ``V`` / ``P`` may live on the host (the session passes host copies): nothing here then waits for the device -- the ramps and offsets
+    are produced on ``device`` by asynchronous kernels -- so the set-up of the next single-use session overlaps the previous one's render.
     """
     V, P = V.to(torch.float32), P.to(torch.float32)
     inv = small_matrix_inverse(torch.stack([V, torch.mm(P, V)]))
@@ -187,19 +198,27 @@ def gather_tile_accumulators(accum: torch.Tensor, H: int, W: int, tile: int, ran
     if dist.get_world_size() != world:
         raise RuntimeError("shard_world=%d does not match the process group's world size %d" % (world, dist.get_world_size()))
     tiles = frame_tiles(H, W, tile)
-    rows = [tile_rows(tiles[r::world], W, accum.device) for r in range(world)]
-    n_max = max(len(r) for r in rows)
     C = accum.shape[-1]
+    frame = accum.view(H, W, C)
+    counts = [sum(w * h for (_, _, w, h) in tiles[r::world]) for r in range(world)]
+    n_max = max(counts)
     recv = accum.new_empty([world, n_max, C])
-    send = recv[rank]                                   # in place: NCCL's all-gather accepts its input inside the output
-    send[:len(rows[rank])] = accum[rows[rank]]
-    if len(rows[rank]) < n_max:
-        send[len(rows[rank]):] = 0
-    dist.all_gather_into_tensor(recv.view(-1), send.reshape(-1)) if dist.get_backend() == 'nccl' else \
-        _all_gather_generic(recv, send.clone(), world)
+
+    def segments(r):   # (tile rectangle, its slice of rank r's packed rows): tiles are rectangles, so packing is one strided copy per tile
+        off = 0
+        for (x0, y0, w, h) in tiles[r::world]:
+            yield (x0, y0, w, h), off
+            off += w * h
+    for (x0, y0, w, h), off in segments(rank):
+        recv[rank, off:off + w * h].view(h, w, C).copy_(frame[y0:y0 + h, x0:x0 + w])
+    if dist.get_backend() == 'nccl':
+        dist.all_gather_into_tensor(recv.view(-1), recv[rank].reshape(-1))   # in place: the input is this rank's slot of the output
+    else:
+        _all_gather_generic(recv, recv[rank].clone(), world)
     for r in range(world):
-        if r != rank and len(rows[r]):
-            accum[rows[r]] = recv[r, :len(rows[r])]
+        if r != rank:
+            for (x0, y0, w, h), off in segments(r):
+                frame[y0:y0 + h, x0:x0 + w].copy_(recv[r, off:off + w * h].view(h, w, C))
     return accum
 
 
@@ -237,16 +256,49 @@ def _scene_signature(scene: Scene, device) -> tuple:
 _SCENE_CACHE: Dict[int, tuple] = {}
 
 
-def _shared_scene_cache(scene: Scene, device, epsilon: float) -> dict:
+def _topology_signature(scene: Scene) -> tuple:
+    """What a refit keeps: per object the identity / shape / version of its index array and its vertex count."""
+    return tuple((o.tris.data_ptr(), tuple(o.tris.shape), o.tris._version, int(o.verts.shape[0])) for o in scene.objects)
+
+
+def _shared_scene_cache(scene: Scene, device, epsilon: float, refit: bool = True) -> dict:
     import weakref
     sig = _scene_signature(scene, device) + (float(epsilon),)
+    topo = _topology_signature(scene)
     key = id(scene)
     ent = _SCENE_CACHE.get(key)
     if ent is not None and ent[0]() is scene and ent[1] == sig:
         return ent[2]
     store: dict = {}
-    _SCENE_CACHE[key] = (weakref.ref(scene, lambda _r, k=key: _SCENE_CACHE.pop(k, None)), sig, store)
+    if refit and ent is not None and ent[0]() is scene and ent[3] == topo and ent[1][0] == sig[0] and ent[1][-1] == sig[-1]:
+        # same device, same epsilon, same connectivity -- only positions / transforms / attributes / materials changed: the next session
+        # re-flattens and REFITS the previous structure (drp_refit) instead of sorting and collapsing again
+        old = ent[2].get('raycaster') or ent[2].get('raycaster_to_refit')
+        if old is not None and old.handle is not None and not getattr(old, 'instanced', False) and len(old.tris) >= 2:
+            store['raycaster_to_refit'] = old
+    _SCENE_CACHE[key] = (weakref.ref(scene, lambda _r, k=key: _SCENE_CACHE.pop(k, None)), sig, store, topo)
     return store
+
+
+def scene_instances(objects):
+    """
+    Instance table of a flattened scene, or None when instancing would not pay: objects that share their vertex AND index tensors are
+    copies of one mesh (any transform / material).  Returns (first_tri (n + 1,) int64, mesh (n,) int32) as numpy arrays for
+    ``drp_build_instanced``.  Used when at least 8 objects share meshes 4 : 1 or better (BASELINE configs[4]: 1000 objects, 1 mesh).
+    """
+    import numpy as np
+    if len(objects) < 8:
+        return None
+    keys, mesh, first = {}, [], [0]
+    for o in objects:
+        if o.tris.shape[0] < 2:
+            return None
+        k = (o.verts.data_ptr(), tuple(o.verts.shape), o.tris.data_ptr(), tuple(o.tris.shape))
+        mesh.append(keys.setdefault(k, len(keys)))
+        first.append(first[-1] + int(o.tris.shape[0]))
+    if 4 * len(keys) > len(objects):
+        return None
+    return np.asarray(first, dtype=np.int64), np.asarray(mesh, dtype=np.int32)
 
 
 def _cached(fn):
@@ -278,12 +330,21 @@ class PathTracingSession:
 
     # ---- camera (mixin.py:19-44) ---------------------------------------------------------------------------------
     @_cached
+    def _camera_host(self):
+        """(V, P) as host fp32 tensors.  Cameras of this package expose them without touching the device; a foreign Camera object
+        (only V() / P(), possibly CUDA tensors) costs one read-back."""
+        cam = self.camera
+        V = cam.V_host() if hasattr(cam, 'V_host') else cam.V().detach().cpu().numpy()
+        Pm = cam.P_host() if hasattr(cam, 'P_host') else cam.P().detach().cpu().numpy()
+        return torch.from_numpy(numpy.ascontiguousarray(V, dtype=numpy.float32)), torch.from_numpy(numpy.ascontiguousarray(Pm, dtype=numpy.float32))
+
+    @_cached
     def camera_V(self):
-        return self.camera.V().to(self.device, torch.float32)
+        return self._camera_host()[0].pin_memory().to(self.device, non_blocking=True)
 
     @_cached
     def camera_P(self):
-        return self.camera.P().to(self.device, torch.float32)
+        return self._camera_host()[1].pin_memory().to(self.device, non_blocking=True)
 
     @_cached
     def camera_VP(self):
@@ -291,19 +352,19 @@ class PathTracingSession:
 
     @_cached
     def camera_far(self) -> float:
-        p = self.camera_P()
+        p = self._camera_host()[1]      # same fp32 operations as mixin.py:44, on the host copy: no device round trip
         return (p[2, 3] / (p[2, 2] + 1)).item()
 
     @_cached
     def camera_near(self) -> float:
-        p = self.camera_P()
+        p = self._camera_host()[1]
         return (p[2, 3] / (p[2, 2] - 1)).item()
 
     # ---- scene flattening (mixin.py:74-113) ------------------------------------------------------------------------
     def _scene_store(self) -> dict:
         """Per-scene cache shared between sessions (options.reuse_scene), else private to this session."""
         if '_store' not in self.__dict__:
-            self._store = (_shared_scene_cache(self.scene, self.device, self.options.raycaster_epsilon)
+            self._store = (_shared_scene_cache(self.scene, self.device, self.options.raycaster_epsilon, self.options.refit_scene)
                            if self.options.reuse_scene and not self._wants_grad() else {})
         return self._store
 
@@ -341,8 +402,17 @@ class PathTracingSession:
         rc = st.get('raycaster')
         if rc is None or rc.handle is None:
             vao = self.vertex_array_object()
+            old = st.pop('raycaster_to_refit', None)
+            if old is not None and old.handle is not None and tuple(old.verts.shape) == tuple(vao.world_pos.shape):
+                old.refit(vao.world_pos.detach())      # same connectivity as the previous session over this scene: keep the topology
+                rc = st['raycaster'] = old
+                return rc
             cfg = {'epsilon': self.options.raycaster_epsilon, 'builder': self.options.raycaster_builder,
                    'optix_log_level': self.options.optix_log_level}
+            if self.options.instancing:
+                inst = scene_instances(self.scene.objects)
+                if inst is not None:
+                    cfg['instances'] = inst
             rc = st['raycaster'] = B200Raycaster(vao.world_pos.detach(), vao.tris, cfg)
         return rc
 
@@ -398,7 +468,8 @@ class PathTracingSession:
         if fused is None:
             raise RuntimeError("scene contains custom Python materials: use pbr() / trace_rays() (generic path)")
         H, W = self.camera.resolution()
-        tab = raygen_tables(self.camera_V(), self.camera_P(), H, W, opt.ray_spp, opt.deterministic, self.device)
+        Vh, Ph = self._camera_host()
+        tab = raygen_tables(Vh, Ph, H, W, opt.ray_spp, opt.deterministic, self.device)
         p = _abi.RenderParams()
         p.height, p.width, p.ray_depth = H, W, opt.ray_depth
         p.last_bounce_skybox = int(opt.pbr_ray_last_bounce == 'skybox')

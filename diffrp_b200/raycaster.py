@@ -61,8 +61,21 @@ class B200Raycaster(Raycaster):
         self.device = self.verts.device
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         handle = C.c_uint64(0)
-        check(self._lib.drp_build(self.verts.data_ptr(), self.tris.data_ptr(), len(self.verts), len(self.tris),
-                                  dev_index, _stream_ptr(self.device), C.byref(handle)), "drp_build")
+        inst = config.get('instances')
+        if inst is not None:
+            # (first_tri (n_inst + 1,) int64, mesh (n_inst,) int32) host arrays: instance q owns triangles [first_tri[q], first_tri[q+1]) and copies mesh[q]
+            import numpy as np
+            first = np.ascontiguousarray(inst[0], dtype=np.int64)
+            mesh = np.ascontiguousarray(inst[1], dtype=np.int32)
+            if len(first) != len(mesh) + 1:
+                raise ValueError("instances: first_tri must have one more entry than mesh")
+            check(self._lib.drp_build_instanced(self.verts.data_ptr(), self.tris.data_ptr(), len(self.verts), len(self.tris), first.ctypes.data,
+                                                mesh.ctypes.data, len(mesh), dev_index, _stream_ptr(self.device), C.byref(handle)), "drp_build_instanced")
+            self.instanced = True
+        else:
+            check(self._lib.drp_build(self.verts.data_ptr(), self.tris.data_ptr(), len(self.verts), len(self.tris),
+                                      dev_index, _stream_ptr(self.device), C.byref(handle)), "drp_build")
+            self.instanced = False
         self.handle = handle.value
         check(self._lib.drp_set_epsilon(self.handle, float(config.get('epsilon', 1e-8))), "drp_set_epsilon")
 
@@ -101,6 +114,20 @@ class B200Raycaster(Raycaster):
                                              float(self.config.get('epsilon', 1e-8)), len(rays_o),
                                              _stream_ptr(rays_o.device)), "drp_trace_bruteforce")
         return out_t, out_i
+
+    @torch.no_grad()
+    def refit(self, verts: torch.Tensor) -> None:
+        """New vertex positions, same triangles: recompute boxes and triangle records of the existing hierarchy (``drp_refit``; one bottom-up
+        pass instead of a rebuild).  Hits are those of a fresh build over the new positions; traversal slows down if the geometry moved far."""
+        if self.handle is None:
+            raise RuntimeError("raycaster has been released")
+        if getattr(self, 'instanced', False):
+            raise RuntimeError("instanced structures are rebuilt, not refitted")
+        if not verts.is_cuda or verts.device != self.device or tuple(verts.shape) != tuple(self.verts.shape):
+            raise ValueError("refit needs a CUDA tensor with the shape of the vertices the structure was built from")
+        self.verts = verts.detach().to(torch.float32).contiguous()
+        check(self._lib.drp_refit(self.handle, self.verts.data_ptr(), self.tris.data_ptr(), len(self.verts), len(self.tris),
+                                  _stream_ptr(self.device)), "drp_refit")
 
     def check_status(self) -> None:
         """Raise if an earlier traversal on this structure failed on the device (drp_status: non-blocking read of the handle's sticky flag)."""

@@ -308,6 +308,23 @@ typedef struct drp_render_stats {
 } drp_render_stats_t;
 int drp_render_stats(uint64_t handle, drp_render_stats_t* out);
 
+/* Dynamic scenes (the reference rebuilds its structure for every session: rendering/path_tracing.py:142-156 builds inside the
+ * single-use session, rendering/mixin.py:74-113 re-flattens the scene): keep the hierarchy's topology and recompute every box and triangle
+ * record for new vertex positions -- one bottom-up pass, no sort, no collapse.  `tris` must be the index array the structure was built
+ * from (n_tris must match); only `verts` may differ.  Boxes stay conservative and triangle records are rounded exactly like the builder's,
+ * so closest hits equal those of a fresh drp_build over the same arrays bit for bit; only traversal speed depends on how far the geometry moved. */
+int drp_refit(uint64_t handle, const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, void* stream);
+
+/* Instanced scenes (BASELINE configs[4]: 1000 MeshObjects sharing one mesh; the reference flattens them, scene/scene.py:33-75,
+ * rendering/mixin.py:74-113): the input is still the flattened world-space geometry (what drp_flatten writes), plus the instance table:
+ * instance q owns triangles [inst_first_tri[q], inst_first_tri[q+1]) and is a copy (same connectivity, any transform) of mesh inst_mesh[q].
+ * One hierarchy is built per mesh; its topology is replicated for every instance and refitted to that instance's world-space triangles, and a
+ * small instance level (built on the host over the instance root boxes) joins them into ONE wide hierarchy over world-space triangles.
+ * Traversal, primitive ids and hits are those of drp_build over the same arrays (bit for bit); the sort / Karras / collapse cost is paid per
+ * mesh instead of per triangle.  B200's 180 GB of HBM holds the replicated nodes (80 B per ~2.6 triangles), so no per-ray transform is needed. */
+int drp_build_instanced(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_tris, const int64_t* inst_first_tri,
+                        const int32_t* inst_mesh, int64_t n_inst, int device, void* stream, uint64_t* out_handle);
+
 /* Health of a handle, without synchronising.  A ray whose traversal outgrows the per-thread stack of the fast kernel is re-traced by a fix-up
  * kernel with a 256-entry stack (deeper than any hierarchy the builder can emit: <= 63 Morton + 27 index levels), so results stay exact on
  * degenerate scenes.  Should even that stack run out, the kernel raises a sticky host-mapped flag: drp_status and EVERY later call on the handle

@@ -10,6 +10,7 @@
 #include "../../diffrp_b200/csrc/lbvh.cuh"
 #include "../../diffrp_b200/csrc/traverse.cuh"
 #include "../../diffrp_b200/csrc/cwbvh.cuh"
+#include "../../diffrp_b200/csrc/instance_level.h"
 #include "../../diffrp_b200/csrc/tonemap.cuh"
 
 struct HsBvh {
@@ -17,6 +18,8 @@ struct HsBvh {
     std::vector<float4> nodes, packed;
     std::vector<float4> cw_nodes, cw_tris;  // wide layout (cwbvh.cuh)
     int cw_count = 0, cw_levels = 0;
+    std::vector<int> level_begin;   // wide nodes of level L: [level_begin[L], level_begin[L + 1])
+    std::vector<uint32_t> bounds_ord;
     float sah;
     float bounds[6];
 };
@@ -92,6 +95,7 @@ static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_t
     }
     if (!wide) for (int j = 0; j < n; ++j) lbvh_pack_tri(b, j);
     for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(bounds[k]);
+    h->bounds_ord = bounds;
     if (wide) {
         CwBuild cw;
         cw.b = b;
@@ -107,9 +111,11 @@ static HsBvh* hs_build_impl(const float* verts, const int32_t* tris, int64_t n_t
             counters[0] = 1;
             int begin = 0, end = 1, levels = 0;
             while (begin < end) {
+                h->level_begin.push_back(begin);
                 for (int ni = begin; ni < end; ++ni) cw_collapse_node(cw, ni, [](int* p, int v) { int o = *p; *p = o + v; return o; });
                 begin = end; end = counters[0]; ++levels;
             }
+            h->level_begin.push_back(counters[0]);
             h->cw_count = counters[0];
             h->cw_levels = levels;
         }
@@ -290,4 +296,85 @@ extern "C" void hs_tonemap(const float* src, int64_t height, int64_t width, cons
             if (out_u8) out_u8[C * o + ch] = tm_byte(v[ch]);
         }
     }
+}
+
+
+// ---- refit / instanced assembly (api.cu: drp_refit, drp_build_instanced), run serially with the same per-node functions ------------------
+static void hs_scene_bounds(const float* verts, const int32_t* tris, int64_t n, std::vector<uint32_t>& bounds) {
+    bounds.assign(12, 0u);
+    for (int i = 0; i < 12; ++i) bounds[i] = ((i / 3) % 2 == 0) ? 0xffffffffu : 0u;
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.verts = verts; b.tris = tris; b.n = (int)n;
+    for (int64_t i = 0; i < n; ++i) {
+        Vec3 lo, hi;
+        lbvh_prim_bounds(b, (int)i, lo, hi);
+        const float v[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+        for (int k = 0; k < 6; ++k) { const uint32_t o = f2ord(v[k]); bounds[k] = k < 3 ? std::min(bounds[k], o) : std::max(bounds[k], o); }
+    }
+}
+extern "C" int hs_refit_wide(HsBvh* h, const float* verts, const int32_t* tris) {
+    if (h->level_begin.size() < 2) return -1;
+    hs_scene_bounds(verts, tris, h->n, h->bounds_ord);
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.bounds = h->bounds_ord.data();
+    const float abs_pad = lbvh_abs_pad(b);
+    std::vector<float4> node_box(2 * (size_t)h->cw_count);
+    for (int L = (int)h->level_begin.size() - 2; L >= 0; --L)
+        for (int ni = h->level_begin[L]; ni < h->level_begin[L + 1]; ++ni)
+            cw_refit_node(h->cw_nodes.data() + CW_NODE_F4 * (size_t)ni, h->cw_tris.data(), h->cw_nodes.data(), h->cw_tris.data(), node_box.data(), ni, 0, 0, 0,
+                          verts, tris, abs_pad);
+    for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(h->bounds_ord[k]);
+    return 0;
+}
+extern "C" HsBvh* hs_build_instanced(const float* verts, const int32_t* tris, int64_t n_tris, const int64_t* first, const int32_t* mesh, int64_t n_inst) {
+    std::vector<int> rep_of;      // mesh id -> representative instance
+    std::vector<HsBvh*> blas;
+    auto find = [&](int m) { for (size_t k = 0; k < rep_of.size(); ++k) if (mesh[rep_of[k]] == m) return (int)k; return -1; };
+    for (int64_t q = 0; q < n_inst; ++q)
+        if (find(mesh[q]) < 0) {
+            rep_of.push_back((int)q);
+            blas.push_back(hs_build_impl(verts, tris + 3 * first[q], first[q + 1] - first[q], CW_MAX_LEAF, true));
+        }
+    HsBvh* h = new HsBvh();
+    h->n = (int)n_tris;
+    const int64_t tlas_cap = 2 * n_inst + 8;
+    std::vector<int> node_off(n_inst);
+    int64_t total = tlas_cap;
+    for (int64_t q = 0; q < n_inst; ++q) { node_off[q] = (int)total; total += blas[find(mesh[q])]->cw_count; }
+    h->cw_nodes.assign(CW_NODE_F4 * (size_t)total, make_float4(0, 0, 0, 0));
+    h->cw_tris.resize(3 * (size_t)n_tris);
+    h->cw_count = (int)total;
+    hs_scene_bounds(verts, tris, n_tris, h->bounds_ord);
+    LbvhBuild b;
+    memset(&b, 0, sizeof(b));
+    b.bounds = h->bounds_ord.data();
+    const float abs_pad = lbvh_abs_pad(b);
+    std::vector<float4> node_box(2 * (size_t)total);
+    std::vector<float> lo(3 * (size_t)n_inst), hi(3 * (size_t)n_inst);
+    for (int64_t q = 0; q < n_inst; ++q) {
+        const HsBvh* t = blas[find(mesh[q])];
+        for (int L = (int)t->level_begin.size() - 2; L >= 0; --L)
+            for (int ni = t->level_begin[L]; ni < t->level_begin[L + 1]; ++ni)
+                cw_refit_node(t->cw_nodes.data() + CW_NODE_F4 * (size_t)ni, t->cw_tris.data(), h->cw_nodes.data(), h->cw_tris.data(), node_box.data(),
+                              ni + node_off[q], node_off[q], (int)first[q], (int)first[q], verts, tris, abs_pad);
+        const float4 l = node_box[2 * (size_t)node_off[q]], u = node_box[2 * (size_t)node_off[q] + 1];
+        lo[3 * q] = l.x; lo[3 * q + 1] = l.y; lo[3 * q + 2] = l.z; hi[3 * q] = u.x; hi[3 * q + 1] = u.y; hi[3 * q + 2] = u.z;
+    }
+    TlasBuilder tb(lo, hi);
+    tb.nodes.resize(CW_NODE_F4, make_float4(0, 0, 0, 0));
+    std::vector<int> ids(n_inst);
+    std::iota(ids.begin(), ids.end(), 0);
+    if (n_inst == 1) tlas_single(tb, lo.data(), hi.data());
+    else tb.build(0, ids.data(), (int)n_inst);
+    if (tb.allocated > tlas_cap) { delete h; h = nullptr; }
+    else {
+        for (size_t k = 0; k < (size_t)tb.allocated * CW_NODE_F4; ++k) h->cw_nodes[k] = tb.nodes[k];
+        for (auto& c : tb.copies)
+            for (int f = 0; f < CW_NODE_F4; ++f) h->cw_nodes[CW_NODE_F4 * (size_t)c.second + f] = h->cw_nodes[CW_NODE_F4 * (size_t)node_off[c.first] + f];
+        for (int k = 0; k < 6; ++k) h->bounds[k] = ord2f(h->bounds_ord[k]);
+    }
+    for (HsBvh* t : blas) delete t;
+    return h;
 }

@@ -251,3 +251,87 @@ def test_node_format2_tables_and_triangle_index(hs):
             for t in range(int(c)):
                 assert hs.hs_cw_tri_index(base, vmask, 3 * slot + t) == base + k
                 k += 1
+
+
+# ---- refit and instanced assembly, node-level code of api.cu run serially ------------------------------------------------
+def _hs_wide_api(L):
+    vp = C.c_void_p
+    L.hs_build_wide.restype = vp
+    L.hs_build_wide.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.hs_trace_wide.restype = C.c_int64
+    L.hs_trace_wide.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp]
+    L.hs_refit_wide.restype = C.c_int
+    L.hs_refit_wide.argtypes = [vp, vp, vp]
+    L.hs_build_instanced.restype = vp
+    L.hs_build_instanced.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int64]
+    L.hs_free.argtypes = [vp]
+
+
+def _hs_trace(L, h, o, d, far=10.0, eps=1e-8):
+    t, i = np.empty(len(o), np.float32), np.empty(len(o), np.int32)
+    overflow = L.hs_trace_wide(h, o.ctypes.data, d.ctypes.data, len(o), far, eps, t.ctypes.data, i.ctypes.data)
+    assert overflow == 0
+    return t, i
+
+
+@pytest.mark.parametrize("amp", [0.02, 0.7])
+def test_refit_keeps_closest_hits_exact(hs, amp):
+    """drp_refit's per-node code (cw_refit_node) over the topology of the undeformed mesh, applied to a deformed one: hits equal the oracle's
+    exhaustive search over the deformed mesh bit for bit, for a small and for a topology-scrambling deformation; then refit back."""
+    import oracle
+    from diffrp_b200 import synthetic as syn
+    _hs_wide_api(hs)
+    v, f = syn.uv_sphere(48, 24, radius=0.8, bump=0.05, noise=0.01, seed=0)
+    v, f = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(f, np.int32)
+    o, d = syn.random_rays(6000, seed=3)
+    ang = amp * v[:, 1:2] * 4.0
+    v2 = np.concatenate([v[:, 0:1] * np.cos(ang) - v[:, 2:3] * np.sin(ang), v[:, 1:2] * (1 + amp), v[:, 0:1] * np.sin(ang) + v[:, 2:3] * np.cos(ang)], 1)
+    v2 = np.ascontiguousarray(v2 + np.random.default_rng(1).normal(0, amp * 0.05, v2.shape), np.float32)
+    h = hs.hs_build_wide(v.ctypes.data, f.ctypes.data, len(v), len(f))
+    assert hs.hs_refit_wide(h, v2.ctypes.data, f.ctypes.data) == 0
+    t, i = _hs_trace(hs, h, o, d)
+    ot, oi = oracle.bruteforce(v2, f, o, d, 10.0, 1e-8)
+    assert np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+    assert 0.2 < (t < 10.0).mean() < 0.95
+    assert hs.hs_refit_wide(h, v.ctypes.data, f.ctypes.data) == 0
+    t, i = _hs_trace(hs, h, o, d)
+    ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)
+    assert np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+    hs.hs_free(h)
+
+
+@pytest.mark.parametrize("n_inst,two_meshes", [(1, False), (2, False), (9, False), (70, False), (12, True)])
+def test_instanced_assembly_keeps_closest_hits_exact(hs, n_inst, two_meshes):
+    """drp_build_instanced's logic (template per mesh, replicate + refit per instance, host-built instance level, copied roots) over
+    rigidly transformed copies of one or two meshes: hits and GLOBAL primitive ids equal the exhaustive search over the flattened geometry."""
+    import oracle
+    from diffrp_b200 import synthetic as syn
+    _hs_wide_api(hs)
+    rng = np.random.default_rng(n_inst)
+    va, fa = syn.uv_sphere(10, 6, radius=0.12, bump=0.01, noise=0.002, seed=1)
+    vb, fb = syn.icosphere(1, 0.1)
+    verts, tris, first, mesh = [], [], [0], []
+    voff = 0
+    for q in range(n_inst):
+        use_b = two_meshes and q % 3 == 1
+        v, f = (vb, fb) if use_b else (va, fa)
+        M = syn.rigid_matrix(rng, 0.6 + rng.random(), rng.uniform(-0.6, 0.6, 3))
+        verts.append(v @ M[:3, :3].T + M[:3, 3])
+        tris.append(f + voff)
+        voff += len(v)
+        first.append(first[-1] + len(f))
+        mesh.append(7 if use_b else 3)
+    verts = np.ascontiguousarray(np.concatenate(verts), np.float32)
+    tris = np.ascontiguousarray(np.concatenate(tris), np.int32)
+    first, mesh = np.asarray(first, np.int64), np.asarray(mesh, np.int32)
+    h = hs.hs_build_instanced(verts.ctypes.data, tris.ctypes.data, len(tris), first.ctypes.data, mesh.ctypes.data, n_inst)
+    assert h
+    o, d = syn.random_rays(5000, seed=8)
+    o = np.ascontiguousarray(o * 0.8, np.float32)
+    t, i = _hs_trace(hs, h, o, d)
+    ot, oi = oracle.bruteforce(verts, tris, o, d, 10.0, 1e-8)
+    assert np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+    assert (t < 10.0).mean() > (0.01 if n_inst < 3 else 0.1)
+    if n_inst > 2:
+        assert len(np.unique(np.searchsorted(first, i[t < 10.0], side='right'))) > 2      # hits land in several instances
+    hs.hs_free(h)

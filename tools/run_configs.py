@@ -63,7 +63,7 @@ def max_over_ranks(x):
     return float(t.item())
 
 
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 S_DEFAULT = 224   # shading bytes per ray-bounce, DefaultMaterial (B_bounce: config 4 = 1204 B, config 5 = 1444 B)
 if args.config == 4:
     scene_host, orbit = syn.datagen_scene('cpu')
@@ -125,12 +125,15 @@ else:
     torch.cuda.synchronize(); ev[0].record()
     acc = sess.render_accumulators()
     ev[1].record()
+    if world > 1:
+        dist.barrier()   # so that exchange_ms is the exchange, not the wait for the rank with the most expensive tiles (that is in render_ms: max over ranks)
+    ev[4].record()
     acc = sess.exchange_accumulators(acc)
     ev[2].record()
     rad, alpha, extras = sess.finalize(acc)
     ev[3].record(); torch.cuda.synchronize()
     ms = max_over_ranks(ev[0].elapsed_time(ev[3]))
-    ms_render, ms_exchange = max_over_ranks(ev[0].elapsed_time(ev[1])), max_over_ranks(ev[1].elapsed_time(ev[2]))
+    ms_render, ms_exchange = max_over_ranks(ev[0].elapsed_time(ev[1])), max_over_ranks(ev[4].elapsed_time(ev[2]))
     assert torch.isfinite(rad).all()
     nominal = H * W * spp * depth
     peak, peak_src = peak_gbs()
