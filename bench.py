@@ -385,13 +385,16 @@ def main():
 
     def e2e_call(spp_total, seed, sharded):
         o = drp.PathTracingSessionOptions(ray_spp=spp_total, ray_depth=DEPTH, rng='native', seed=seed, reuse_scene=False,  # nothing cached between calls
-                                          shard_rank=rank if sharded else 0, shard_world=world if sharded else 1)
+                                          shard_rank=rank if sharded else 0, shard_world=world if sharded else 1,
+                                          result_rank=0 if (sharded and world > 1) else None)   # one job, one frame: rank 0 receives the sum and reads it back
         s = drp.PathTracingSession(scene_host, cam, o)          # pinned host tensors: H2D of the whole scene happens inside
-        r, a, x = s.pbr()                                       # flatten + LBVH build + wavefront (+ all-reduce) + finalize
-        out_host["radiance"].copy_(r, non_blocking=True)        # D2H of every output
-        out_host["alpha"].copy_(a, non_blocking=True)
-        for k in ("albedo", "emission", "world_normal", "world_position"):
-            out_host[k].copy_(x[k], non_blocking=True)
+        res = s.pbr()                                           # flatten + LBVH build + wavefront (+ reduce to rank 0) + finalize
+        if res is not None:
+            r, a, x = res
+            out_host["radiance"].copy_(r, non_blocking=True)    # D2H of every output
+            out_host["alpha"].copy_(a, non_blocking=True)
+            for k in ("albedo", "emission", "world_normal", "world_position"):
+                out_host[k].copy_(x[k], non_blocking=True)
         torch.cuda.synchronize()
         s.raycaster().release()
 
@@ -568,12 +571,13 @@ def main():
         "live_ray_fraction": prof["extend_rays"] / max(1, K * S * HW * DEPTH),
         "bvh_build_ms": build_ms,
         "clocks": clk, "host_issue_ms": host_issue_ms,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": world * d2h / K, "steps": K,
-                "bytes_note": "job totals over all ranks: the scene crosses PCIe once in total (each rank uploads 1/N of every tensor, NVLink all-gather "
-                              "completes it: options.scene_upload), every rank reads the full result back",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "steps": K,
+                "bytes_note": "job totals over all ranks: the scene crosses PCIe once in total (each rank uploads 1/N of every tensor, one coalesced NVLink "
+                              "all-gather completes it: options.scene_upload); the accumulators are reduced to rank 0, which reads the frame back once "
+                              "(options.result_rank)",
                 "ms_per_step": e2e_job_ms / K, "ms_total": e2e_job_ms, "h2d_bytes_total": h2d, "d2h_bytes_total": d2h,
                 "what": "ONE public-API call for the whole job: PathTracingSession(host-pinned scene, camera, options(ray_spp=%d, spp-sharded x%d)).pbr() "
-                        "+ D2H of all outputs; timed region = H2D scene upload, flatten, LBVH build, %d sections, all-reduce, finalize, D2H"
+                        "+ D2H of all outputs on rank 0; timed region = H2D scene upload, flatten, LBVH build, %d sections, reduce, finalize, D2H"
                         % (world * K * S, world, K),
                 "single_section_session": {"value": e2e_sec_value, "unit": UNIT, "ms_per_call": e2e_sec_ms, "calls": E,
                                            "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,

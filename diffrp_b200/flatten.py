@@ -78,12 +78,39 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
 SHARD_MIN_BYTES = 1 << 20
 
 
-def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
+class PendingGathers:
+    """All-gathers of a batch of sharded uploads, issued as ONE coalesced NCCL group (one launch) by ``flush()``: a scene is ~300 tensors
+    and a collective per tensor costs more host time than the copies it replaces (tools/e2e_phases.py at N = 8)."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, out, part):
+        self.items.append((out, part))
+
+    def flush(self):
+        if not self.items:
+            return
+        import torch.distributed as dist
+        items, self.items = self.items, []
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(device=items[0][0].device):
+                for out, part in items:
+                    dist.all_gather_into_tensor(out, part)
+        except (ImportError, TypeError, RuntimeError):
+            for out, part in items:
+                dist.all_gather_into_tensor(out, part)
+
+
+def upload(t: torch.Tensor, dev, dtype, shard=None, pending: Optional[PendingGathers] = None) -> torch.Tensor:
     """
     Host -> device move of one scene tensor.  ``shard=(rank, world)`` (scene replicated over the ranks of an initialised NCCL group, the
     precondition of spp / tile sharding): every rank DMA-copies only its 1/world slice of the (identical) host tensor over its own PCIe link and
     an in-place all-gather over NVLink completes it on every GPU -- world x less host-memory and PCIe traffic than ``world`` full uploads
     from one host, at NVLink instead of PCIe speed.  Collective: every rank must upload the same tensors in the same order.
+    With ``pending`` the all-gather is deferred to ``pending.flush()`` (one coalesced group for many tensors); the returned tensor is complete
+    only after that.
     """
     if (shard is not None and shard[1] > 1 and not t.is_cuda and t.dtype == dtype and t.is_contiguous()
             and t.numel() * t.element_size() >= SHARD_MIN_BYTES):
@@ -95,7 +122,10 @@ def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
         lo, hi = min(rank * per, n), min((rank + 1) * per, n)
         if hi > lo:
             out[lo:hi].copy_(t.view(-1)[lo:hi], non_blocking=True)
-        dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
+        if pending is not None:   # the caller flushes before the first kernel that reads the tensor
+            pending.add(out, out[rank * per:(rank + 1) * per])
+        else:
+            dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
         return out[:n].view(t.shape)
     return t.to(dev, dtype, non_blocking=True)
 
@@ -112,11 +142,12 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     from ._lib import lib, check
     dev = torch.device(dev)
     keep = []
+    pending = PendingGathers()
 
     def src(t, dtype):
         ok = t.dtype == dtype and t.is_contiguous() and t.is_cuda and t.device == dev
         if not ok:
-            t = upload(t, dev, dtype, shard).contiguous()
+            t = upload(t, dev, dtype, shard, pending).contiguous()
         keep.append(t)
         return t
 
@@ -142,6 +173,7 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     i = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
     out = dict(world_pos=f(V, 3), world_nrm=f(V, 3), color=f(V, 4), uv=f(V, 2), world_tan=f(V, 4), tris=i(F, 3), tri_material=i(F),
                stencils=i(F + 1), records=f(V, 16), verts=f(V, 3), normals=f(V, 3), tangents=f(V, 4))
+    pending.flush()
     check(lib().drp_flatten(descs, len(objs), out['world_pos'].data_ptr(), out['world_nrm'].data_ptr(), out['color'].data_ptr(),
                             out['uv'].data_ptr(), out['world_tan'].data_ptr(), out['tris'].data_ptr(), out['tri_material'].data_ptr(),
                             out['stencils'].data_ptr(), out['records'].data_ptr(), out['verts'].data_ptr(), out['normals'].data_ptr(),
@@ -204,7 +236,9 @@ def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Op
     or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
     descs = []
     uploaded = {}
-    for o in objs:
+    pending = PendingGathers()
+    raw = []
+    for o in objs:   # pass 1: start every upload (sharded uploads defer their all-gather to ONE coalesced group)
         d = o.material.fused_description() if hasattr(o.material, 'fused_description') else None
         if d is None:
             return None
@@ -214,15 +248,24 @@ def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Op
                 src = d[k]['image']
                 key = (src.data_ptr(), tuple(src.shape))
                 if key not in uploaded:
-                    img = upload(src, dev, torch.float32, shard)
-                    uploaded[key] = pad_rgba(img) if rgba else img.contiguous()
-                d[k] = dict(d[k], image=uploaded[key])
+                    uploaded[key] = upload(src, dev, torch.float32, shard, pending)
+                d[k] = dict(d[k], image=uploaded[key], _key=key)
+        raw.append(d)
+    pending.flush()
+    padded = {}
+    for d in raw:    # pass 2: RGBA padding and texel interleaving on the device
+        for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):
+            if d.get(k) is not None:
+                key = d[k].pop('_key')
+                if key not in padded:
+                    padded[key] = pad_rgba(uploaded[key]) if rgba else uploaded[key].contiguous()
+                d[k] = dict(d[k], image=padded[key])
         if rgba and INTERLEAVE_TEXELS:  # CUDA path: interleaved texels, shared between the objects that share the material
             key = ('records',) + tuple(d[k]['image'].data_ptr() if d.get(k) is not None else 0 for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
-            if key not in uploaded:
-                uploaded[key] = texel_records(d)
-            if uploaded[key] is not None:
-                d['texel_records'] = uploaded[key]
+            if key not in padded:
+                padded[key] = texel_records(d)
+            if padded[key] is not None:
+                d['texel_records'] = padded[key]
         descs.append(d)
     if not descs:
         descs = [dict(kind='default', tint=None)]

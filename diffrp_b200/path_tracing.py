@@ -69,7 +69,10 @@ class PathTracingSessionOptions:
             are summed with ``torch.distributed.all_reduce`` when a process group exists.  ``shard_mode='spp'``: global
             sample indices ``rank::world`` of every pixel; ``shard_mode='tile'``: every sample of the ``tile_size``^2 tiles
             ``rank::world`` (row-major tile order), the rest of the accumulator stays zero; the exchange is then an all-gather of the owned
-            tiles (``tile_collective``), not a sum of whole frames.
+            tiles when ``tile_collective='gather'``.  Measured on 8 B200 at 4K (531 MB frames, profiles/r2/c5_n8*.json): all-reduce 1.47 ms
+            (NVLS: the switch reduces), gather 1.90 ms (17 pack + 118 unpack copies per rank around a 465 MB all-gather) -- so the default is
+            the all-reduce; at 2 GPUs 1.17 vs 2.08 ms.
+        result_rank: when only one rank consumes the frame, a ``reduce`` to it replaces the all-reduce and the other ranks skip the epilogue.
     """
     ray_depth: int = 3
     ray_spp: int = 16
@@ -88,7 +91,8 @@ class PathTracingSessionOptions:
     shard_world: int = 1
     shard_mode: str = 'spp'   # 'spp': samples rank::world of every pixel; 'tile': all samples of the tiles rank::world
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
-    tile_collective: str = 'gather'   # 'gather': all-gather of the owned tiles' rows; 'allreduce': sum whole frames
+    tile_collective: str = 'allreduce'  # 'allreduce': sum whole frames (NVSwitch reduces in the fabric); 'gather': all-gather of the owned tiles
+    result_rank: Optional[int] = None   # sharded renders: None = every rank gets the frame (all-reduce); r = only rank r does (reduce), the others' pbr() returns None
     refit_scene: bool = True          # a later session over the same Scene with unchanged connectivity refits the structure instead of rebuilding
     instancing: bool = True           # objects sharing vertex + index tensors: one hierarchy per mesh, replicated and refitted per instance
     scene_upload: str = 'auto'        # host scenes under sharding: 'sharded' = 1/world of every tensor per rank over PCIe + all-gather over NVLink
@@ -156,8 +160,9 @@ def shard_sample_ids(spp: int, rank: int, world: int, device=None) -> torch.Tens
     return ids[rank::world] if world > 1 else ids
 
 
-def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
-    """The path's one exchange step: sum the packed fp32 accumulators over all ranks (NCCL on GPUs, gloo in CPU tests)."""
+def reduce_accumulators(accum: torch.Tensor, world: int, dst: Optional[int] = None) -> torch.Tensor:
+    """The path's one exchange step: sum the packed fp32 accumulators over all ranks (NCCL on GPUs, gloo in CPU tests).
+    ``dst``: only that rank receives the sum (``reduce``); None: every rank does (``all_reduce``)."""
     if world > 1:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
@@ -165,7 +170,10 @@ def reduce_accumulators(accum: torch.Tensor, world: int) -> torch.Tensor:
                                "Initialise a process group, or combine render_accumulators() of the shards yourself." % (world, world))
         if dist.get_world_size() != world:
             raise RuntimeError("shard_world=%d does not match the process group's world size %d" % (world, dist.get_world_size()))
-        dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+        if dst is None:
+            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+        else:
+            dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
 
 
@@ -559,10 +567,10 @@ class PathTracingSession:
         """The path's one exchange step between ranks: spp shards are summed (all-reduce); tile shards have disjoint supports and are gathered
         (``options.tile_collective='gather'``, the default; ``'allreduce'`` sums whole frames like spp sharding -- kept for the A/B)."""
         opt = self.options
-        if opt.shard_world > 1 and opt.shard_mode == 'tile' and opt.tile_collective == 'gather':
+        if opt.shard_world > 1 and opt.shard_mode == 'tile' and opt.tile_collective == 'gather' and opt.result_rank is None:
             H, W = self.camera.resolution()
             return gather_tile_accumulators(accum, H, W, opt.tile_size, opt.shard_rank, opt.shard_world)
-        return reduce_accumulators(accum, opt.shard_world)
+        return reduce_accumulators(accum, opt.shard_world, opt.result_rank)
 
     def finalize(self, accum: torch.Tensor):
         """Epilogue of trace_rays (path_tracing.py:348-352): /spp, saturate(alpha), flipud -- one kernel."""
@@ -621,9 +629,11 @@ class PathTracingSession:
             return self.trace_rays(self.sampler_brdf)
         with torch.no_grad():
             accum = self.exchange_accumulators(self.render_accumulators())
-            out = self.finalize(accum)
-        self.raycaster().check_status()
-        return out
+            self.raycaster().check_status()
+            opt = self.options
+            if opt.shard_world > 1 and opt.result_rank is not None and opt.shard_rank != opt.result_rank:
+                return None   # the frame exists on options.result_rank only
+            return self.finalize(accum)
 
     @torch.no_grad()
     def pbr_image(self, tone='agx', lut: torch.Tensor = None):

@@ -42,9 +42,17 @@ class MeshObject:
     custom_attrs: Optional[Dict[str, torch.Tensor]] = None
     metadata: Optional[Dict[str, Any]] = None
 
-    def to(self, device):
-        """Copy of this object with every tensor on ``device`` (the material object is shared)."""
-        mv = lambda x: x.to(device) if isinstance(x, torch.Tensor) else x
+    def to(self, device, memo: Optional[dict] = None):
+        """Copy of this object with every tensor on ``device`` (the material object is shared).  ``memo`` (id of the source tensor -> moved
+        tensor) keeps tensors that several objects share -- the mesh of instanced objects -- shared after the move."""
+        def mv(x):
+            if not isinstance(x, torch.Tensor):
+                return x
+            if memo is None:
+                return x.to(device)
+            if id(x) not in memo:
+                memo[id(x)] = (x, x.to(device))   # the source is kept alive so that its id stays unique
+            return memo[id(x)][1]
         return MeshObject(self.material, mv(self.verts), mv(self.tris), mv(self.normals), mv(self.M), mv(self.color), mv(self.uv),
                           mv(self.tangents), None if self.custom_attrs is None else {k: mv(v) for k, v in self.custom_attrs.items()},
                           self.metadata)
@@ -129,7 +137,8 @@ class Scene:
     def to(self, device):
         """Copy of the scene with geometry and light tensors on ``device`` (objects must already be preprocessed)."""
         out = Scene()
-        out.objects = [o.to(device) for o in self.objects]
+        memo: dict = {}
+        out.objects = [o.to(device, memo) for o in self.objects]
         for l in self.lights:
             if isinstance(l, ImageEnvironmentLight):
                 out.lights.append(ImageEnvironmentLight(l.intensity, l.color.to(device), l.image.to(device), l.render_skybox))

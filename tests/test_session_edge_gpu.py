@@ -97,8 +97,15 @@ def test_scene_cache_is_shared_between_sessions_and_invalidated_by_in_place_edit
     torch.testing.assert_close(private.pbr()[0], ra, rtol=1e-5, atol=1e-6)
     scene.objects[1].verts.mul_(0.5)  # in-place edit bumps the tensor version -> the cache entry is stale
     c = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1))
-    assert c.raycaster() is not a.raycaster()
-    assert (c.pbr()[0] - ra).abs().max() > 1e-3
+    assert c.vertex_array_object() is not a.vertex_array_object()      # re-flattened ...
+    assert c.raycaster() is a.raycaster()                              # ... and, the connectivity being unchanged, REFITTED (drp_refit), not rebuilt
+    rc_img = c.pbr()[0]
+    assert (rc_img - ra).abs().max() > 1e-3
+    fresh = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1, reuse_scene=False))
+    torch.testing.assert_close(fresh.pbr()[0], rc_img, rtol=1e-5, atol=1e-6)   # the refitted structure renders what a rebuilt one renders
+    scene.objects[1].verts.mul_(2.0)
+    d = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=2, seed=1, refit_scene=False))
+    assert d.raycaster() is not a.raycaster()                          # opt-out: rebuilt
 
 
 def test_torchoptix_shaped_module_drives_raw_pointers():

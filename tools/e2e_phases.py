@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--upload", default="auto", choices=["auto", "direct", "sharded"], help="options.scene_upload")
     ap.add_argument("--strided-d2h", action="store_true", help="read the outputs back into channel slices of one (H,W,16) pinned array (round 1's bench)")
+    ap.add_argument("--all-ranks-read", action="store_true", help="all-reduce + finalize + D2H on every rank (round-2a behaviour) instead of reduce to rank 0")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -46,7 +47,8 @@ def main():
     extra = {'scene_upload': args.upload}
 
     def options(seed):
-        return drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=4, rng='native', seed=seed, reuse_scene=False, shard_rank=rank, shard_world=world, **extra)
+        return drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=4, rng='native', seed=seed, reuse_scene=False, shard_rank=rank, shard_world=world,
+                                                result_rank=0 if (world > 1 and not args.all_ranks_read) else None, **extra)
 
     def d2h(r, a, x):
         if args.strided_d2h:
@@ -82,14 +84,17 @@ def main():
         timed(s._fused_scene)
         timed(s._render_setup)
         acc = timed(s.render_accumulators)
-        acc = timed(lambda: reduce_accumulators(acc, world))
-        out = timed(lambda: s.finalize(acc))
-        timed(lambda: d2h(*out))
+        acc = timed(lambda: s.exchange_accumulators(acc))
+        mine_out = world == 1 or args.all_ranks_read or rank == 0
+        out = timed(lambda: s.finalize(acc) if mine_out else None)
+        timed(lambda: d2h(*out) if mine_out else None)
         timed(lambda: s.raycaster().release())
         barrier()
         t0 = time.perf_counter()
         s = drp.PathTracingSession(scene_host, cam, options(100 + rep))
-        d2h(*s.pbr())
+        res = s.pbr()
+        if res is not None:
+            d2h(*res)
         torch.cuda.synchronize()
         t_fused = (time.perf_counter() - t0) * 1e3
         s.raycaster().release()

@@ -27,6 +27,7 @@ ap.add_argument("--scale", type=float, default=1.0, help="scale spp (and views f
 ap.add_argument("--no-reuse", action="store_true", help="config 4: rebuild the BVH for every view (the reference's behaviour)")
 ap.add_argument("--tile-collective", default="gather", choices=["gather", "allreduce"])
 ap.add_argument("--out", default=None)
+ap.add_argument("--no-instancing", action="store_true", help="config 5: flat drp_build over the 10 M flattened triangles instead of drp_build_instanced")
 ap.add_argument("--profile", action="store_true", help="config 4: cProfile of the view loop on rank 0 (host overhead per session)")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -112,9 +113,19 @@ else:
     H, W, spp, depth = 2160, 3840, max(1, int(256 * args.scale)), 3
     cam = drp.PerspectiveCamera.from_orbit(h=H, w=W, **camkw)
     opt = drp.PathTracingSessionOptions(ray_spp=spp, ray_depth=depth, seed=2, shard_rank=rank, shard_world=world, shard_mode='tile', tile_size=256,
-                                        tile_collective=args.tile_collective)
+                                        tile_collective=args.tile_collective, instancing=not args.no_instancing)
     sess = drp.PathTracingSession(scene, cam, opt)
-    torch.cuda.synchronize(); t0 = time.perf_counter(); sess.raycaster(); sess._fused_scene(); torch.cuda.synchronize(); build_s = time.perf_counter() - t0
+    torch.cuda.synchronize(); t0 = time.perf_counter(); sess.vertex_array_object(); torch.cuda.synchronize(); flatten_s = time.perf_counter() - t0
+    t0 = time.perf_counter(); sess.raycaster(); torch.cuda.synchronize(); structure_s = time.perf_counter() - t0
+    t0 = time.perf_counter(); sess._fused_scene(); torch.cuda.synchronize(); build_s = flatten_s + structure_s + time.perf_counter() - t0
+    # steady-state structure time (the first build pays the stream-ordered pool's growth)
+    v_ = sess.vertex_array_object()
+    from diffrp_b200.path_tracing import scene_instances
+    cfg_ = {'epsilon': 1e-8}
+    if not args.no_instancing:
+        cfg_['instances'] = scene_instances(scene.objects)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); rc2 = drp.B200Raycaster(v_.world_pos, v_.tris, cfg_); torch.cuda.synchronize(); structure2_s = time.perf_counter() - t0
+    rc2.release()
     n_tris = int(sess.vertex_array_object().tris.shape[0])
     warm = sess.new_accumulators()
     sess.render_samples(torch.arange(1, dtype=torch.int32, device=dev), warm, tile=sess.tiles()[rank])   # workspace at its full size, kernels loaded
@@ -139,7 +150,8 @@ else:
     peak, peak_src = peak_gbs()
     bb = b_query(n_tris) + S_DEFAULT
     res_d = dict(config=5, n_gpus=world, sharding="256-pixel tiles rank::world, exchange = %s" % args.tile_collective, triangles=n_tris, objects=len(scene.objects),
-                 resolution=[W, H], spp=spp, ray_depth=depth, upload_flatten_build_s=build_s, seconds=ms / 1e3, render_ms=ms_render, exchange_ms=ms_exchange,
+                 resolution=[W, H], spp=spp, ray_depth=depth, upload_flatten_build_s=build_s, flatten_s=flatten_s, structure_first_s=structure_s, structure_steady_s=structure2_s,
+                 structure="drp_build_instanced" if sess.raycaster().instanced else "drp_build", seconds=ms / 1e3, render_ms=ms_render, exchange_ms=ms_exchange,
                  exchange_bytes_per_rank=(H * W * 64 * (world - 1) // world) * (1 if args.tile_collective == 'gather' else 2), mrays_s=nominal / ms / 1e3,
                  coverage=float((alpha > 0).float().mean()), mean_radiance=float(rad.mean()), bvh=sess.raycaster().stats(),
                  roofline=dict(bound="hbm", B_bounce=bb, peak=peak, unit="GB/s per GPU", peak_source=peak_src,
