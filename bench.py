@@ -475,6 +475,10 @@ def main():
         roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
         tj = json.load(open(traffic_file))
+        if tj.get("issue"):
+            # the limiter of this kernel is neither memory level but warp-instruction issue x SIMT efficiency (ncu, same capture): report that roofline too
+            roofline["issue"] = {k: tj["issue"][k] for k in ("ipc_per_smsp", "active_lanes", "frac", "ipc_by_bounce", "active_lanes_by_bounce", "note")}
+            roofline["issue"]["source"] = tj.get("source")
         if tj.get("l2_bytes_per_launch") and tj.get("l2_read_peak_gbs") and roofline["avg_launch_ms"] > 0:
             # L2-level view (SURVEY 8d asks for % of the L2 roofline too): ncu L2 sector bytes per launch / live launch time / measured L2 peak
             l2_gbs = tj["l2_bytes_per_launch"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9

@@ -447,45 +447,94 @@ DRP_HD RayHit cw_trace_one(const float4* __restrict__ nodes, const float4* __res
 
 // ---- refit: new boxes and triangle records for an existing topology ------------------------------------------------
 // Re-derive wide node `src` (5 float4 of a template hierarchy) for new vertex positions and write it as node `dst_ni` of the output
-// hierarchy.  The topology is kept: slot occupancy (imask / V), child order, triangle order; child / triangle bases are shifted by
-// `node_off` / `tri_off` and primitive ids by `prim_off` (0 for an in-place refit; block offsets when the template is replicated for one
-// instance of a shared mesh).  Internal children must already have been refitted (deeper levels first): their exact boxes are read
-// from node_box.  Triangles of leaf slots are re-packed from (verts, tris) -- rounded exactly like the builder's -- and their padded
+// hierarchy.  The tree is kept -- which children a node has, which triangles a leaf child holds -- while child / triangle bases are shifted
+// by `node_off` / `tri_off` and primitive ids by `prim_off` (0 for an in-place refit; block offsets when the template is replicated for
+// one instance of a shared mesh).  Internal children must already have been refitted (deeper levels first): their exact boxes are read
+// from node_box.  Triangles of leaf children are re-packed from (verts, tris) -- rounded exactly like the builder's -- and their padded
 // boxes enter the node, so the slab tests stay conservative and closest hits stay the exhaustive ones, whatever the hierarchy.
+// The SLOTS are re-assigned for the new boxes (cw_assign_slots: slot = octant direction, which is what orders the traversal front to back):
+// a rotated instance or a deformed mesh would otherwise be walked in an arbitrary order.  Re-slotting permutes the node's children, so the
+// (already refitted) child records and their boxes are permuted inside the node's contiguous child run and the triangle records are written
+// in the new slot order; nothing outside the node's own children / triangles moves.
 DRP_HD void cw_refit_node(const float4* src, const float4* src_tris, float4* out_nodes, float4* out_tris,   // (may alias: in-place refit)
                           float4* node_box, int dst_ni, int node_off, int tri_off, int prim_off, const float* __restrict__ verts,
                           const int32_t* __restrict__ tris, float abs_pad) {
     const uint32_t imask = f2u(src[0].w) >> 24, vmask = f2u(src[1].z);
-    const int cb = f2i(src[1].x), tb = f2i(src[1].y);
-    float slo[8][3], shi[8][3];
-    int rank = 0;
+    const int cb = f2i(src[1].x) + node_off, tb = f2i(src[1].y);
+    // children in old slot order: box, kind, payload (internal: old position in the child run; leaf: primitive ids)
+    float lo[8][3], hi[8][3], nlo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {-3e38f, -3e38f, -3e38f};
+    int inner_pos[8], prim[8][3], cnt[8];
+    int k = 0, rank = 0;
     for (int s = 0; s < 8; ++s) {
         if (imask & (1u << s)) {
-            const int child = cb + node_off + rank++;
+            const int child = cb + rank;
             const float4 l = node_box[2 * (int64_t)child], h = node_box[2 * (int64_t)child + 1];
-            slo[s][0] = l.x; slo[s][1] = l.y; slo[s][2] = l.z;
-            shi[s][0] = h.x; shi[s][1] = h.y; shi[s][2] = h.z;
-            continue;
+            lo[k][0] = l.x; lo[k][1] = l.y; lo[k][2] = l.z;
+            hi[k][0] = h.x; hi[k][1] = h.y; hi[k][2] = h.z;
+            inner_pos[k] = rank++;
+            cnt[k] = 0;
+        } else {
+            const uint32_t bits = (vmask >> (3 * s)) & 7u;
+            if (!bits) continue;
+            float4 l = make_float4(3e38f, 3e38f, 3e38f, 0.0f), h = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
+            int c = 0;
+            for (int q = 0; q < 3; ++q) {
+                if (!(bits & (1u << q))) continue;
+                const int j = cw_tri_index((uint32_t)tb, vmask, 3 * s + q);
+                const int pr = f2i(src_tris[3 * (int64_t)j + 2].y) + prim_off;
+                prim[k][c++] = pr;
+                const Vec3 A = load_vert(verts, tris[3 * (int64_t)pr]), B = load_vert(verts, tris[3 * (int64_t)pr + 1]), C = load_vert(verts, tris[3 * (int64_t)pr + 2]);
+                l.x = fminf(l.x, fminf(fminf(A.x, B.x), C.x)); l.y = fminf(l.y, fminf(fminf(A.y, B.y), C.y)); l.z = fminf(l.z, fminf(fminf(A.z, B.z), C.z));
+                h.x = fmaxf(h.x, fmaxf(fmaxf(A.x, B.x), C.x)); h.y = fmaxf(h.y, fmaxf(fmaxf(A.y, B.y), C.y)); h.z = fmaxf(h.z, fmaxf(fmaxf(A.z, B.z), C.z));
+            }
+            pad_box(l, h, abs_pad);
+            lo[k][0] = l.x; lo[k][1] = l.y; lo[k][2] = l.z;
+            hi[k][0] = h.x; hi[k][1] = h.y; hi[k][2] = h.z;
+            inner_pos[k] = -1;
+            cnt[k] = c;
         }
-        const uint32_t bits = (vmask >> (3 * s)) & 7u;
-        if (!bits) continue;
-        float4 l = make_float4(3e38f, 3e38f, 3e38f, 0.0f), h = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
-        for (int k = 0; k < 3; ++k) {
-            if (!(bits & (1u << k))) continue;
-            const int j = cw_tri_index((uint32_t)tb, vmask, 3 * s + k);
-            const int prim = f2i(src_tris[3 * (int64_t)j + 2].y) + prim_off;
-            const Vec3 A = load_vert(verts, tris[3 * (int64_t)prim]), B = load_vert(verts, tris[3 * (int64_t)prim + 1]),
-                       C = load_vert(verts, tris[3 * (int64_t)prim + 2]);
-            pack_triangle(out_tris + 3 * (int64_t)(j + tri_off), A, B, C, prim);
-            l.x = fminf(l.x, fminf(fminf(A.x, B.x), C.x)); l.y = fminf(l.y, fminf(fminf(A.y, B.y), C.y)); l.z = fminf(l.z, fminf(fminf(A.z, B.z), C.z));
-            h.x = fmaxf(h.x, fmaxf(fmaxf(A.x, B.x), C.x)); h.y = fmaxf(h.y, fmaxf(fmaxf(A.y, B.y), C.y)); h.z = fmaxf(h.z, fmaxf(fmaxf(A.z, B.z), C.z));
-        }
-        pad_box(l, h, abs_pad);
-        slo[s][0] = l.x; slo[s][1] = l.y; slo[s][2] = l.z;
-        shi[s][0] = h.x; shi[s][1] = h.y; shi[s][2] = h.z;
+        for (int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], lo[k][a]); nhi[a] = fmaxf(nhi[a], hi[k][a]); }
+        ++k;
     }
-    float nlo[3], nhi[3];
-    cw_encode_node(out_nodes + CW_NODE_F4 * (int64_t)dst_ni, slo, shi, imask, vmask, cb + node_off, tb + tri_off, nlo, nhi);
-    node_box[2 * (int64_t)dst_ni] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
-    node_box[2 * (int64_t)dst_ni + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+    int slot_child[8];
+    cw_assign_slots(lo, hi, k, nlo, nhi, slot_child);
+    // new masks, triangles in the new slot order, permutation of the internal children
+    uint32_t new_imask = 0, new_vmask = 0;
+    float slo[8][3], shi[8][3];
+    int new_of_old[8], n_inner = 0, toff = 0;
+    for (int s = 0; s < 8; ++s) {
+        const int j = slot_child[s];
+        if (j < 0) continue;
+        for (int a = 0; a < 3; ++a) { slo[s][a] = lo[j][a]; shi[s][a] = hi[j][a]; }
+        if (inner_pos[j] >= 0) {
+            new_imask |= 1u << s;
+            new_of_old[inner_pos[j]] = n_inner++;
+        } else {
+            new_vmask |= ((1u << cnt[j]) - 1u) << (3 * s);
+            for (int c = 0; c < cnt[j]; ++c) {
+                const int pr = prim[j][c];
+                const Vec3 A = load_vert(verts, tris[3 * (int64_t)pr]), B = load_vert(verts, tris[3 * (int64_t)pr + 1]), C = load_vert(verts, tris[3 * (int64_t)pr + 2]);
+                pack_triangle(out_tris + 3 * (int64_t)(tb + tri_off + toff + c), A, B, C, pr);
+            }
+            toff += cnt[j];
+        }
+    }
+    bool moved = false;
+    for (int r = 0; r < n_inner; ++r) moved = moved || new_of_old[r] != r;
+    if (moved) {   // permute the child records (and their boxes) inside this node's child run
+        float4 rec[8][CW_NODE_F4], box[8][2];
+        for (int r = 0; r < n_inner; ++r) {
+            for (int f = 0; f < CW_NODE_F4; ++f) rec[r][f] = out_nodes[CW_NODE_F4 * (int64_t)(cb + r) + f];
+            box[r][0] = node_box[2 * (int64_t)(cb + r)]; box[r][1] = node_box[2 * (int64_t)(cb + r) + 1];
+        }
+        for (int r = 0; r < n_inner; ++r) {
+            const int d = cb + new_of_old[r];
+            for (int f = 0; f < CW_NODE_F4; ++f) out_nodes[CW_NODE_F4 * (int64_t)d + f] = rec[r][f];
+            node_box[2 * (int64_t)d] = box[r][0]; node_box[2 * (int64_t)d + 1] = box[r][1];
+        }
+    }
+    float elo[3], ehi[3];
+    cw_encode_node(out_nodes + CW_NODE_F4 * (int64_t)dst_ni, slo, shi, new_imask, new_vmask, cb, tb + tri_off, elo, ehi);
+    node_box[2 * (int64_t)dst_ni] = make_float4(elo[0], elo[1], elo[2], 0.0f);
+    node_box[2 * (int64_t)dst_ni + 1] = make_float4(ehi[0], ehi[1], ehi[2], 0.0f);
 }

@@ -134,12 +134,6 @@ __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restr
 #ifndef CWK_POSTPONE
 #define CWK_POSTPONE 0.2f
 #endif
-#ifndef CWK_STACK64
-#define CWK_STACK64 0   // A/B (round 2): stack entries as uint2 (one LDL.64 / STL.64) instead of two 32-bit arrays
-#endif
-#ifndef CWK_TOPREG
-#define CWK_TOPREG 0    // A/B (round 2): top stack entry mirrored in registers (ncu r1: 7.2 % of the stall samples wait for the popped word)
-#endif
 
 #define SRC_QUEUE 0    // rays from the float4 queues, result to hit[]
 #define SRC_PRIMARY 1  // rays generated from the ray index, result to hit[]
@@ -203,15 +197,9 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     float t_best = 0.0f;
     int id_best = 0, sp = 0;
     uint32_t ng_x = 0, ng_y = 0, tg_x = 0, tg_y = 0;
-    // Traversal stack: all in local memory (L1-resident; 8 entries per thread in shared memory were 5 % slower, profiles/README.md)
-#if CWK_STACK64
-    uint2 st[CW_STACK];                 // one 64-bit local store / load per entry
-#else
+    // Traversal stack: two 32-bit arrays in local memory (L1-resident).  Measured and removed: 8 entries per thread in shared memory (-5 %,
+    // profiles/README.md), 64-bit entries (-1.7 %), top entry mirrored in registers (-4 ... -6 %) -- profiles/r2/ab_stack_r2b.json
     uint32_t st_x[CW_STACK], st_y[CW_STACK];
-#endif
-#if CWK_TOPREG
-    uint32_t top_x = 0, top_y = 0;      // write-through copy of the top entry: a pop takes it from registers and requests the next one early
-#endif
     bool overflow = false;              // this lane's current ray dropped a stack entry
     // the two expansions of the per-slot hit byte as tables (cwbvh.cuh: cw_perm8, cw_spread3x7); arithmetic instead: +4 %
     __shared__ uint8_t s_perm[8 * 256];
@@ -221,28 +209,12 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     __syncthreads();
     uint32_t tri_base = 0, tri_valid = 0;  // of the node the current triangle group belongs to
     uint32_t oct_row = 0;                  // octinv << 8: this ray's row of s_perm
-#if CWK_STACK64
-#define CWK_ST(I, X, Y) st[I] = make_uint2((X), (Y))
-#define CWK_LD(I, X, Y) do { const uint2 _e = st[I]; (X) = _e.x; (Y) = _e.y; } while (0)
-#else
-#define CWK_ST(I, X, Y) do { st_x[I] = (X); st_y[I] = (Y); } while (0)
-#define CWK_LD(I, X, Y) do { (X) = st_x[I]; (Y) = st_y[I]; } while (0)
-#endif
-#if CWK_TOPREG
-#define CWK_PUSH(X, Y)                                                                             \
-    do {                                                                                           \
-        if (sp < ovf.stack_cap) { CWK_ST(sp, (X), (Y)); top_x = (X); top_y = (Y); ++sp; }          \
-        else overflow = true;                                                                      \
-    } while (0)
-#define CWK_POP(X, Y) do { --sp; (X) = top_x; (Y) = top_y; if (sp > 0) CWK_LD(sp - 1, top_x, top_y); } while (0)
-#else
 #define CWK_PUSH(X, Y)                                                     \
     do {                                                                   \
-        if (sp < ovf.stack_cap) { CWK_ST(sp, (X), (Y)); ++sp; }            \
+        if (sp < ovf.stack_cap) { st_x[sp] = (X); st_y[sp] = (Y); ++sp; }  \
         else overflow = true;                                              \
     } while (0)
-#define CWK_POP(X, Y) do { --sp; CWK_LD(sp, (X), (Y)); } while (0)
-#endif
+#define CWK_POP(X, Y) do { --sp; (X) = st_x[sp]; (Y) = st_y[sp]; } while (0)
     for (;;) {
         // ---- refill idle lanes --------------------------------------------------------------------------------
         const unsigned need = __ballot_sync(0xffffffffu, k < 0);
@@ -345,8 +317,6 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(co
     }
 #undef CWK_PUSH
 #undef CWK_POP
-#undef CWK_ST
-#undef CWK_LD
 }
 
 // Re-trace of the rays k_extend_cw flagged (see Overflow): one ray per thread, stack of CW_DEEP_STACK entries per thread in global memory
@@ -841,7 +811,7 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
 extern "C" const char* drp_build_config(void) {
     return "compiled " __DATE__ " " __TIME__ "; DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS) " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS)
            " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW) " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE)
-           " CW_STACK=" DRP_STR(CW_STACK) " CW_DEEP_STACK=" DRP_STR(CW_DEEP_STACK) " CWK_STACK64=" DRP_STR(CWK_STACK64) " CWK_TOPREG=" DRP_STR(CWK_TOPREG);
+           " CW_STACK=" DRP_STR(CW_STACK) " CW_DEEP_STACK=" DRP_STR(CW_DEEP_STACK);
 }
 
 extern "C" int drp_status(uint64_t handle) {

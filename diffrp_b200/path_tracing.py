@@ -94,7 +94,7 @@ class PathTracingSessionOptions:
     tile_collective: str = 'allreduce'  # 'allreduce': sum whole frames (NVSwitch reduces in the fabric); 'gather': all-gather of the owned tiles
     result_rank: Optional[int] = None   # sharded renders: None = every rank gets the frame (all-reduce); r = only rank r does (reduce), the others' pbr() returns None
     refit_scene: bool = True          # a later session over the same Scene with unchanged connectivity refits the structure instead of rebuilding
-    instancing: bool = True           # objects sharing vertex + index tensors: one hierarchy per mesh, replicated and refitted per instance
+    instancing: bool = False          # objects sharing vertex + index tensors: one hierarchy per mesh, replicated and refitted per instance
     scene_upload: str = 'auto'        # host scenes under sharding: 'sharded' = 1/world of every tensor per rank over PCIe + all-gather over NVLink
     reuse_scene: bool = True  # share the flattened scene + BVH between sessions over the same, unmodified Scene
     reproducible: bool = False  # bit-identical images run to run: one sample per launch batch, fixed fp32 accumulation order

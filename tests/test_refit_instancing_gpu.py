@@ -96,7 +96,7 @@ def test_instanced_build_gives_the_hits_of_the_flat_build(n_inst, mesh_res):
     to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
     a, b = inst.query(to, td, 10.0), flat.query(to, td, 10.0)
     assert _same_hits(a, b)
-    assert float((a[0] < 10.0).float().mean()) > (0.0005 if n_inst == 1 else 0.05)
+    assert float((a[0] < 10.0).float().mean()) > (0.0005 if n_inst == 1 else 0.02)
     st = inst.stats()
     assert st['n_tris'] == n_inst * nt and st['n_leaves'] > 0
     inst.check_status()

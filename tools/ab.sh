@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 prefix=$1; shift
 for v in "$@"; do
   if [ "$v" = default ]; then unset DIFFRP_B200_LIB; else export DIFFRP_B200_LIB=$PWD/build/variants/$v.so; fi
-  DIFFRP_B200_NO_BUILD=1 timeout 600 python bench.py --steps 64 --warmup 3 --no-torch-baseline --no-cpu-baseline --e2e-steps 1 \
+  DIFFRP_B200_NO_BUILD=1 timeout 600 python bench.py --steps 64 --warmup 3 --no-torch-baseline --no-cpu-baseline --no-strong --e2e-steps 1 \
       > gpurun_out/${prefix}_$v.json 2> gpurun_out/${prefix}_$v.err
   DIFFRP_B200_NO_BUILD=1 timeout 300 python tools/microbench_trace.py > gpurun_out/${prefix}_$v.micro 2>&1
   python - <<PY
