@@ -447,10 +447,12 @@ def main():
         if world > 1:
             dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
         s_dev_ms = float(t_s.item())
-        s_e2e_ms = timed_calls(1, FRAME_SPP, True)
+        e2e_call(FRAME_SPP, 98, True)                      # warm-up at the job's own size (allocator pools, collectives at this message size)
+        s_e2e_runs = [timed_calls(1, FRAME_SPP, True) for _ in range(2)]
+        s_e2e_ms = min(s_e2e_runs)
         rays = FRAME_SPP * HW * DEPTH
         strong = {"job": "one %dx%d frame, %d spp, %d bounces (fixed total work), spp-sharded x%d" % (RES, RES, FRAME_SPP, DEPTH, world),
-                  "device_ms": s_dev_ms, "e2e_ms": s_e2e_ms, "value": rays / (s_dev_ms * 1e-3) / 1e6, "e2e_value": rays / (s_e2e_ms * 1e-3) / 1e6,
+                  "device_ms": s_dev_ms, "e2e_ms": s_e2e_ms, "e2e_ms_runs": s_e2e_runs, "value": rays / (s_dev_ms * 1e-3) / 1e6, "e2e_value": rays / (s_e2e_ms * 1e-3) / 1e6,
                   "unit": UNIT, "scaling": "strong"}
         del s_out, s_acc
 

@@ -115,7 +115,7 @@ class Profile(C.Structure):
 EXPORTED_SYMBOLS = (
     "drp_abi_version", "drp_build_config", "drp_last_error", "drp_set_log_level", "drp_build", "drp_trace", "drp_trace_bruteforce",
     "drp_release", "drp_set_epsilon", "drp_bvh_stats", "drp_flatten", "drp_render", "drp_finalize", "drp_render_stats", "drp_set_profiling", "drp_get_profile",
-    "drp_tonemap", "drp_conv3x3", "drp_denoise_pack", "drp_denoise_unpack", "drp_surface_attrs", "drp_status", "drp_debug_set_stack_limit", "drp_refit", "drp_build_instanced",
+    "drp_tonemap", "drp_conv3x3", "drp_denoise_pack", "drp_denoise_unpack", "drp_surface_attrs", "drp_status", "drp_debug_set_stack_limit", "drp_refit", "drp_build_instanced", "drp_upload_batch",
 )
 
 

@@ -30,6 +30,7 @@ def _declare(L):
     L.drp_render.argtypes = [u64, C.POINTER(_abi.Scene), C.POINTER(_abi.RenderParams), vp, vp]
     L.drp_finalize.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.drp_render_stats.argtypes = [u64, C.POINTER(_abi.RenderStats)]
+    L.drp_upload_batch.argtypes = [i32, vp, vp, vp, vp]
     L.drp_status.argtypes = [u64]
     L.drp_refit.argtypes = [u64, vp, vp, i64, i64, vp]
     L.drp_build_instanced.argtypes = [vp, vp, i64, i64, vp, vp, i64, C.c_int, vp, C.POINTER(C.c_uint64)]

@@ -120,3 +120,16 @@ extern "C" int drp_flatten(const drp_object_t* objects, int32_t n_objects, float
     DRP_CUDA_CHECK(cudaFreeAsync(scratch, s));
     return DRP_OK;
 }
+
+
+// Batched host -> device upload: n stream-ordered copies issued from one C call.  A scene is ~300 small tensors (6 per object, 4 per
+// material); issuing them one by one from Python costs more host time than the PCIe transfer takes (tools/e2e_phases.py).
+extern "C" int drp_upload_batch(int32_t n, void* const* dst, const void* const* src, const int64_t* bytes, void* stream) {
+    if (n < 0 || (n > 0 && (!dst || !src || !bytes))) { drp_set_error("drp_upload_batch: invalid argument"); return DRP_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int32_t k = 0; k < n; ++k) {
+        if (bytes[k] < 0 || (bytes[k] > 0 && (!dst[k] || !src[k]))) { drp_set_error("drp_upload_batch: invalid segment"); return DRP_ERR_INVALID; }
+        if (bytes[k] > 0) DRP_CUDA_CHECK(cudaMemcpyAsync(dst[k], src[k], (size_t)bytes[k], cudaMemcpyDefault, s));
+    }
+    return DRP_OK;
+}

@@ -78,56 +78,59 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
 SHARD_MIN_BYTES = 1 << 20
 
 
-class PendingGathers:
-    """All-gathers of a batch of sharded uploads, issued as ONE coalesced NCCL group (one launch) by ``flush()``: a scene is ~300 tensors
-    and a collective per tensor costs more host time than the copies it replaces (tools/e2e_phases.py at N = 8)."""
+class PackedUpload:
+    """
+    Host -> device move of MANY scene tensors as one packed device buffer: ``add()`` registers a tensor and returns a ticket, ``commit()``
+    allocates one buffer, issues every copy from ONE C call (``drp_upload_batch``) and returns the device tensors (views into the buffer).
+    ``shard=(rank, world)`` (scene replicated over the ranks of an NCCL group -- the precondition of spp / tile sharding): every rank copies
+    only its 1/world byte range of the packed layout over its own PCIe link and ONE in-place all-gather over NVLink completes the buffer on
+    every GPU: the scene crosses PCIe once in total, at one collective instead of one per tensor.  Collective: every rank must register
+    the same tensors in the same order.  Tensors that already live on the device, or need a dtype / layout conversion, are passed through
+    ``.to()`` immediately.
+    """
+    ALIGN = 256
 
-    def __init__(self):
-        self.items = []
+    def __init__(self, dev, shard=None):
+        self.dev, self.shard = torch.device(dev), shard if (shard is not None and shard[1] > 1) else None
+        self.items, self.ready, self.total = [], {}, 0
 
-    def add(self, out, part):
-        self.items.append((out, part))
+    def add(self, t: torch.Tensor, dtype) -> int:
+        ticket = len(self.items) + len(self.ready)
+        if self.dev.type != 'cuda' or t.is_cuda or t.dtype != dtype or not t.is_contiguous() or t.numel() == 0:
+            self.ready[ticket] = t.to(self.dev, dtype, non_blocking=True).contiguous()
+            return ticket
+        nbytes = t.numel() * t.element_size()
+        self.items.append((ticket, t, self.total, nbytes))
+        self.total += -(-nbytes // self.ALIGN) * self.ALIGN
+        return ticket
 
-    def flush(self):
+    def commit(self) -> dict:
+        out = dict(self.ready)
         if not self.items:
-            return
-        import torch.distributed as dist
-        items, self.items = self.items, []
-        try:
-            from torch.distributed.distributed_c10d import _coalescing_manager
-            with _coalescing_manager(device=items[0][0].device):
-                for out, part in items:
-                    dist.all_gather_into_tensor(out, part)
-        except (ImportError, TypeError, RuntimeError):
-            for out, part in items:
-                dist.all_gather_into_tensor(out, part)
-
-
-def upload(t: torch.Tensor, dev, dtype, shard=None, pending: Optional[PendingGathers] = None) -> torch.Tensor:
-    """
-    Host -> device move of one scene tensor.  ``shard=(rank, world)`` (scene replicated over the ranks of an initialised NCCL group, the
-    precondition of spp / tile sharding): every rank DMA-copies only its 1/world slice of the (identical) host tensor over its own PCIe link and
-    an in-place all-gather over NVLink completes it on every GPU -- world x less host-memory and PCIe traffic than ``world`` full uploads
-    from one host, at NVLink instead of PCIe speed.  Collective: every rank must upload the same tensors in the same order.
-    With ``pending`` the all-gather is deferred to ``pending.flush()`` (one coalesced group for many tensors); the returned tensor is complete
-    only after that.
-    """
-    if (shard is not None and shard[1] > 1 and not t.is_cuda and t.dtype == dtype and t.is_contiguous()
-            and t.numel() * t.element_size() >= SHARD_MIN_BYTES):
-        import torch.distributed as dist
-        rank, world = shard
-        n = t.numel()
-        per = -(-n // world)
-        out = torch.empty([world * per], dtype=dtype, device=dev)
-        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
-        if hi > lo:
-            out[lo:hi].copy_(t.view(-1)[lo:hi], non_blocking=True)
-        if pending is not None:   # the caller flushes before the first kernel that reads the tensor
-            pending.add(out, out[rank * per:(rank + 1) * per])
-        else:
-            dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
-        return out[:n].view(t.shape)
-    return t.to(dev, dtype, non_blocking=True)
+            return out
+        import ctypes as C
+        from ._lib import lib, check
+        world = self.shard[1] if self.shard else 1
+        per = -(-self.total // (world * self.ALIGN)) * self.ALIGN
+        buf = torch.empty([per * world], dtype=torch.uint8, device=self.dev)
+        lo, hi = (self.shard[0] * per, (self.shard[0] + 1) * per) if self.shard else (0, per)
+        base = buf.data_ptr()
+        dst, src, nb = [], [], []
+        for _, t, off, nbytes in self.items:
+            a, b = max(off, lo), min(off + nbytes, hi)
+            if b > a:
+                dst.append(base + a); src.append(t.data_ptr() + (a - off)); nb.append(b - a)
+        n = len(dst)
+        if n:
+            check(lib().drp_upload_batch(n, (C.c_void_p * n)(*dst), (C.c_void_p * n)(*src), (C.c_int64 * n)(*nb),
+                                         torch.cuda.current_stream(self.dev).cuda_stream), "drp_upload_batch")
+        if self.shard:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(buf, buf[lo:hi])
+        for ticket, t, off, nbytes in self.items:
+            out[ticket] = buf[off:off + nbytes].view(t.dtype).view(t.shape)
+        self._sources = [t for _, t, _, _ in self.items]   # host sources stay referenced until the caller drops this object
+        return out
 
 
 def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
@@ -142,21 +145,32 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     from ._lib import lib, check
     dev = torch.device(dev)
     keep = []
-    pending = PendingGathers()
-
-    def src(t, dtype):
-        ok = t.dtype == dtype and t.is_contiguous() and t.is_cuda and t.device == dev
-        if not ok:
-            t = upload(t, dev, dtype, shard, pending).contiguous()
-        keep.append(t)
-        return t
+    pack = PackedUpload(dev, shard)
+    tickets, local = [], {}
+    for o in objs:   # pass 1: register every source tensor (tensors shared between objects -- instanced meshes -- are moved once)
+        row = []
+        for t, dtype in ((o.verts, torch.float32), (o.normals, torch.float32), (o.color, torch.float32), (o.uv, torch.float32),
+                         (o.tangents, torch.float32), (o.tris, torch.int32)):
+            if t.dtype == dtype and t.is_contiguous() and t.is_cuda and t.device == dev:
+                row.append(t)
+            else:
+                key = (t.data_ptr(), tuple(t.shape), t.dtype, str(t.device))
+                if key not in local:
+                    local[key] = pack.add(t, dtype)
+                row.append(local[key])
+        tickets.append(row)
+    moved = pack.commit()
+    keep.append(pack)
 
     descs = (_abi.Object * max(1, len(objs)))()
     V = F = 0
+    host_M = [o.M.detach() for o in objs]
+    if any(m.is_cuda for m in host_M):   # one read-back for all model matrices instead of one per object
+        host_M = list(torch.stack([m.to(dev, torch.float32) for m in host_M]).cpu())
     for k, o in enumerate(objs):
         assert o.tris.shape[-1] == 3, "Expected 3 vertices per triangle, got %d" % o.tris.shape[-1]
-        v, n, col, uv, tg, tr = (src(o.verts, torch.float32), src(o.normals, torch.float32), src(o.color, torch.float32),
-                                 src(o.uv, torch.float32), src(o.tangents, torch.float32), src(o.tris, torch.int32))
+        v, n, col, uv, tg, tr = (x if isinstance(x, torch.Tensor) else moved[x] for x in tickets[k])
+        keep.extend((v, n, col, uv, tg, tr))
         nv = v.shape[0]
         for name, a, c in (("normals", n, 3), ("uv", uv, 2), ("tangents", tg, 4), ("color", col, None)):
             assert a.shape[0] == nv, "attribute length not the same as number of vertices"
@@ -165,7 +179,7 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
         d = descs[k]
         d.verts, d.normals, d.color, d.uv, d.tangents, d.tris = (v.data_ptr(), n.data_ptr(), col.data_ptr(), uv.data_ptr(),
                                                                  tg.data_ptr(), tr.data_ptr())
-        d.M[:] = [float(x) for x in o.M.detach().to('cpu', torch.float32).reshape(-1)]
+        d.M[:] = host_M[k].to(torch.float32).reshape(-1).tolist()
         d.n_verts, d.n_tris, d.color_channels = nv, tr.shape[0], col.shape[-1]
         V += nv
         F += tr.shape[0]
@@ -173,7 +187,6 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     i = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
     out = dict(world_pos=f(V, 3), world_nrm=f(V, 3), color=f(V, 4), uv=f(V, 2), world_tan=f(V, 4), tris=i(F, 3), tri_material=i(F),
                stencils=i(F + 1), records=f(V, 16), verts=f(V, 3), normals=f(V, 3), tangents=f(V, 4))
-    pending.flush()
     check(lib().drp_flatten(descs, len(objs), out['world_pos'].data_ptr(), out['world_nrm'].data_ptr(), out['color'].data_ptr(),
                             out['uv'].data_ptr(), out['world_tan'].data_ptr(), out['tris'].data_ptr(), out['tri_material'].data_ptr(),
                             out['stencils'].data_ptr(), out['records'].data_ptr(), out['verts'].data_ptr(), out['normals'].data_ptr(),
@@ -236,9 +249,9 @@ def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Op
     or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
     descs = []
     uploaded = {}
-    pending = PendingGathers()
+    pack = PackedUpload(dev, shard)
     raw = []
-    for o in objs:   # pass 1: start every upload (sharded uploads defer their all-gather to ONE coalesced group)
+    for o in objs:   # pass 1: register every texture; ONE packed upload (+ one all-gather when sharded) moves them all
         d = o.material.fused_description() if hasattr(o.material, 'fused_description') else None
         if d is None:
             return None
@@ -248,10 +261,11 @@ def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Op
                 src = d[k]['image']
                 key = (src.data_ptr(), tuple(src.shape))
                 if key not in uploaded:
-                    uploaded[key] = upload(src, dev, torch.float32, shard, pending)
-                d[k] = dict(d[k], image=uploaded[key], _key=key)
+                    uploaded[key] = pack.add(src, torch.float32)
+                d[k] = dict(d[k], _key=key)
         raw.append(d)
-    pending.flush()
+    moved = pack.commit()
+    uploaded = {key: moved[ticket] for key, ticket in uploaded.items()}
     padded = {}
     for d in raw:    # pass 2: RGBA padding and texel interleaving on the device
         for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'):

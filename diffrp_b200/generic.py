@@ -305,8 +305,25 @@ def primary_rays(sess, grid):
     return cam + d * (P[2, 3] / (P[2, 2] - 1)), d
 
 
-def trace_rays(sess, sampler: Callable, radiance_channels: int = 3):
-    """Section x bounce loop with a user sampler (path_tracing.py:310-352); intersection = B200Raycaster.query."""
+def ray_may_reach_box(o: torch.Tensor, d: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+    """(R,) bool: can the ray o + t d, t >= 0, touch the box [lo, hi]?  Tensor version of csrc/shade.cuh:ray_may_reach_box (same rule)."""
+    par = d == 0
+    safe = torch.where(par, torch.ones_like(d), d)
+    t1, t2 = (lo - o) / safe, (hi - o) / safe
+    tn = torch.where(par, torch.zeros_like(d), torch.minimum(t1, t2)).max(-1).values.clamp_min(0.0)
+    tf = torch.where(par, torch.full_like(d, 3.0e38), torch.maximum(t1, t2)).min(-1).values
+    outside = (par & ((o < lo) | (o > hi))).any(-1)
+    return (tn <= tf) & ~outside
+
+
+def trace_rays(sess, sampler: Callable, radiance_channels: int = 3, compact: bool = False):
+    """Section x bounce loop with a user sampler (path_tracing.py:310-352); intersection = B200Raycaster.query.
+
+    ``compact=True`` (extension): the sampler only sees the rays that can still contribute.  After every bounce a ray is
+    dropped iff it hit nothing, its throughput is zero in every channel and its continuation cannot reach the padded scene box -- it would
+    miss at every later bounce and add zero radiance.  Exact for any sampler that returns zero ``alpha`` for rays that miss (the built-in
+    sampler does); the arrays passed to the sampler then shrink from bounce to bounce (open scenes: about half of the rays after bounce 0)
+    and sums are scattered back by pixel."""
     from .path_tracing import hammersley
     opt, dev = sess.options, sess.device
     rc = sess.raycaster()
@@ -320,17 +337,27 @@ def trace_rays(sess, sampler: Callable, radiance_channels: int = 3):
     radiance = zeros_like_vec(pix, radiance_channels)
     alpha = zeros_like_vec(pix, 1)
     extras_sum, extras_cnt = {}, {}
+    if compact:
+        b = rc.stats()['bounds']
+        lo, hi = torch.tensor(b[:3], dtype=torch.float32, device=dev), torch.tensor(b[3:], dtype=torch.float32, device=dev)
+        pad = 1e-5 * torch.maximum(lo.abs(), hi.abs()).clamp_min(1e-30) + 1e-5 * (hi - lo).clamp_min(0)
+        lo, hi = lo - pad, hi + pad
     for sx, sy in zip(torch.tensor_split(qx, sections), torch.tensor_split(qy, sections)):
         n = len(sx)
         sx, sy = sx[:, None, None], sy[:, None, None]
         grid = torch.cat([pix[:, 0:1] + (sx - 0.5) * (2 / W), pix[:, 1:2] + (sy - 0.5) * (2 / H), pix[:, 2:].expand(n, -1, -1)], -1).reshape(-1, 4)
         rays_o, rays_d = primary_rays(sess, grid)
         throughput = ones_like_vec(rays_o, radiance_channels)
+        owner = torch.arange(H * W, device=dev).repeat(n) if compact else None   # pixel of every live ray
         for d in range(opt.ray_depth):
             t, i = rc.query(rays_o.detach(), rays_d.detach(), far)
             out = sampler(rays_o, rays_d, t, i, d)
-            radiance = radiance + (throughput * out.radiance).view(n, -1, radiance_channels).sum(0)
-            alpha = alpha + out.alpha.reshape(n, -1, 1).sum(0)
+            if compact and d > 0:
+                radiance = radiance.index_add(0, owner, throughput * out.radiance)
+                alpha = alpha.index_add(0, owner, out.alpha.reshape(-1, 1))
+            else:
+                radiance = radiance + (throughput * out.radiance).view(n, -1, radiance_channels).sum(0)
+                alpha = alpha + out.alpha.reshape(n, -1, 1).sum(0)
             throughput = throughput * out.transfer
             rays_o, rays_d = out.next_rays_o, out.next_rays_d
             if d == 0:
@@ -338,6 +365,10 @@ def trace_rays(sess, sampler: Callable, radiance_channels: int = 3):
                     s = v.reshape(n, H, W, v.shape[-1]).sum(0)
                     extras_sum[k] = extras_sum[k] + s if k in extras_sum else s
                     extras_cnt[k] = extras_cnt.get(k, 0) + n
+            if compact and d + 1 < opt.ray_depth:
+                dead = (t >= far) & (throughput == 0).all(-1) & ~ray_may_reach_box(rays_o.detach(), rays_d.detach(), lo, hi)
+                keep = (~dead).nonzero(as_tuple=True)[0]
+                rays_o, rays_d, throughput, owner = rays_o[keep], rays_d[keep], throughput[keep], owner[keep]
     radiance = radiance.reshape(H, W, radiance_channels) / opt.ray_spp
     alpha = saturate(alpha.reshape(H, W, 1) / opt.ray_spp)
     extras = {k: torch.flipud(extras_sum[k] / extras_cnt[k]) for k in extras_sum}

@@ -677,10 +677,11 @@ class PathTracingSession:
         from . import generic
         return generic.sampler_brdf(self, rays_o, rays_d, t, i, d)
 
-    def trace_rays(self, sampler: Callable, radiance_channels: int = 3):
-        """Differentiable through the sampler / material torch code; only ``raycaster.query`` is detached (as in the reference)."""
+    def trace_rays(self, sampler: Callable, radiance_channels: int = 3, compact: bool = False):
+        """Differentiable through the sampler / material torch code; only ``raycaster.query`` is detached (as in the reference).
+        ``compact=True`` (extension): the sampler is only called with the rays that can still contribute (see ``generic.trace_rays``)."""
         from . import generic
-        return generic.trace_rays(self, sampler, radiance_channels)
+        return generic.trace_rays(self, sampler, radiance_channels, compact)
 
     # the helper names the reference's docstring points sampler authors to (path_tracing.py:296, mixin.py:115-155)
     def _gbuffer_collect_layer_impl_stencil_masked(self, mats, operator, initial):

@@ -216,6 +216,10 @@ int drp_flatten(const drp_object_t* objects, int32_t n_objects, float* world_pos
                 float* world_tan, int32_t* tris, int32_t* tri_material, int32_t* stencils, float* records, float* verts_raw,
                 float* normals_raw, float* tangents_raw, void* stream);
 
+/* n stream-ordered memcpys (host or device sources, cudaMemcpyDefault) from one call: the upload of a host-resident scene -- the `.to(device)`
+ * of every MeshObject / texture tensor that precedes mixin.py:74-113 in the reference -- without one host round trip per tensor. */
+int drp_upload_batch(int32_t n, void* const* dst, const void* const* src, const int64_t* bytes, void* stream);
+
 /* Fused wavefront: raygen -> [extend -> shade/sample/accumulate/compact] x ray_depth over
  * n_samples samples of every pixel, added into accum (H*W, 16).  `handle` must have been built over
  * scene->world_pos / scene->tris.  workspace may be NULL (internally allocated and cached on the handle). */

@@ -87,3 +87,29 @@ def test_texel_records_layout_and_eligibility():
     assert texel_records(dict(d, normal_tex=dict(d['normal_tex'], wrap='clamp'))) is None
     assert texel_records(dict(d, emissive_tex=None)) is None
     assert texel_records(dict(kind='default', tint=None)) is None
+
+
+@pytest.mark.gpu
+def test_library_builds_from_source_on_this_box_and_traces(tmp_path):
+    """The shipped .so is what the other tests load; this one proves the SOURCES build where they run: nvcc compiles csrc/ for sm_100a into a
+    scratch directory, a fresh interpreter loads that library (DIFFRP_B200_LIB) and reproduces the oracle's hits bit for bit."""
+    import subprocess
+    import sys
+    from diffrp_b200 import build as b
+    out = str(tmp_path / "libdiffrp_b200_fresh.so")
+    cmd = [b.find_nvcc()] + [f for f in b.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-o", out] + [os.path.join(b.CSRC, s) for s in b.SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0 and os.path.getsize(out) > 1_000_000, res.stderr[-2000:]
+    code = (
+        "import numpy as np, torch, oracle\n"
+        "from diffrp_b200 import synthetic as syn, _lib\n"
+        "from diffrp_b200.raycaster import B200Raycaster\n"
+        "v, f = syn.icosphere(3, 0.8); o, d = syn.random_rays(50000, seed=4)\n"
+        "rc = B200Raycaster(torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda(), {'epsilon': 1e-8})\n"
+        "t, i = rc.query(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), 10.0)\n"
+        "ot, oi = oracle.bruteforce(v, f, o, d, 10.0, 1e-8)\n"
+        "assert np.array_equal(t.cpu().numpy().view(np.int32), ot.view(np.int32)) and np.array_equal(i.cpu().numpy(), oi)\n"
+        "print('FRESH_OK', _lib.build_config())\n")
+    env = dict(os.environ, DIFFRP_B200_LIB=out, DIFFRP_B200_NO_BUILD="1")
+    res = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert res.returncode == 0 and "FRESH_OK" in res.stdout, res.stderr[-2000:]

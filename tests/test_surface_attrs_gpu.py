@@ -85,3 +85,36 @@ def test_errors_and_empty_batch():
     i = torch.tensor([0, 5, 3, 10 ** 9], dtype=torch.int32, device='cuda')      # out-of-range id -> treated as a miss, no fault
     a = sess.surface_attributes(o, d, t, i)
     assert torch.isfinite(a).all() and (a[2] == 0).all() and (a[3] == 0).all()
+
+
+def test_trace_rays_compact_view_equals_the_full_loop():
+    """trace_rays(sampler, compact=True) calls a user sampler with the live rays only.  A deterministic custom sampler (mirror
+    bounces shaded by the material layer kernel, no RNG) gives the same image either way; the per-bounce batch really shrinks."""
+    from diffrp_b200.path_tracing import RayOutputs
+    scene = scenes.mixed_scene().to(torch.device('cuda'))
+    cam = drp.PerspectiveCamera.from_orbit(h=72, w=96, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32)
+    sizes = {}
+
+    def run(compact):
+        sess = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=2, ray_depth=4))
+        far = sess.camera_far()
+        seen = sizes.setdefault(compact, [])
+
+        def sampler(rays_o, rays_d, t, i, d):
+            seen.append(len(rays_o))
+            a = sess.surface_attributes(rays_o, rays_d, t, i)
+            hit = (t < far)[:, None]
+            n = a[:, 3:6]
+            pos = rays_o + rays_d * t[:, None]
+            refl = rays_d - 2.0 * (rays_d * n).sum(-1, keepdim=True) * n
+            sky = 0.5 + 0.5 * rays_d[:, 1:2].expand(-1, 3)
+            return RayOutputs(radiance=torch.where(hit, a[:, 9:12], sky), transfer=torch.where(hit, a[:, 0:3] * 0.8, torch.zeros_like(n)),
+                              next_rays_o=pos + refl * 1e-3, next_rays_d=torch.where(hit, refl, rays_d), alpha=hit.float() * a[:, 8:9],
+                              extras=dict(albedo=a[:, 0:3]))
+        return sess.trace_rays(sampler, compact=compact)
+    full, comp = run(False), run(True)
+    torch.testing.assert_close(comp[0], full[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(comp[1], full[1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(comp[2]['albedo'], full[2]['albedo'], rtol=1e-5, atol=1e-6)
+    assert sizes[False] == [72 * 96 * 2] * 4
+    assert sizes[True][0] == 72 * 96 * 2 and sizes[True][1] < 0.9 * sizes[True][0] and sizes[True][3] <= sizes[True][2] <= sizes[True][1]
