@@ -133,6 +133,24 @@ class PackedUpload:
         return out
 
 
+def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
+    """Host -> device move of ONE scene tensor (e.g. the environment map; whole scenes go through ``PackedUpload``).  ``shard=(rank, world)``:
+    every rank copies its 1/world slice and an in-place all-gather completes it (collective: same call on every rank)."""
+    if (shard is not None and shard[1] > 1 and not t.is_cuda and t.dtype == dtype and t.is_contiguous()
+            and t.numel() * t.element_size() >= SHARD_MIN_BYTES):
+        import torch.distributed as dist
+        rank, world = shard
+        n = t.numel()
+        per = -(-n // world)
+        out = torch.empty([world * per], dtype=dtype, device=dev)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        if hi > lo:
+            out[lo:hi].copy_(t.view(-1)[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
+        return out[:n].view(t.shape)
+    return t.to(dev, dtype, non_blocking=True)
+
+
 def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     """
     ``flatten_scene`` in one CUDA pass (``drp_flatten``): sources that already live on ``dev`` are read in place, host tensors are

@@ -113,3 +113,25 @@ def test_library_builds_from_source_on_this_box_and_traces(tmp_path):
     env = dict(os.environ, DIFFRP_B200_LIB=out, DIFFRP_B200_NO_BUILD="1")
     res = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True)
     assert res.returncode == 0 and "FRESH_OK" in res.stdout, res.stderr[-2000:]
+
+
+def test_every_intra_package_import_resolves():
+    """`from .module import name` statements inside functions only fail when that code path runs -- on the GPU box.  Resolve all of them here."""
+    import ast
+    import importlib
+    pkg = os.path.join(ROOT, "diffrp_b200")
+    missing = []
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.ImportFrom) and node.level == 1:
+                mod = importlib.import_module("diffrp_b200" + ("." + node.module if node.module else ""))
+                for alias in node.names:
+                    if alias.name != "*" and not hasattr(mod, alias.name):
+                        try:
+                            importlib.import_module(mod.__name__ + "." + alias.name)
+                        except ImportError:
+                            missing.append((fn, node.module, alias.name))
+    assert not missing, missing
