@@ -309,6 +309,18 @@ def scene_instances(objects):
     return np.asarray(first, dtype=np.int64), np.asarray(mesh, dtype=np.int32)
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """One upload stream per device for the texture path of ``_build_fused_scene`` (always entered with ``wait_stream(current)``, so memory
+    freed by an earlier session is never reused before the caller's stream has passed that session's kernels)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[idx]
+
+
 def _cached(fn):
     name = fn.__name__
 
@@ -428,6 +440,7 @@ class PathTracingSession:
         st = self._scene_store()
         if 'env' not in st:
             st['env'] = self._load_env_light()
+        self._wait_textures()   # (the fused path loads it on the upload stream)
         return st['env']
 
     def _load_env_light(self):
@@ -448,16 +461,37 @@ class PathTracingSession:
         return st['fused']
 
     def _build_fused_scene(self):
-        """drp_scene_t for the fused kernels, or None when some material only exists as Python code."""
-        descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard())
+        """drp_scene_t for the fused kernels, or None when some material only exists as Python code.
+
+        Textures and the environment map are first read by the first ``k_shade`` launch, long after the geometry: they are uploaded (one packed
+        DMA), RGBA-padded and interleaved on a SIDE stream that starts where the caller's stream stands, so that the copy engine moves the
+        0.45 GB of texels while the SMs flatten the geometry and build the hierarchy on the caller's stream; ``_wait_textures`` joins the two
+        before the first kernel that samples them."""
+        main = torch.cuda.current_stream(self.device)
+        side = _side_stream(self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard())
+            if descs is not None:
+                env = self._single_env_light()
+                env_desc = None if env is None else dict(image=pad_rgba(env))
+            ready = side.record_event()
         if descs is None:
+            main.wait_event(ready)
             return None
+        self._scene_store()['textures_ready'] = ready
         vao = self.vertex_array_object()
         records = vao.records if vao.records is not None else torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
                       tris=vao.tris, tri_material=vao.tri_material, vertex_records=records)
-        env = self._single_env_light()
-        return _abi.pack_scene(arrays, descs, None if env is None else dict(image=pad_rgba(env)), lambda t: t.data_ptr())
+        return _abi.pack_scene(arrays, descs, env_desc, lambda t: t.data_ptr())
+
+    def _wait_textures(self):
+        """Order the current stream after the side-stream texture upload of this scene (no-op once it has been waited for on this stream)."""
+        st = self._scene_store()
+        ev = st.get('textures_ready')
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def _section_sample_ids(self, ids: torch.Tensor):
         """Split like the reference: sections = min(spp, ceil(H*W*spp / ray_split_size)) (path_tracing.py:318-320)."""
@@ -545,6 +579,7 @@ class PathTracingSession:
                 p.replay_u, p.rng_mode = u.data_ptr(), _abi.RNG_REPLAY
             else:
                 p.replay_u, p.rng_mode = None, _abi.RNG_NATIVE
+            self._wait_textures()
             check(L.drp_render(rc.handle, C.byref(scene_struct), C.byref(p), accum.data_ptr(), stream), "drp_render")
         return accum
 
@@ -664,6 +699,7 @@ class PathTracingSession:
         attrs = torch.empty([n, 12], dtype=torch.float32, device=self.device)
         f32 = lambda x: x.to(self.device, torch.float32).contiguous()  # noqa: E731
         o, d, tt, ii = f32(rays_o), f32(rays_d), f32(t), i.to(self.device, torch.int32).contiguous()
+        self._wait_textures()
         check(lib().drp_surface_attrs(self.raycaster().handle, C.byref(fused[0]), o.data_ptr(), d.data_ptr(), tt.data_ptr(), ii.data_ptr(),
                                       self.camera_far(), n, attrs.data_ptr(), _stream_ptr(self.device)), "drp_surface_attrs")
         return attrs

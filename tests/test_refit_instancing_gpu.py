@@ -115,7 +115,7 @@ def test_instanced_build_gives_the_hits_of_the_flat_build(n_inst, mesh_res):
             sc2.add_mesh_object(x).add_mesh_object(y)
         tab = scene_instances(sc2.objects)
         assert tab is not None and len(tab[1]) == 18 and len(set(tab[1].tolist())) == 2
-        s2 = drp.PathTracingSession(sc2, drp.PerspectiveCamera.from_orbit(h=8, w=8, **camkw), drp.PathTracingSessionOptions())
+        s2 = drp.PathTracingSession(sc2, drp.PerspectiveCamera.from_orbit(h=8, w=8, **camkw), drp.PathTracingSessionOptions(instancing=True))
         assert s2.raycaster().instanced
         v = s2.vertex_array_object()
         assert _same_hits(s2.raycaster().query(to, td, 10.0), B200Raycaster(v.world_pos, v.tris, {'epsilon': 1e-8}).query(to, td, 10.0))

@@ -101,7 +101,8 @@ def main():
         if rep > 0:  # the first repetition warms allocator pools and the workspace
             rows.append(t)
             fused.append(t_fused)
-    mine = torch.tensor([[sum(r[k] for r in rows) / len(rows) for k in range(len(phases))] + [sum(fused) / len(fused)]], device=dev)
+    med = lambda xs: sorted(xs)[len(xs) // 2]   # median over the repetitions: one slow repetition (allocator growth, a host hiccup) must not set the figure
+    mine = torch.tensor([[med([r[k] for r in rows]) for k in range(len(phases))] + [med(fused)]], device=dev)
     if world > 1:
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
