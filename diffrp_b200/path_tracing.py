@@ -470,6 +470,7 @@ class PathTracingSession:
         main = torch.cuda.current_stream(self.device)
         side = _side_stream(self.device)
         side.wait_stream(main)
+        vao = self.vertex_array_object()   # geometry first: the copy engine serves requests in issue order, and the SMs need it first
         with torch.cuda.stream(side):
             descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard())
             if descs is not None:
@@ -480,7 +481,6 @@ class PathTracingSession:
             main.wait_event(ready)
             return None
         self._scene_store()['textures_ready'] = ready
-        vao = self.vertex_array_object()
         records = vao.records if vao.records is not None else torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
                       tris=vao.tris, tri_material=vao.tri_material, vertex_records=records)
