@@ -78,6 +78,20 @@ def flatten_scene(objs: List, dev) -> VertexArrayObject:
 SHARD_MIN_BYTES = 1 << 20
 
 
+def merge_runs(items, arena):
+    """items: (buffer offset, source address, bytes) in registration order; arena: (first, last + 1) address of a page-locked arena or None.
+    Consecutive items whose sources lie in the arena at the same relative offsets as in the buffer become ONE copy (alignment gaps, which
+    are arena bytes too, included)."""
+    runs = []
+    for off, p, nbytes in items:
+        in_arena = arena is not None and arena[0] <= p and p + nbytes <= arena[1]
+        if runs and in_arena and runs[-1][3] and p - runs[-1][1] == off - runs[-1][0]:
+            runs[-1][2] = off + nbytes - runs[-1][0]
+        else:
+            runs.append([off, p, nbytes, in_arena])
+    return [(r[0], r[1], r[2]) for r in runs]
+
+
 class PackedUpload:
     """
     Host -> device move of MANY scene tensors as one packed device buffer: ``add()`` registers a tensor and returns a ticket, ``commit()``
@@ -90,9 +104,11 @@ class PackedUpload:
     """
     ALIGN = 256
 
-    def __init__(self, dev, shard=None):
+    def __init__(self, dev, shard=None, arena: Optional[torch.Tensor] = None):
         self.dev, self.shard = torch.device(dev), shard if (shard is not None and shard[1] > 1) else None
         self.items, self.ready, self.total = [], {}, 0
+        # Scene.pin_memory(): sources that are views of one page-locked arena, laid out like this buffer, merge into a few large copies
+        self.arena = None if arena is None else (arena.data_ptr(), arena.data_ptr() + arena.numel())
 
     def add(self, t: torch.Tensor, dtype) -> int:
         ticket = len(self.items) + len(self.ready)
@@ -116,10 +132,10 @@ class PackedUpload:
         lo, hi = (self.shard[0] * per, (self.shard[0] + 1) * per) if self.shard else (0, per)
         base = buf.data_ptr()
         dst, src, nb = [], [], []
-        for _, t, off, nbytes in self.items:
+        for off, p, nbytes in merge_runs([(off, t.data_ptr(), nbytes) for _, t, off, nbytes in self.items], self.arena):
             a, b = max(off, lo), min(off + nbytes, hi)
             if b > a:
-                dst.append(base + a); src.append(t.data_ptr() + (a - off)); nb.append(b - a)
+                dst.append(base + a); src.append(p + (a - off)); nb.append(b - a)
         n = len(dst)
         if n:
             check(lib().drp_upload_batch(n, (C.c_void_p * n)(*dst), (C.c_void_p * n)(*src), (C.c_int64 * n)(*nb),
@@ -151,7 +167,7 @@ def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
     return t.to(dev, dtype, non_blocking=True)
 
 
-def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
+def flatten_scene_cuda(objs: List, dev, shard=None, arena=None) -> VertexArrayObject:
     """
     ``flatten_scene`` in one CUDA pass (``drp_flatten``): sources that already live on ``dev`` are read in place, host tensors are
     first moved with one asynchronous DMA copy each (measured on B200: letting the kernel read pinned host memory directly works --
@@ -163,7 +179,7 @@ def flatten_scene_cuda(objs: List, dev, shard=None) -> VertexArrayObject:
     from ._lib import lib, check
     dev = torch.device(dev)
     keep = []
-    pack = PackedUpload(dev, shard)
+    pack = PackedUpload(dev, shard, arena)
     tickets, local = [], {}
     for o in objs:   # pass 1: register every source tensor (tensors shared between objects -- instanced meshes -- are moved once)
         row = []
@@ -262,12 +278,12 @@ def texel_records(d: dict) -> Optional[torch.Tensor]:
 INTERLEAVE_TEXELS = True
 
 
-def material_descriptions(objs: List, dev, rgba: bool = False, shard=None) -> Optional[List[dict]]:
+def material_descriptions(objs: List, dev, rgba: bool = False, shard=None, arena=None) -> Optional[List[dict]]:
     """Per-object drp_material_t descriptions (textures moved to ``dev``, RGBA-padded for the CUDA path when ``rgba``),
     or None if any material is Python-only.  Objects sharing a material share its uploaded textures."""
     descs = []
     uploaded = {}
-    pack = PackedUpload(dev, shard)
+    pack = PackedUpload(dev, shard, arena)
     raw = []
     for o in objs:   # pass 1: register every texture; ONE packed upload (+ one all-gather when sharded) moves them all
         d = o.material.fused_description() if hasattr(o.material, 'fused_description') else None

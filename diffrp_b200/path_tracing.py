@@ -410,7 +410,7 @@ class PathTracingSession:
             if self._wants_grad():
                 st['vao'] = flatten_scene(self.scene.objects, self.device)
             else:
-                st['vao'] = flatten_scene_cuda(self.scene.objects, self.device, self._upload_shard())
+                st['vao'] = flatten_scene_cuda(self.scene.objects, self.device, self._upload_shard(), getattr(self.scene, '_arena', None))
         return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
@@ -472,7 +472,8 @@ class PathTracingSession:
         side.wait_stream(main)
         vao = self.vertex_array_object()   # geometry first: the copy engine serves requests in issue order, and the SMs need it first
         with torch.cuda.stream(side):
-            descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard())
+            descs = material_descriptions(self.scene.objects, self.device, rgba=True, shard=self._upload_shard(),
+                                          arena=getattr(self.scene, '_arena', None))
             if descs is not None:
                 env = self._single_env_light()
                 env_desc = None if env is None else dict(image=pad_rgba(env))

@@ -147,6 +147,72 @@ class Scene:
         out.metadata = dict(self.metadata)
         return out
 
+    def pin_memory(self, pin: bool = True):
+        """
+        Copy of a host scene whose tensors are views of ONE page-locked arena, laid out in the order the session uploads them (per object:
+        verts, normals, color, uv, tangents, tris; then every material's textures; then the lights' images), each 256-byte aligned.
+        ``PathTracingSession`` recognises the arena (``flatten.PackedUpload``) and moves the whole scene with a handful of large DMA copies
+        instead of one per tensor (a scene is ~300 tensors; issuing 300 copies costs more host time than the transfer takes).
+        Tensors shared between objects (instanced meshes) stay shared.  Model matrices and material factors are left where they are.
+        """
+        import copy
+        ALIGN = 256
+        order, seen = [], {}
+
+        def want(t):
+            if isinstance(t, torch.Tensor) and not t.is_cuda and id(t) not in seen:
+                seen[id(t)] = len(order)
+                order.append(t)
+        tex_fields = ('base_color_texture', 'metallic_roughness_texture', 'normal_texture', 'emissive_texture', 'occlusion_texture')
+        for o in self.objects:
+            for t in (o.verts, o.normals, o.color, o.uv, o.tangents, o.tris):
+                want(t)
+        mats = []
+        for o in self.objects:
+            if id(o.material) not in [id(m) for m in mats]:
+                mats.append(o.material)
+        for m in mats:
+            for f in tex_fields:
+                smp = getattr(m, f, None)
+                if smp is not None and hasattr(smp, 'image'):
+                    want(smp.image)
+        for l in self.lights:
+            want(getattr(l, 'image', None))
+        offs, total = [], 0
+        for t in order:
+            offs.append(total)
+            total += -(-(t.numel() * t.element_size()) // ALIGN) * ALIGN
+        arena = torch.empty([max(total, ALIGN)], dtype=torch.uint8)
+        if pin:   # (False: the same arena in pageable memory -- layout tests on machines without a GPU)
+            arena = arena.pin_memory()
+        views = []
+        for t, off in zip(order, offs):
+            v = arena[off:off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t)
+            views.append(v)
+        mv = lambda t: views[seen[id(t)]] if isinstance(t, torch.Tensor) and id(t) in seen else t   # noqa: E731
+        new_mats = {}
+        for m in mats:
+            nm = copy.copy(m)
+            for f in tex_fields:
+                smp = getattr(m, f, None)
+                if smp is not None and hasattr(smp, 'image'):
+                    ns = copy.copy(smp)
+                    ns.image = mv(smp.image)
+                    setattr(nm, f, ns)
+            new_mats[id(m)] = nm
+        out = Scene()
+        out.objects = [MeshObject(new_mats[id(o.material)], mv(o.verts), mv(o.tris), mv(o.normals), o.M, mv(o.color), mv(o.uv), mv(o.tangents),
+                                  o.custom_attrs, o.metadata) for o in self.objects]
+        for l in self.lights:
+            if isinstance(l, ImageEnvironmentLight):
+                out.lights.append(ImageEnvironmentLight(l.intensity, l.color, mv(l.image), l.render_skybox))
+            else:
+                out.lights.append(l)
+        out.metadata = dict(self.metadata)
+        out._arena = arena
+        return out
+
     def static_batching(self):
         """Merge meshes that share a material object into one world-space mesh, in place (scene.py:33-75)."""
         groups = collections.OrderedDict()

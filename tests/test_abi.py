@@ -135,3 +135,32 @@ def test_every_intra_package_import_resolves():
                         except ImportError:
                             missing.append((fn, node.module, alias.name))
     assert not missing, missing
+
+
+def test_pinned_arena_scene_uploads_in_a_few_large_copies():
+    """Scene.pin_memory() lays the scene out in ONE arena in upload order, so PackedUpload's copy list collapses: one run for the geometry,
+    one for the textures (layout logic only: pageable arena, no GPU)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes
+    from diffrp_b200.flatten import PackedUpload, merge_runs
+    src = scenes.mixed_scene()
+    sc = src.pin_memory(pin=False)
+    arena = (sc._arena.data_ptr(), sc._arena.data_ptr() + sc._arena.numel())
+    for a, b in zip(src.objects, sc.objects):
+        for f in ('verts', 'normals', 'color', 'uv', 'tangents', 'tris'):
+            assert torch.equal(getattr(a, f), getattr(b, f)) and arena[0] <= getattr(b, f).data_ptr() < arena[1]
+        assert b.material is not a.material or not hasattr(a.material, 'base_color_texture')
+    assert torch.equal(src.lights[0].image, sc.lights[0].image)
+    items, off = [], 0
+    for o in sc.objects:            # the registration order of flatten_scene_cuda
+        for t in (o.verts, o.normals, o.color, o.uv, o.tangents, o.tris):
+            nbytes = t.numel() * t.element_size()
+            items.append((off, t.data_ptr(), nbytes))
+            off += -(-nbytes // PackedUpload.ALIGN) * PackedUpload.ALIGN
+    runs = merge_runs(items, arena)
+    assert len(items) == 6 * len(sc.objects) and len(runs) == 1 and runs[0][2] == items[-1][0] + items[-1][2]
+    assert len(merge_runs(items, None)) == len(items)                  # unrelated host tensors are never merged
+    shuffled = [items[1], items[0]] + items[2:]
+    assert len(merge_runs([(o, p, n) for (o, _, _), (_, p, n) in zip(items, shuffled)], arena)) > 1
