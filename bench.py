@@ -297,7 +297,8 @@ def main():
     HW = RES * RES
 
     # ---- device-resident arm -------------------------------------------------------------------------------------
-    scene_host, camkw = syn.teaser_scene('cpu', tex=args.tex).pin_memory()   # one page-locked arena in upload order (Scene.pin_memory)
+    scene_host, camkw = syn.teaser_scene('cpu', tex=args.tex)
+    scene_host = scene_host.pin_memory()   # one page-locked arena in upload order (Scene.pin_memory)
     scene = scene_host.to(dev)
     cam = drp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
     total_spp = max(1, world * K * S)

@@ -5,7 +5,8 @@ import torch
 import diffrp_b200 as drp
 from diffrp_b200 import synthetic as syn
 
-scene, camkw = syn.teaser_scene('cpu', tex=1024).pin_memory()
+scene, camkw = syn.teaser_scene('cpu', tex=1024)
+scene = scene.pin_memory()
 cam = drp.PerspectiveCamera.from_orbit(h=1024, w=1024, **camkw)
 
 

@@ -38,7 +38,8 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    scene_host, camkw = syn.teaser_scene('cpu', tex=args.tex).pin_memory()   # one page-locked arena in upload order (Scene.pin_memory)
+    scene_host, camkw = syn.teaser_scene('cpu', tex=args.tex)
+    scene_host = scene_host.pin_memory()   # one page-locked arena in upload order (Scene.pin_memory)
     cam = drp.PerspectiveCamera.from_orbit(h=1024, w=1024, **camkw)
     out_keys = ("radiance", "alpha", "albedo", "emission", "world_normal", "world_position")
     out_host = {k: torch.empty([1024, 1024, 1 if k == "alpha" else 3], dtype=torch.float32).pin_memory() for k in out_keys}

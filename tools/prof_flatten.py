@@ -3,7 +3,8 @@ sys.path.insert(0, os.getcwd())
 import torch
 import diffrp_b200 as drp
 from diffrp_b200 import synthetic as syn
-scene, camkw = syn.teaser_scene('cpu', tex=1024).pin_memory()
+scene, camkw = syn.teaser_scene('cpu', tex=1024)
+scene = scene.pin_memory()
 cam = drp.PerspectiveCamera.from_orbit(h=1024, w=1024, **camkw)
 for it in range(3):
     s = drp.PathTracingSession(scene, cam, drp.PathTracingSessionOptions(ray_spp=8, ray_depth=4, seed=it, reuse_scene=False))
