@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -66,6 +66,7 @@ class RenderParams(C.Structure):
         ("jitter_x", C.c_void_p), ("jitter_y", C.c_void_p),
         ("sample_ids", C.c_void_p),
         ("replay_u", C.c_void_p),
+        ("shade_wait_event", C.c_void_p),
     ]
 
 

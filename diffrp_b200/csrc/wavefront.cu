@@ -691,6 +691,7 @@ extern "C" int drp_render(uint64_t handle, const drp_scene_t* scene, const drp_r
                 k_extend_cw<SRC_PRIMARY><<<ge, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, hit, nullptr, cursors + 0, AosRays(), ovf);
                 k_extend_fixup<SRC_PRIMARY><<<WF_FIXUP_BLOCKS, WF_BLOCK, 0, s>>>(c, nullptr, nullptr, hit, nullptr, AosRays(), ovf, ws->deep_stack, h->sticky_dev);
                 span_end(sp);
+                if (p.shade_wait_event && s0 == 0) DRP_CUDA_CHECK(cudaStreamWaitEvent(s, (cudaEvent_t)p.shade_wait_event, 0));
                 sp = span_begin(1, nullptr);
                 k_shade<true><<<gs, WF_BLOCK, 0, s>>>(c, b, nullptr, nullptr, nullptr, hit, qa_out, qb_out, qt_out, nullptr, counts + 1, cursors + 1);
                 span_end(sp);

@@ -580,7 +580,8 @@ class PathTracingSession:
                 p.replay_u, p.rng_mode = u.data_ptr(), _abi.RNG_REPLAY
             else:
                 p.replay_u, p.rng_mode = None, _abi.RNG_NATIVE
-            self._wait_textures()
+            ev = self._scene_store().get('textures_ready')
+            p.shade_wait_event = ev.cuda_event if ev is not None else None   # joined inside drp_render, after the first extend launch
             check(L.drp_render(rc.handle, C.byref(scene_struct), C.byref(p), accum.data_ptr(), stream), "drp_render")
         return accum
 

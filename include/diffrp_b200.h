@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 5
+#define DRP_ABI_VERSION 6
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -145,6 +145,8 @@ typedef struct drp_render_params {
     const float* jitter_y;      /* (n_samples,)                                     device  */
     const int32_t* sample_ids;  /* (n_samples,) global sample index (RNG counter)   device  */
     const float* replay_u;      /* replay: (ray_depth, 6, n_samples*H*W)            device  */
+    void* shade_wait_event;     /* optional cudaEvent_t (ABI v6): `stream` waits for it right before the first shade launch of the call --
+                                   textures / environment still being uploaded on another stream; the first extend does not need them    */
 } drp_render_params_t;
 
 /* Accumulator layout: (H*W, 16) fp32, un-normalised sums, row 0 = bottom pixel row:
