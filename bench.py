@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--torch-baseline-spp", type=int, default=8)
     ap.add_argument("--torch-baseline-steps", type=int, default=1)
     ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--separate-textures", action="store_true", help="A/B: four separate RGBA textures per material instead of the interleaved texel records")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 1024-spp frame split over the ranks)")
     ap.add_argument("--strong-spp", type=int, default=1024)
     args = ap.parse_args()
@@ -290,6 +291,9 @@ def main():
     from diffrp_b200._lib import loaded_path, build_config
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.separate_textures:
+        import diffrp_b200.flatten as _flatten_mod
+        _flatten_mod.INTERLEAVE_TEXELS = False
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)

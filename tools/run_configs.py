@@ -25,7 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, required=True, choices=[4, 5])
 ap.add_argument("--scale", type=float, default=1.0, help="scale spp (and views for config 4) for quick runs")
 ap.add_argument("--no-reuse", action="store_true", help="config 4: rebuild the BVH for every view (the reference's behaviour)")
-ap.add_argument("--tile-collective", default="gather", choices=["gather", "allreduce"])
+ap.add_argument("--tile-collective", default="allreduce", choices=["gather", "allreduce"])
 ap.add_argument("--out", default=None)
 ap.add_argument("--no-instancing", action="store_true", help="config 5: flat drp_build over the 10 M flattened triangles instead of drp_build_instanced")
 ap.add_argument("--profile", action="store_true", help="config 4: cProfile of the view loop on rank 0 (host overhead per session)")
