@@ -278,7 +278,6 @@ def main():
     ap.add_argument("--torch-baseline-steps", type=int, default=1)
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--separate-textures", action="store_true", help="A/B: four separate RGBA textures per material instead of the interleaved texel records")
-    ap.add_argument("--indexed-vertices", action="store_true", help="A/B: shade from triangle indices + shared vertex records instead of the de-indexed triangle records")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 1024-spp frame split over the ranks)")
     ap.add_argument("--strong-spp", type=int, default=1024)
     args = ap.parse_args()
@@ -307,8 +306,7 @@ def main():
     scene = scene_host.to(dev)
     cam = drp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
     total_spp = max(1, world * K * S)
-    opts = drp.PathTracingSessionOptions(ray_spp=total_spp, ray_depth=DEPTH, rng='native', seed=1, shard_rank=rank, shard_world=world,
-                                         triangle_records=not args.indexed_vertices)
+    opts = drp.PathTracingSessionOptions(ray_spp=total_spp, ray_depth=DEPTH, rng='native', seed=1, shard_rank=rank, shard_world=world)
     sess = drp.PathTracingSession(scene, cam, opts)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     e0, e1 = ev(), ev()

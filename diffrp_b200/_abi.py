@@ -5,7 +5,7 @@ Kept separate from :mod:`diffrp_b200._lib` so that struct layouts can be inspect
 """
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 6
 
 WRAP_REPEAT, WRAP_CLAMP, WRAP_MIRROR = 0, 1, 2
 INTERP_POINT, INTERP_LINEAR = 0, 1
@@ -48,7 +48,6 @@ class Scene(C.Structure):
         ("n_verts", C.c_int64), ("n_tris", C.c_int64),
         ("n_materials", C.c_int32), ("_pad", C.c_int32),
         ("env", Texture),
-        ("tri_records", C.c_void_p),
     ]
 
 
@@ -188,9 +187,6 @@ def pack_scene(arrays, materials, env, ptr_of):
     if arrays.get("vertex_records") is not None:
         keep.append(arrays["vertex_records"])
         s.vertex_records = ptr_of(arrays["vertex_records"])
-    if arrays.get("tri_records") is not None:
-        keep.append(arrays["tri_records"])
-        s.tri_records = ptr_of(arrays["tri_records"])
     s.n_verts = int(arrays["world_pos"].shape[0])
     s.n_tris = int(arrays["tris"].shape[0])
     mats = (Material * max(1, len(materials)))()

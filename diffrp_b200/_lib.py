@@ -35,7 +35,7 @@ def _declare(L):
     L.drp_refit.argtypes = [u64, vp, vp, i64, i64, vp]
     L.drp_build_instanced.argtypes = [vp, vp, i64, i64, vp, vp, i64, C.c_int, vp, C.POINTER(C.c_uint64)]
     L.drp_debug_set_stack_limit.argtypes = [u64, i32]
-    L.drp_flatten.argtypes = [C.POINTER(_abi.Object), i32] + [vp] * 14
+    L.drp_flatten.argtypes = [C.POINTER(_abi.Object), i32] + [vp] * 13
     L.drp_set_profiling.argtypes = [u64, C.c_int]
     L.drp_get_profile.argtypes = [u64, C.POINTER(_abi.Profile)]
     L.drp_tonemap.argtypes = [vp, i64, i64, C.POINTER(_abi.TonemapParams), vp, vp, vp]

@@ -16,7 +16,7 @@ struct FlattenArgs {
     const int64_t* vert_offsets;  // (n_objects + 1)
     const int64_t* tri_offsets;   // (n_objects + 1)
     int n_objects;
-    float *world_pos, *world_nrm, *color4, *uv, *world_tan, *records, *verts_raw, *normals_raw, *tangents_raw, *tri_records;
+    float *world_pos, *world_nrm, *color4, *uv, *world_tan, *records, *verts_raw, *normals_raw, *tangents_raw;
     int32_t *tris, *tri_material, *stencils;
 };
 
@@ -79,24 +79,13 @@ __global__ void __launch_bounds__(256) k_flatten_tris(FlattenArgs a, int64_t n_t
     a.tris[3 * i + 2] = o.tris[3 * j + 2] + off;
     a.tri_material[i] = k;
     a.stencils[i + 1] = k + 1;
-    if (a.tri_records && a.records) {   // de-indexed shading records: the three vertex records written by k_flatten_verts (launched before), 192 B per triangle
-        const float4* r = reinterpret_cast<const float4*>(a.records);
-        float4* o4 = reinterpret_cast<float4*>(a.tri_records) + 12 * i;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int64_t vi = (int64_t)a.tris[3 * i + c];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) o4[4 * c + f] = r[4 * vi + f];
-        }
-    }
 }
 
 extern "C" int drp_flatten(const drp_object_t* objects, int32_t n_objects, float* world_pos, float* world_nrm, float* color4, float* uv,
                            float* world_tan, int32_t* tris, int32_t* tri_material, int32_t* stencils, float* records, float* verts_raw,
-                           float* normals_raw, float* tangents_raw, float* tri_records, void* stream) {
+                           float* normals_raw, float* tangents_raw, void* stream) {
     if (n_objects < 0 || (n_objects > 0 && !objects)) { drp_set_error("drp_flatten: invalid argument"); return DRP_ERR_INVALID; }
     if (!stencils) { drp_set_error("drp_flatten: stencils is required"); return DRP_ERR_INVALID; }
-    if (tri_records && !records) { drp_set_error("drp_flatten: tri_records are built from the vertex records: pass `records` too"); return DRP_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<int64_t> voff(n_objects + 1, 0), toff(n_objects + 1, 0);
     for (int k = 0; k < n_objects; ++k) {
@@ -123,7 +112,7 @@ extern "C" int drp_flatten(const drp_object_t* objects, int32_t n_objects, float
     a.tri_offsets = (const int64_t*)(scratch + ob + fb);
     a.n_objects = n_objects;
     a.world_pos = world_pos; a.world_nrm = world_nrm; a.color4 = color4; a.uv = uv; a.world_tan = world_tan; a.records = records;
-    a.verts_raw = verts_raw; a.normals_raw = normals_raw; a.tangents_raw = tangents_raw; a.tri_records = tri_records;
+    a.verts_raw = verts_raw; a.normals_raw = normals_raw; a.tangents_raw = tangents_raw;
     a.tris = tris; a.tri_material = tri_material; a.stencils = stencils;
     if (V > 0) k_flatten_verts<<<(unsigned)((V + 255) / 256), 256, 0, s>>>(a, V);
     k_flatten_tris<<<(unsigned)((std::max<int64_t>(F, 1) + 255) / 256), 256, 0, s>>>(a, F);

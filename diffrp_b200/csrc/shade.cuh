@@ -178,20 +178,16 @@ struct VertexIn {
     float2 uv;
     float4 color, tan;
 };
-DRP_HD VertexIn unpack_vertex(float4 a, float4 b, float4 c, float4 d) {   // [pos3 nrm3 uv2 | color4 | tan4]
-    VertexIn v;
-    v.pos = v3(a.x, a.y, a.z);
-    v.nrm = v3(a.w, b.x, b.y);
-    v.uv = make_float2(b.z, b.w);
-    v.color = c;
-    v.tan = d;
-    return v;
-}
 DRP_HD VertexIn load_vertex(const drp_scene_t& sc, int i) {
     VertexIn v;
     if (sc.vertex_records) {
         const float4* r = reinterpret_cast<const float4*>(sc.vertex_records) + 4 * (int64_t)i;
-        v = unpack_vertex(ldg(r), ldg(r + 1), ldg(r + 2), ldg(r + 3));
+        const float4 a = ldg(r), b = ldg(r + 1);
+        v.pos = v3(a.x, a.y, a.z);
+        v.nrm = v3(a.w, b.x, b.y);
+        v.uv = make_float2(b.z, b.w);
+        v.color = ldg(r + 2);
+        v.tan = ldg(r + 3);
     } else {
         v.pos = ld3(sc.world_pos, i);
         v.nrm = ld3(sc.world_nrm, i);
@@ -229,17 +225,9 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
             return s;
         }
     }
-    VertexIn q0, q1, q2;
-    if (sc.tri_records) {   // de-indexed: 12 x 128-bit loads from one contiguous 192-byte record, no index round trip
-        const float4* r = reinterpret_cast<const float4*>(sc.tri_records) + 12 * (int64_t)tri_id;
-        q0 = unpack_vertex(ldg(r), ldg(r + 1), ldg(r + 2), ldg(r + 3));
-        q1 = unpack_vertex(ldg(r + 4), ldg(r + 5), ldg(r + 6), ldg(r + 7));
-        q2 = unpack_vertex(ldg(r + 8), ldg(r + 9), ldg(r + 10), ldg(r + 11));
-    } else {
-        const int i0 = pre ? pre->i0 : ldg(sc.tris + 3 * (int64_t)tri_id), i1 = pre ? pre->i1 : ldg(sc.tris + 3 * (int64_t)tri_id + 1),
-                  i2 = pre ? pre->i2 : ldg(sc.tris + 3 * (int64_t)tri_id + 2);
-        q0 = load_vertex(sc, i0); q1 = load_vertex(sc, i1); q2 = load_vertex(sc, i2);
-    }
+    const int i0 = pre ? pre->i0 : ldg(sc.tris + 3 * (int64_t)tri_id), i1 = pre ? pre->i1 : ldg(sc.tris + 3 * (int64_t)tri_id + 1),
+              i2 = pre ? pre->i2 : ldg(sc.tris + 3 * (int64_t)tri_id + 2);
+    const VertexIn q0 = load_vertex(sc, i0), q1 = load_vertex(sc, i1), q2 = load_vertex(sc, i2);
     float u, v;
     hit_barycentric(q0.pos, q1.pos, q2.pos, hit_pos, u, v);
     const drp_material_t& m = mats[mat_id];

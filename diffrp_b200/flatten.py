@@ -31,7 +31,6 @@ class VertexArrayObject:
     world_tan: torch.Tensor = None
     tri_material: torch.Tensor = None
     records: torch.Tensor = None  # (V,16) interleaved [pos3 nrm3 uv2 | color4 tan4] shading records (CUDA path)
-    tri_records: torch.Tensor = None  # (F,48) the three records of every triangle, de-indexed (CUDA path)
 
 
 
@@ -168,7 +167,7 @@ def upload(t: torch.Tensor, dev, dtype, shard=None) -> torch.Tensor:
     return t.to(dev, dtype, non_blocking=True)
 
 
-def flatten_scene_cuda(objs: List, dev, shard=None, arena=None, triangle_records: bool = True) -> VertexArrayObject:
+def flatten_scene_cuda(objs: List, dev, shard=None, arena=None) -> VertexArrayObject:
     """
     ``flatten_scene`` in one CUDA pass (``drp_flatten``): sources that already live on ``dev`` are read in place, host tensors are
     first moved with one asynchronous DMA copy each (measured on B200: letting the kernel read pinned host memory directly works --
@@ -222,12 +221,10 @@ def flatten_scene_cuda(objs: List, dev, shard=None, arena=None, triangle_records
     i = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
     out = dict(world_pos=f(V, 3), world_nrm=f(V, 3), color=f(V, 4), uv=f(V, 2), world_tan=f(V, 4), tris=i(F, 3), tri_material=i(F),
                stencils=i(F + 1), records=f(V, 16), verts=f(V, 3), normals=f(V, 3), tangents=f(V, 4))
-    tri_records = f(F, 48) if triangle_records else None   # de-indexed copy of the vertex records: 192 B per triangle (drp_scene_t.tri_records)
     check(lib().drp_flatten(descs, len(objs), out['world_pos'].data_ptr(), out['world_nrm'].data_ptr(), out['color'].data_ptr(),
                             out['uv'].data_ptr(), out['world_tan'].data_ptr(), out['tris'].data_ptr(), out['tri_material'].data_ptr(),
                             out['stencils'].data_ptr(), out['records'].data_ptr(), out['verts'].data_ptr(), out['normals'].data_ptr(),
-                            out['tangents'].data_ptr(), None if tri_records is None else tri_records.data_ptr(),
-                            torch.cuda.current_stream(dev).cuda_stream), "drp_flatten")
+                            out['tangents'].data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "drp_flatten")
     keys = set().union(*(o.custom_attrs.keys() for o in objs)) if objs else set()
     customs = {}
     for key in keys:
@@ -243,7 +240,6 @@ def flatten_scene_cuda(objs: List, dev, shard=None, arena=None, triangle_records
     vao = VertexArrayObject(out['verts'], out['normals'], out['world_pos'], out['tris'], out['stencils'], out['color'], out['uv'],
                             out['tangents'], customs, out['world_nrm'], out['world_tan'], out['tri_material'])
     vao.records = out['records']
-    vao.tri_records = tri_records
     vao._sources = keep  # pinned / converted sources stay alive until the stream has consumed them
     return vao
 

@@ -55,8 +55,6 @@ class PathTracingSessionOptions:
         reuse_scene (bool): sessions are single-use like the reference's, but the flattened buffers, uploaded textures and the BVH
             of a ``Scene`` are kept (one entry per scene, keyed by the identity, shape and in-place version counter of every tensor)
             and adopted by the next session over the same unmodified scene -- multi-view rendering builds once, not per view.
-        triangle_records (bool): the fused path shades from per-triangle copies of the three vertex records (``drp_scene_t.tri_records``) instead
-            of triangle indices + shared vertex records: same values (images bit-identical), one DRAM round trip less per hit.
         refit_scene (bool): when a later session renders the same ``Scene`` object and only positions / transforms / attributes changed (every
             object's index tensor is the same, unmodified tensor), the structure of the previous session is refitted -- boxes and triangle
             records recomputed bottom-up over the old topology (``drp_refit``) -- instead of rebuilt.  Hits are exact either way.
@@ -95,7 +93,6 @@ class PathTracingSessionOptions:
     tile_size: int = 256      # tile edge in pixels for shard_mode='tile'
     tile_collective: str = 'allreduce'  # 'allreduce': sum whole frames (NVSwitch reduces in the fabric); 'gather': all-gather of the owned tiles
     result_rank: Optional[int] = None   # sharded renders: None = every rank gets the frame (all-reduce); r = only rank r does (reduce), the others' pbr() returns None
-    triangle_records: bool = True     # de-indexed 192-byte shading records per triangle (one dependent DRAM round trip less per hit; +192 B per triangle)
     refit_scene: bool = True          # a later session over the same Scene with unchanged connectivity refits the structure instead of rebuilding
     instancing: bool = False          # objects sharing vertex + index tensors: one hierarchy per mesh, replicated and refitted per instance
     scene_upload: str = 'auto'        # host scenes under sharding: 'sharded' = 1/world of every tensor per rank over PCIe + all-gather over NVLink
@@ -413,8 +410,7 @@ class PathTracingSession:
             if self._wants_grad():
                 st['vao'] = flatten_scene(self.scene.objects, self.device)
             else:
-                st['vao'] = flatten_scene_cuda(self.scene.objects, self.device, self._upload_shard(), getattr(self.scene, '_arena', None),
-                                               triangle_records=self.options.triangle_records)
+                st['vao'] = flatten_scene_cuda(self.scene.objects, self.device, self._upload_shard(), getattr(self.scene, '_arena', None))
         return st['vao']
 
     # ---- the Raycaster seam (path_tracing.py:142-156) --------------------------------------------------------------
@@ -488,8 +484,7 @@ class PathTracingSession:
         self._scene_store()['textures_ready'] = ready
         records = vao.records if vao.records is not None else torch.cat([vao.world_pos, vao.world_nrm, vao.uv, vao.color, vao.world_tan], 1).contiguous()  # (V,16), 64 B / vertex
         arrays = dict(world_pos=vao.world_pos, world_nrm=vao.world_nrm, color=vao.color, uv=vao.uv, world_tan=vao.world_tan,
-                      tris=vao.tris, tri_material=vao.tri_material, vertex_records=records,
-                      tri_records=getattr(vao, 'tri_records', None) if self.options.triangle_records else None)
+                      tris=vao.tris, tri_material=vao.tri_material, vertex_records=records)
         return _abi.pack_scene(arrays, descs, env_desc, lambda t: t.data_ptr())
 
     def _wait_textures(self):

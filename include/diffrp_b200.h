@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DRP_ABI_VERSION 7
+#define DRP_ABI_VERSION 6
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define DRP_OK 0
@@ -116,9 +116,6 @@ typedef struct drp_scene {
     int32_t n_materials;
     int32_t _pad;
     drp_texture_t env; /* ImageEnvironmentLight.image_rh() (lights.py:49-50); NULL data => black */
-    const float* tri_records;    /* optional (F,48), ABI v7: the three 64-byte vertex records of every triangle, de-indexed (192 B, contiguous):
-                                    the shade kernel then goes hit -> record -> texels, one dependent DRAM round trip less than
-                                    hit -> indices -> three vertex records -> texels.  Same values, same arithmetic: images are bit-identical. */
 } drp_scene_t;
 
 #define DRP_RNG_NATIVE 0 /* Philox4x32-10 keyed by (seed; pixel, global sample, bounce) */
@@ -219,7 +216,7 @@ int drp_bvh_stats(uint64_t handle, drp_bvh_stats_t* out);
  * concatenations.  `objects` is a HOST array; outputs are device buffers sized from the descriptor totals. */
 int drp_flatten(const drp_object_t* objects, int32_t n_objects, float* world_pos, float* world_nrm, float* color4, float* uv,
                 float* world_tan, int32_t* tris, int32_t* tri_material, int32_t* stencils, float* records, float* verts_raw,
-                float* normals_raw, float* tangents_raw, float* tri_records, void* stream);
+                float* normals_raw, float* tangents_raw, void* stream);
 
 /* n stream-ordered memcpys (host or device sources, cudaMemcpyDefault) from one call: the upload of a host-resident scene -- the `.to(device)`
  * of every MeshObject / texture tensor that precedes mixin.py:74-113 in the reference -- without one host round trip per tensor. */

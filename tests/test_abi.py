@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     # sizes computed from the header's field lists (LP64)
     assert ctypes.sizeof(_abi.Texture) == 32
     assert ctypes.sizeof(_abi.Material) == 16 + 3 * 16 + 16 + 4 * 32 + 8
-    assert ctypes.sizeof(_abi.Scene) == 9 * 8 + 16 + 8 + 32 + 8
+    assert ctypes.sizeof(_abi.Scene) == 9 * 8 + 16 + 8 + 32
     assert ctypes.sizeof(_abi.RenderParams) == 32 + 16 + 16 + 16 + 64 + 8 + 7 * 8
     assert ctypes.sizeof(_abi.RenderStats) == 24
 

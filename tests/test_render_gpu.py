@@ -172,21 +172,3 @@ def test_texel_records_equal_separate_textures(monkeypatch):
         imgs.append(as_numpy(*sess.pbr()))
     for k in imgs[0]:
         assert np.array_equal(imgs[0][k], imgs[1][k]), k
-
-
-def test_triangle_records_equal_indexed_vertex_records():
-    """drp_scene_t.tri_records (the three vertex records of every triangle de-indexed into one 192-byte record) is a layout change only:
-    images are bit-identical to the indexed path, for every material kind of the mixed scene."""
-    imgs = []
-    for flag in (True, False):
-        scene = scenes.to_device(scenes.mixed_scene(), 'cuda')
-        sess = run_session(scene, drp.PerspectiveCamera(h=96, w=128), ray_spp=8, ray_depth=3, rng='native', seed=21, reproducible=True,
-                           triangle_records=flag, reuse_scene=False)
-        vao = sess.vertex_array_object()
-        assert (vao.tri_records is not None) == flag
-        if flag:
-            assert tuple(vao.tri_records.shape) == (vao.tris.shape[0], 48)
-            assert torch.equal(vao.tri_records.view(-1, 3, 16), vao.records[vao.tris.long()])
-        imgs.append(as_numpy(*sess.pbr()))
-    for k in imgs[0]:
-        assert np.array_equal(imgs[0][k], imgs[1][k]), k
