@@ -158,6 +158,9 @@ struct Overflow {
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
 #endif
+#ifndef DRP_EXTEND_MINBLOCKS_QUEUE   // secondary bounces (latency-bound) may want a different occupancy than bounce 0 (ALU-bound)
+#define DRP_EXTEND_MINBLOCKS_QUEUE DRP_EXTEND_MINBLOCKS
+#endif
 #ifndef DRP_SHADE_MINBLOCKS
 #define DRP_SHADE_MINBLOCKS 6   // B200 A/B with the interleaved texels (shade ms per step): 4 -> 2.30, 5 -> 2.12, 6 -> 2.04 (80 registers)
 #endif
@@ -184,7 +187,7 @@ __device__ __forceinline__ void store_hit(float2* __restrict__ hit, const AosRay
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(WF_BLOCK, DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
+__global__ void __launch_bounds__(WF_BLOCK, SRC == SRC_QUEUE ? DRP_EXTEND_MINBLOCKS_QUEUE : DRP_EXTEND_MINBLOCKS) k_extend_cw(const __grid_constant__ WfConst c, const float4* __restrict__ qa, const float4* __restrict__ qb,
                                                         float2* __restrict__ hit, const int* __restrict__ count_ptr, int* __restrict__ cursor, AosRays aos,
                                                         Overflow ovf) {
     const int count = SRC == SRC_QUEUE ? *count_ptr : (int)c.R;
