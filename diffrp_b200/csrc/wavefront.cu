@@ -158,8 +158,8 @@ struct Overflow {
 #ifndef DRP_EXTEND_MINBLOCKS
 #define DRP_EXTEND_MINBLOCKS 9
 #endif
-#ifndef DRP_EXTEND_MINBLOCKS_QUEUE   // secondary bounces (latency-bound) may want a different occupancy than bounce 0 (ALU-bound)
-#define DRP_EXTEND_MINBLOCKS_QUEUE DRP_EXTEND_MINBLOCKS
+#ifndef DRP_EXTEND_MINBLOCKS_QUEUE   // secondary bounces: 8 CTAs / 64 registers, no spills (profiles/r2/ab_extend_occupancy_r2.json: 9 -> +0.5 %,
+#define DRP_EXTEND_MINBLOCKS_QUEUE 8 // 10 -> +6 % (spills), 7 -> +2 % (too few warps for the node-fetch latency)); bounce 0 (ALU-bound) stays at 9
 #endif
 #ifndef DRP_SHADE_MINBLOCKS
 #define DRP_SHADE_MINBLOCKS 6   // B200 A/B with the interleaved texels (shade ms per step): 4 -> 2.30, 5 -> 2.12, 6 -> 2.04 (80 registers)
@@ -813,7 +813,7 @@ extern "C" int drp_render_stats(uint64_t handle, drp_render_stats_t* out) {
 #define DRP_STR2(x) #x
 #define DRP_STR(x) DRP_STR2(x)
 extern "C" const char* drp_build_config(void) {
-    return "compiled " __DATE__ " " __TIME__ "; DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS) " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS)
+    return "compiled " __DATE__ " " __TIME__ "; DRP_EXTEND_MINBLOCKS=" DRP_STR(DRP_EXTEND_MINBLOCKS) " DRP_EXTEND_MINBLOCKS_QUEUE=" DRP_STR(DRP_EXTEND_MINBLOCKS_QUEUE) " DRP_SHADE_MINBLOCKS=" DRP_STR(DRP_SHADE_MINBLOCKS)
            " CWK_CHUNK=" DRP_STR(CWK_CHUNK) " CWK_ND=" DRP_STR(CWK_ND) " CWK_NW=" DRP_STR(CWK_NW) " CWK_POSTPONE=" DRP_STR(CWK_POSTPONE)
            " CW_STACK=" DRP_STR(CW_STACK) " CW_DEEP_STACK=" DRP_STR(CW_DEEP_STACK);
 }
