@@ -685,6 +685,10 @@ class PathTracingSession:
             radiance, alpha, _ = self.trace_rays(self.sampler_brdf)
             return tonemap(torch.cat([radiance, alpha], -1), tone, lut=lut, alpha_offset=3)[1]
         accum = self.exchange_accumulators(self.render_accumulators())
+        self.raycaster().check_status()
+        opt = self.options
+        if opt.shard_world > 1 and opt.result_rank is not None and opt.shard_rank != opt.result_rank:
+            return None   # the frame exists on options.result_rank only
         H, W = self.camera.resolution()
         return tonemap(accum.view(H, W, _abi.ACCUM_CHANNELS), tone, lut=lut, scale=1.0 / self.options.ray_spp, alpha_offset=3, flip_rows=True)[1]
 
