@@ -44,9 +44,8 @@ class ReferenceWorkload:
         self.diffrp = ref_loader.load_reference(device)
         scene_host, camkw = syn.teaser_scene('cpu', tex=tex)
         self.scene = ref_scene.to_reference_scene(self.diffrp, scene_host, device)
-        full = self.diffrp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
-        lo = RES // 2 - window // 2
-        self.camera = ref_scene.window_camera(self.diffrp, full.V(), full.P(), RES, RES, lo, lo, window, window)
+        self._full = self.diffrp.PerspectiveCamera.from_orbit(h=RES, w=RES, **camkw)
+        self.set_window(window)
         self.options = self.diffrp.PathTracingSessionOptions(ray_spp=spp, ray_depth=DEPTH, raycaster_impl='naive-pbbvh', raycaster_builder=builder)
         t0 = time.perf_counter()
         first = self.diffrp.PathTracingSession(self.scene, self.camera, self.options)
@@ -57,6 +56,12 @@ class ReferenceWorkload:
         # what later sessions adopt: flattened scene + BVH (keys = the @cached qualnames, utils/cache.py:13-27)
         self.shared = {k: v for k, v in first._cache.items() if k.endswith(('.raycaster', '.vertex_array_object'))}
         assert len(self.shared) == 2, sorted(first._cache)
+
+    def set_window(self, window: int):
+        """Central ``window`` x ``window`` crop of the 1024^2 frame (same camera, cropped projection)."""
+        self.window = window
+        lo = RES // 2 - window // 2
+        self.camera = ref_scene.window_camera(self.diffrp, self._full.V(), self._full.P(), RES, RES, lo, lo, window, window)
 
     def _sync(self):
         if self.device != 'cpu':
@@ -82,9 +87,20 @@ class ReferenceWorkload:
                    self.window * self.window * self.spp * DEPTH, self.n_tris, self.build_s))
 
 
-def run(device: str, tex: int, window: int, spp: int, steps: int, warmup: int):
-    """-> dict(value Mrays/s, ms_per_step, cores, sample, kind='reference')."""
+def run(device: str, tex: int, window: int, spp: int, steps: int, warmup: int, budget_s: float = None):
+    """-> dict(value Mrays/s, ms_per_step, cores, sample, kind='reference').
+    ``budget_s``: bound on the timed region.  The first (untimed) step is clocked; if ``steps`` such steps would exceed the budget the window is
+    shrunk (area ~ budget / projected time, with a margin because the reference's throughput falls with the batch size) -- every step stays
+    a sample of the same workload, and the sample actually used is what ``sample`` describes."""
     wl = ReferenceWorkload(device, tex, window, spp)
+    shrunk = ""
+    if budget_s is not None and steps > 0:
+        dt, _ = wl.step(999)
+        if dt * steps > budget_s:
+            w2 = max(32, int(window * (0.6 * budget_s / (dt * steps)) ** 0.5) // 8 * 8)
+            if w2 < window:
+                shrunk = " [window shrunk from %d to keep %d steps within %.0f s: one %d^2 step took %.1f s]" % (window, steps, budget_s, window, dt)
+                wl.set_window(w2)
     for k in range(warmup):
         wl.step(1000 + k)
     tot_t, tot_n = 0.0, 0
@@ -93,4 +109,4 @@ def run(device: str, tex: int, window: int, spp: int, steps: int, warmup: int):
         tot_t += dt
         tot_n += n
     return dict(value=tot_n / tot_t / 1e6, ms_per_step=tot_t / max(1, steps) * 1e3, cores=host_threads() if device == 'cpu' else None,
-                kind="reference", sample=wl.describe(), n_tris=wl.n_tris, seconds=tot_t)
+                kind="reference", sample=wl.describe() + shrunk, n_tris=wl.n_tris, seconds=tot_t)

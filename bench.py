@@ -220,7 +220,7 @@ def run_reference(args, world, rank):
         return
     from baseline import ref_bench
     if ref_bench.reference_available() and not args.ref_port:
-        r = ref_bench.run('cpu', args.tex, args.ref_window, args.ref_spp, args.steps, min(args.warmup, args.ref_max_warmup))
+        r = ref_bench.run('cpu', args.tex, args.ref_window, args.ref_spp, args.steps, min(args.warmup, args.ref_max_warmup), budget_s=args.ref_budget_s)
         val, cores, kind, sample, ms_step, n_tris = r["value"], r["cores"], r["kind"], r["sample"], r["ms_per_step"], r["n_tris"]
     else:
         oracle, bvh, hs, p, keep, build_s, n_tris = cpu_oracle_setup(args.tex)
@@ -258,7 +258,7 @@ def workload_config(n_tris, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=None, help="default: 128 (20 for --impl reference, whose steps are seconds of CPU work each)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=8)
@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--cpu-baseline-window", type=int, default=512)
     ap.add_argument("--ref-spp", type=int, default=4)
     ap.add_argument("--ref-port", action="store_true", help="reference legs: time the CPU oracle port instead of the installed reference")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: bound on the timed region; the per-step window shrinks when K steps would exceed it")
     ap.add_argument("--ref-max-warmup", type=int, default=2, help="--impl reference: cap on the untimed warm-up steps (each is seconds of CPU work)")
     ap.add_argument("--cpu-baseline-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,6 +282,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 1024-spp frame split over the ranks)")
     ap.add_argument("--strong-spp", type=int, default=1024)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 128
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
         return run_reference(args, world, rank)
