@@ -92,6 +92,17 @@ def merge_runs(items, arena):
     return [(r[0], r[1], r[2]) for r in runs]
 
 
+def clip_runs(runs, lo, hi):
+    """The part of every (buffer offset, source address, bytes) run that falls into the byte range [lo, hi) of the packed buffer: what ONE rank
+    copies when the upload is sharded (the ranks' ranges tile the buffer, so the union of their segments is every byte exactly once)."""
+    out = []
+    for off, p, nbytes in runs:
+        a, b = max(off, lo), min(off + nbytes, hi)
+        if b > a:
+            out.append((a, p + (a - off), b - a))
+    return out
+
+
 class PackedUpload:
     """
     Host -> device move of MANY scene tensors as one packed device buffer: ``add()`` registers a tensor and returns a ticket, ``commit()``
@@ -131,11 +142,8 @@ class PackedUpload:
         buf = torch.empty([per * world], dtype=torch.uint8, device=self.dev)
         lo, hi = (self.shard[0] * per, (self.shard[0] + 1) * per) if self.shard else (0, per)
         base = buf.data_ptr()
-        dst, src, nb = [], [], []
-        for off, p, nbytes in merge_runs([(off, t.data_ptr(), nbytes) for _, t, off, nbytes in self.items], self.arena):
-            a, b = max(off, lo), min(off + nbytes, hi)
-            if b > a:
-                dst.append(base + a); src.append(p + (a - off)); nb.append(b - a)
+        segs = clip_runs(merge_runs([(off, t.data_ptr(), nbytes) for _, t, off, nbytes in self.items], self.arena), lo, hi)
+        dst, src, nb = [base + a for a, _, _ in segs], [p for _, p, _ in segs], [n for _, _, n in segs]
         n = len(dst)
         if n:
             check(lib().drp_upload_batch(n, (C.c_void_p * n)(*dst), (C.c_void_p * n)(*src), (C.c_int64 * n)(*nb),

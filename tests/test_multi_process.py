@@ -83,3 +83,34 @@ def test_two_rank_tile_gather_equals_allreduce(tmp_path):
     world, port = 2, 31000 + (os.getpid() % 2000)
     mp.spawn(_tile_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert np.load(tmp_path / "ok.npy")[0] == 1
+
+
+def test_sharded_upload_segments_tile_the_packed_buffer():
+    """Host logic of the sharded scene upload (flatten.PackedUpload): every rank copies the part of each source run that falls into ITS 1/world
+    byte range of the packed buffer; over all ranks every payload byte is copied exactly once, from the right source address."""
+    sys.path.insert(0, ROOT)
+    from diffrp_b200.flatten import clip_runs, merge_runs, PackedUpload
+    rng = np.random.default_rng(0)
+    sizes = [int(x) for x in rng.integers(1, 5000, 37)]
+    items, off, addr = [], 0, 10_000_000
+    for n in sizes:
+        items.append((off, addr, n))
+        step = -(-n // PackedUpload.ALIGN) * PackedUpload.ALIGN
+        off += step
+        addr += step if rng.random() < 0.7 else step + 4096          # some sources are laid out like the buffer, some are not
+    total = off
+    for arena in (None, (10_000_000, addr + 10)):
+        runs = merge_runs(items, arena)
+        assert sum(n for _, _, n in runs) >= sum(sizes) and (arena is None) == (len(runs) == len(items))
+        for world in (1, 2, 3, 8):
+            per = -(-total // (world * PackedUpload.ALIGN)) * PackedUpload.ALIGN
+            covered = np.zeros(per * world, np.int64)
+            source = np.zeros(per * world, np.int64)
+            for r in range(world):
+                for a, p, n in clip_runs(runs, r * per, (r + 1) * per):
+                    assert r * per <= a and a + n <= (r + 1) * per
+                    covered[a:a + n] += 1
+                    source[a:a + n] = p + np.arange(n)
+            for o, p, n in items:                                        # payload bytes: exactly once, from their own source
+                assert (covered[o:o + n] == 1).all() and (source[o:o + n] == p + np.arange(n)).all()
+            assert covered.max() <= 1
