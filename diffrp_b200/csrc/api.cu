@@ -597,6 +597,8 @@ extern "C" int drp_build_instanced(const float* verts, const int32_t* tris, int6
 #undef DRP_TRY
     cudaFreeAsync(d_node_off, s); cudaFreeAsync(d_tri_off, s); cudaFreeAsync(d_prim_off, s); cudaFreeAsync(d_root_boxes, s); cudaFreeAsync(d_copies, s);
     cleanup();
+    cudaFreeAsync(h->node_box, s);   // only the assembly needed the exact boxes (instanced structures are rebuilt, not refitted)
+    h->node_box = nullptr;
     h->level_begin.clear();   // a mixed structure: refit goes through a rebuild
     drp_register_handle(h, out_handle);
     if (g_drp_log_level >= 4) fprintf(stderr, "[diffrp_b200] instanced build: %lld instances of %zu meshes, %lld triangles, %lld nodes (instance level %d)\n",

@@ -69,3 +69,20 @@ def test_degenerate_deep_scene_is_exact():
     from diffrp_b200._lib import lib, check
     check(lib().drp_status(rc.handle), "drp_status")
     assert rc.stats()["max_depth"] >= 4
+
+
+def test_fixup_scan_mode_when_more_rays_overflow_than_the_list_holds():
+    """More than 2^20 flagged rays in one launch: the overflow list is incomplete and k_extend_fixup scans the results for the sentinel id
+    instead.  3 M rays with the fast path's stack at 0 entries (every ray that would push once is flagged): bit-identical to the normal run."""
+    from diffrp_b200._lib import lib, check
+    v, f = syn.uv_sphere(96, 48)
+    o, d = syn.random_rays(3_000_000, seed=12)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    rc = B200Raycaster(torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda(), {'epsilon': 1e-8})
+    ref_t, ref_i = rc.query(to, td, 10.0)
+    check(lib().drp_debug_set_stack_limit(rc.handle, 0), "drp_debug_set_stack_limit")
+    t, i = rc.query(to, td, 10.0)
+    assert torch.equal(t.view(torch.int32), ref_t.view(torch.int32)) and torch.equal(i, ref_i)
+    assert int((ref_t < 10.0).sum()) > (1 << 20)       # more hits than list entries: the scan path really ran
+    assert int(i.min()) >= 0
+    check(lib().drp_status(rc.handle), "drp_status")
