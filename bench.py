@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--ref-port", action="store_true", help="reference legs: time the CPU oracle port instead of the installed reference")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: bound on the timed region; the per-step window shrinks when K steps would exceed it")
     ap.add_argument("--ref-max-warmup", type=int, default=2, help="--impl reference: cap on the untimed warm-up steps (each is seconds of CPU work)")
-    ap.add_argument("--cpu-baseline-steps", type=int, default=1)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-baseline-res", type=int, default=1024, help="window edge of the reference's GPU leg: 1024 x 8 spp = one real section of the "
                     "reference (ray_split_size = 8M rays, path_tracing.py:74,318) = exactly one bench step")
