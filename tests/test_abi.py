@@ -164,3 +164,23 @@ def test_pinned_arena_scene_uploads_in_a_few_large_copies():
     assert len(merge_runs(items, None)) == len(items)                  # unrelated host tensors are never merged
     shuffled = [items[1], items[0]] + items[2:]
     assert len(merge_runs([(o, p, n) for (o, _, _), (_, p, n) in zip(items, shuffled)], arena)) > 1
+
+
+def test_instance_table_of_a_scene_and_shared_tensors_survive_moves():
+    """Host logic of the instanced build: objects sharing vertex + index tensors form the instance table (first_tri, mesh); Scene.to() and
+    Scene.pin_memory() keep shared tensors shared, so the table is the same after a move."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from diffrp_b200 import synthetic as syn
+    from diffrp_b200.path_tracing import scene_instances
+    sc, _ = syn.instanced_scene('cpu', n_instances=16, mesh_res=(6, 4), env_res=(8, 16))
+    first, mesh = scene_instances(sc.objects)
+    assert mesh.tolist() == [0] * 16 and first.tolist() == [48 * k for k in range(17)]
+    for moved in (sc.to('cpu'), sc.pin_memory(pin=False)):
+        f2, m2 = scene_instances(moved.objects)
+        assert m2.tolist() == mesh.tolist() and f2.tolist() == first.tolist()
+        assert len({o.verts.data_ptr() for o in moved.objects}) == 1
+    few, _ = syn.instanced_scene('cpu', n_instances=4, mesh_res=(6, 4), env_res=(8, 16))
+    assert scene_instances(few.objects) is None                       # too few objects to pay
+    import scenes
+    assert scene_instances(scenes.mixed_scene().objects) is None      # nothing shared
