@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--torch-baseline-spp", type=int, default=8)
     ap.add_argument("--torch-baseline-steps", type=int, default=1)
     ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--texel-tile", type=int, default=None, help="A/B: log2 of the texel-record tile edge (0 = row-major; default: the library's)")
     ap.add_argument("--separate-textures", action="store_true", help="A/B: four separate RGBA textures per material instead of the interleaved texel records")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 1024-spp frame split over the ranks)")
     ap.add_argument("--strong-spp", type=int, default=1024)
@@ -297,6 +298,9 @@ def main():
     if args.separate_textures:
         import diffrp_b200.flatten as _flatten_mod
         _flatten_mod.INTERLEAVE_TEXELS = False
+    if args.texel_tile is not None:
+        import diffrp_b200.flatten as _flatten_mod
+        _flatten_mod.TEXEL_TILE_LOG2 = args.texel_tile
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)

@@ -33,7 +33,7 @@ class Material(C.Structure):
         ("tint", C.c_float * 4),
         ("base_color_factor", C.c_float * 4),
         ("emissive_factor", C.c_float * 4),
-        ("metallic_factor", C.c_float), ("roughness_factor", C.c_float), ("alpha_cutoff", C.c_float), ("_pad", C.c_float),
+        ("metallic_factor", C.c_float), ("roughness_factor", C.c_float), ("alpha_cutoff", C.c_float), ("texel_tile_log2", C.c_int32),
         ("base_color_tex", Texture), ("mr_tex", Texture), ("normal_tex", Texture), ("emissive_tex", Texture),
         ("texel_records", C.c_void_p),
     ]
@@ -165,9 +165,10 @@ def pack_material(desc, ptr_of, keep) -> Material:
     m.emissive_tex = pack_texture(desc.get('emissive_tex'), ptr_of, keep)
     rec = desc.get('texel_records')
     if rec is not None:  # (H,W,12) interleaved copy of the four textures (flatten.texel_records)
-        assert tuple(rec.shape) == (m.base_color_tex.h, m.base_color_tex.w, 12)
+        assert int(rec.numel()) == m.base_color_tex.h * m.base_color_tex.w * 12
         keep.append(rec)
         m.texel_records = ptr_of(rec)
+        m.texel_tile_log2 = int(desc.get('texel_tile_log2', 0))
     return m
 
 

@@ -77,7 +77,7 @@ __device__ __noinline__
 #else
 inline
 #endif
-TexTaps tex_taps(int h, int w, int wrap, int interp, float u, float v) {
+TexTaps tex_taps(int h, int w, int wrap, int interp, float u, float v, int tile_log2 = 0) {
     TexTaps t;
     if (wrap == DRP_WRAP_REPEAT) {  // uv.remainder(1.0)
         u = u - floorf(u); v = v - floorf(v);
@@ -93,10 +93,24 @@ TexTaps tex_taps(int h, int w, int wrap, int interp, float u, float v) {
     const int X = (int)x0, Y = (int)y0;
     const bool xin = X + 1 < w, yin = Y + 1 < h;  // X, Y themselves are in range after the clamp
     const int X1 = xin ? X + 1 : X, Y1 = yin ? Y + 1 : Y;
-    t.off[0] = Y * w + X;   t.wt[0] = gx * gy;
-    t.off[1] = Y * w + X1;  t.wt[1] = xin ? fx * gy : 0.0f;
-    t.off[2] = Y1 * w + X;  t.wt[2] = yin ? gx * fy : 0.0f;
-    t.off[3] = Y1 * w + X1; t.wt[3] = (xin && yin) ? fx * fy : 0.0f;
+    if (tile_log2 > 0) {   // tiled texel records (drp_material_t.texel_tile_log2): tile-major, row-major inside a 2^L x 2^L tile
+        const int L = tile_log2, mask = (1 << L) - 1, tw = w >> L;
+        const int ty0 = (Y >> L) * tw, ty1 = (Y1 >> L) * tw, iy0 = (Y & mask) << L, iy1 = (Y1 & mask) << L;
+        const int tx0 = X >> L, tx1 = X1 >> L, ix0 = X & mask, ix1 = X1 & mask;
+        t.off[0] = ((ty0 + tx0) << (2 * L)) | iy0 | ix0;
+        t.off[1] = ((ty0 + tx1) << (2 * L)) | iy0 | ix1;
+        t.off[2] = ((ty1 + tx0) << (2 * L)) | iy1 | ix0;
+        t.off[3] = ((ty1 + tx1) << (2 * L)) | iy1 | ix1;
+    } else {
+        t.off[0] = Y * w + X;
+        t.off[1] = Y * w + X1;
+        t.off[2] = Y1 * w + X;
+        t.off[3] = Y1 * w + X1;
+    }
+    t.wt[0] = gx * gy;
+    t.wt[1] = xin ? fx * gy : 0.0f;
+    t.wt[2] = yin ? gx * fy : 0.0f;
+    t.wt[3] = (xin && yin) ? fx * fy : 0.0f;
     return t;
 }
 
@@ -254,7 +268,7 @@ DRP_HD SurfaceAttrs surface_attrs(const drp_scene_t& sc, const drp_material_t* _
                       (!use_nt || m.normal_tex.c == 4) && (!use_em || m.emissive_tex.c == 4);
 #endif
     if (m.texel_records) {  // interleaved texels: one address stage, the taps of all four textures in the same sectors
-        const TexTaps tp = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv);
+        const TexTaps tp = tex_taps(m.base_color_tex.h, m.base_color_tex.w, m.base_color_tex.wrap, m.base_color_tex.interp, tu, tv, m.texel_tile_log2);
         float4 r0 = make_float4(1.0f, 1.0f, 1.0f, 1.0f), r1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r2 = r1;
         if (use_bc) r0 = tex_fetch_record(m.texel_records, tp, 0);
         if (use_mr || use_nt) r1 = tex_fetch_record(m.texel_records, tp, 1);

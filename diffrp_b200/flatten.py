@@ -279,11 +279,19 @@ def texel_records(d: dict) -> Optional[torch.Tensor]:
     b, m, n, e = (t['image'] for t in tex)
     if any(x.shape[-1] != 4 for x in (b, m, n, e)):
         return None
-    return torch.cat([b, m[..., 1:3], n[..., :3], e[..., :3]], -1).contiguous()
+    rec = torch.cat([b, m[..., 1:3], n[..., :3], e[..., :3]], -1).contiguous()
+    T = 1 << TEXEL_TILE_LOG2
+    if TEXEL_TILE_LOG2 > 0 and rec.shape[0] % T == 0 and rec.shape[1] % T == 0:   # tile-major: (H/T, W/T, T, T, 12)
+        d['texel_tile_log2'] = TEXEL_TILE_LOG2
+        return rec.view(rec.shape[0] // T, T, rec.shape[1] // T, T, 12).permute(0, 2, 1, 3, 4).contiguous()
+    d['texel_tile_log2'] = 0
+    return rec
 
 
 #: interleave the four textures of a material into 48-byte texel records (layout only; tests flip it to prove bit-equality with separate textures)
 INTERLEAVE_TEXELS = True
+#: texel records are stored in tiles of 2^L x 2^L texels (0 = row-major); layout only, the taps / weights / sums are the same
+TEXEL_TILE_LOG2 = 2
 
 
 def material_descriptions(objs: List, dev, rgba: bool = False, shard=None, arena=None) -> Optional[List[dict]]:
@@ -319,9 +327,10 @@ def material_descriptions(objs: List, dev, rgba: bool = False, shard=None, arena
         if rgba and INTERLEAVE_TEXELS:  # CUDA path: interleaved texels, shared between the objects that share the material
             key = ('records',) + tuple(d[k]['image'].data_ptr() if d.get(k) is not None else 0 for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
             if key not in padded:
-                padded[key] = texel_records(d)
-            if padded[key] is not None:
-                d['texel_records'] = padded[key]
+                rec = texel_records(d)
+                padded[key] = (rec, d.get('texel_tile_log2', 0))
+            if padded[key][0] is not None:
+                d['texel_records'], d['texel_tile_log2'] = padded[key]
         descs.append(d)
     if not descs:
         descs = [dict(kind='default', tint=None)]

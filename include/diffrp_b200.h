@@ -84,7 +84,9 @@ typedef struct drp_material {
     float metallic_factor;
     float roughness_factor;
     float alpha_cutoff;
-    float _pad;
+    int32_t texel_tile_log2;    /* layout of texel_records: 0 = row-major (H,W,12); L > 0 = tiles of 2^L x 2^L texels stored contiguously
+                                   (tile-major, row-major inside a tile; H and W multiples of 2^L): the four bilinear taps of a hit then
+                                   mostly share one 768-byte (L = 2) block instead of two rows W * 48 bytes apart                         */
     drp_texture_t base_color_tex;
     drp_texture_t mr_tex;
     drp_texture_t normal_tex;

@@ -74,13 +74,22 @@ def test_texel_records_layout_and_eligibility():
     d = with_rec[0]
     rec = d['texel_records']
     b, m, n, e = (d[k]['image'] for k in ('base_color_tex', 'mr_tex', 'normal_tex', 'emissive_tex'))
-    assert rec.shape == (b.shape[0], b.shape[1], 12) and rec.dtype == torch.float32 and rec.is_contiguous()
-    assert torch.equal(rec[..., 0:4], b) and torch.equal(rec[..., 4:6], m[..., 1:3])
-    assert torch.equal(rec[..., 6:9], n[..., :3]) and torch.equal(rec[..., 9:12], e[..., :3])
+    H, W = b.shape[:2]
+    L = d['texel_tile_log2']
+    T = 1 << L
+    assert L == 2 and H % T == 0 and W % T == 0                      # tile-major: (H/T, W/T, T, T, 12)
+    assert rec.shape == (H // T, W // T, T, T, 12) and rec.dtype == torch.float32 and rec.is_contiguous()
+    flat = rec.permute(0, 2, 1, 3, 4).reshape(H, W, 12)              # back to row-major
+    assert torch.equal(flat[..., 0:4], b) and torch.equal(flat[..., 4:6], m[..., 1:3])
+    assert torch.equal(flat[..., 6:9], n[..., :3]) and torch.equal(flat[..., 9:12], e[..., :3])
+    # the kernel's tap index (csrc/shade.cuh: tex_taps): texel (y, x) sits at ((y>>L)*(W>>L) + (x>>L)) << 2L | (y & (T-1)) << L | (x & (T-1))
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    idx = (((ys >> L) * (W >> L) + (xs >> L)) << (2 * L)) | ((ys & (T - 1)) << L) | (xs & (T - 1))
+    assert torch.equal(rec.reshape(-1, 12)[idx.reshape(-1)].reshape(H, W, 12), flat)
     # packing into the C struct keeps the pointer and checks the shape
     keep = []
     mat = _abi.pack_material(d, lambda t: t.data_ptr(), keep)
-    assert mat.texel_records == rec.data_ptr() and any(k is rec for k in keep)
+    assert mat.texel_records == rec.data_ptr() and any(k is rec for k in keep) and mat.texel_tile_log2 == 2
     # fall-backs: a texture of another size, another wrap mode, a missing texture
     other = dict(d, mr_tex=dict(d['mr_tex'], image=pad_rgba(torch.rand(8, 8, 3))))
     assert texel_records(other) is None

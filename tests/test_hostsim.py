@@ -123,6 +123,8 @@ def test_texel_records_match_separate_textures_on_the_host(hs):
         if rec is not None:
             recs.append(rec)
             hscene.struct.materials[k].texel_records = rec.data_ptr()
+            hscene.struct.materials[k].texel_tile_log2 = d['texel_tile_log2']   # tiled layout: the tap index is remapped in tex_taps
+            assert d['texel_tile_log2'] == 2
             n_rec += 1
     assert n_rec >= 1  # the OPAQUE / repeat / linear sphere has all four textures
     acc_b = np.zeros_like(acc_a)
