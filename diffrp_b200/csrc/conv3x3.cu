@@ -388,198 +388,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tf32_persistent(cons
     }
 }
 
-// ---- halo variant (round 2): ONE activation tile per channel chunk serves all nine taps -----------------------------------------------
-// The kernels above load the activations three times per channel chunk (one 16-pixel-wide box per filter column) because a SWIZZLE_64B operand
-// cannot be re-addressed at a one-pixel offset.  On the full-resolution layers (K = 9 cin small against the pixel count) that L2 -> SM
-// stream, not the MMA, sets the pace.  Here the tile is stored WITHOUT swizzle in the canonical core-matrix layout
-//     smem_a[c / 4][y 0..17][x 0..17][c % 4]            (one 4-D TMA box (4, 18, 18, 4): 16 bytes per pixel and 4-channel group)
-// so that a core matrix (8 M-rows x 16 bytes, contiguous) is 8 consecutive pixels of one image row, the M = 128 rows of an accumulator are
-// 16 image rows x 8 pixels (stride-byte-offset = 18 pixels x 16 B), two accumulators sit side by side (x halves of the 16 x 16 tile), the K
-// direction steps by the 4-channel planes (leading-byte-offset = 18 x 18 x 16 B) -- and tap (ky, kx) is the SAME tile at a start address
-// (ky * 18 + kx) * 16 bytes further on.  Activations cross L2 -> SM (18 x 18) / (16 x 16) = 1.27 times per layer instead of 3.4.
-// Weights keep the SWIZZLE_64B K-major layout (UMMA descriptors carry their layout per operand).
-// Two mbarrier rings: activations per channel chunk, weights per (chunk, filter row).
-constexpr int HALO = 18, HALO_PLANE = HALO * HALO * 16, HALO_A_BYTES = 4 * HALO_PLANE;   // 20,736 B per 16-channel chunk
-constexpr int HALO_A_STAGES = 2;
-
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-// UMMA shared-memory descriptor without swizzle, K-major: core matrices of 8 rows x 16 B; LBO = distance between core matrices along K,
-// SBO = distance between 8-row groups along M
-__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;                                                // layout type 0 = no swizzle
-}
-
-// Epilogue of the halo kernel for one warp: TMEM lane l = 8 * row + x of an accumulator (16 rows x 8 pixels); warp quadrant q holds rows
-// 4q .. 4q+3.  Per 16-channel group and x half: bias / ReLU / TF32 rounding / 2x2 max (lanes l, l^1, l^8) -> 2 KB staging -> one TMA store
-// of a (16 ch, 8 px, 4 rows) box (pooled: (16, 4, 2); upsampled: four replicated stores).
-__device__ __forceinline__ void epilogue_tile_halo(const ConvArgs& a, const CUtensorMap* map_out, uint32_t tacc, int quad, int lane, int x0, int y0,
-                                                   uint8_t* warp_stage, int& buf) {
-    constexpr int WARP_OUT_BYTES = 32 * OG * 4;
-    const uint64_t mo = reinterpret_cast<uint64_t>(map_out);
-    for (int c0 = 0; c0 < a.cout_store; c0 += 16) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half, buf ^= 1) {
-            uint8_t* stage_out = warp_stage + buf * WARP_OUT_BYTES;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-            float v[16];
-            tmem_ld16(tacc + (uint32_t)(half * a.cout_pad + c0), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                v[i] += __ldg(a.bias + c0 + i);
-                if (a.relu) v[i] = fmaxf(v[i], 0.0f);
-                if (a.round_tf32) v[i] = round_tf32(v[i]);
-            }
-            int row = lane;                                   // staging row = pixel of the (8 px, 4 rows) box, x fastest
-            bool writer = true;
-            if (a.mode == DRP_CONV_POOL2) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                    v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 8));
-                }
-                writer = (lane & 9) == 0;
-                row = ((lane >> 4) << 2) | ((lane & 7) >> 1);  // (4 px, 2 rows) box
-            }
-            if (writer) {
-                float4* dst = reinterpret_cast<float4*>(stage_out + row * (OG * 4));
-                const int sw = (row >> 1) & 3;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t src = smem_u32(stage_out);
-                const int xx = x0 + half * 8, yy = y0 + quad * 4;
-                if (a.mode == DRP_CONV_PLAIN) {
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                 ::"l"(mo), "r"(src), "r"(c0), "r"(xx), "r"(yy) : "memory");
-                } else if (a.mode == DRP_CONV_POOL2) {
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                 ::"l"(mo), "r"(src), "r"(c0), "r"(xx >> 1), "r"(yy >> 1) : "memory");
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                                     ::"l"(mo), "r"(src), "r"(c0), "r"(r & 1), "r"(xx), "r"(r >> 1), "r"(yy) : "memory");
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(NUM_THREADS) k_conv3x3_tf32_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                                   const __grid_constant__ CUtensorMap map_out, const ConvArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tap_bytes = a.cout_pad * 64;                 // 16 channels x cout rows of 64 B, SWIZZLE_64B
-    const int b_stage_bytes = 3 * b_tap_bytes;               // one filter row (three taps) per weight stage
-    uint8_t* smem_b = smem;                                  // a.stages weight stages (1024-byte multiples)
-    uint8_t* smem_a = smem + a.stages * b_stage_bytes;       // HALO_A_STAGES activation tiles
-    uint64_t* full_b = reinterpret_cast<uint64_t*>(smem_a + HALO_A_STAGES * HALO_A_BYTES);
-    uint64_t* empty_b = full_b + MAX_STAGES;
-    uint64_t* full_a = empty_b + MAX_STAGES;
-    uint64_t* empty_a = full_a + HALO_A_STAGES;
-    uint64_t* acc_ready = empty_a + HALO_A_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
-    const int chunks = a.cin / 16;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
-        for (int s = 0; s < a.stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < HALO_A_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-        mbar_init(acc_ready, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer: per chunk one activation tile, then three weight stages (filter rows) ----
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int chunk = 0; chunk < chunks; ++chunk) {
-                mbar_wait(&empty_a[sa], pa ^ 1u);
-                mbar_expect_tx(&full_a[sa], (uint32_t)HALO_A_BYTES);
-                tma_load_4d(&map_a, &full_a[sa], smem_a + sa * HALO_A_BYTES, 0, x0 - 1, y0 - 1, chunk * 4);
-                if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1u; }
-                for (int ky = 0; ky < 3; ++ky) {
-                    mbar_wait(&empty_b[sb], pb ^ 1u);
-                    mbar_expect_tx(&full_b[sb], (uint32_t)b_stage_bytes);
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-                        tma_load_2d(&map_b, &full_b[sb], smem_b + sb * b_stage_bytes + kx * b_tap_bytes, (ky * 3 + kx) * a.cin + chunk * 16, 0);
-                    if (++sb == a.stages) { sb = 0; pb ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer ----
-            const uint32_t idesc = umma_idesc_tf32(a.cout_pad);
-            const uint32_t b_tap16 = (uint32_t)b_tap_bytes >> 4;
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int chunk = 0; chunk < chunks; ++chunk) {
-                mbar_wait(&full_a[sa], pa);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t abase = smem_u32(smem_a + sa * HALO_A_BYTES);
-                for (int ky = 0; ky < 3; ++ky) {
-                    mbar_wait(&full_b[sb], pb);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t db0 = umma_desc<64>(smem_u32(smem_b + sb * b_stage_bytes));
-#pragma unroll
-                    for (int half = 0; half < 2; ++half)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {   // UMMA K = 8 TF32 = two 4-channel planes
-                                const uint32_t aaddr = abase + (uint32_t)(2 * k) * HALO_PLANE + (uint32_t)((ky * HALO + kx + half * 8) * 16);
-                                umma_tf32(tmem_base + (uint32_t)(half * a.cout_pad), umma_desc_noswizzle(aaddr, HALO_PLANE, HALO * 16),
-                                          db0 + (uint64_t)(kx * b_tap16 + k * 2), idesc, (chunk | ky | kx | k) != 0);
-                            }
-                    umma_commit(&empty_b[sb]);
-                    if (++sb == a.stages) { sb = 0; pb ^= 1u; }
-                }
-                umma_commit(&empty_a[sa]);
-                if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1u; }
-            }
-            umma_commit(acc_ready);
-        }
-    } else {
-        const int quad = warp & 3;
-        mbar_wait(acc_ready, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int buf = 0;
-        epilogue_tile_halo(a, &map_out, tmem_base + ((uint32_t)(quad * 32) << 16), quad, lane, x0, y0, smem_b + (warp - 2) * (2 * 32 * OG * 4), buf);
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
-    }
-}
-
 // ---- host side ----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -612,7 +420,6 @@ static ConvDeviceState* conv_device_state() {
                                   (const void*)k_conv3x3_tf32_persistent<16, 16>, (const void*)k_conv3x3_tf32_persistent<8, 32>,
                                   (const void*)k_conv3x3_tf32_persistent<16, 32>};
         for (int k = 0; k < 8 && st.err == cudaSuccess; ++k) st.err = cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-        if (st.err == cudaSuccess) st.err = cudaFuncSetAttribute((const void*)k_conv3x3_tf32_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) st.sm_count = prop.multiProcessorCount;
         st.ready = true;
@@ -742,53 +549,6 @@ extern "C" int drp_conv3x3(const drp_conv3x3_params_t* pp, void* stream) {
             else k_conv3x3_tf32_persistent<8, 16><<<grid, NUM_THREADS, psmem, st>>>(map_a, map_b, map_out, a);
             DRP_CUDA_CHECK(cudaGetLastError());
             return DRP_OK;
-        }
-    }
-    // halo variant: full- and half-resolution layers (many 16-row tiles, 16-channel k-steps), where the activation stream from L2 sets the pace
-    bool halo = tr == 16 && kch == 16 && !persistent && 2 * p.cout_pad <= 512;
-    if (const char* e = tune_env("DRP_CONV_HALO")) halo = halo && atoi(e) != 0;
-    if (halo) {
-        CUtensorMap map_a4, map_o;
-        {   // activations as (c % 4, x, y, c / 4): box (4, 18, 18, 4) lands as [c / 4][y][x][c % 4], zero fill outside = padding 1
-            const cuuint64_t dims[4] = {4, (cuuint64_t)p.width, (cuuint64_t)p.height, (cuuint64_t)(p.cin / 4)};
-            const cuuint64_t strides[3] = {(cuuint64_t)p.in_stride * 4, (cuuint64_t)p.in_stride * 4 * (cuuint64_t)p.width, 16};
-            const cuuint32_t box[4] = {4, HALO, HALO, 4}, estr[4] = {1, 1, 1, 1};
-            CUresult r = encode(&map_a4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in + p.in_offset), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(activations, 4-D halo view) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
-        }
-        if (halo) {   // output boxes of one warp: (16 ch, 8 px, 4 rows); pooled (16, 4, 2); upsampled (16, 1, 8, 1, 4)
-            float* base = p.out + p.out_offset;
-            const cuuint64_t ps = (cuuint64_t)p.out_stride * 4;
-            CUresult r;
-            if (p.mode == DRP_CONV_UPSAMPLE2) {
-                const cuuint64_t dims[5] = {(cuuint64_t)p.cout_store, 2, (cuuint64_t)p.width, 2, (cuuint64_t)p.height};
-                const cuuint64_t strides[4] = {ps, 2 * ps, 2 * (cuuint64_t)p.width * ps, 4 * (cuuint64_t)p.width * ps};
-                const cuuint32_t box[5] = {OG, 1, 8, 1, 4}, estr[5] = {1, 1, 1, 1, 1};
-                r = encode(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            } else {
-                const int sh = p.mode == DRP_CONV_POOL2 ? 1 : 0;
-                const cuuint64_t ow = (cuuint64_t)(p.width >> sh), oh = (cuuint64_t)(p.height >> sh);
-                const cuuint64_t dims[3] = {(cuuint64_t)p.cout_store, ow, oh};
-                const cuuint64_t strides[2] = {ps, ow * ps};
-                const cuuint32_t box[3] = {OG, (cuuint32_t)(8 >> sh), (cuuint32_t)(4 >> sh)}, estr[3] = {1, 1, 1};
-                r = encode(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            }
-            if (r != CUDA_SUCCESS) { drp_set_error("drp_conv3x3: cuTensorMapEncodeTiled(output, halo boxes) failed: " + std::to_string((int)r)); return DRP_ERR_CUDA; }
-        }
-        if (halo) {
-            ConvArgs h = a;
-            const size_t b_stage = 3 * (size_t)p.cout_pad * 64;
-            h.stages = (int)std::min<size_t>(MAX_STAGES, std::max<size_t>(3, (24 * 1024) / b_stage));   // weight stages (filter rows) in flight
-            const size_t hsmem = 1024 + (size_t)h.stages * b_stage + (size_t)HALO_A_STAGES * HALO_A_BYTES + (2 * MAX_STAGES + 2 * HALO_A_STAGES + 1) * sizeof(uint64_t) + 16;
-            if (hsmem <= 220 * 1024) {
-                const dim3 hgrid((unsigned)((p.width + 15) / 16), (unsigned)((p.height + 15) / 16));
-                k_conv3x3_tf32_halo<<<hgrid, NUM_THREADS, hsmem, (cudaStream_t)stream>>>(map_a4, map_b, map_o, h);
-                DRP_CUDA_CHECK(cudaGetLastError());
-                return DRP_OK;
-            }
         }
     }
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * MAX_STAGES + 1) * sizeof(uint64_t) + 16;
