@@ -233,3 +233,19 @@ def test_unsharded_process_cannot_silently_lose_samples():
     scene = scenes.icosphere_scene()
     with pytest.raises(RuntimeError):
         drp.PathTracingSession(scene, drp.PerspectiveCamera(h=8, w=8), drp.PathTracingSessionOptions(ray_spp=4, shard_world=2)).pbr()
+
+
+def test_host_scene_paths_render_the_same_image():
+    """The session accepts scenes on the device, in pageable host memory and in one page-locked arena (Scene.pin_memory(): packed upload with a
+    few large copies, textures on the side stream): same image bit for bit in reproducible mode."""
+    host = scenes.mixed_scene()
+    cam = drp.PerspectiveCamera(h=48, w=64)
+    opt = dict(ray_spp=4, ray_depth=3, seed=13, reproducible=True, reuse_scene=False)
+    outs = []
+    for sc in (host.to(torch.device('cuda')), host, host.pin_memory()):
+        rad, alpha, extras = drp.PathTracingSession(sc, cam, drp.PathTracingSessionOptions(**opt)).pbr()
+        outs.append(torch.cat([rad, alpha] + [extras[k] for k in sorted(extras)], -1))
+    pinned = host.pin_memory()
+    assert pinned._arena.is_pinned() and all(o.verts.is_pinned() for o in pinned.objects)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert float(outs[0][..., 3].mean()) > 0.1
