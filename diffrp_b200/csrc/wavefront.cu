@@ -103,7 +103,9 @@ __device__ __forceinline__ void load_ray(const WfConst& c, const float4* __restr
         float gy = __ldg(c.p.ndc_y + y) + __ldg(c.p.jitter_y + s);
         gen_primary_ray(c.p.inv_vp, c.p.cam_pos, c.p.t_near, gx, gy, o, d);
     } else {
-        float4 a = __ldg(qa + k), b = __ldg(qb + k);
+        // queue entries are read once: streaming loads (evict-first) keep them from displacing hierarchy nodes in L1 / L2
+        // (profiles/r2/ab_cache_policy_r2.json: extend -0.5 %)
+        float4 a = __ldcs(qa + k), b = __ldcs(qb + k);
         o = v3(a.x, a.y, a.z);
         d = v3(a.w, b.x, b.y);
         ray_index = __float_as_int(b.z);
@@ -182,7 +184,7 @@ __device__ __forceinline__ void store_hit(float2* __restrict__ hit, const AosRay
         aos.out_t[k] = t;
         aos.out_i[k] = id;
     } else {
-        hit[k] = make_float2(t, __int_as_float(id));
+        __stcs(hit + k, make_float2(t, __int_as_float(id)));
     }
 }
 
