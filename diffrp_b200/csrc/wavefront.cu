@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
             if (k < count) {
                 Vec3 o, d;
                 load_ray<PRIMARY>(c, qa, qb, k, o, d, ri);
-                if (!PRIMARY) { float4 t4 = __ldg(qt + k); T = v3(t4.x, t4.y, t4.z); }
-                const float2 h = __ldg(hit + k);
+                if (!PRIMARY) { float4 t4 = __ldcs(qt + k); T = v3(t4.x, t4.y, t4.z); }   // queue / hit entries: touched once, streaming
+                const float2 h = __ldcs(hit + k);
                 const float t = h.x;
                 const bool is_hit = t < c.p.t_far;
                 SurfaceAttrs s;
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(WF_BLOCK, DRP_SHADE_MINBLOCKS) k_shade(const _
                 pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1);
                 if (alive) {
                     int w = pos + __popc(m & ((1u << lane) - 1u));
-                    oa[w] = make_float4(no.x, no.y, no.z, nd.x);
-                    ob[w] = make_float4(nd.y, nd.z, __int_as_float(ri), 0.0f);
-                    ot[w] = make_float4(T.x, T.y, T.z, 0.0f);
+                    __stcs(oa + w, make_float4(no.x, no.y, no.z, nd.x));
+                    __stcs(ob + w, make_float4(nd.y, nd.z, __int_as_float(ri), 0.0f));
+                    __stcs(ot + w, make_float4(T.x, T.y, T.z, 0.0f));
                 }
             }
         }
