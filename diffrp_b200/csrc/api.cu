@@ -112,10 +112,27 @@ __global__ void __launch_bounds__(128) k_cw_collapse(CwBuild cw, int level, floa
 }
 __global__ void k_cw_advance(CwBuild cw, int level) { cw.counters[10 + level] = cw.counters[0]; }
 
-template <typename T>
-static cudaError_t alloc_async(T** p, size_t count, cudaStream_t s) {
-    return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s);
-}
+// Build scratch: stream-ordered allocations that are freed (stream-ordered as well) when the builder returns -- on the error paths too, so a
+// failed build (out of memory half way through the list) leaves nothing behind in the pool.
+struct BuildScratch {
+    cudaStream_t s;
+    std::vector<void*> blocks;
+    explicit BuildScratch(cudaStream_t stream) : s(stream) {}
+    template <typename T>
+    cudaError_t get(T** p, size_t count) { return get_bytes((void**)p, sizeof(T) * (count ? count : 1)); }
+    cudaError_t get_bytes(void** p, size_t bytes) {
+        const cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+        if (e == cudaSuccess) blocks.push_back(*p);
+        return e;
+    }
+    cudaError_t release() {
+        cudaError_t first = cudaSuccess;
+        for (void* p : blocks) { const cudaError_t e = cudaFreeAsync(p, s); if (first == cudaSuccess) first = e; }
+        blocks.clear();
+        return first;
+    }
+    ~BuildScratch() { release(); }
+};
 
 // Build the wide hierarchy over (verts, tris[0 .. n_tris)) into *h (not registered): device, eps and stack_cap are set by the caller.
 int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, int64_t n_tris, cudaStream_t s) {
@@ -154,25 +171,26 @@ int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, i
     *h->sticky_host = 0;
     DRP_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->sticky_dev, h->sticky_host, 0));
     b.bounds = h->bounds; b.nodes = h->nodes; b.packed = h->packed;
-    DRP_CUDA_CHECK(alloc_async(&b.prim_lo, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.prim_hi, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&keys_in, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&vals_in, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.keys, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.vals, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.left, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.right, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.parent, 2 * nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.range_first, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.range_last, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.box_lo, 2 * nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.box_hi, 2 * nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.arrive, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.collapsed, nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.count, 2 * nn, s));
+    BuildScratch scratch(s);
+    DRP_CUDA_CHECK(scratch.get(&b.prim_lo, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.prim_hi, nn));
+    DRP_CUDA_CHECK(scratch.get(&keys_in, nn));
+    DRP_CUDA_CHECK(scratch.get(&vals_in, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.keys, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.vals, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.left, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.right, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.parent, 2 * nn));
+    DRP_CUDA_CHECK(scratch.get(&b.range_first, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.range_last, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.box_lo, 2 * nn));
+    DRP_CUDA_CHECK(scratch.get(&b.box_hi, 2 * nn));
+    DRP_CUDA_CHECK(scratch.get(&b.arrive, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.collapsed, nn));
+    DRP_CUDA_CHECK(scratch.get(&b.count, 2 * nn));
     // optimal (DP) collapse tables; the greedy collapse measured 2 % slower traversal and 40 % more nodes (profiles/README.md)
-    DRP_CUDA_CHECK(alloc_async(&b.dp_cost, 16 * nn, s));
-    DRP_CUDA_CHECK(alloc_async(&b.dp_dec, 16 * nn, s));
+    DRP_CUDA_CHECK(scratch.get(&b.dp_cost, 16 * nn));
+    DRP_CUDA_CHECK(scratch.get(&b.dp_dec, 16 * nn));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.arrive, 0, sizeof(int) * nn, s));
     DRP_CUDA_CHECK(cudaMemsetAsync(b.collapsed, 0, nn, s));
 
@@ -187,7 +205,7 @@ int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, i
         b2.keys = keys_in; b2.vals = vals_in;
         k_morton<<<G, T, 0, s>>>(b2);
         DRP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, b.keys, vals_in, b.vals, n, 0, 63, s));
-        DRP_CUDA_CHECK(cudaMallocAsync(&sort_tmp, sort_bytes ? sort_bytes : 1, s));
+        DRP_CUDA_CHECK(scratch.get_bytes(&sort_tmp, sort_bytes));
         DRP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, b.keys, vals_in, b.vals, n, 0, 63, s));
         if (n > 1) {
             k_karras<<<G, T, 0, s>>>(b);
@@ -199,8 +217,8 @@ int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, i
         CwBuild cw;
         cw.b = b;
         cw.cw_nodes = h->nodes; cw.cw_tris = h->packed; cw.capacity = (int)h->n_nodes;
-        DRP_CUDA_CHECK(alloc_async(&cw_work, (size_t)h->n_nodes, s));
-        DRP_CUDA_CHECK(alloc_async(&cw_counters, 160, s));
+        DRP_CUDA_CHECK(scratch.get(&cw_work, (size_t)h->n_nodes));
+        DRP_CUDA_CHECK(scratch.get(&cw_counters, 160));
         DRP_CUDA_CHECK(cudaMemsetAsync(cw_counters, 0, sizeof(int) * 160, s));
         cw.work = cw_work; cw.counters = cw_counters;
         k_cw_init<<<1, 1, 0, s>>>(cw);
@@ -232,10 +250,7 @@ int drp_build_structure(BvhHandle* h, const float* verts, const int32_t* tris, i
     }
     DRP_CUDA_CHECK(cudaGetLastError());
     const double t_launch = now();
-    void* temps[] = {b.prim_lo, b.prim_hi, keys_in, vals_in, b.keys, b.vals, b.left, b.right, b.parent, b.range_first,
-                     b.range_last, b.box_lo, b.box_hi, b.arrive, b.collapsed, sort_tmp, cw_work, cw_counters, b.count, b.dp_cost, b.dp_dec};
-    for (void* p : temps)
-        if (p) DRP_CUDA_CHECK(cudaFreeAsync(p, s));
+    DRP_CUDA_CHECK(scratch.release());
     if (timing) fprintf(stderr, "[diffrp_b200] build n=%d: alloc %.2f ms, launch+collapse-sync %.2f ms, free %.2f ms\n", n, t_alloc - t_begin,
                         t_launch - t_alloc, now() - t_launch);
     return DRP_OK;

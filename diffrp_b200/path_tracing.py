@@ -601,8 +601,9 @@ class PathTracingSession:
         return self.render_samples(shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device))
 
     def exchange_accumulators(self, accum: torch.Tensor) -> torch.Tensor:
-        """The path's one exchange step between ranks: spp shards are summed (all-reduce); tile shards have disjoint supports and are gathered
-        (``options.tile_collective='gather'``, the default; ``'allreduce'`` sums whole frames like spp sharding -- kept for the A/B)."""
+        """The path's one exchange step between ranks: the packed accumulators are summed -- all-reduce, or reduce to ``options.result_rank``.
+        Tile shards have disjoint supports, so ``options.tile_collective='gather'`` moves only the owned tiles instead (same bits; measured
+        slower than the in-fabric all-reduce on NVSwitch, which therefore stays the default: profiles/r2/c5_n8*.json)."""
         opt = self.options
         if opt.shard_world > 1 and opt.shard_mode == 'tile' and opt.tile_collective == 'gather' and opt.result_rank is None:
             H, W = self.camera.resolution()
