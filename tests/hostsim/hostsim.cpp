@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 #include <numeric>
+#include <omp.h>
 #include "../../diffrp_b200/csrc/common.cuh"
 #include "../../diffrp_b200/csrc/lbvh.cuh"
 #include "../../diffrp_b200/csrc/traverse.cuh"
@@ -134,6 +135,41 @@ extern "C" int64_t hs_trace_wide(const HsBvh* h, const float* ro, const float* r
         out_i[r] = hit.id;
         overflow += of;
     }
+    return overflow;
+}
+
+// The walk of k_extend_fixup (wavefront.cu): the same traversal over a caller-supplied stack of `cap` entries laid out [entry][thread] like the
+// kernel's global-memory deep stack (CwStridedStack), here with one "thread" per OpenMP thread.  out_overflow[r] = 1 when ray r had to drop an
+// entry (its result is then not trustworthy -- what the kernels hand to the next stage / report through the sticky flag); *max_depth = the
+// deepest stack use over all rays, measured with an instrumented stack of the same interface.
+struct HsCountingStack {
+    uint2* base;
+    int64_t stride;
+    int* deepest;
+    void put(int i, uint32_t a, uint32_t b) const { uint2 v; v.x = a; v.y = b; base[i * stride] = v; if (i + 1 > *deepest) *deepest = i + 1; }
+    void get(int i, uint32_t& a, uint32_t& b) const { const uint2 v = base[i * stride]; a = v.x; b = v.y; }
+};
+extern "C" int64_t hs_trace_wide_strided(const HsBvh* h, const float* ro, const float* rd, int64_t n, float t_far, float eps, int cap, float* out_t,
+                                         int32_t* out_i, uint8_t* out_overflow, int* max_depth) {
+    int64_t overflow = 0;
+    int deepest_all = 0;
+    const int64_t nthreads = 8;
+    std::vector<uint2> stack((size_t)(cap > 0 ? cap : 1) * nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(8) reduction(+ : overflow) reduction(max : deepest_all)
+    for (int64_t r = 0; r < n; ++r) {
+        bool of = false;
+        int deepest = 0;
+        const int tid = omp_get_thread_num();
+        const RayHit hit = cw_trace_one_stack(h->cw_nodes.data(), h->cw_tris.data(), v3(ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]),
+                                              v3(rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]), t_far, eps, HsCountingStack{stack.data() + tid, nthreads, &deepest},
+                                              cap, of);
+        out_t[r] = hit.t;
+        out_i[r] = hit.id;
+        if (out_overflow) out_overflow[r] = of ? 1 : 0;
+        overflow += of;
+        if (deepest > deepest_all) deepest_all = deepest;
+    }
+    if (max_depth) *max_depth = deepest_all;
     return overflow;
 }
 

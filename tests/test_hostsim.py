@@ -337,3 +337,90 @@ def test_instanced_assembly_keeps_closest_hits_exact(hs, n_inst, two_meshes):
     if n_inst > 2:
         assert len(np.unique(np.searchsorted(first, i[t < 10.0], side='right'))) > 2      # hits land in several instances
     hs.hs_free(h)
+
+
+# ---- deep hierarchies: the stack bound behind k_extend_fixup (wavefront.cu) ------------------------------------------------------------------
+def _bind_strided(L):
+    vp = C.c_void_p
+    L.hs_build_wide.restype = vp
+    L.hs_build_wide.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.hs_trace_wide_strided.restype = C.c_int64
+    L.hs_trace_wide_strided.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
+    L.hs_stats_wide.argtypes = [vp, vp]
+
+
+def _trace_strided(L, h, o, d, far, eps, cap):
+    t, i, of = np.empty(len(o), np.float32), np.empty(len(o), np.int32), np.zeros(len(o), np.uint8)
+    deepest = C.c_int(0)
+    n_of = L.hs_trace_wide_strided(h, o.ctypes.data, d.ctypes.data, len(o), far, eps, cap, t.ctypes.data, i.ctypes.data, of.ctypes.data, C.byref(deepest))
+    return t, i, of.astype(bool), int(n_of), deepest.value
+
+
+def _adversarial_scene(kind, rng, m=6000):
+    """Triangle sets that drive the Karras tree to its depth limit, and rays aimed where the hierarchy is deepest."""
+    if kind == "morton_chain":
+        # centres whose 63-bit Morton keys are 2^k, k = 0..62: every split of the radix tree peels off ONE key -> a 63-level chain of nested
+        # boxes around one corner; 24 exact duplicates per centre add index-bit levels underneath (equal keys are split by primitive index);
+        # triangle size ~ distance from the corner, so that the peeled-off clusters overlap the rest of the chain
+        ext, cs = 4.0, [np.zeros(3), np.full(3, 1.0)]
+        for k in range(63):
+            c = np.zeros(3)
+            c[k % 3] = 2.0 ** (k // 3) / 2.0 ** 21
+            cs.append(c)
+        cs = np.asarray(cs) * ext
+        size = np.maximum(np.linalg.norm(cs, axis=-1), 1e-7)[:, None, None]
+        tri = cs[:, None, :] + size * np.asarray([[0, 0, 0], [1, 0, 0.3], [0, 1, 0.6]])[None]
+        tri = np.repeat(tri, 24, axis=0) - ext / 2
+        corner = np.full(3, -ext / 2)
+        org = corner + rng.normal(0, 1, (m, 3)) * np.exp(rng.uniform(-14, 1, (m, 1)))    # every scale of the chain gets rays
+        tgt = corner + rng.normal(0, 1, (m, 3)) * np.exp(rng.uniform(-14, 1, (m, 1)))
+    elif kind == "duplicates":
+        one = np.asarray([[-0.3, -0.2, 0.0], [0.4, -0.1, 0.1], [0.0, 0.5, -0.1]])
+        tri = np.repeat(one[None], 6000, axis=0)
+        org = rng.uniform(-3, 3, (m, 3))
+        tgt = rng.uniform(-0.3, 0.3, (m, 3))
+    else:  # "slivers": long needles through the whole scene, every box overlaps every other
+        a = rng.uniform(-1, 1, (3000, 3))
+        b = a + rng.normal(0, 1.0, (3000, 3))
+        tri = np.stack([a, b, b + rng.normal(0, 1e-3, (3000, 3))], 1)
+        org = rng.uniform(-3, 3, (m, 3))
+        tgt = rng.uniform(-1, 1, (m, 3))
+    v = tri.reshape(-1, 3).astype(np.float32)
+    f = np.arange(len(v), dtype=np.int32).reshape(-1, 3)
+    d = tgt - org
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    return v, f, org.astype(np.float32), d.astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["morton_chain", "duplicates", "slivers"])
+def test_deep_hierarchies_fit_the_deep_stack_and_overflow_is_always_flagged(hs, kind):
+    """k_extend_cw walks with CW_STACK = 48 entries and hands rays that need more to k_extend_fixup, whose CW_DEEP_STACK = 256 entries 'cannot run
+    out' (wavefront.cu).  Checked here on the host build of the same traversal: on scenes built to maximise the depth (a 63-level Morton chain
+    with duplicate-key subtrees, thousands of identical triangles, scene-spanning slivers) (i) 256 entries are never exhausted and the hits equal
+    the exhaustive search bit for bit, (ii) with a deliberately tiny stack every ray whose result could be wrong is FLAGGED -- a ray that is not
+    flagged is exact -- which is what makes the hand-off to the fix-up kernel (and the sticky error flag behind it) sufficient."""
+    L = hs
+    _bind_strided(L)
+    rng = np.random.default_rng(7)
+    v, f, org, d = _adversarial_scene(kind, rng)
+    far = 50.0
+    ot, oi = oracle.bruteforce(v, f, org, d, far, 0.0)
+    h = L.hs_build_wide(v.ctypes.data, f.ctypes.data, len(v), len(f))
+    try:
+        st = np.zeros(6, np.int64)
+        L.hs_stats_wide(h, st.ctypes.data)
+        t, i, flagged, n_of, deepest = _trace_strided(L, h, org, d, far, 0.0, 256)
+        assert n_of == 0 and not flagged.any(), "the 256-entry deep stack overflowed on '%s' (%d rays)" % (kind, n_of)
+        assert deepest <= st[1], "a ray stacked %d entries in a hierarchy of %d levels: more than one node group per level" % (deepest, st[1])
+        assert deepest < 128, "deepest stack use %d leaves less than 2x headroom in CW_DEEP_STACK" % deepest
+        assert np.array_equal(t.view(np.int32), ot.view(np.int32)) and np.array_equal(i, oi)
+        assert deepest >= 2, "no ray ever stacked two entries: the scene does not exercise the stack"
+        for cap in (0, 1, deepest - 1):
+            t, i, flagged, n_of, _ = _trace_strided(L, h, org, d, far, 0.0, cap)
+            assert n_of == int(flagged.sum()) and flagged.any(), "a %d-entry stack did not overflow although %d entries are needed" % (cap, deepest)
+            ok = ~flagged
+            assert np.array_equal(t[ok].view(np.int32), ot[ok].view(np.int32)) and np.array_equal(i[ok], oi[ok]), \
+                "cap %d: an unflagged ray differs from the exhaustive search" % cap
+        print("%s: %d wide nodes in %d levels, deepest stack use %d" % (kind, st[0], st[1], deepest))
+    finally:
+        L.hs_free(h)
