@@ -241,8 +241,14 @@ def denoiser_fixture():
     save("denoiser", hdr=hdr.numpy(), albedo=albedo.numpy(), normal=normal.numpy(), out=out.numpy(), seed=np.int32(11))
 
 
+AFFINE_ORBIT = dict(h=40, w=56, radius=3.2, azim=-35, elev=22, origin=[0.0, 0.0, 0.0], fov=34, near=0.1, far=10.0)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "affine":   # only the fixture added last (the others regenerate bit for bit)
+        pbr_fixture("pbr_affine_instances", scenes.affine_instances_scene(), None, 3, 3, 'skybox', 7, orbit=AFFINE_ORBIT)
+        sys.exit(0)
     denoiser_fixture()
     tonemap_fixture()
     scene_api_fixture()
@@ -257,3 +263,5 @@ if __name__ == "__main__":
     pbr_fixture("pbr_mixed_256spp", scenes.mixed_scene(), None, 256, 3, 'skybox', 5, orbit=dict(orbit, h=36, w=48), impl='naive-pbbvh')
     # config 1 in full: icosphere, 64x64, 16 spp, 2 bounces (reference on CPU)
     pbr_fixture("pbr_config1", scenes.icosphere_scene(rotate=False, colors=False), dict(h=64, w=64), 16, 2, 'void', 0, impl='naive-pbbvh')
+    # config-5-like: objects sharing one mesh under NON-rigid transforms (normals by M, not its inverse transpose) + a sheared GLTF sphere
+    pbr_fixture("pbr_affine_instances", scenes.affine_instances_scene(), None, 3, 3, 'skybox', 7, orbit=AFFINE_ORBIT)

@@ -67,6 +67,42 @@ def mixed_scene(n_theta=48, n_phi=24):
     return scene
 
 
+def affine(seed, translate=(0, 0, 0), scale=(1.0, 1.0, 1.0), shear=0.0):
+    """Seeded NON-rigid transform: rotation x anisotropic scale x shear + translation (normals must follow the reference's rule --
+    normalize(M3x3 n), not the inverse transpose, base_material.py:183-210 -- which only shows under such matrices)."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    sh = np.eye(3)
+    sh[0, 1], sh[2, 0] = shear, -0.5 * shear
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = q @ np.diag(scale) @ sh
+    m[:3, 3] = translate
+    return T(m)
+
+
+def affine_instances_scene(n_inst=6):
+    """Config-5-like scene at test size: ``n_inst`` MeshObjects SHARING one mesh (vertex, index and normal tensors) under seeded non-rigid
+    transforms with tinted DefaultMaterials, plus one textured, normal-mapped GLTF sphere under a sheared transform (tangent frame under a
+    non-rigid M), env-lit."""
+    scene = drp.Scene()
+    v, f, n, uv, tg = syn.uv_sphere(24, 12, radius=0.22, bump=0.03, noise=0.004, seed=3, with_attrs=True)
+    Vt, Ft, Nt = T(v), T(f), T(n)
+    tints = ([1, .3, .3], [.3, 1, .3], [.3, .3, 1], [1, 1, .3], [1, .3, 1], [.3, 1, 1])
+    rng = np.random.default_rng(11)
+    for k in range(n_inst):
+        pos = (0.9 * np.cos(2 * np.pi * k / n_inst), 0.25 * np.sin(3.0 * k), 0.9 * np.sin(2 * np.pi * k / n_inst))
+        sc = tuple(rng.uniform(0.5, 1.8, 3))
+        scene.add_mesh_object(drp.MeshObject(drp.DefaultMaterial(torch.tensor(tints[k % 6], dtype=torch.float32)), Vt, Ft, normals=Nt,
+                                             M=affine(50 + k, pos, sc, shear=0.15 * (k % 3))))
+    v2, f2, n2, uv2, tg2 = syn.uv_sphere(32, 16, radius=0.3, bump=0.02, noise=0.003, seed=5, with_attrs=True)
+    scene.add_mesh_object(drp.MeshObject(gltf_material(4), T(v2), T(f2), normals=T(n2), M=affine(60, (0.0, -0.05, 0.0), (1.4, 0.7, 1.0), shear=0.3),
+                                         uv=T(uv2 * 2.0), tangents=T(tg2)))
+    scene.add_light(drp.ImageEnvironmentLight(intensity=1.2, color=torch.tensor([0.9, 1.0, 1.0]), image=T(syn.smooth_texture(32, 64, 3, 78, 0.0, 2.0))))
+    return scene
+
+
 def to_device(scene, dev):
     return scene.to(dev)
 

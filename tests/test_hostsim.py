@@ -82,9 +82,10 @@ def test_axis_aligned_rays_on_box_planes(hs):
     assert (t == 1.0).all()
 
 
-@pytest.mark.parametrize("scene_name,last,records", [("ico", "void", False), ("mixed", "void", False), ("mixed", "skybox", True)])
+@pytest.mark.parametrize("scene_name,last,records", [("ico", "void", False), ("mixed", "void", False), ("mixed", "skybox", True),
+                                                     ("affine", "skybox", True)])
 def test_shading_logic_matches_oracle(hs, scene_name, last, records):
-    scene = scenes.icosphere_scene() if scene_name == "ico" else scenes.mixed_scene()
+    scene = {"ico": scenes.icosphere_scene, "mixed": scenes.mixed_scene, "affine": scenes.affine_instances_scene}[scene_name]()
     cam = make_camera(None, dict(h=40, w=56, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32))
     vao, hscene, p, keep = scenes.oracle_inputs(scene, cam, 3, 3, last_bounce=last, seed=123)
     acc, n = oracle.render(oracle.BVH(vao.world_pos.numpy(), vao.tris.numpy()), hscene, p)
