@@ -177,15 +177,10 @@ PBR_CASES = {
     "pbr_mixed_void": (lambda: scenes.mixed_scene(), None, dict(h=48, w=64, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32, near=0.1, far=10.0)),
     "pbr_mixed_skybox": (lambda: scenes.mixed_scene(), None, dict(h=48, w=64, radius=3.0, azim=25, elev=15, origin=[0.0, -0.1, 0.0], fov=32, near=0.1, far=10.0)),
     "pbr_config1": (lambda: scenes.icosphere_scene(rotate=False, colors=False), dict(h=64, w=64), None),
-}
-
-
-# reference images that pin the ORACLE only (the GPU suite iterates PBR_CASES; these were added after the last GPU session of the round)
-AFFINE_ORBIT = dict(h=40, w=56, radius=3.2, azim=-35, elev=22, origin=[0.0, 0.0, 0.0], fov=34, near=0.1, far=10.0)
-PBR_CASES_ORACLE_ONLY = {
     # config-5-like: six objects sharing one mesh under NON-rigid transforms (normalize(M n), not the inverse transpose:
     # base_material.py:183-210) with tinted DefaultMaterials + a sheared, normal-mapped GLTF sphere
-    "pbr_affine_instances": (lambda: scenes.affine_instances_scene(), None, AFFINE_ORBIT),
+    "pbr_affine_instances": (lambda: scenes.affine_instances_scene(), None,
+                             dict(h=40, w=56, radius=3.2, azim=-35, elev=22, origin=[0.0, 0.0, 0.0], fov=34, near=0.1, far=10.0)),
 }
 
 
@@ -209,10 +204,10 @@ def image_errors(out, g, keys=('radiance', 'alpha', 'albedo', 'emission', 'world
     return res
 
 
-@pytest.mark.parametrize("name", list(PBR_CASES) + list(PBR_CASES_ORACLE_ONLY))
+@pytest.mark.parametrize("name", list(PBR_CASES))
 def test_oracle_render_matches_reference_pbr(name):
     g = load(name)
-    make_scene, cam_kwargs, orbit = PBR_CASES.get(name) or PBR_CASES_ORACLE_ONLY[name]
+    make_scene, cam_kwargs, orbit = PBR_CASES[name]
     cam = make_camera(cam_kwargs, orbit)
     spp, depth, H, W = int(g['spp']), int(g['depth']), int(g['H']), int(g['W'])
     u = seeded_uniforms(g['seed'], spp, H, W, depth, g['u_crc'])
