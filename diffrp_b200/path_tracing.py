@@ -177,6 +177,10 @@ def reduce_accumulators(accum: torch.Tensor, world: int, dst: Optional[int] = No
     return accum
 
 
+#: pixels one drp_render call may cover (csrc/wavefront.cu: WF_MAX_BATCH_RAYS)
+MAX_PIXELS_PER_CALL = 1 << 24
+
+
 def frame_tiles(H: int, W: int, tile: int):
     """Row-major list of (x0, y0, w, h) tiles of an H x W frame (y counted from the bottom row, like the accumulator)."""
     T = max(1, int(tile))
@@ -598,7 +602,17 @@ class PathTracingSession:
             return accum
         if opt.shard_mode not in ('spp', 'tile'):
             raise ValueError("shard_mode must be 'spp' or 'tile'")
-        return self.render_samples(shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device))
+        ids = shard_sample_ids(opt.ray_spp, opt.shard_rank, opt.shard_world, self.device)
+        H, W = self.camera.resolution()
+        if H * W > MAX_PIXELS_PER_CALL:
+            # one drp_render call covers at most 2^24 pixels (a launch batch holds at least one sample of every pixel of the call): larger frames
+            # (8K and up) are rendered tile by tile into the same accumulator -- RNG streams and rows are keyed by the global pixel, so the
+            # image does not depend on the tiling (the property tile sharding rests on)
+            accum = self.new_accumulators()
+            for tile in frame_tiles(H, W, 4096):
+                self.render_samples(ids, accum, tile=tile)
+            return accum
+        return self.render_samples(ids)
 
     def exchange_accumulators(self, accum: torch.Tensor) -> torch.Tensor:
         """The path's one exchange step between ranks: the packed accumulators are summed -- all-reduce, or reduce to ``options.result_rank``.

@@ -193,3 +193,20 @@ def test_instance_table_of_a_scene_and_shared_tensors_survive_moves():
     assert scene_instances(few.objects) is None                       # too few objects to pay
     import scenes
     assert scene_instances(scenes.mixed_scene().objects) is None      # nothing shared
+
+
+def test_frames_beyond_one_call_are_tiled_within_the_per_call_pixel_limit():
+    """drp_render covers at most 2^24 pixels per call; render_accumulators() tiles larger frames (8K: 33 M pixels).  The tiles must partition
+    the frame, and each must fit one call."""
+    import numpy as np
+    from diffrp_b200.path_tracing import frame_tiles, MAX_PIXELS_PER_CALL
+    for H, W in ((4320, 7680), (4096, 4097), (8192, 8192), (1, 1 << 25)):
+        assert H * W > MAX_PIXELS_PER_CALL
+        cover = np.zeros((H, W), np.uint8) if H * W <= (1 << 26) else None
+        total = 0
+        for (x0, y0, w, h) in frame_tiles(H, W, 4096):
+            assert 0 < w * h <= MAX_PIXELS_PER_CALL and x0 + w <= W and y0 + h <= H
+            total += w * h
+            if cover is not None:
+                cover[y0:y0 + h, x0:x0 + w] += 1
+        assert total == H * W and (cover is None or (cover == 1).all())
