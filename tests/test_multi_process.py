@@ -114,3 +114,49 @@ def test_sharded_upload_segments_tile_the_packed_buffer():
             for o, p, n in items:                                        # payload bytes: exactly once, from their own source
                 assert (covered[o:o + n] == 1).all() and (source[o:o + n] == p + np.arange(n)).all()
             assert covered.max() <= 1
+
+
+def _reduce_to_rank_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffrp_b200.path_tracing import reduce_accumulators
+    g = torch.Generator().manual_seed(11)
+    parts = [torch.rand(97, 16, generator=g) for _ in range(world)]
+    mine = parts[rank].clone()
+    out = reduce_accumulators(mine, world, dst=1)                    # options.result_rank = 1: only that rank receives the sum
+    ok = True
+    if rank == 1:
+        ok = torch.allclose(out, sum(parts), rtol=0, atol=1e-6)
+    try:                                                             # a shard_world that is not the group's size must fail loudly
+        reduce_accumulators(parts[rank].clone(), world + 1)
+        ok = False
+    except RuntimeError as e:
+        ok = ok and "does not match" in str(e)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([int(all(flags))]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduce_to_result_rank_and_world_size_check(tmp_path):
+    """options.result_rank: `reduce` to one rank instead of the all-reduce; and the guard against a shard_world that does not match the group."""
+    world, port = 2, 33000 + (os.getpid() % 2000)
+    mp.spawn(_reduce_to_rank_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / "ok.npy")[0] == 1
+
+
+def test_sharded_exchange_without_a_process_group_raises():
+    """A sharded render whose accumulators are never summed would silently return 1/world of the energy: it must raise instead."""
+    import pytest
+    sys.path.insert(0, ROOT)
+    from diffrp_b200.path_tracing import reduce_accumulators, gather_tile_accumulators
+    assert not (dist.is_available() and dist.is_initialized())
+    acc = torch.zeros(16, 16)
+    with pytest.raises(RuntimeError, match="not initialised"):
+        reduce_accumulators(acc, 2)
+    with pytest.raises(RuntimeError, match="not initialised"):
+        gather_tile_accumulators(acc, 4, 4, 2, 0, 2)
+    assert reduce_accumulators(acc, 1) is acc and gather_tile_accumulators(acc, 4, 4, 2, 0, 1) is acc   # unsharded: no exchange, no group needed
