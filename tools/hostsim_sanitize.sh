@@ -11,3 +11,9 @@ g++ -O1 -g -std=c++17 -fPIC -fopenmp -mavx2 -mfma -ffp-contract=off -DDRP_HOSTSI
 nm -D tests/hostsim/libhostsim.so | grep -c "__asan\|__ubsan" | sed 's/^/instrumented symbols: /'
 LD_PRELOAD="$ASAN $UBSAN" ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_hostsim.py -q 2>&1 | tail -5
 rm -f tests/hostsim/libhostsim.so; make -C tests/hostsim > /dev/null   # back to the plain build
+# the same for the CPU oracle (the checker itself): oracle/*.c under ASan + UBSan over its golden-vector tests
+cp oracle/liborc.so /tmp/liborc_orig.so 2>/dev/null || true
+gcc -O1 -g -fPIC -fopenmp -mavx2 -mfma -ffp-contract=off -fno-fast-math -fsanitize=address,undefined -fno-sanitize-recover=undefined \
+    -shared -o oracle/liborc.so oracle/orc_raycast.c oracle/orc_shade.c oracle/orc_tonemap.c -lm
+LD_PRELOAD="$ASAN $UBSAN" ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_oracle_golden.py -q 2>&1 | tail -3
+rm -f oracle/liborc.so; make -C oracle > /dev/null   # back to the plain build
